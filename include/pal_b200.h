@@ -1,0 +1,94 @@
+/* pal_b200.h -- C ABI of libpal_b200.so, the B200-native (sm_100a) implementation of the
+ * PyAudioLocalization data-parallel hot path.
+ *
+ * The reference (zeynelacikgoez/PyAudioLocalization) is pure Python and has no FFI of its own
+ * (SURVEY.md section 8b); its interface for this path is a handful of module-level functions.
+ * Each entry point below names the reference function(s) it replaces (file:line relative to
+ * the reference repository).  The Python host layer (pyaudiolocalization_b200/) binds these
+ * with ctypes and mirrors the reference signatures; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer named *_dev is DEVICE memory owned by the caller (e.g. a torch tensor);
+ *     the library never allocates, frees or synchronises; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *   - return value 0 = success, negative = error; pal_last_error() gives the text
+ *     (thread-local, never NULL).  No C++ exception crosses this boundary.
+ *   - integer decisions that the reference takes in float64 on the host (window half-width,
+ *     peak distance: utils.py:151,163) are taken by the caller and passed as integers.
+ */
+#ifndef PAL_B200_H
+#define PAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAL_ABI_VERSION 1
+
+/* error codes */
+#define PAL_OK 0
+#define PAL_ERR_INVALID (-1)    /* bad argument (NULL pointer, negative size, unsupported option) */
+#define PAL_ERR_WORKSPACE (-2)  /* workspace too small; see pal_gcc_phat_workspace */
+#define PAL_ERR_CUDA (-3)       /* a CUDA runtime call or kernel launch failed */
+#define PAL_ERR_UNSUPPORTED (-4)
+
+/* per-row flag bits written to flags_dev */
+#define PAL_FLAG_NEAR_TIE 1u
+#define PAL_FLAG_CHAIN 2u
+#define PAL_FLAG_PLATEAU 4u
+#define PAL_FLAG_REFINED 8u
+#define PAL_FLAG_FALLBACK_ARGMAX 16u
+#define PAL_FLAG_ALT_THRESHOLD 32u
+#define PAL_FLAG_STACK_OVERFLOW 64u
+
+/* Options of utils.get_time_delays_phat (utils.py:121-127) in integer form. */
+typedef struct pal_tdoa_params {
+  int32_t win_half;    /* largest |lag| in samples with |lag|/fs <= max_expected_delay (utils.py:163);
+                          -1 = max_expected_delay is None, -2 = nothing passes */
+  int32_t peak_dist;   /* int(fs*0.001) >= 1 (utils.py:151) */
+  int32_t thr_method;  /* 0 = 'median' (and any unknown string, utils.py:148-149), 1 = 'adaptive' */
+  float thr_mult;      /* threshold_multiplier */
+  int32_t num_peaks;   /* 1..16 */
+  float tie_eps;       /* fp32 fast path: decisions closer than this are re-evaluated in float64 */
+  int32_t refine;      /* 1 = run the float64 re-evaluation of flagged rows (default), 0 = skip */
+} pal_tdoa_params;
+
+int pal_abi_version(void);
+const char* pal_last_error(void);
+
+/* number of kernels this library has launched since load (for bench accounting) */
+unsigned long long pal_launch_count(void);
+
+/* Bytes of device workspace pal_gcc_phat_tdoa needs to process all B frames in one pass
+ * (it accepts less and then walks the batch in chunks; `min_bytes`, if not NULL, receives the
+ * smallest usable size). */
+int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, size_t* bytes,
+                           size_t* min_bytes);
+
+/* Batched GCC-PHAT + TDOA pick.
+ * Replaces, for every frame b and mic pair p = (i, j):
+ *     utils.phat_correlation(sig[b][i], sig[b][j])          utils.py:108-119
+ *     utils.get_time_delays_phat(..., num_peaks, ...)       utils.py:121-181
+ *     np.max(corr)                                          main.py:223
+ * i.e. the double loop main.py:202-228.
+ *   sig_dev   [B][M][n_samples] float32
+ *   pairs_dev [P][2] int32 (i, j)
+ *   k_idx_dev [B][P][num_peaks] int32: raw IFFT index k of each selected peak, -1 padded;
+ *             the reference's time delay is (k - (n_samples-1)) / fs  (utils.py:141-142)
+ *   k_count_dev [B][P] int32 or NULL; peak_dev/gmax_dev [B][P] float32: corr[k0], max(corr)
+ *   flags_dev [B][P] uint32; corr_opt_dev NULL or [B][P][2*n_samples-1] float32 (FFT order)
+ */
+int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples,
+                      const int32_t* pairs_dev, int32_t P, const pal_tdoa_params* prm,
+                      int32_t* k_idx_dev, int32_t* k_count_dev, float* peak_dev, float* gmax_dev,
+                      uint32_t* flags_dev, float* corr_opt_dev, void* ws_dev, size_t ws_bytes,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAL_B200_H */

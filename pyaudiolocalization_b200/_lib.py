@@ -1,0 +1,71 @@
+"""ctypes binding of libpal_b200.so (the C ABI declared in include/pal_b200.h).
+
+There is no CPU fallback: if the CUDA library has not been built, importing any compute
+entry point raises.  Build it with `python -m pyaudiolocalization_b200.build`.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpal_b200.so")
+
+PAL_ABI_VERSION = 1
+
+# per-row flag bits (include/pal_b200.h)
+FLAG_NEAR_TIE = 1
+FLAG_CHAIN = 2
+FLAG_PLATEAU = 4
+FLAG_REFINED = 8
+FLAG_FALLBACK_ARGMAX = 16
+FLAG_ALT_THRESHOLD = 32
+FLAG_STACK_OVERFLOW = 64
+
+
+class PalError(RuntimeError):
+    pass
+
+
+class TdoaParams(C.Structure):
+    _fields_ = [("win_half", C.c_int32), ("peak_dist", C.c_int32), ("thr_method", C.c_int32),
+                ("thr_mult", C.c_float), ("num_peaks", C.c_int32), ("tie_eps", C.c_float),
+                ("refine", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; fail loudly when it is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PalError(f"{LIB_PATH} not found: the CUDA extension is not built "
+                       "(run `python -m pyaudiolocalization_b200.build`); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.pal_abi_version.restype = C.c_int
+    L.pal_last_error.restype = C.c_char_p
+    L.pal_launch_count.restype = C.c_ulonglong
+    L.pal_gcc_phat_workspace.restype = C.c_int
+    L.pal_gcc_phat_workspace.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                         C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.pal_gcc_phat_tdoa.restype = C.c_int
+    L.pal_gcc_phat_tdoa.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                    C.POINTER(TdoaParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    if L.pal_abi_version() != PAL_ABI_VERSION:
+        raise PalError(f"libpal_b200.so ABI {L.pal_abi_version()} != expected {PAL_ABI_VERSION}; rebuild")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().pal_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise PalError(f"{what} failed ({rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().pal_launch_count())

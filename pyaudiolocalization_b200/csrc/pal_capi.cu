@@ -1,0 +1,207 @@
+// pal_capi.cu -- __global__ wrappers and the extern "C" boundary of libpal_b200.so.
+// Build: nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+
+#include "../../include/pal_b200.h"
+#include "pal_pfa4095.cuh"
+
+using namespace pal;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(PAL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define PAL_CUDA(call)                                  \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+constexpr int kFwdThreads = 256;
+constexpr int kFastWarps = 8;
+constexpr int kExactThreads = 256;
+
+__global__ void __launch_bounds__(kFwdThreads) k_fwd4095(const float* __restrict__ sig, int M, long long units,
+                                                       cpxf* __restrict__ spec) {
+  extern __shared__ __align__(128) char smem[];
+  fwd4095_body<kFwdThreads>(sig, M, units, spec, smem);
+}
+
+template <bool WRITE_CORR>
+__global__ void __launch_bounds__(kFastWarps * 32, 1)
+    k_pair4095_fast(const cpxf* __restrict__ spec, const int* __restrict__ pairs, int M, int P, long long n_items,
+                    int win_half, int dist, float eps, int* __restrict__ k_idx, float* __restrict__ peak,
+                    float* __restrict__ gmax, unsigned* __restrict__ flags, float* __restrict__ corr_out) {
+  extern __shared__ __align__(128) char smem[];
+  pair4095_fast_body<kFastWarps, WRITE_CORR>(spec, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax,
+                                             flags, corr_out, smem);
+}
+
+template <typename T, bool FROM_SPECTRA>
+__global__ void __launch_bounds__(kExactThreads, 1)
+    k_pair4095_exact(const float* __restrict__ sig, const cpxf* __restrict__ spec, const int* __restrict__ pairs,
+                     int M, int P, long long n_items, const int* __restrict__ item_list,
+                     const int* __restrict__ item_count, PickParams pp, int* k_idx, int* k_count, float* peak,
+                     float* gmax, unsigned* flags, unsigned extra_flag, unsigned keep_mask, float* corr_out) {
+  extern __shared__ __align__(128) char smem[];
+  pair4095_exact_body<T, kExactThreads, FROM_SPECTRA>(sig, spec, pairs, M, P, n_items, item_list, item_count, pp,
+                                                      k_idx, k_count, peak, gmax, flags, extra_flag, keep_mask,
+                                                      corr_out, smem);
+}
+
+// rows whose fast-path decision was flagged -> compact list for the float64 kernel
+__global__ void k_compact_flagged(const unsigned* __restrict__ flags, long long n_items, long long item0,
+                                  unsigned mask, int* __restrict__ list, int* __restrict__ count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_items && (flags[i] & mask)) list[atomicAdd(count, 1)] = int(item0 + i);
+}
+__global__ void k_fill_count(int* k_count, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) k_count[i] = 1;
+}
+
+struct DevInfo {
+  int sms = 0;
+  int dev = -1;
+};
+int device_info(DevInfo& d) {
+  PAL_CUDA(cudaGetDevice(&d.dev));
+  PAL_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.dev));
+  return PAL_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr unsigned kRefineMask = PAL_FLAG_NEAR_TIE | PAL_FLAG_CHAIN | PAL_FLAG_PLATEAU;
+
+}  // namespace
+
+extern "C" {
+
+int pal_abi_version(void) { return PAL_ABI_VERSION; }
+const char* pal_last_error(void) { return g_err.c_str(); }
+unsigned long long pal_launch_count(void) { return g_launches.load(); }
+
+int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, size_t* bytes, size_t* min_bytes) {
+  if (B < 0 || M < 2 || P < 1 || n_samples < 1 || !bytes) return fail(PAL_ERR_INVALID, "pal_gcc_phat_workspace: bad argument");
+  if (n_samples != kFrame2048)
+    return fail(PAL_ERR_UNSUPPORTED, "pal_gcc_phat_workspace: only n_samples == 2048 is implemented in this build");
+  const size_t per_frame = align_up(size_t(M) * kSpecSlots * sizeof(cpxf), 256);
+  const size_t list = align_up(size_t(B) * P * sizeof(int), 256) + 256;
+  *bytes = per_frame * size_t(B > 0 ? B : 1) + list;
+  if (min_bytes) *min_bytes = per_frame + list;
+  return PAL_OK;
+}
+
+int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, const int32_t* pairs_dev,
+                      int32_t P, const pal_tdoa_params* prm, int32_t* k_idx_dev, int32_t* k_count_dev,
+                      float* peak_dev, float* gmax_dev, uint32_t* flags_dev, float* corr_opt_dev, void* ws_dev,
+                      size_t ws_bytes, void* stream_) {
+  if (!prm) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: prm is NULL");
+  if (B < 0 || M < 2 || P < 1) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: need B >= 0, M >= 2, P >= 1");
+  if (B == 0) return PAL_OK;
+  if (!sig_dev || !pairs_dev || !k_idx_dev || !peak_dev || !gmax_dev || !flags_dev || !ws_dev)
+    return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: NULL device pointer");
+  if (prm->peak_dist < 1) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: peak_dist must be >= 1 (scipy: `distance` must be greater or equal to 1)");
+  if (prm->num_peaks < 1 || prm->num_peaks > 16) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: num_peaks must be in 1..16");
+  if (n_samples != kFrame2048)
+    return fail(PAL_ERR_UNSUPPORTED, "pal_gcc_phat_tdoa: only n_samples == 2048 is implemented in this build");
+  if ((reinterpret_cast<uintptr_t>(sig_dev) & 15u) || (reinterpret_cast<uintptr_t>(ws_dev) & 255u))
+    return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: sig_dev must be 16-byte and ws_dev 256-byte aligned");
+  if (B * (int64_t)P > 0x7fffffffLL) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: B*P exceeds 2^31-1; split the batch");
+
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+
+  const size_t per_frame = align_up(size_t(M) * kSpecSlots * sizeof(cpxf), 256);
+  const size_t list_bytes = align_up(size_t(B) * P * sizeof(int), 256) + 256;
+  if (ws_bytes < per_frame + list_bytes) return fail(PAL_ERR_WORKSPACE, "pal_gcc_phat_tdoa: workspace too small");
+  char* ws = static_cast<char*>(ws_dev);
+  int* list = reinterpret_cast<int*>(ws);
+  int* count = reinterpret_cast<int*>(ws + list_bytes - 256);
+  cpxf* spec = reinterpret_cast<cpxf*>(ws + list_bytes);
+  const int64_t chunk = std::min<int64_t>(B, int64_t((ws_bytes - list_bytes) / per_frame));
+
+  const PickParams pp{prm->win_half, prm->peak_dist, prm->thr_method, prm->thr_mult, prm->num_peaks};
+  const size_t fwd_smem = sizeof(FwdSmem);
+  const size_t fast_smem = kFastWarps * sizeof(FastWarpSmem);
+  const size_t exd_smem = sizeof(ExactSmem<double>);
+  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_exact<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exd_smem));
+  PAL_CUDA(cudaFuncSetAttribute(k_fwd4095, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+
+  if (prm->num_peaks != 1) {
+    // num_peaks > 1: every row goes through the exact float64 kernel, straight from the raw
+    // frames (not the hot path: main.py:204 always asks for one peak)
+    const long long n_items = (long long)B * P;
+    const int ge = (int)std::min<long long>(n_items, (long long)di.sms);
+    k_pair4095_exact<double, false><<<ge, kExactThreads, exd_smem, stream>>>(
+        sig_dev, nullptr, pairs_dev, M, P, n_items, nullptr, nullptr, pp, k_idx_dev, k_count_dev, peak_dev,
+        gmax_dev, flags_dev, PAL_FLAG_REFINED, 0u, corr_opt_dev);
+    ++g_launches;
+    PAL_CUDA(cudaGetLastError());
+    return PAL_OK;
+  }
+  PAL_CUDA(cudaMemsetAsync(count, 0, sizeof(int), stream));
+
+  for (int64_t f0 = 0; f0 < B; f0 += chunk) {
+    const int64_t nb = std::min<int64_t>(chunk, B - f0);
+    const long long n_items = (long long)nb * P;
+    const long long item0 = (long long)f0 * P;
+    const float* sig = sig_dev + f0 * M * kFrame2048;
+    {
+      const long long units = (long long)nb * ((M + 1) / 2);
+      const int gf = (int)std::min<long long>(units, (long long)di.sms * 6);
+      k_fwd4095<<<gf, kFwdThreads, fwd_smem, stream>>>(sig, M, units, spec);
+      ++g_launches;
+      const int gp = (int)std::min<long long>((n_items + kFastWarps - 1) / kFastWarps, (long long)di.sms);
+      float* corr = corr_opt_dev ? corr_opt_dev + item0 * kN4095 : nullptr;
+      if (corr)
+        k_pair4095_fast<true><<<gp, kFastWarps * 32, fast_smem, stream>>>(
+            spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist, prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
+            gmax_dev + item0, flags_dev + item0, corr);
+      else
+        k_pair4095_fast<false><<<gp, kFastWarps * 32, fast_smem, stream>>>(
+            spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist, prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
+            gmax_dev + item0, flags_dev + item0, nullptr);
+      ++g_launches;
+      if (prm->refine) {
+        k_compact_flagged<<<(unsigned)((n_items + 255) / 256), 256, 0, stream>>>(flags_dev + item0, n_items, item0,
+                                                                                 kRefineMask, list, count);
+        ++g_launches;
+      }
+    }
+    PAL_CUDA(cudaGetLastError());
+  }
+  {
+    if (k_count_dev) {
+      k_fill_count<<<(unsigned)((B * P + 255) / 256), 256, 0, stream>>>(k_count_dev, B * P);
+      ++g_launches;
+    }
+    if (prm->refine) {
+      // float64 re-evaluation of the flagged rows, straight from the raw frames (global item ids)
+      k_pair4095_exact<double, false><<<di.sms, kExactThreads, exd_smem, stream>>>(
+          sig_dev, nullptr, pairs_dev, M, P, (long long)B * P, list, count, pp, k_idx_dev, nullptr, peak_dev,
+          gmax_dev, flags_dev, PAL_FLAG_REFINED, kRefineMask, nullptr);
+      ++g_launches;
+    }
+    PAL_CUDA(cudaGetLastError());
+  }
+  return PAL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,474 @@
+// pal_pfa4095.cuh -- exact length-4095 GCC-PHAT kernels (2048-sample frames, n = n1+n2-1 = 4095).
+//
+//   fwd4095_body        utils.py:114-115  np.fft.fft(sig, n) of every channel (two real channels
+//                                         per complex transform), spectra stored in the
+//                                         Hermitian-half "[q][r]" layout the pair kernels read
+//   pair4095_fast_body  utils.py:116-118 + 140-181 + main.py:223   one WARP per mic pair:
+//                                         cross-spectrum, PHAT weighting, inverse DFT, peak pick,
+//                                         all in registers / shared memory; R never touches HBM
+//   pair4095_exact_body same semantics in one BLOCK per pair, templated on the scalar type;
+//                                         in float64 it is the exact re-evaluation of the rows the
+//                                         fast kernel flags (near ties below the fp32 error bound)
+//
+// 4095 = 5*7*9*13 = 63*65: the transform is a Good-Thomas prime-factor DFT -- no twiddle
+// multiplications between stages (pal_dft_small.h).
+#pragma once
+#include "pal_dft_small.h"
+#include "pal_peakpick.cuh"
+
+namespace pal {
+
+constexpr int kN4095 = 4095;
+constexpr int kFrame2048 = 2048;
+constexpr int kSpecSlots = 65 * 32;  // Hermitian half in (q, r) labels: r = e mod 63 in [0, 32)
+
+// ---------------------------------------------------------------- 4-stage in-place PFA (smem)
+PAL_HD constexpr int pfa_inv_mod(int a, int m) {
+  for (int t = 1; t < m; ++t)
+    if ((a * t) % m == 1) return t;
+  return 0;
+}
+// CRT basis element of factor f: 1 (mod f), 0 (mod 4095/f)
+PAL_HD constexpr int pfa_u(int f) { return (kN4095 / f) * pfa_inv_mod((kN4095 / f) % f, f); }
+struct Pfa4095 {
+  static constexpr int N = kN4095;
+  static PAL_HD constexpr int u(int f) { return pfa_u(f); }
+  static constexpr int G = (pfa_inv_mod((N / 5) % 5, 5) * pfa_u(5) + pfa_inv_mod((N / 7) % 7, 7) * pfa_u(7) +
+                            pfa_inv_mod((N / 9) % 9, 9) * pfa_u(9) + pfa_inv_mod((N / 13) % 13, 13) * pfa_u(13)) % N;
+  // after the four in-place stages, output index k sits at location (G*k) mod N
+  static PAL_HD constexpr int loc(int k) { return (G * k) % N; }
+};
+static_assert(pfa_u(5) == 3276 && pfa_u(7) == 1170 && pfa_u(9) == 910 && pfa_u(13) == 2835, "CRT basis");
+static_assert(Pfa4095::G == 1829, "output map");
+
+template <int F, int SIGN, typename T, int NT> PAL_DEV void pfa_stage(T* re, T* im) {
+  constexpr int U = pfa_u(F);
+  for (int g = simt::tid(); g < kN4095 / F; g += NT) {
+    T xr[F], xi[F];
+    int idx = F * g;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      xr[j] = re[idx];
+      xi[j] = im[idx];
+      idx += U;
+      if (idx >= kN4095) idx -= kN4095;
+    }
+    dft_odd<F, SIGN, T>(xr, xi);
+    idx = F * g;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      re[idx] = xr[j];
+      im[idx] = xi[j];
+      idx += U;
+      if (idx >= kN4095) idx -= kN4095;
+    }
+  }
+}
+template <int SIGN, typename T, int NT> PAL_DEV void pfa4095_inplace(T* re, T* im) {
+  pfa_stage<13, SIGN, T, NT>(re, im);
+  simt::sync_block();
+  pfa_stage<9, SIGN, T, NT>(re, im);
+  simt::sync_block();
+  pfa_stage<7, SIGN, T, NT>(re, im);
+  simt::sync_block();
+  pfa_stage<5, SIGN, T, NT>(re, im);
+  simt::sync_block();
+}
+
+// Z = DFT(x1 + i x2) of two real signals -> S1[e], S2[e]  (zL = Z[e], zM = Z[n-e])
+template <typename T>
+PAL_DEV void split_two_real(T zLr, T zLi, T zMr, T zMi, T& s1r, T& s1i, T& s2r, T& s2i) {
+  s1r = T(0.5) * (zLr + zMr);
+  s1i = T(0.5) * (zLi - zMi);
+  s2r = T(0.5) * (zLi + zMi);
+  s2i = T(-0.5) * (zLr - zMr);
+}
+
+// PHAT weighting of one cross-spectrum bin, pre-scaled by 1/n (utils.py:116-118)
+template <typename T> PAL_DEV void phat_bin(T ar, T ai, T br, T bi, T inv_n, T& rr, T& ri) {
+  const T xr = fma_(ar, br, ai * bi);
+  const T xi = fma_(ai, br, -(ar * bi));
+  const T mag = sqrt_(fma_(xr, xr, xi * xi));
+  const T sc = inv_n / (mag + T(1e-10));
+  rr = xr * sc;
+  ri = xi * sc;
+}
+// fp32 hot-path flavour: MUFU.SQRT + MUFU.RCP (about 1 ulp each) instead of the branchy IEEE
+// sqrt/divide sequences; only the MAGNITUDE of the weight is affected (2e-7 relative), never
+// the phase, so the correlation moves far less than the 1e-4 tolerance.
+PAL_DEV void phat_bin_fast(float ar, float ai, float br, float bi, float inv_n, float& rr, float& ri) {
+#if PAL_GPU
+  const float xr = fmaf(ar, br, ai * bi);
+  const float xi = fmaf(ai, br, -(ar * bi));
+  float mag, rcp;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(xr, xr, xi * xi)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(mag + 1e-10f));
+  const float sc = inv_n * rcp;
+  rr = xr * sc;
+  ri = xi * sc;
+#else
+  phat_bin<float>(ar, ai, br, bi, inv_n, rr, ri);
+#endif
+}
+
+// ---------------------------------------------------------------- forward kernel
+// grid: one block per (frame, channel pair).  sig: [B][M][2048] float32.
+// spec: [B][M][65][32] complex64 -- S[e(r,q)] with e = (2080 r + 2016 q) mod 4095.
+struct FwdSmem {
+  float re[4096];
+  float im[4096];
+  mbar_t bar;
+};
+
+template <int NT>
+PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil(M/2) */, cpxf* spec, char* smem_raw) {
+  FwdSmem* sm = reinterpret_cast<FwdSmem*>(smem_raw);
+  const int tid = simt::tid();
+  const int cpairs = (M + 1) / 2;
+  if (tid == 0) simt::mbar_init(&sm->bar, 1);
+  simt::sync_block();
+  unsigned parity = 0;
+  for (long long unit = simt::bid(); unit < n_units; unit += simt::nblocks()) {
+    const long long frame = unit / cpairs;
+    const int ch0 = 2 * int(unit % cpairs);
+    const bool two = (ch0 + 1) < M;
+    const float* row0 = sig + (frame * M + ch0) * kFrame2048;
+    // TMA bulk load of the signal frame(s): two contiguous 8 KB rows straight into the re/im planes
+    if (tid == 0) {
+      simt::fence_async_smem();
+      simt::mbar_expect_tx(&sm->bar, two ? 2u * kFrame2048 * 4u : kFrame2048 * 4u);
+      simt::bulk_g2s(sm->re, row0, kFrame2048 * 4u, &sm->bar);
+      if (two) simt::bulk_g2s(sm->im, row0 + kFrame2048, kFrame2048 * 4u, &sm->bar);
+    }
+    for (int k = kFrame2048 + tid; k < 4096; k += NT) { sm->re[k] = 0.f; sm->im[k] = 0.f; }
+    if (!two)
+      for (int k = tid; k < kFrame2048; k += NT) sm->im[k] = 0.f;
+    simt::mbar_wait(&sm->bar, parity);
+    parity ^= 1u;
+    simt::sync_block();
+    pfa4095_inplace<-1, float, NT>(sm->re, sm->im);
+    cpxf* o0 = spec + (frame * M + ch0) * kSpecSlots;
+    cpxf* o1 = o0 + kSpecSlots;
+    for (int o = tid; o < kSpecSlots; o += NT) {
+      const int q = o >> 5, r = o & 31;
+      const int e = Idx4095::elem(r, q);
+      const int L = Pfa4095::loc(e);
+      const int L2 = (L == 0) ? 0 : kN4095 - L;
+      float s1r, s1i, s2r, s2i;
+      split_two_real(sm->re[L], sm->im[L], sm->re[L2], sm->im[L2], s1r, s1i, s2r, s2i);
+      o0[o] = cpxf{s1r, s1i};
+      if (two) o1[o] = cpxf{s2r, s2i};
+    }
+    simt::sync_block();
+  }
+}
+
+// ---------------------------------------------------------------- exact pair kernel (block per pair)
+template <typename T> struct ExactSmem {
+  T a_re[4096];
+  T a_im[4096];
+  T b_re[4096];
+  T b_im[4096];
+  unsigned char pkmap[4096];
+  PickScratch ps;
+  int out_k[16];
+  T out_gmax, out_peak;
+};
+
+struct PickParams {
+  int win_half;   // samples; -1 unbounded; -2 empty window
+  int dist;       // int(fs*0.001) >= 1           (utils.py:151)
+  int method;     // 0 median, 1 adaptive         (utils.py:144-149)
+  float mult;     // threshold_multiplier
+  int num_peaks;  // <= 16
+};
+
+// items: either all B*P (item_list == nullptr) or the compacted list of flagged items.
+// FROM_SPECTRA: read the fp32 spectra written by fwd4095; otherwise transform the two raw
+// frames here in precision T (the float64 refinement never sees an fp32-rounded spectrum).
+template <typename T, int NT, bool FROM_SPECTRA>
+PAL_DEV void pair4095_exact_body(const float* sig, const cpxf* spec, const int* pairs, int M, int P,
+                                 long long n_items, const int* item_list, const int* item_count,
+                                 PickParams pp, int* k_idx, int* k_count, float* peak, float* gmax,
+                                 unsigned* flags, unsigned extra_flag, unsigned keep_mask, float* corr_out,
+                                 char* smem_raw) {
+  ExactSmem<T>* sm = reinterpret_cast<ExactSmem<T>*>(smem_raw);
+  const int tid = simt::tid();
+  const long long total = item_list ? (long long)(*item_count) : n_items;
+  const T inv_n = T(1) / T(kN4095);
+  for (long long it = simt::bid(); it < total; it += simt::nblocks()) {
+    const long long item = item_list ? (long long)item_list[it] : it;
+    const long long frame = item / P;
+    const int p = int(item % P);
+    const int mi = pairs[2 * p], mj = pairs[2 * p + 1];
+    if (FROM_SPECTRA) {
+      const cpxf* si = spec + (frame * M + mi) * kSpecSlots;
+      const cpxf* sj = spec + (frame * M + mj) * kSpecSlots;
+      for (int o = tid; o < kSpecSlots; o += NT) {
+        const int q = o >> 5, r = o & 31;
+        const int e = Idx4095::elem(r, q);
+        const cpxf a = si[o], b = sj[o];
+        T rr, ri;
+        phat_bin<T>(T(a.x), T(a.y), T(b.x), T(b.y), inv_n, rr, ri);
+        sm->b_re[e] = rr;
+        sm->b_im[e] = ri;
+        if (e != 0) { sm->b_re[kN4095 - e] = rr; sm->b_im[kN4095 - e] = -ri; }
+      }
+    } else {
+      const float* xi = sig + (frame * M + mi) * kFrame2048;
+      const float* xj = sig + (frame * M + mj) * kFrame2048;
+      for (int k = tid; k < 4096; k += NT) {
+        sm->a_re[k] = (k < kFrame2048) ? T(xi[k]) : T(0);
+        sm->a_im[k] = (k < kFrame2048) ? T(xj[k]) : T(0);
+      }
+      simt::sync_block();
+      pfa4095_inplace<-1, T, NT>(sm->a_re, sm->a_im);
+      for (int e = tid; e < kN4095; e += NT) {
+        const int L = Pfa4095::loc(e);
+        const int L2 = (L == 0) ? 0 : kN4095 - L;
+        T s1r, s1i, s2r, s2i;
+        split_two_real<T>(sm->a_re[L], sm->a_im[L], sm->a_re[L2], sm->a_im[L2], s1r, s1i, s2r, s2i);
+        T rr, ri;
+        phat_bin<T>(s1r, s1i, s2r, s2i, inv_n, rr, ri);
+        sm->b_re[e] = rr;
+        sm->b_im[e] = ri;
+      }
+    }
+    simt::sync_block();
+    pfa4095_inplace<+1, T, NT>(sm->b_re, sm->b_im);
+    for (int k = tid; k < kN4095; k += NT) sm->a_re[k] = sm->b_re[Pfa4095::loc(k)];
+    simt::sync_block();
+    if (corr_out)
+      for (int k = tid; k < kN4095; k += NT) corr_out[item * kN4095 + k] = float(sm->a_re[k]);
+    PickResult pr = peakpick_row<T, NT>(sm->a_re, kN4095, kFrame2048 - 1, pp.win_half, pp.dist, pp.method,
+                                        T(pp.mult), pp.num_peaks, sm->pkmap, &sm->ps, sm->out_k,
+                                        &sm->out_gmax, &sm->out_peak);
+    simt::sync_block();
+    if (tid == 0) {
+      for (int t = 0; t < pp.num_peaks; ++t) k_idx[item * pp.num_peaks + t] = (t < pr.count) ? sm->out_k[t] : -1;
+      if (k_count) k_count[item] = pr.count;
+      peak[item] = float(sm->out_peak);
+      gmax[item] = float(sm->out_gmax);
+      // keep_mask != 0: this is a re-evaluation; remember why the fast path asked for it
+      flags[item] = (keep_mask ? (flags[item] & keep_mask) : 0u) | pr.flags | extra_flag;
+    }
+    simt::sync_block();
+  }
+}
+
+// ---------------------------------------------------------------- fast pair kernel (warp per pair)
+// Per-warp shared memory: the phase-A -> phase-B exchange Y[r][kq] (r < 32 by Hermitian symmetry),
+// later overwritten by the 4095-sample correlation row the peak pick scans.
+struct alignas(16) FastWarpSmem {
+  union {
+    struct {
+      cpxf ya[32 * 33];   // Y[r][kq], kq odd  -> column (kq-1)/2
+      cpxf yb[32 * 33];   // Y[r][kq], kq even >= 2 -> column (kq-2)/2
+      cpxf y0[32];        // Y[r][0]
+    } y;
+    float corr[4096];
+  };
+  cpxf lx[64];            // exchange of the odd column kq = 0 (DFT-7 -> DFT-9)
+};
+
+template <int WARPS, bool WRITE_CORR>
+PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P, long long n_items,
+                                int win_half, int dist, float eps, int* k_idx, float* peak, float* gmax,
+                                unsigned* flags, float* corr_out, char* smem_raw) {
+  using P65 = Pfa2<5, 13>;
+  using P63 = Pfa2<7, 9>;
+  const int lane = simt::lane();
+  FastWarpSmem* sm = reinterpret_cast<FastWarpSmem*>(smem_raw) + simt::warp();
+  const float inv_n = 1.0f / float(kN4095);
+  const int c0 = kFrame2048 - 1;
+  int lo = 1, hi = kN4095 - 2;
+  if (win_half >= 0) {
+    lo = (c0 - win_half > 1) ? c0 - win_half : 1;
+    hi = (c0 + win_half < kN4095 - 2) ? c0 + win_half : kN4095 - 2;
+  } else if (win_half < -1) {
+    lo = 1; hi = 0;
+  }
+
+  for (long long item = (long long)simt::bid() * WARPS + simt::warp(); item < n_items;
+       item += (long long)simt::nblocks() * WARPS) {
+    const long long frame = item / P;
+    const int p = int(item % P);
+    const int mi = pairs[2 * p], mj = pairs[2 * p + 1];
+    const cpxf* si = spec + (frame * M + mi) * kSpecSlots + lane;
+    const cpxf* sj = spec + (frame * M + mj) * kSpecSlots + lane;
+
+    // ---- phase A: lane r owns elements e(r, q), q = 0..64: PHAT, then DFT-65 over q ------
+    {
+      float zr[65], zi[65];
+#pragma unroll
+      for (int q = 0; q < 65; ++q) {
+        const cpxf a = si[q * 32], b = sj[q * 32];
+        phat_bin_fast(a.x, a.y, b.x, b.y, inv_n, zr[q], zi[q]);
+      }
+      dft_pfa2<5, 13, +1, float>(zr, zi);
+#pragma unroll
+      for (int s = 0; s < 65; ++s) {
+        const int kq = P65::out_index(s);
+        const cpxf v{zr[s], zi[s]};
+        if (kq == 0) sm->y.y0[lane] = v;
+        else if (kq & 1) sm->y.ya[lane * 33 + (kq - 1) / 2] = v;
+        else sm->y.yb[lane * 33 + (kq - 2) / 2] = v;
+      }
+    }
+    simt::sync_warp();
+
+    // ---- phase B: lane l owns output columns kq = 2l+1 (real part) and 2l+2 (imaginary part)
+    {
+      float wr[63], wi[63];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const cpxf a = sm->y.ya[r * 33 + lane], b = sm->y.yb[r * 33 + lane];
+        if (r == 0) {
+          wr[0] = a.x;
+          wi[0] = b.x;
+        } else {
+          wr[r] = a.x - b.y;       wi[r] = a.y + b.x;
+          wr[63 - r] = a.x + b.y;  wi[63 - r] = b.x - a.y;
+        }
+      }
+      // odd column kq = 0: nine DFT-7 on lanes 0..8 now, seven DFT-9 on lanes 0..6 below
+      float tr[7], ti[7];
+      if (lane < 9) {
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+          const int r = (a * P63::UA + lane * P63::UB) % 63;
+          const cpxf v = sm->y.y0[r < 32 ? r : 63 - r];
+          tr[a] = v.x;
+          ti[a] = (r == 0) ? 0.f : (r < 32 ? v.y : -v.y);
+        }
+      }
+      simt::sync_warp();            // every read of Y is done: the union now holds the correlation row
+      if (lane < 9) {
+        dft_odd<7, +1, float>(tr, ti);
+#pragma unroll
+        for (int a = 0; a < 7; ++a) sm->lx[(a * P63::UA + lane * P63::UB) % 63] = cpxf{tr[a], ti[a]};
+      }
+      dft_pfa2<7, 9, +1, float>(wr, wi);
+      const int b0 = 63 * (2 * lane + 1);
+#pragma unroll
+      for (int s = 0; s < 63; ++s) {
+        const int kr = P63::out_index(s);
+        int k1 = b0 + 65 * kr;
+        if (k1 >= kN4095) k1 -= kN4095;
+        int k2 = k1 + 63;
+        if (k2 >= kN4095) k2 -= kN4095;
+        sm->corr[k1] = wr[s];
+        sm->corr[k2] = wi[s];
+      }
+      simt::sync_warp();
+      if (lane < 7) {
+        float ur[9], ui[9];
+#pragma unroll
+        for (int b = 0; b < 9; ++b) {
+          const cpxf v = sm->lx[(lane * P63::UA + b * P63::UB) % 63];
+          ur[b] = v.x;
+          ui[b] = v.y;
+        }
+        dft_odd<9, +1, float>(ur, ui);
+#pragma unroll
+        for (int b = 0; b < 9; ++b) {
+          const int kr = (9 * lane + 7 * b) % 63;
+          sm->corr[(65 * kr) % kN4095] = ur[b];
+        }
+      }
+    }
+    simt::sync_warp();
+
+    // ---- peak pick (num_peaks = 1), utils.py:140-181 in the reduced form ----------------
+    const float* c = sm->corr;
+    if (WRITE_CORR) {
+      float* dst = corr_out + item * kN4095;
+      for (int k = lane; k < kN4095; k += 32) dst[k] = c[k];
+    }
+    float s_abs = 0.f, gm = -3.0e38f;
+#pragma unroll 8
+    for (int k = lane; k < kN4095; k += 32) {
+      const float v = c[k];
+      s_abs += fabsf(v);
+      gm = fmaxf(gm, v);
+    }
+    s_abs = warp_sum(s_abs);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) gm = fmaxf(gm, simt::shfl_xor(gm, m));
+    const float mean_abs = s_abs * inv_n;
+
+    // best and second-best strict local maximum inside the window; equal neighbours
+    float b1 = 0.f, b2 = -3.0e38f, pl = -3.0e38f;
+    int i1 = -1;
+    for (int k = lo + lane; k <= hi; k += 32) {
+      const float v = c[k], vl = c[k - 1], vr = c[k + 1];
+      if (v == vl || v == vr) pl = fmaxf(pl, v);
+      if (vl < v && v > vr) {
+        if (i1 < 0 || v >= b1) { if (i1 >= 0) b2 = fmaxf(b2, b1); b1 = v; i1 = k; }
+        else b2 = fmaxf(b2, v);
+      }
+    }
+    float bv = b1;
+    int bi = i1;
+    warp_argmax<true>(bv, bi);
+    float cand2 = (i1 == bi) ? b2 : ((i1 >= 0) ? b1 : -3.0e38f);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      cand2 = fmaxf(cand2, simt::shfl_xor(cand2, m));
+      pl = fmaxf(pl, simt::shfl_xor(pl, m));
+    }
+
+    unsigned fl = 0;
+    int kbest;
+    float hbest;
+    if (bi >= 0 && bv >= mean_abs + eps) {
+      kbest = bi;
+      hbest = bv;
+      if (cand2 >= bv - eps) fl |= PAL_FLAG_NEAR_TIE;
+      if (pl >= bv - eps) fl |= PAL_FLAG_PLATEAU;
+      // anything within `dist` samples that is as high as the winner (up to eps) needs the
+      // full greedy resolution of the distance rule -> exact kernel
+      bool hit = false;
+      for (int o = -dist + lane; o <= dist; o += 32) {
+        const int q = bi + o;
+        if (o != 0 && q >= 0 && q < kN4095 && c[q] >= bv - eps) hit = true;
+      }
+      if (simt::ballot(hit)) fl |= PAL_FLAG_CHAIN;
+    } else if (bi >= 0) {
+      // winner not clearly above mean|c|: the median / fallback logic decides -> exact kernel
+      kbest = bi;
+      hbest = bv;
+      fl |= PAL_FLAG_NEAR_TIE;
+    } else {
+      // no local maximum in the window: unbounded first argmax (utils.py:168-172)
+      int gi = 0x7fffffff;
+      int near = 0;
+      for (int k = lane; k < kN4095; k += 32) {
+        const float v = c[k];
+        if (v == gm && k < gi) gi = k;
+        if (v >= gm - eps) ++near;
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        const int og = simt::shfl_xor(gi, m);
+        gi = og < gi ? og : gi;
+        near += simt::shfl_xor(near, m);
+      }
+      kbest = gi;
+      hbest = gm;
+      fl |= PAL_FLAG_FALLBACK_ARGMAX;
+      const bool all_zero = (s_abs == 0.f);
+      if (near > 1 && !all_zero) fl |= PAL_FLAG_NEAR_TIE;
+      if (pl > -3.0e38f && win_half != -2 && !all_zero && lo <= hi) fl |= PAL_FLAG_PLATEAU;
+    }
+    if (lane == 0) {
+      k_idx[item] = kbest;
+      peak[item] = hbest;
+      gmax[item] = gm;
+      flags[item] = fl;
+    }
+    simt::sync_warp();   // the next item overwrites the union
+  }
+}
+
+}  // namespace pal

@@ -1,0 +1,212 @@
+// pal_simt.h -- the thin SIMT layer every kernel body in this directory is written against.
+//
+// Compiled by nvcc (sm_100a) it maps 1:1 onto CUDA intrinsics (threadIdx, __syncthreads,
+// warp shuffles, mbarrier + cp.async.bulk "TMA" bulk copies).  Compiled by a host C++20
+// compiler with -DPAL_EMU it runs the SAME kernel bodies on OS threads (one std::thread per
+// CUDA thread, std::barrier for block/warp barriers).  The emulation exists only for the
+// CPU test-suite (tests/emu/): there is no GPU in the build container, so kernel logic is
+// checked against the oracle on the host before a GPU minute is spent.  The product library
+// (libpal_b200.so) never contains the emulation.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cmath>
+
+#if defined(__CUDACC__) && !defined(PAL_EMU)
+#define PAL_GPU 1
+#define PAL_HD __host__ __device__ __forceinline__
+#define PAL_DEV __device__ __forceinline__
+#else
+#define PAL_GPU 0
+#define PAL_HD inline
+#define PAL_DEV inline
+#include <atomic>
+#include <barrier>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+#endif
+
+namespace pal {
+
+template <typename T> struct alignas(2 * sizeof(T)) cpx { T x, y; };
+using cpxf = cpx<float>;
+using cpxd = cpx<double>;
+
+struct alignas(8) mbar_t { unsigned long long v; };
+
+#if PAL_GPU
+// ------------------------------------------------------------------ device
+namespace simt {
+PAL_DEV int tid() { return threadIdx.x; }
+PAL_DEV int nthreads() { return blockDim.x; }
+PAL_DEV int bid() { return blockIdx.x; }
+PAL_DEV int nblocks() { return gridDim.x; }
+PAL_DEV int lane() { return threadIdx.x & 31; }
+PAL_DEV int warp() { return threadIdx.x >> 5; }
+PAL_DEV void sync_block() { __syncthreads(); }
+PAL_DEV void sync_warp() { __syncwarp(); }
+template <class T> PAL_DEV T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <class T> PAL_DEV T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PAL_DEV unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+
+// mbarrier + 1-D TMA bulk copy (cp.async.bulk, SASS: UBLKCP)
+PAL_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+PAL_DEV void mbar_init(mbar_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PAL_DEV void mbar_expect_tx(mbar_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
+               : "memory");
+}
+PAL_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, mbar_t* b) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(b))
+      : "memory");
+}
+// order earlier generic-proxy accesses of shared memory before a following bulk (async-proxy) copy
+PAL_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+PAL_DEV void mbar_wait(mbar_t* b, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+}  // namespace simt
+
+PAL_DEV float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+PAL_DEV double fma_(double a, double b, double c) { return fma(a, b, c); }
+PAL_DEV float sqrt_(float a) { return sqrtf(a); }
+PAL_DEV double sqrt_(double a) { return sqrt(a); }
+PAL_DEV float abs_(float a) { return fabsf(a); }
+PAL_DEV double abs_(double a) { return fabs(a); }
+PAL_DEV float max_(float a, float b) { return fmaxf(a, b); }
+PAL_DEV double max_(double a, double b) { return fmax(a, b); }
+PAL_DEV float min_(float a, float b) { return fminf(a, b); }
+PAL_DEV double min_(double a, double b) { return fmin(a, b); }
+
+#else
+// ------------------------------------------------------------------ host emulation
+namespace simt {
+struct WarpCtx {
+  std::unique_ptr<std::barrier<>> bar;
+  unsigned long long slot[32];
+  int width;
+};
+struct BlockCtx {
+  std::unique_ptr<std::barrier<>> bar;
+  std::vector<WarpCtx> warps;
+  int nthreads, bid, nblocks;
+};
+struct ThreadCtx {
+  BlockCtx* blk = nullptr;
+  int tid = 0;
+};
+inline thread_local ThreadCtx tctx;
+
+inline int tid() { return tctx.tid; }
+inline int nthreads() { return tctx.blk->nthreads; }
+inline int bid() { return tctx.blk->bid; }
+inline int nblocks() { return tctx.blk->nblocks; }
+inline int lane() { return tctx.tid & 31; }
+inline int warp() { return tctx.tid >> 5; }
+inline void sync_block() { tctx.blk->bar->arrive_and_wait(); }
+inline void sync_warp() { tctx.blk->warps[warp()].bar->arrive_and_wait(); }
+template <class T> inline T shfl(T v, int src) {
+  static_assert(sizeof(T) <= 8, "shfl payload");
+  WarpCtx& w = tctx.blk->warps[warp()];
+  unsigned long long raw = 0;
+  std::memcpy(&raw, &v, sizeof(T));
+  w.slot[lane()] = raw;
+  w.bar->arrive_and_wait();
+  unsigned long long got = w.slot[(src & 31) < w.width ? (src & 31) : lane()];
+  w.bar->arrive_and_wait();
+  T out;
+  std::memcpy(&out, &got, sizeof(T));
+  return out;
+}
+template <class T> inline T shfl_xor(T v, int m) { return shfl(v, lane() ^ m); }
+inline unsigned ballot(bool p) {
+  unsigned bit = p ? (1u << lane()) : 0u;
+  unsigned acc = 0;
+  WarpCtx& w = tctx.blk->warps[warp()];
+  w.slot[lane()] = bit;
+  w.bar->arrive_and_wait();
+  for (int i = 0; i < w.width; ++i) acc |= (unsigned)w.slot[i];
+  w.bar->arrive_and_wait();
+  return acc;
+}
+
+// mbarrier emulation: v = (completed_phases << 32) | pending_bytes ; single producer thread.
+inline std::atomic<unsigned long long>* mb(mbar_t* b) {
+  return reinterpret_cast<std::atomic<unsigned long long>*>(&b->v);
+}
+inline void mbar_init(mbar_t* b, int) { mb(b)->store(0); }
+inline void mbar_expect_tx(mbar_t* b, unsigned bytes) { mb(b)->fetch_add(bytes); }
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t* b) {
+  if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | bytes) & 15u) std::abort();
+  std::memcpy(dst, src, bytes);
+  unsigned long long before = mb(b)->fetch_sub(bytes);
+  if ((before & 0xffffffffull) == bytes) mb(b)->fetch_add(1ull << 32);  // phase complete
+}
+inline void fence_async_smem() {}
+inline void mbar_wait(mbar_t* b, unsigned parity) {
+  while (((mb(b)->load(std::memory_order_acquire) >> 32) & 1ull) == parity) std::this_thread::yield();
+}
+
+// Run `body(smem)` as a grid of `grid` blocks of `block` threads (blocks sequentially).
+template <class F> inline void launch(int grid, int block, size_t smem_bytes, F body) {
+  for (int b = 0; b < grid; ++b) {
+    BlockCtx blk;
+    blk.nthreads = block;
+    blk.bid = b;
+    blk.nblocks = grid;
+    blk.bar = std::make_unique<std::barrier<>>(block);
+    int nw = (block + 31) / 32;
+    blk.warps.resize(nw);
+    for (int w = 0; w < nw; ++w) {
+      int width = (w == nw - 1) ? block - 32 * w : 32;
+      blk.warps[w].width = width;
+      blk.warps[w].bar = std::make_unique<std::barrier<>>(width);
+    }
+    void* smem = nullptr;
+    if (posix_memalign(&smem, 1024, smem_bytes ? smem_bytes : 16)) std::abort();
+    std::memset(smem, 0xA5, smem_bytes);  // poison: catches reads of unwritten shared memory
+    std::vector<std::thread> th;
+    th.reserve(block);
+    for (int t = 0; t < block; ++t)
+      th.emplace_back([&, t] {
+        tctx.blk = &blk;
+        tctx.tid = t;
+        body(static_cast<char*>(smem));
+      });
+    for (auto& x : th) x.join();
+    std::free(smem);
+  }
+}
+}  // namespace simt
+
+inline float fma_(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline double fma_(double a, double b, double c) { return std::fma(a, b, c); }
+inline float sqrt_(float a) { return std::sqrt(a); }
+inline double sqrt_(double a) { return std::sqrt(a); }
+inline float abs_(float a) { return std::fabs(a); }
+inline double abs_(double a) { return std::fabs(a); }
+inline float max_(float a, float b) { return std::fmax(a, b); }
+inline double max_(double a, double b) { return std::fmax(a, b); }
+inline float min_(float a, float b) { return std::fmin(a, b); }
+inline double min_(double a, double b) { return std::fmin(a, b); }
+#endif
+
+}  // namespace pal

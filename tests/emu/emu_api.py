@@ -1,0 +1,76 @@
+"""ctypes bindings of the host-emulated kernels (tests only)."""
+import ctypes as C
+
+import numpy as np
+
+from .build_emu import build
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def pairs_of(m):
+    return np.array([(i, j) for i in range(m) for j in range(i + 1, m)], dtype=np.int32)
+
+
+def fwd4095(sig):
+    b, m, n = sig.shape
+    assert n == 2048 and sig.dtype == np.float32
+    spec = np.zeros((b, m, 2080, 2), np.float32)
+    lib().emu_fwd4095(_p(sig, C.c_float), m, C.c_longlong(b), _p(spec, C.c_float), 2)
+    return spec
+
+
+def pair_fast(spec, pairs, win_half, dist, eps=2e-6, want_corr=False):
+    b, m = spec.shape[:2]
+    p = len(pairs)
+    k = np.zeros((b, p), np.int32)
+    pk = np.zeros((b, p), np.float32)
+    gm = np.zeros((b, p), np.float32)
+    fl = np.zeros((b, p), np.uint32)
+    corr = np.zeros((b, p, 4095), np.float32) if want_corr else None
+    lib().emu_pair4095_fast(_p(spec, C.c_float), _p(pairs, C.c_int), m, p, C.c_longlong(b), win_half, dist,
+                            C.c_float(eps), _p(k, C.c_int), _p(pk, C.c_float), _p(gm, C.c_float),
+                            _p(fl, C.c_uint), _p(corr, C.c_float), 3)
+    return k, pk, gm, fl, corr
+
+
+def pair_exact(mode, sig, spec, pairs, win_half, dist, method=0, mult=1.0, num_peaks=1, items=None,
+               want_corr=False):
+    b, m = sig.shape[:2]
+    p = len(pairs)
+    k = np.full((b, p, num_peaks), -7, np.int32)
+    cnt = np.zeros((b, p), np.int32)
+    pk = np.zeros((b, p), np.float32)
+    gm = np.zeros((b, p), np.float32)
+    fl = np.zeros((b, p), np.uint32)
+    corr = np.zeros((b, p, 4095), np.float32) if want_corr else None
+    il = ic = None
+    if items is not None:
+        il = np.asarray(items, np.int32)
+        ic = np.array([len(il)], np.int32)
+    lib().emu_pair4095_exact(mode, _p(sig, C.c_float), _p(spec, C.c_float), _p(pairs, C.c_int), m, p,
+                             C.c_longlong(b), _p(il, C.c_int), _p(ic, C.c_int), win_half, dist, method,
+                             C.c_float(mult), num_peaks, _p(k, C.c_int), _p(cnt, C.c_int), _p(pk, C.c_float),
+                             _p(gm, C.c_float), _p(fl, C.c_uint), _p(corr, C.c_float), 2)
+    return k, cnt, pk, gm, fl, corr
+
+
+def peakpick_f64(c, c0, win_half, dist, method=0, mult=1.0, num_peaks=1):
+    c = np.ascontiguousarray(c, np.float64)
+    out = np.zeros(16, np.int32)
+    cnt = np.zeros(1, np.int32)
+    fl = np.zeros(1, np.uint32)
+    lib().emu_peakpick_f64(_p(c, C.c_double), len(c), c0, win_half, dist, method, C.c_double(mult), num_peaks,
+                           _p(out, C.c_int), _p(cnt, C.c_int), _p(fl, C.c_uint))
+    return list(out[: cnt[0]]), int(fl[0])

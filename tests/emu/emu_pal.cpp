@@ -1,0 +1,74 @@
+// Host emulation harness (TEST ONLY): runs the kernel bodies of pyaudiolocalization_b200/csrc
+// on OS threads via pal_simt.h's -DPAL_EMU mode so the CPU test-suite can check kernel logic
+// against the oracle without a GPU.  Built by tests/emu/build_emu.py into tests/emu/_build/.
+#include "pal_pfa4095.cuh"
+
+using namespace pal;
+
+extern "C" {
+
+void emu_fwd4095(const float* sig, int M, long long B, float* spec /* [B][M][2080][2] */, int grid) {
+  const long long units = B * ((M + 1) / 2);
+  simt::launch(grid, 128, sizeof(FwdSmem), [&](char* smem) {
+    fwd4095_body<128>(sig, M, units, reinterpret_cast<cpxf*>(spec), smem);
+  });
+}
+
+void emu_pair4095_fast(const float* spec, const int* pairs, int M, int P, long long B, int win_half, int dist,
+                       float eps, int* k_idx, float* peak, float* gmax, unsigned* flags, float* corr_out,
+                       int grid) {
+  constexpr int W = 2;
+  simt::launch(grid, 32 * W, W * sizeof(FastWarpSmem), [&](char* smem) {
+    if (corr_out)
+      pair4095_fast_body<W, true>(reinterpret_cast<const cpxf*>(spec), pairs, M, P, B * P, win_half, dist, eps,
+                                  k_idx, peak, gmax, flags, corr_out, smem);
+    else
+      pair4095_fast_body<W, false>(reinterpret_cast<const cpxf*>(spec), pairs, M, P, B * P, win_half, dist, eps,
+                                   k_idx, peak, gmax, flags, corr_out, smem);
+  });
+}
+
+// mode: 0 = float from spectra, 1 = float from signals, 2 = double from signals
+void emu_pair4095_exact(int mode, const float* sig, const float* spec, const int* pairs, int M, int P, long long B,
+                        const int* item_list, const int* item_count, int win_half, int dist, int method,
+                        float mult, int num_peaks, int* k_idx, int* k_count, float* peak, float* gmax,
+                        unsigned* flags, float* corr_out, int grid) {
+  PickParams pp{win_half, dist, method, mult, num_peaks};
+  constexpr int NT = 64;
+  const cpxf* sp = reinterpret_cast<const cpxf*>(spec);
+  if (mode == 0)
+    simt::launch(grid, NT, sizeof(ExactSmem<float>), [&](char* smem) {
+      pair4095_exact_body<float, NT, true>(sig, sp, pairs, M, P, B * P, item_list, item_count, pp, k_idx,
+                                            k_count, peak, gmax, flags, 0u, 0u, corr_out, smem);
+    });
+  else if (mode == 1)
+    simt::launch(grid, NT, sizeof(ExactSmem<float>), [&](char* smem) {
+      pair4095_exact_body<float, NT, false>(sig, sp, pairs, M, P, B * P, item_list, item_count, pp, k_idx,
+                                             k_count, peak, gmax, flags, 0u, 0u, corr_out, smem);
+    });
+  else
+    simt::launch(grid, NT, sizeof(ExactSmem<double>), [&](char* smem) {
+      pair4095_exact_body<double, NT, false>(sig, sp, pairs, M, P, B * P, item_list, item_count, pp, k_idx,
+                                              k_count, peak, gmax, flags, PAL_FLAG_REFINED, 0u, corr_out, smem);
+    });
+}
+
+// stand-alone row pick (any n) for fuzzing the peak selection against the oracle
+void emu_peakpick_f64(const double* c, int n, int c0, int win_half, int dist, int method, double mult,
+                      int num_peaks, int* out_k, int* out_count, unsigned* out_flags) {
+  constexpr int NT = 64;
+  struct Sm { PickScratch ps; int ok[16]; double g, p; };
+  std::vector<unsigned char> pk(n);
+  simt::launch(1, NT, sizeof(Sm), [&](char* smem) {
+    Sm* sm = reinterpret_cast<Sm*>(smem);
+    PickResult r = peakpick_row<double, NT>(c, n, c0, win_half, dist, method, mult, num_peaks, pk.data(),
+                                            &sm->ps, sm->ok, &sm->g, &sm->p);
+    simt::sync_block();
+    if (simt::tid() == 0) {
+      for (int t = 0; t < r.count; ++t) out_k[t] = sm->ok[t];
+      *out_count = r.count;
+      *out_flags = r.flags;
+    }
+  });
+}
+}

@@ -1,0 +1,116 @@
+"""Kernel bodies of pyaudiolocalization_b200/csrc run on the host (tests/emu: the same source
+compiled with -DPAL_EMU, OS threads instead of CUDA threads) against the oracle.  This is how
+kernel logic is checked in the GPU-less build container; the GPU parity tests proper are in
+test_gpu_*.py."""
+import numpy as np
+import pytest
+
+from oracle import pal_oracle as O
+from tests.emu import emu_api as E
+
+N = 4095
+
+
+def _elem(r, q):
+    return (2080 * r + 2016 * q) % N
+
+
+@pytest.fixture(scope="module")
+def frames(golden):
+    return np.ascontiguousarray(golden["cfg3_frames"][:1, :5])     # 1 frame, 5 mics (odd: single-channel tail)
+
+
+@pytest.fixture(scope="module")
+def spectra(frames):
+    return E.fwd4095(frames)
+
+
+def test_forward_spectra_layout(frames, spectra):
+    for m in range(frames.shape[1]):
+        s = np.fft.fft(frames[0, m].astype(np.float64), N)
+        want = np.array([[s[_elem(r, q)] for r in range(32)] for q in range(65)]).reshape(-1)
+        got = spectra[0, m, :, 0] + 1j * spectra[0, m, :, 1]
+        assert np.abs(got - want).max() <= 2e-7 * np.abs(want).max() * 8
+
+
+@pytest.mark.parametrize("med", [0.05, 0.01, None])
+def test_fast_pair_kernel_vs_oracle(frames, spectra, med):
+    pairs = E.pairs_of(frames.shape[1])
+    w = O.window_half_width(2048, 2048, 16000.0, med)
+    k, pk, gm, fl, corr = E.pair_fast(spectra, pairs, w, 16, want_corr=True)
+    for p, (i, j) in enumerate(pairs):
+        c = O.phat_correlation(frames[0, i].astype(np.float64), frames[0, j].astype(np.float64))
+        assert np.abs(corr[0, p] - c).max() <= 1e-4 * np.abs(c).max()
+        assert np.abs(corr[0, p] - c).max() < 5e-7          # what the tie_eps = 2e-6 margin relies on
+        want = O.tdoa_pick_restated(c, 2048, w, 16)
+        if fl[0, p] & 7 == 0:                                 # unflagged rows must already be exact
+            assert k[0, p] == want[0]
+        assert abs(gm[0, p] - c.max()) <= 1e-4 * abs(c.max())
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_exact_pair_kernel_vs_oracle(frames, spectra, mode):
+    pairs = E.pairs_of(3)
+    fr = np.ascontiguousarray(frames[:, :3])
+    sp = np.ascontiguousarray(spectra[:, :3])
+    k, cnt, pk, gm, fl, corr = E.pair_exact(mode, fr, sp, pairs, 800, 16, num_peaks=3, want_corr=True)
+    for p, (i, j) in enumerate(pairs):
+        c = O.phat_correlation(fr[0, i].astype(np.float64), fr[0, j].astype(np.float64))
+        want = O.tdoa_pick_restated(c, 2048, 800, 16, num_peaks=3)
+        assert list(k[0, p, :cnt[0, p]]) == want
+        assert np.abs(corr[0, p] - c).max() <= 1e-4 * np.abs(c).max()
+
+
+def test_exact_kernel_item_list(frames, spectra):
+    pairs = E.pairs_of(5)
+    k_all, *_ = E.pair_exact(2, frames, spectra, pairs, 800, 16, items=[7, 2])
+    for it in (7, 2):
+        i, j = pairs[it]
+        c = O.phat_correlation(frames[0, i].astype(np.float64), frames[0, j].astype(np.float64))
+        assert k_all[0, it, 0] == O.tdoa_pick_restated(c, 2048, 800, 16)[0]
+    assert k_all[0, 0, 0] == -7          # untouched rows keep the sentinel
+
+
+def test_zero_and_identical_channels():
+    fr = np.zeros((1, 2, 2048), np.float32)
+    sp = E.fwd4095(fr)
+    k, pk, gm, fl, _ = E.pair_fast(sp, E.pairs_of(2), 800, 16)
+    assert k[0, 0] == 0 and gm[0, 0] == 0 and fl[0, 0] & 16      # SURVEY §8c golden (5): k = 0, max = 0
+    k2, cnt, *_ = E.pair_exact(2, fr, sp, E.pairs_of(2), 800, 16)
+    assert k2[0, 0, 0] == 0 and cnt[0, 0] == 1
+
+
+def test_peakpick_fuzz_vs_oracle(golden):
+    """The block-level pick (any n, windows, methods, num_peaks, plateaus) on the fuzz rows."""
+    meta = golden["fuzz_meta"]
+    methods = ["median", "adaptive", "other"]
+    checked = 0
+    for i in range(0, len(meta), 2):
+        n1, n2, fs, mi, mult, med, npk, _ = meta[i]
+        a, b = golden[f"fuzz_a{i}"], golden[f"fuzz_b{i}"]
+        med = None if med < 0 else float(med)
+        c = O.phat_correlation(a, b)
+        w = O.window_half_width(len(a), len(b), fs, med)
+        d = O.peak_distance(fs)
+        want = O.tdoa_pick_restated(c, len(b), w, d, int(npk), methods[int(mi)], mult)
+        got, _ = E.peakpick_f64(c, len(b) - 1, w, d, 1 if int(mi) == 1 else 0, mult, int(npk))
+        assert got == want, (i, got, want)
+        checked += 1
+    assert checked >= 80
+
+
+def test_peakpick_plateaus_and_chains():
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        n = int(rng.integers(30, 200))
+        c = np.round(rng.standard_normal(n) * 2) / 2 if trial % 2 else rng.standard_normal(n)
+        if trial % 5 == 0:                       # staircase: long kill chains under the distance rule
+            c = np.sort(rng.standard_normal(n)) + 0.5 * ((np.arange(n) % 2) * 2 - 1)
+        n2 = n // 2 + 1
+        w = int(rng.integers(0, n // 2))
+        d = int(rng.integers(1, 12))
+        if len(set(np.round(c[O.local_maxima_restated(c)], 12))) < len(O.local_maxima_restated(c)):
+            continue                             # equal peak heights: tie order undefined in the reference
+        want = O.tdoa_pick_restated(c, n2, w, d, 2)
+        got, _ = E.peakpick_f64(c, n2 - 1, w, d, 0, 1.0, 2)
+        assert got == want, (trial, got, want)
