@@ -63,6 +63,14 @@ const char* pal_last_error(void);
 /* number of kernels this library has launched since load (for bench accounting) */
 unsigned long long pal_launch_count(void);
 
+/* Measurement hook: while set (stage != 0) the library records `start_event` right before and
+ * `stop_event` right after every launch of the named stage on the stream of that launch, so a
+ * caller can time ONE kernel inside the pipeline with CUDA events.  Both are cudaEvent_t
+ * created by the caller (timing enabled).  stage: 0 = off, 1 = forward transforms,
+ * 2 = fused pair kernel (cross-spectrum + PHAT + inverse DFT + peak pick), 3 = float64
+ * re-evaluation of flagged rows.  Process-global; not for concurrent use. */
+int pal_profile_hook(int32_t stage, void* start_event, void* stop_event);
+
 /* Bytes of device workspace pal_gcc_phat_tdoa needs to process all B frames in one pass
  * (it accepts less and then walks the batch in chunks; `min_bytes`, if not NULL, receives the
  * smallest usable size). */

@@ -46,6 +46,8 @@ def lib():
     L.pal_abi_version.restype = C.c_int
     L.pal_last_error.restype = C.c_char_p
     L.pal_launch_count.restype = C.c_ulonglong
+    L.pal_profile_hook.restype = C.c_int
+    L.pal_profile_hook.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
     L.pal_gcc_phat_workspace.restype = C.c_int
     L.pal_gcc_phat_workspace.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                          C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
@@ -69,3 +71,12 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(lib().pal_launch_count())
+
+
+def profile_hook(stage: int, start_event=None, stop_event=None):
+    """Time one pipeline stage with the caller's CUDA events (see pal_profile_hook).  Pass
+    torch.cuda.Event(enable_timing=True) objects that have been recorded once (so that their
+    handles exist); stage 0 switches the hook off."""
+    s = None if start_event is None else start_event.cuda_event
+    e = None if stop_event is None else stop_event.cuda_event
+    check(lib().pal_profile_hook(int(stage), s, e), "pal_profile_hook")

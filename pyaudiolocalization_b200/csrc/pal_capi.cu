@@ -15,6 +15,18 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
+int g_prof_stage = 0;
+cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+struct ProfScope {   // records the caller's events around one stage (pal_profile_hook)
+  bool on;
+  cudaStream_t s;
+  ProfScope(int stage, cudaStream_t st) : on(g_prof_stage == stage && g_prof_start && g_prof_stop), s(st) {
+    if (on) cudaEventRecord(g_prof_start, s);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(g_prof_stop, s);
+  }
+};
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -93,6 +105,13 @@ extern "C" {
 int pal_abi_version(void) { return PAL_ABI_VERSION; }
 const char* pal_last_error(void) { return g_err.c_str(); }
 unsigned long long pal_launch_count(void) { return g_launches.load(); }
+int pal_profile_hook(int32_t stage, void* start_event, void* stop_event) {
+  if (stage < 0 || stage > 3) return fail(PAL_ERR_INVALID, "pal_profile_hook: stage must be 0..3");
+  g_prof_stage = stage;
+  g_prof_start = static_cast<cudaEvent_t>(start_event);
+  g_prof_stop = static_cast<cudaEvent_t>(stop_event);
+  return PAL_OK;
+}
 
 int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, size_t* bytes, size_t* min_bytes) {
   if (B < 0 || M < 2 || P < 1 || n_samples < 1 || !bytes) return fail(PAL_ERR_INVALID, "pal_gcc_phat_workspace: bad argument");
@@ -166,18 +185,24 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
     {
       const long long units = (long long)nb * ((M + 1) / 2);
       const int gf = (int)std::min<long long>(units, (long long)di.sms * 6);
-      k_fwd4095<<<gf, kFwdThreads, fwd_smem, stream>>>(sig, M, units, spec);
+      {
+        ProfScope ps(1, stream);
+        k_fwd4095<<<gf, kFwdThreads, fwd_smem, stream>>>(sig, M, units, spec);
+      }
       ++g_launches;
       const int gp = (int)std::min<long long>((n_items + kFastWarps - 1) / kFastWarps, (long long)di.sms);
       float* corr = corr_opt_dev ? corr_opt_dev + item0 * kN4095 : nullptr;
-      if (corr)
-        k_pair4095_fast<true><<<gp, kFastWarps * 32, fast_smem, stream>>>(
-            spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist, prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
-            gmax_dev + item0, flags_dev + item0, corr);
-      else
-        k_pair4095_fast<false><<<gp, kFastWarps * 32, fast_smem, stream>>>(
-            spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist, prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
-            gmax_dev + item0, flags_dev + item0, nullptr);
+      {
+        ProfScope ps(2, stream);
+        if (corr)
+          k_pair4095_fast<true><<<gp, kFastWarps * 32, fast_smem, stream>>>(
+              spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist, prm->tie_eps, k_idx_dev + item0,
+              peak_dev + item0, gmax_dev + item0, flags_dev + item0, corr);
+        else
+          k_pair4095_fast<false><<<gp, kFastWarps * 32, fast_smem, stream>>>(
+              spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist, prm->tie_eps, k_idx_dev + item0,
+              peak_dev + item0, gmax_dev + item0, flags_dev + item0, nullptr);
+      }
       ++g_launches;
       if (prm->refine) {
         k_compact_flagged<<<(unsigned)((n_items + 255) / 256), 256, 0, stream>>>(flags_dev + item0, n_items, item0,
@@ -194,6 +219,7 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
     }
     if (prm->refine) {
       // float64 re-evaluation of the flagged rows, straight from the raw frames (global item ids)
+      ProfScope ps(3, stream);
       k_pair4095_exact<double, false><<<di.sms, kExactThreads, exd_smem, stream>>>(
           sig_dev, nullptr, pairs_dev, M, P, (long long)B * P, list, count, pp, k_idx_dev, nullptr, peak_dev,
           gmax_dev, flags_dev, PAL_FLAG_REFINED, kRefineMask, nullptr);

@@ -81,7 +81,9 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
                           threshold_multiplier: float = 1.0, pairs: Optional[Sequence] = None,
                           return_corr: bool = False, tie_eps: float = 2e-6, refine: bool = True,
                           workspace: Optional[torch.Tensor] = None,
-                          max_workspace_bytes: Optional[int] = None) -> TdoaBatch:
+                          max_workspace_bytes: Optional[int] = None,
+                          out: Optional["TdoaBatch"] = None, pairs_dev: Optional[torch.Tensor] = None
+                          ) -> TdoaBatch:
     """frames: [B, M, N] float32 CUDA tensor.  Same options as utils.get_time_delays_phat
     (utils.py:121-127), applied to every pair of every frame.  Everything stays on the device
     and on the current CUDA stream; nothing synchronises."""
@@ -94,20 +96,26 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
         frames = frames.float()
     b, m, n = frames.shape
     dev = frames.device
-    pr = all_pairs(m) if pairs is None else np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
-    if pr.size and (pr.min() < 0 or pr.max() >= m):
-        raise ValueError("pair index out of range")
-    p = len(pr)
-    pairs_dev = torch.from_numpy(pr).to(dev)
+    if pairs_dev is None:
+        pr = all_pairs(m) if pairs is None else np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        if pr.size and (pr.min() < 0 or pr.max() >= m):
+            raise ValueError("pair index out of range")
+        pairs_dev = torch.from_numpy(pr).to(dev)
+    p = pairs_dev.shape[0]
     prm = _lib.TdoaParams(window_half_width(n, n, fs, max_expected_delay), peak_distance(fs),
                           _METHODS.get(threshold_method, 0), float(threshold_multiplier), int(num_peaks),
                           float(tie_eps), 1 if refine else 0)
-    k_idx = torch.empty((b, p, num_peaks), dtype=torch.int32, device=dev)
-    k_count = torch.empty((b, p), dtype=torch.int32, device=dev)
-    peak = torch.empty((b, p), dtype=torch.float32, device=dev)
-    gmax = torch.empty((b, p), dtype=torch.float32, device=dev)
-    flags = torch.empty((b, p), dtype=torch.int32, device=dev)
-    corr = torch.empty((b, p, 2 * n - 1), dtype=torch.float32, device=dev) if return_corr else None
+    if out is not None:
+        k_idx, k_count, peak, gmax, flags, corr = out.k_idx, out.k_count, out.peak, out.gmax, out.flags, out.corr
+        if tuple(k_idx.shape) != (b, p, num_peaks) or not all(t.is_contiguous() for t in (k_idx, k_count, peak, gmax, flags)):
+            raise ValueError("`out` tensors must be contiguous with shapes [B,P,num_peaks] / [B,P]")
+    else:
+        k_idx = torch.empty((b, p, num_peaks), dtype=torch.int32, device=dev)
+        k_count = torch.empty((b, p), dtype=torch.int32, device=dev)
+        peak = torch.empty((b, p), dtype=torch.float32, device=dev)
+        gmax = torch.empty((b, p), dtype=torch.float32, device=dev)
+        flags = torch.empty((b, p), dtype=torch.int32, device=dev)
+        corr = torch.empty((b, p, 2 * n - 1), dtype=torch.float32, device=dev) if return_corr else None
     if workspace is None:
         full, small = workspace_bytes(b, m, n, p)
         want = full if max_workspace_bytes is None else max(small, min(full, int(max_workspace_bytes)))
@@ -125,3 +133,64 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
     for t in (frames, pairs_dev, workspace):
         t.record_stream(torch.cuda.current_stream(dev))
     return TdoaBatch(k_idx, k_count, peak, gmax, flags, corr, n, float(fs))
+
+
+def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_delay: Optional[float] = None,
+                            chunk_frames: int = 1024, device=None, **kw) -> dict:
+    """End-to-end call with HOST buffers: frames_host [B, M, N] float32 on the CPU (pinned memory
+    makes the copies asynchronous).  Frames are streamed to the device in chunks on a copy
+    stream while the previous chunk is processed on a compute stream; the integer lag indices
+    and max(corr) come back to pinned host memory.  Returns numpy arrays."""
+    if frames_host.is_cuda:
+        raise TypeError("frames_host must live in host memory")
+    if kw.get("return_corr"):
+        raise ValueError("return_corr is not supported by the streaming host entry point")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    b, m, n = frames_host.shape
+    num_peaks = int(kw.get("num_peaks", 1))
+    pr = all_pairs(m) if kw.get("pairs") is None else np.asarray(kw.pop("pairs"), dtype=np.int32).reshape(-1, 2)
+    kw.pop("pairs", None)
+    p = len(pr)
+    pairs_dev = torch.from_numpy(np.ascontiguousarray(pr)).to(dev)
+    chunk = max(1, min(int(chunk_frames), b))
+    full, _ = workspace_bytes(chunk, m, n, p)
+    ws = torch.empty(full + 256, dtype=torch.uint8, device=dev)
+    bufs = [torch.empty((chunk, m, n), dtype=torch.float32, device=dev) for _ in range(2)]
+    res = TdoaBatch(torch.empty((b, p, num_peaks), dtype=torch.int32, device=dev),
+                    torch.empty((b, p), dtype=torch.int32, device=dev),
+                    torch.empty((b, p), dtype=torch.float32, device=dev),
+                    torch.empty((b, p), dtype=torch.float32, device=dev),
+                    torch.empty((b, p), dtype=torch.int32, device=dev), None, n, float(fs))
+    copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    cur = torch.cuda.current_stream(dev)
+    copy_s.wait_stream(cur)
+    comp_s.wait_stream(cur)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    for c, f0 in enumerate(range(0, b, chunk)):
+        nb = min(chunk, b - f0)
+        sl = c & 1
+        with torch.cuda.stream(copy_s):
+            if c >= 2:
+                copy_s.wait_event(consumed[sl])
+            bufs[sl][:nb].copy_(frames_host[f0:f0 + nb], non_blocking=True)
+            copied[sl].record(copy_s)
+        with torch.cuda.stream(comp_s):
+            comp_s.wait_event(copied[sl])
+            view = TdoaBatch(res.k_idx[f0:f0 + nb], res.k_count[f0:f0 + nb], res.peak[f0:f0 + nb],
+                             res.gmax[f0:f0 + nb], res.flags[f0:f0 + nb], None, n, float(fs))
+            gcc_phat_tdoa_batched(bufs[sl][:nb], fs, max_expected_delay, workspace=ws, out=view,
+                                  pairs_dev=pairs_dev, **kw)
+            consumed[sl].record(comp_s)
+    with torch.cuda.stream(comp_s):
+        k_host = torch.empty(res.k_idx.shape, dtype=torch.int32, pin_memory=True)
+        g_host = torch.empty(res.gmax.shape, dtype=torch.float32, pin_memory=True)
+        k_host.copy_(res.k_idx, non_blocking=True)
+        g_host.copy_(res.gmax, non_blocking=True)
+    comp_s.synchronize()
+    cur.wait_stream(comp_s)
+    k = k_host.numpy()
+    td = (k.astype(np.int64) - (n - 1)) / float(fs)
+    td[k < 0] = np.nan
+    return {"k_idx": k, "tdoa": td, "gmax": g_host.numpy(), "h2d_bytes": int(frames_host.numel() * 4),
+            "d2h_bytes": int(k_host.numel() * 4 + g_host.numel() * 4)}
