@@ -92,7 +92,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_frames = args.ref_frames or max(cores, min(4 * cores, 64))
+    n_frames = args.ref_frames or 16 * cores
     rate, sec_per_step, per_step = cpu_reference_rate(n_frames, MICS, cores, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
@@ -270,7 +270,7 @@ def run_gpu_arm(args):
     cores = os.cpu_count() or 1
     cpu = None
     if not args.no_cpu:
-        nfr = max(cores, min(2 * cores, 32))
+        nfr = 48 * cores      # about 10-20 s of work on the box's cores
         rate, sec, per = cpu_reference_rate(nfr, MICS, cores)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{nfr} cfg3 frames x {PAIRS} pairs ({per} pair-corr, {sec:.1f} s), oracle port of "

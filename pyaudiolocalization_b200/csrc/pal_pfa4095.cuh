@@ -262,8 +262,8 @@ PAL_DEV void pair4095_exact_body(const float* sig, const cpxf* spec, const int* 
 struct alignas(16) FastWarpSmem {
   union {
     struct {
-      cpxf ya[32 * 33];   // Y[r][kq], kq odd  -> column (kq-1)/2
-      cpxf yb[32 * 33];   // Y[r][kq], kq even >= 2 -> column (kq-2)/2
+      cpxf ya[32 * 33];   // Y[r][kq], kq = 1..32  -> column kq-1
+      cpxf yb[32 * 33];   // Y[r][kq], kq = 33..64 -> column kq-33
       cpxf y0[32];        // Y[r][0]
     } y;
     float corr[4096];
@@ -271,7 +271,43 @@ struct alignas(16) FastWarpSmem {
   cpxf lx[64];            // exchange of the odd column kq = 0 (DFT-7 -> DFT-9)
 };
 
-template <int WARPS, bool WRITE_CORR>
+constexpr float kNegBig = -3.0e38f;
+
+// (k mod 4095) for 0 <= k < 8190 in two integer instructions (unsigned min trick)
+PAL_DEV int wrap4095(int k) {
+  const unsigned a = unsigned(k), b = unsigned(k - kN4095);
+  return int(a < b ? a : b);
+}
+
+// Careful scan of the window (strict local maxima, runner-up, equal neighbours).  Only used when
+// the plain maximum of the window is not itself a strict local maximum (window edge / plateau).
+PAL_DEV void window_scan_slow(const float* c, int lo, int hi, int lane, float& bv, int& bi, float& cand2,
+                              float& pl) {
+  float b1 = 0.f, b2 = kNegBig;
+  pl = kNegBig;
+  int i1 = -1;
+  for (int k = lo + lane; k <= hi; k += 32) {
+    const float v = c[k], vl = c[k - 1], vr = c[k + 1];
+    if (v == vl || v == vr) pl = fmaxf(pl, v);
+    if (vl < v && v > vr) {
+      if (i1 < 0 || v >= b1) { if (i1 >= 0) b2 = fmaxf(b2, b1); b1 = v; i1 = k; }
+      else b2 = fmaxf(b2, v);
+    }
+  }
+  bv = b1;
+  bi = i1;
+  warp_argmax<true>(bv, bi);
+  cand2 = (i1 == bi) ? b2 : ((i1 >= 0) ? b1 : kNegBig);
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    cand2 = fmaxf(cand2, simt::shfl_xor(cand2, m));
+    pl = fmaxf(pl, simt::shfl_xor(pl, m));
+  }
+}
+
+// PHASE_SYNC: the warps of a block walk through the (large, fully unrolled) phases together,
+// separated by block barriers, so that one instruction-cache fill serves all of them.
+template <int WARPS, bool WRITE_CORR, bool PHASE_SYNC>
 PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P, long long n_items,
                                 int win_half, int dist, float eps, int* k_idx, float* peak, float* gmax,
                                 unsigned* flags, float* corr_out, char* smem_raw) {
@@ -288,17 +324,24 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
   } else if (win_half < -1) {
     lo = 1; hi = 0;
   }
+  // window split into 16-byte groups [g_lo, g_hi) plus at most 3 + 3 edge samples
+  const int g_lo = (lo + 3) & ~3;
+  const int g_hi = (hi + 1) & ~3;
 
-  for (long long item = (long long)simt::bid() * WARPS + simt::warp(); item < n_items;
-       item += (long long)simt::nblocks() * WARPS) {
-    const long long frame = item / P;
-    const int p = int(item % P);
-    const int mi = pairs[2 * p], mj = pairs[2 * p + 1];
-    const cpxf* si = spec + (frame * M + mi) * kSpecSlots + lane;
-    const cpxf* sj = spec + (frame * M + mj) * kSpecSlots + lane;
+  for (long long base = (long long)simt::bid() * WARPS; base < n_items; base += (long long)simt::nblocks() * WARPS) {
+    const long long item = base + simt::warp();
+    const bool active = item < n_items;
+    if (PHASE_SYNC) simt::sync_block();
+    if (!PHASE_SYNC && !active) break;
+    float s_abs = 0.f, gm = kNegBig;
+    if (active) {
+      const long long frame = item / P;
+      const int p = int(item % P);
+      const int mi = pairs[2 * p], mj = pairs[2 * p + 1];
+      const cpxf* si = spec + (frame * M + mi) * kSpecSlots + lane;
+      const cpxf* sj = spec + (frame * M + mj) * kSpecSlots + lane;
 
-    // ---- phase A: lane r owns elements e(r, q), q = 0..64: PHAT, then DFT-65 over q ------
-    {
+      // ---- phase A: lane r owns elements e(r, q), q = 0..64: PHAT, then DFT-65 over q ------
       float zr[65], zi[65];
 #pragma unroll
       for (int q = 0; q < 65; ++q) {
@@ -311,14 +354,14 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
         const int kq = P65::out_index(s);
         const cpxf v{zr[s], zi[s]};
         if (kq == 0) sm->y.y0[lane] = v;
-        else if (kq & 1) sm->y.ya[lane * 33 + (kq - 1) / 2] = v;
-        else sm->y.yb[lane * 33 + (kq - 2) / 2] = v;
+        else if (kq <= 32) sm->y.ya[lane * 33 + (kq - 1)] = v;
+        else sm->y.yb[lane * 33 + (kq - 33)] = v;
       }
     }
-    simt::sync_warp();
+    if (PHASE_SYNC) simt::sync_block(); else simt::sync_warp();
 
-    // ---- phase B: lane l owns output columns kq = 2l+1 (real part) and 2l+2 (imaginary part)
-    {
+    if (active) {
+      // ---- phase B: lane l owns output columns kq = l+1 (real part) and l+33 (imaginary part)
       float wr[63], wi[63];
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
@@ -349,17 +392,24 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
         for (int a = 0; a < 7; ++a) sm->lx[(a * P63::UA + lane * P63::UB) % 63] = cpxf{tr[a], ti[a]};
       }
       dft_pfa2<7, 9, +1, float>(wr, wi);
-      const int b0 = 63 * (2 * lane + 1);
+      // scatter to natural order: k = (65 kr + 63 kq) mod 4095; consecutive lanes are 63 floats
+      // apart -> conflict-free.  sum|c| and max(c) are taken from the registers on the way.
+      const int b0 = 63 * (lane + 1);
+      float sa0 = 0.f, sa1 = 0.f, g0 = kNegBig, g1 = kNegBig;
 #pragma unroll
       for (int s = 0; s < 63; ++s) {
         const int kr = P63::out_index(s);
-        int k1 = b0 + 65 * kr;
-        if (k1 >= kN4095) k1 -= kN4095;
-        int k2 = k1 + 63;
-        if (k2 >= kN4095) k2 -= kN4095;
+        const int k1 = wrap4095(b0 + 65 * kr);
+        const int k2 = wrap4095(b0 + 65 * kr + 63 * 32);
         sm->corr[k1] = wr[s];
         sm->corr[k2] = wi[s];
+        sa0 += fabsf(wr[s]);
+        sa1 += fabsf(wi[s]);
+        g0 = fmaxf(g0, wr[s]);
+        g1 = fmaxf(g1, wi[s]);
       }
+      s_abs = sa0 + sa1;
+      gm = fmaxf(g0, g1);
       simt::sync_warp();
       if (lane < 7) {
         float ur[9], ui[9];
@@ -374,10 +424,13 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
         for (int b = 0; b < 9; ++b) {
           const int kr = (9 * lane + 7 * b) % 63;
           sm->corr[(65 * kr) % kN4095] = ur[b];
+          s_abs += fabsf(ur[b]);
+          gm = fmaxf(gm, ur[b]);
         }
       }
     }
-    simt::sync_warp();
+    if (PHASE_SYNC) simt::sync_block(); else simt::sync_warp();
+    if (!active) continue;
 
     // ---- peak pick (num_peaks = 1), utils.py:140-181 in the reduced form ----------------
     const float* c = sm->corr;
@@ -385,37 +438,49 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
       float* dst = corr_out + item * kN4095;
       for (int k = lane; k < kN4095; k += 32) dst[k] = c[k];
     }
-    float s_abs = 0.f, gm = -3.0e38f;
-#pragma unroll 8
-    for (int k = lane; k < kN4095; k += 32) {
-      const float v = c[k];
-      s_abs += fabsf(v);
-      gm = fmaxf(gm, v);
-    }
     s_abs = warp_sum(s_abs);
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) gm = fmaxf(gm, simt::shfl_xor(gm, m));
     const float mean_abs = s_abs * inv_n;
 
-    // best and second-best strict local maximum inside the window; equal neighbours
-    float b1 = 0.f, b2 = -3.0e38f, pl = -3.0e38f;
-    int i1 = -1;
-    for (int k = lo + lane; k <= hi; k += 32) {
-      const float v = c[k], vl = c[k - 1], vr = c[k + 1];
-      if (v == vl || v == vr) pl = fmaxf(pl, v);
-      if (vl < v && v > vr) {
-        if (i1 < 0 || v >= b1) { if (i1 >= 0) b2 = fmaxf(b2, b1); b1 = v; i1 = k; }
-        else b2 = fmaxf(b2, v);
+    // largest and second largest SAMPLE of the window (vectorised, no neighbour tests): the
+    // largest one is the answer whenever it is a strict local maximum, which is then verified
+    float b1 = kNegBig, b2 = kNegBig;
+    int gsel = -1;
+    for (int g = g_lo + 4 * lane; g < g_hi; g += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(c + g);
+      const float before = b1;
+      b2 = fmaxf(b2, fminf(b1, v.x)); b1 = fmaxf(b1, v.x);
+      b2 = fmaxf(b2, fminf(b1, v.y)); b1 = fmaxf(b1, v.y);
+      b2 = fmaxf(b2, fminf(b1, v.z)); b1 = fmaxf(b1, v.z);
+      b2 = fmaxf(b2, fminf(b1, v.w)); b1 = fmaxf(b1, v.w);
+      if (b1 > before) gsel = g;
+    }
+    if (lane < 6) {                      // the <= 3 + 3 samples outside the aligned groups
+      const int k = (lane < 3) ? lo + lane : g_hi + (lane - 3);
+      const bool ok = (lane < 3) ? (k < g_lo && k <= hi) : (k <= hi && g_hi >= g_lo);
+      if (ok) {
+        const float v = c[k];
+        const float before = b1;
+        b2 = fmaxf(b2, fminf(b1, v)); b1 = fmaxf(b1, v);
+        if (b1 > before) gsel = k | 0x40000000;    // tagged: a single sample, not a group
       }
     }
     float bv = b1;
-    int bi = i1;
+    int bi = gsel;
     warp_argmax<true>(bv, bi);
-    float cand2 = (i1 == bi) ? b2 : ((i1 >= 0) ? b1 : -3.0e38f);
+    float cand2 = (gsel == bi) ? b2 : b1;
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      cand2 = fmaxf(cand2, simt::shfl_xor(cand2, m));
-      pl = fmaxf(pl, simt::shfl_xor(pl, m));
+    for (int m = 16; m >= 1; m >>= 1) cand2 = fmaxf(cand2, simt::shfl_xor(cand2, m));
+    float pl = kNegBig;
+    if (bi >= 0) {
+      if (bi & 0x40000000) {
+        bi &= 0x3fffffff;
+      } else {
+        const float4 v = *reinterpret_cast<const float4*>(c + bi);
+        bi += (v.w == bv) ? 3 : (v.z == bv) ? 2 : (v.y == bv) ? 1 : 0;
+      }
+      if (!(c[bi - 1] < bv && bv > c[bi + 1])) window_scan_slow(c, lo, hi, lane, bv, bi, cand2, pl);
     }
 
     unsigned fl = 0;
@@ -459,7 +524,7 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
       fl |= PAL_FLAG_FALLBACK_ARGMAX;
       const bool all_zero = (s_abs == 0.f);
       if (near > 1 && !all_zero) fl |= PAL_FLAG_NEAR_TIE;
-      if (pl > -3.0e38f && win_half != -2 && !all_zero && lo <= hi) fl |= PAL_FLAG_PLATEAU;
+      if (pl > kNegBig && !all_zero) fl |= PAL_FLAG_PLATEAU;
     }
     if (lane == 0) {
       k_idx[item] = kbest;
@@ -467,7 +532,7 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
       gmax[item] = gm;
       flags[item] = fl;
     }
-    simt::sync_warp();   // the next item overwrites the union
+    if (!PHASE_SYNC) simt::sync_warp();   // the next item overwrites the union
   }
 }
 

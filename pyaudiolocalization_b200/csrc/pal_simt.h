@@ -98,6 +98,9 @@ PAL_DEV double min_(double a, double b) { return fmin(a, b); }
 
 #else
 // ------------------------------------------------------------------ host emulation
+}  // namespace pal
+struct alignas(16) float4 { float x, y, z, w; };
+namespace pal {
 namespace simt {
 struct WarpCtx {
   std::unique_ptr<std::barrier<>> bar;

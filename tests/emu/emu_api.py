@@ -31,7 +31,7 @@ def fwd4095(sig):
     return spec
 
 
-def pair_fast(spec, pairs, win_half, dist, eps=2e-6, want_corr=False):
+def pair_fast(spec, pairs, win_half, dist, eps=2e-6, want_corr=False, phase_sync=True):
     b, m = spec.shape[:2]
     p = len(pairs)
     k = np.zeros((b, p), np.int32)
@@ -41,7 +41,7 @@ def pair_fast(spec, pairs, win_half, dist, eps=2e-6, want_corr=False):
     corr = np.zeros((b, p, 4095), np.float32) if want_corr else None
     lib().emu_pair4095_fast(_p(spec, C.c_float), _p(pairs, C.c_int), m, p, C.c_longlong(b), win_half, dist,
                             C.c_float(eps), _p(k, C.c_int), _p(pk, C.c_float), _p(gm, C.c_float),
-                            _p(fl, C.c_uint), _p(corr, C.c_float), 3)
+                            _p(fl, C.c_uint), _p(corr, C.c_float), 3, int(phase_sync))
     return k, pk, gm, fl, corr
 
 

@@ -16,15 +16,22 @@ void emu_fwd4095(const float* sig, int M, long long B, float* spec /* [B][M][208
 
 void emu_pair4095_fast(const float* spec, const int* pairs, int M, int P, long long B, int win_half, int dist,
                        float eps, int* k_idx, float* peak, float* gmax, unsigned* flags, float* corr_out,
-                       int grid) {
+                       int grid, int phase_sync) {
   constexpr int W = 2;
+  const cpxf* sp = reinterpret_cast<const cpxf*>(spec);
   simt::launch(grid, 32 * W, W * sizeof(FastWarpSmem), [&](char* smem) {
-    if (corr_out)
-      pair4095_fast_body<W, true>(reinterpret_cast<const cpxf*>(spec), pairs, M, P, B * P, win_half, dist, eps,
-                                  k_idx, peak, gmax, flags, corr_out, smem);
+    if (corr_out && phase_sync)
+      pair4095_fast_body<W, true, true>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags,
+                                        corr_out, smem);
+    else if (corr_out)
+      pair4095_fast_body<W, true, false>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags,
+                                         corr_out, smem);
+    else if (phase_sync)
+      pair4095_fast_body<W, false, true>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags,
+                                         corr_out, smem);
     else
-      pair4095_fast_body<W, false>(reinterpret_cast<const cpxf*>(spec), pairs, M, P, B * P, win_half, dist, eps,
-                                   k_idx, peak, gmax, flags, corr_out, smem);
+      pair4095_fast_body<W, false, false>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags,
+                                          corr_out, smem);
   });
 }
 
