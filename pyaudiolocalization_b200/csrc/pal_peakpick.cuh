@@ -130,33 +130,13 @@ struct PickScratch {  // lives in shared memory
   int bcast[4];
 };
 
-// One block, NT threads.  c: row of n values (shared or global memory).  pkmap: n bytes of
-// scratch (shared or global).  Returns (in every thread) the result; out_k written by thread 0.
+// threshold_multiplier * median|c|  ('adaptive': * (mean|c| + population std|c|)), utils.py:144-149
 template <typename T, int NT>
-PAL_DEV PickResult peakpick_row(const T* c, int n, int c0, int win_half, int dist, int method, T mult,
-                                int num_peaks, unsigned char* pkmap, PickScratch* ps, int* out_k,
-                                T* out_gmax, T* out_peak) {
+PAL_DEV T pick_threshold(const T* c, int n, int method, T mult, T mean_abs, PickScratch* ps) {
   const int tid = simt::tid();
   T* tsum = reinterpret_cast<T*>(ps->dsum);
-  unsigned flags = 0;
-
-  // ---- pass A: mean|c|, global max (first index), zero the peak map --------------------
-  T s_abs = T(0);
-  T gm = T(0);
-  int gi = -1;
-  for (int k = tid; k < n; k += NT) {
-    const T v = c[k];
-    s_abs += abs_(v);
-    if (vi_better<false>(v, k, gm, gi)) { gm = v; gi = k; }
-    pkmap[k] = 0;
-  }
-  s_abs = block_sum<T, NT>(s_abs, tsum);
-  block_argmax<false, T, NT>(gm, gi, tsum, ps->iarg);
-  const T mean_abs = s_abs / T(n);
-
-  // ---- threshold (utils.py:144-149) ------------------------------------------------------
   T thr;
-  if (method == 1) {  // 'adaptive': mult * (mean + population std of |c|)
+  if (method == 1) {
     T ss = T(0);
     for (int k = tid; k < n; k += NT) {
       const T d = abs_(c[k]) - mean_abs;
@@ -185,6 +165,32 @@ PAL_DEV PickResult peakpick_row(const T* c, int n, int c0, int win_half, int dis
     }
     thr = mult * med;
   }
+  return thr;
+}
+
+// One block, NT threads.  c: row of n values (shared or global memory).  pkmap: n bytes of
+// scratch (shared or global).  Returns (in every thread) the result; out_k written by thread 0.
+template <typename T, int NT>
+PAL_DEV PickResult peakpick_row(const T* c, int n, int c0, int win_half, int dist, int method, T mult,
+                                int num_peaks, unsigned char* pkmap, PickScratch* ps, int* out_k,
+                                T* out_gmax, T* out_peak) {
+  const int tid = simt::tid();
+  T* tsum = reinterpret_cast<T*>(ps->dsum);
+  unsigned flags = 0;
+
+  // ---- pass A: mean|c|, global max (first index), zero the peak map --------------------
+  T s_abs = T(0);
+  T gm = T(0);
+  int gi = -1;
+  for (int k = tid; k < n; k += NT) {
+    const T v = c[k];
+    s_abs += abs_(v);
+    if (vi_better<false>(v, k, gm, gi)) { gm = v; gi = k; }
+    pkmap[k] = 0;
+  }
+  s_abs = block_sum<T, NT>(s_abs, tsum);
+  block_argmax<false, T, NT>(gm, gi, tsum, ps->iarg);
+  const T mean_abs = s_abs / T(n);
 
   // ---- local maxima with plateaus (scipy _local_maxima_1d) -> pkmap, highest peak ------
   T gpk = T(0);
@@ -204,13 +210,25 @@ PAL_DEV PickResult peakpick_row(const T* c, int n, int c0, int win_half, int dis
   block_argmax<true, T, NT>(gpk, gpk_i, tsum, ps->iarg);   // also a barrier: pkmap complete
 
   if (tid == 0) *out_gmax = gm;
-  if (gpk_i < 0 || (gpk < thr && gpk < mean_abs)) {          // utils.py:153-160
+  // The median costs 31 (63 in float64) counting sweeps, and for num_peaks == 1 the answer does
+  // not depend on it whenever the best surviving in-window peak reaches mean|c| (it is then
+  // accepted either directly or through the alternative threshold, utils.py:155,166).  So the
+  // threshold is evaluated lazily; every condition below is block-uniform.
+  bool have_thr = false;
+  T thr = T(0), thr_eff = T(0);
+  if (gpk_i >= 0 && (num_peaks != 1 || gpk < mean_abs)) {
+    thr = pick_threshold<T, NT>(c, n, method, mult, mean_abs, ps);
+    have_thr = true;
+  }
+  if (gpk_i < 0 || (have_thr && gpk < thr && gpk < mean_abs)) {          // utils.py:153-160
     if (tid == 0) { out_k[0] = gi; *out_peak = gm; }
     PickResult r{1, flags | PAL_FLAG_FALLBACK_ARGMAX};
     return r;
   }
-  T thr_eff = thr;
-  if (gpk < thr) { thr_eff = mean_abs; flags |= PAL_FLAG_ALT_THRESHOLD; }
+  if (have_thr) {
+    thr_eff = thr;
+    if (gpk < thr) { thr_eff = mean_abs; flags |= PAL_FLAG_ALT_THRESHOLD; }
+  }
 
   int lo = 1, hi = n - 2;
   if (win_half >= 0) {
@@ -236,9 +254,15 @@ PAL_DEV PickResult peakpick_row(const T* c, int n, int c0, int win_half, int dis
     }
     block_argmax<true, T, NT>(bv, bi, tsum, ps->iarg);
     bool stop = false;
+    if (bi >= 0 && !have_thr && bv < mean_abs) {     // lazy threshold needed after all
+      thr = pick_threshold<T, NT>(c, n, method, mult, mean_abs, ps);
+      have_thr = true;
+      thr_eff = thr;
+      if (gpk < thr) { thr_eff = mean_abs; flags |= PAL_FLAG_ALT_THRESHOLD; }
+    }
     if (bi < 0) {
       stop = true;
-    } else if (bv < thr_eff) {
+    } else if (have_thr && bv < thr_eff) {
       if (count == 0 && win_half != -1 && !relaxed && bv >= mean_abs) {
         relaxed = true;                     // retry with the alternative threshold
         thr_eff = mean_abs;

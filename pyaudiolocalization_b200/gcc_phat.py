@@ -79,7 +79,7 @@ def workspace_bytes(b: int, m: int, n_samples: int, p: int) -> tuple[int, int]:
 def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: Optional[float] = None,
                           num_peaks: int = 1, threshold_method: str = "median",
                           threshold_multiplier: float = 1.0, pairs: Optional[Sequence] = None,
-                          return_corr: bool = False, tie_eps: float = 2e-6, refine: bool = True,
+                          return_corr: bool = False, tie_eps: float = 1e-6, refine: bool = True,
                           workspace: Optional[torch.Tensor] = None,
                           max_workspace_bytes: Optional[int] = None,
                           out: Optional["TdoaBatch"] = None, pairs_dev: Optional[torch.Tensor] = None
