@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PAL_ABI_VERSION 1
+#define PAL_ABI_VERSION 2
 
 /* error codes */
 #define PAL_OK 0
@@ -55,6 +55,9 @@ typedef struct pal_tdoa_params {
   int32_t num_peaks;   /* 1..16 */
   float tie_eps;       /* fp32 fast path: decisions closer than this are re-evaluated in float64 */
   int32_t refine;      /* 1 = run the float64 re-evaluation of flagged rows (default), 0 = skip */
+  int32_t len_first;   /* valid samples of the first signal of a pair (n1); 0 = n_samples */
+  int32_t len_second;  /* valid samples of the second signal (n2); 0 = n_samples.  n1 != n2 is only
+                          meaningful for M == 2 (row 0 = sig1, row 1 = sig2, zero beyond their lengths) */
 } pal_tdoa_params;
 
 int pal_abi_version(void);
@@ -88,7 +91,10 @@ int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, s
  *   k_idx_dev [B][P][num_peaks] int32: raw IFFT index k of each selected peak, -1 padded;
  *             the reference's time delay is (k - (n_samples-1)) / fs  (utils.py:141-142)
  *   k_count_dev [B][P] int32 or NULL; peak_dev/gmax_dev [B][P] float32: corr[k0], max(corr)
- *   flags_dev [B][P] uint32; corr_opt_dev NULL or [B][P][2*n_samples-1] float32 (FFT order)
+ *   flags_dev [B][P] uint32; corr_opt_dev NULL or [B][P][n1+n2-1] float32 (FFT order)
+ * n_samples == 2048 (n = 4095 = 5*7*9*13) takes the fused prime-factor kernels and never
+ * synchronises; any other length takes the Bluestein path, which synchronises `stream` once
+ * when refine != 0 (to learn how many rows were flagged).
  */
 int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples,
                       const int32_t* pairs_dev, int32_t P, const pal_tdoa_params* prm,

@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libpal_b200.so")
 
-PAL_ABI_VERSION = 1
+PAL_ABI_VERSION = 2
 
 # per-row flag bits (include/pal_b200.h)
 FLAG_NEAR_TIE = 1
@@ -28,7 +28,7 @@ class PalError(RuntimeError):
 class TdoaParams(C.Structure):
     _fields_ = [("win_half", C.c_int32), ("peak_dist", C.c_int32), ("thr_method", C.c_int32),
                 ("thr_mult", C.c_float), ("num_peaks", C.c_int32), ("tie_eps", C.c_float),
-                ("refine", C.c_int32)]
+                ("refine", C.c_int32), ("len_first", C.c_int32), ("len_second", C.c_int32)]
 
 
 _lib = None

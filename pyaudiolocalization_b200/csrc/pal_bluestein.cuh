@@ -1,0 +1,417 @@
+// pal_bluestein.cuh -- exact DFT of ARBITRARY length n (Bluestein / chirp-z over power-of-two
+// FFTs) for the GCC-PHAT path when n = n1+n2-1 is not 4095.
+//
+// The reference transforms at exactly n = n1+n2-1 points (utils.py:113-118; n = 88199 for the
+// README's 1 s @ 44.1 kHz signals, 7999 for 0.25 s @ 16 kHz); padding to a power of two would
+// change the PHAT-whitened result (SURVEY.md headline fact 2), so the length-n DFT is evaluated
+// exactly as a length-M circular convolution, M = 2^p >= 2n-1:
+//     X[k] = w[k] * sum_j (x[j] w[j]) conj(w)[k-j],   w[m] = exp(-+ i pi m^2 / n)
+// with m^2 reduced mod 2n in 64-bit integers before the phase is formed (m^2 reaches 7.8e9).
+//
+// The length-M FFTs are two-pass ("four-step", M = M1 x M2, both <= 1024) radix-2 transforms
+// staged in shared memory: a decimation-in-frequency forward pass leaves the spectrum in
+// bit-reversed order, the pointwise product with the (equally permuted) chirp spectrum does not
+// care, and a decimation-in-time inverse pass restores natural order -- no transposes and no
+// bit-reversal copies ever touch global memory.
+//   colpass_fwd : load (fused: chirp pre-multiply / PHAT weighting), column FFTs, twiddle
+//   rowpass     : row FFT, x chirp spectrum, inverse row FFT, twiddle      (one kernel)
+//   colpass_inv : inverse column FFTs, chirp post-multiply, store (fused: spectrum / corr row)
+#pragma once
+#include "pal_simt.h"
+#include "pal_peakpick.cuh"
+
+namespace pal {
+
+struct BluePlan {
+  int n;        // DFT length
+  int M;        // convolution length (power of two >= 2n-1)
+  int M1, M2;   // M = M1 * M2, M1 >= M2
+  int lg1, lg2;
+};
+
+PAL_HD int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+PAL_HD BluePlan make_blue_plan(int n) {
+  BluePlan p;
+  p.n = n;
+  int lg = ilog2(2 * n - 1);
+  if (lg < 2) lg = 2;
+  p.M = 1 << lg;
+  p.lg1 = (lg + 1) / 2;
+  p.lg2 = lg - p.lg1;
+  p.M1 = 1 << p.lg1;
+  p.M2 = 1 << p.lg2;
+  return p;
+}
+PAL_DEV unsigned bitrev(unsigned v, int bits) {
+#if PAL_GPU
+  return __brev(v) >> (32 - bits);
+#else
+  unsigned r = 0;
+  for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1u) << (bits - 1 - i);
+  return r;
+#endif
+}
+
+template <typename T> PAL_DEV cpx<T> cmul(cpx<T> a, cpx<T> b) {
+  return cpx<T>{fma_(a.x, b.x, -(a.y * b.y)), fma_(a.x, b.y, a.y * b.x)};
+}
+template <typename T> PAL_DEV cpx<T> cmulc(cpx<T> a, cpx<T> b) {   // a * conj(b)
+  return cpx<T>{fma_(a.x, b.x, a.y * b.y), fma_(a.y, b.x, -(a.x * b.y))};
+}
+
+// Device tables of one plan (all in precision T, generated in float64):
+//   chirp[m] = exp(-i pi (m^2 mod 2n) / n), m < n        (forward-DFT sign)
+//   tw1[k] = exp(-2 pi i k / M1), k < M1/2 ; tw2 likewise ; twM[k] = exp(-2 pi i k / M), k < M
+//   bhat[M]  = FFT_M of the wrapped conj(chirp) sequence, in the [k1'][k2'] two-pass layout
+template <typename T> struct BlueTables {
+  const cpx<T>* chirp;
+  const cpx<T>* tw1;
+  const cpx<T>* tw2;
+  const cpx<T>* twM;
+  const cpx<T>* bhat;
+};
+
+template <typename T> PAL_DEV void sincospi_(double x, T& s, T& c) {
+  double sd, cd;
+#if PAL_GPU
+  sincospi(x, &sd, &cd);
+#else
+  sd = std::sin(3.14159265358979323846 * x);
+  cd = std::cos(3.14159265358979323846 * x);
+#endif
+  s = T(sd);
+  c = T(cd);
+}
+
+// grid-stride fill of chirp / twiddle tables
+template <typename T>
+PAL_DEV void blue_init_tables_body(BluePlan p, cpx<T>* chirp, cpx<T>* tw1, cpx<T>* tw2, cpx<T>* twM) {
+  const long long gtid = (long long)simt::bid() * simt::nthreads() + simt::tid();
+  const long long gsz = (long long)simt::nblocks() * simt::nthreads();
+  for (long long m = gtid; m < p.n; m += gsz) {
+    const long long r = (m * m) % (2LL * p.n);
+    T s, c;
+    sincospi_<T>(double(r) / double(p.n), s, c);
+    chirp[m] = cpx<T>{c, -s};
+  }
+  for (long long k = gtid; k < p.M1 / 2; k += gsz) {
+    T s, c;
+    sincospi_<T>(2.0 * double(k) / double(p.M1), s, c);
+    tw1[k] = cpx<T>{c, -s};
+  }
+  for (long long k = gtid; k < p.M2 / 2; k += gsz) {
+    T s, c;
+    sincospi_<T>(2.0 * double(k) / double(p.M2), s, c);
+    tw2[k] = cpx<T>{c, -s};
+  }
+  for (long long k = gtid; k < p.M; k += gsz) {
+    T s, c;
+    sincospi_<T>(2.0 * double(k) / double(p.M), s, c);
+    twM[k] = cpx<T>{c, -s};
+  }
+}
+
+// ---- radix-2 FFT of a tile in shared memory --------------------------------------------------
+// Element (l, c) of the tile sits at l*sl + c*sc.  L = 1 << lg points along l, TC independent
+// transforms along c.  Forward: decimation in frequency, natural in -> bit-reversed out.
+// Inverse: decimation in time with conjugate twiddles, bit-reversed in -> natural out (unscaled).
+template <typename T, int NT>
+PAL_DEV void fft_tile(T* re, T* im, int lg, int TC, int sl, int sc, const cpx<T>* tw, bool inverse) {
+  const int L = 1 << lg;
+  const int nb = (L >> 1) * TC;
+  for (int st = 0; st < lg; ++st) {
+    const int hl = inverse ? st : (lg - 1 - st);     // log2(half)
+    const int half = 1 << hl;
+    const int tws = lg - 1 - hl;                     // twiddle stride = L / (2*half)
+    for (int t = simt::tid(); t < nb; t += NT) {
+      const int c = t % TC;
+      const int b = t / TC;
+      const int i = b & (half - 1);
+      const int p = ((b >> hl) << (hl + 1)) + i;
+      const int ap = p * sl + c * sc, aq = (p + half) * sl + c * sc;
+      const cpx<T> w = tw[i << tws];
+      const T ur = re[ap], ui = im[ap], vr = re[aq], vi = im[aq];
+      if (!inverse) {
+        re[ap] = ur + vr;
+        im[ap] = ui + vi;
+        const T dr = ur - vr, di = ui - vi;
+        re[aq] = fma_(dr, w.x, -(di * w.y));
+        im[aq] = fma_(dr, w.y, di * w.x);
+      } else {
+        const T tr = fma_(vr, w.x, vi * w.y);        // v * conj(w)
+        const T ti = fma_(vi, w.x, -(vr * w.y));
+        re[ap] = ur + tr;
+        im[ap] = ui + ti;
+        re[aq] = ur - tr;
+        im[aq] = ui - ti;
+      }
+    }
+    simt::sync_block();
+  }
+}
+
+// ---- what is transformed: loaders (time/frequency sample j of transform t) and storers ------
+// All loaders return the Bluestein-premultiplied sample a[j] (zero for j >= n).
+
+// the chirp kernel itself: b[m] = conj(chirp[|m|]) wrapped on the M-circle (used once per plan)
+template <typename T> struct LoadBhat {
+  BluePlan p;
+  const cpx<T>* chirp;
+  PAL_DEV cpx<T> operator()(long long, int j) const {
+    int m = j < p.n ? j : ((p.M - j) < p.n ? p.M - j : -1);
+    if (m < 0) return cpx<T>{T(0), T(0)};
+    const cpx<T> w = chirp[m];
+    return cpx<T>{w.x, -w.y};
+  }
+};
+
+// forward DFT of one real channel: a[j] = x[j] * chirp[j]          (np.fft.fft(sig, n), utils.py:114-115)
+// transform t = channel row; rows have `ld` floats of which `len` are signal (zero beyond)
+template <typename T> struct LoadSignal {
+  BluePlan p;
+  const cpx<T>* chirp;
+  const float* sig;
+  long long ld;
+  int len_even, len_odd;   // valid samples of even / odd rows (n1, n2 of a single unequal pair)
+  const int* row_list;     // optional indirection: transform t -> channel row
+  PAL_DEV cpx<T> operator()(long long t, int j) const {
+    const long long row = row_list ? row_list[t] : t;
+    const int len = (row & 1) ? len_odd : len_even;
+    if (j >= len) return cpx<T>{T(0), T(0)};
+    const T x = T(sig[row * ld + j]);
+    const cpx<T> w = chirp[j];
+    return cpx<T>{x * w.x, x * w.y};
+  }
+};
+
+// inverse DFT of the PHAT-weighted cross spectrum of pair (i, j) of frame f:
+//   a[k] = R[k] * conj(chirp[k]) / n,  R = Si conj(Sj) / (|Si conj(Sj)| + 1e-10)   (utils.py:116-118)
+template <typename T> struct LoadPhat {
+  BluePlan p;
+  const cpx<T>* chirp;
+  const cpx<T>* spec;      // spectrum rows of the frames (or flagged items) currently resident
+  const int* pairs;        // [P][2]
+  int Mics, P;
+  long long t_off;         // resident item index of transform 0 of this launch
+  bool rows2;              // true: item i owns rows 2i, 2i+1 (flagged-item list); false: frame-major
+  PAL_DEV cpx<T> operator()(long long t, int k) const {
+    if (k >= p.n) return cpx<T>{T(0), T(0)};
+    const long long it = t + t_off;
+    long long ri, rj;
+    if (rows2) {
+      ri = 2 * it;
+      rj = 2 * it + 1;
+    } else {
+      const long long f = it / P;
+      const int pr = int(it % P);
+      ri = f * Mics + pairs[2 * pr];
+      rj = f * Mics + pairs[2 * pr + 1];
+    }
+    const cpx<T> a = spec[ri * p.n + k], b = spec[rj * p.n + k];
+    const T xr = fma_(a.x, b.x, a.y * b.y);
+    const T xi = fma_(a.y, b.x, -(a.x * b.y));
+    const T mag = sqrt_(fma_(xr, xr, xi * xi));
+    const T sc = (T(1) / T(p.n)) / (mag + T(1e-10));
+    const cpx<T> w = chirp[k];
+    return cmulc(cpx<T>{xr * sc, xi * sc}, w);
+  }
+};
+
+// storers receive y[j] = (a conv b)[j] already scaled by 1/M
+template <typename T> struct StoreSpectrum {      // S[t][k] = y[k] * chirp[k]
+  BluePlan p;
+  const cpx<T>* chirp;
+  cpx<T>* spec;
+  PAL_DEV void operator()(long long t, int k, cpx<T> y) const {
+    if (k < p.n) spec[t * p.n + k] = cmul(y, chirp[k]);
+  }
+};
+template <typename T> struct StoreCorr {          // corr[t][k] = Re(y[k] * conj(chirp[k]))
+  BluePlan p;
+  const cpx<T>* chirp;
+  T* corr;
+  PAL_DEV void operator()(long long t, int k, cpx<T> y) const {
+    if (k < p.n) {
+      const cpx<T> w = chirp[k];
+      corr[t * p.n + k] = fma_(y.x, w.x, y.y * w.y);
+    }
+  }
+};
+template <typename T> struct StoreRaw {           // the chirp spectrum itself (plan set-up)
+  cpx<T>* out;
+  long long M;
+  PAL_DEV void operator()(long long t, int j, cpx<T> y) const { out[t * M + j] = y; }
+};
+
+// ---- pass 1: columns forward -------------------------------------------------------------------
+// work unit = (transform t, tile of TC adjacent columns j2).  buf[t][r][j2] <- twiddled column FFT
+template <typename T, int NT, int TC, class Loader>
+PAL_DEV void colpass_fwd_body(BluePlan p, BlueTables<T> tb, Loader load, long long n_tr, cpx<T>* buf, char* smem) {
+  const int tc = p.M2 < TC ? p.M2 : TC;
+  const int tiles = p.M2 / tc;
+  T* re = reinterpret_cast<T*>(smem);
+  T* im = re + p.M1 * tc;
+  for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks()) {
+    const long long t = u / tiles;
+    const int j20 = int(u % tiles) * tc;
+    for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
+      const int j1 = e / tc, c = e % tc;
+      const cpx<T> a = load(t, j1 * p.M2 + j20 + c);
+      re[e] = a.x;
+      im[e] = a.y;
+    }
+    simt::sync_block();
+    fft_tile<T, NT>(re, im, p.lg1, tc, tc, 1, tb.tw1, false);
+    cpx<T>* out = buf + t * p.M;
+    for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
+      const int r = e / tc, c = e % tc;
+      const unsigned k1 = bitrev(unsigned(r), p.lg1);
+      const int j2 = j20 + c;
+      const cpx<T> w = tb.twM[((long long)k1 * j2) & (p.M - 1)];
+      out[(long long)r * p.M2 + j2] = cmul(cpx<T>{re[e], im[e]}, w);
+    }
+    simt::sync_block();
+  }
+}
+
+// ---- pass 2: rows: forward FFT, (x chirp spectrum, inverse FFT, conj twiddle) ------------------
+// work unit = (transform t, row r).  CONV=false stops after the forward FFT (plan set-up).
+template <typename T, int NT, bool CONV, bool CONJ_BHAT>
+PAL_DEV void rowpass_body(BluePlan p, BlueTables<T> tb, long long n_tr, cpx<T>* buf, char* smem) {
+  T* re = reinterpret_cast<T*>(smem);
+  T* im = re + p.M2;
+  for (long long u = simt::bid(); u < n_tr * p.M1; u += simt::nblocks()) {
+    const long long t = u / p.M1;
+    const int r = int(u % p.M1);
+    cpx<T>* row = buf + t * p.M + (long long)r * p.M2;
+    for (int e = simt::tid(); e < p.M2; e += NT) {
+      const cpx<T> v = row[e];
+      re[e] = v.x;
+      im[e] = v.y;
+    }
+    simt::sync_block();
+    fft_tile<T, NT>(re, im, p.lg2, 1, 1, 0, tb.tw2, false);
+    if (CONV) {
+      const cpx<T>* bh = tb.bhat + (long long)r * p.M2;
+      for (int e = simt::tid(); e < p.M2; e += NT) {
+        const cpx<T> b = bh[e];
+        const cpx<T> v = CONJ_BHAT ? cmulc(cpx<T>{re[e], im[e]}, b) : cmul(cpx<T>{re[e], im[e]}, b);
+        re[e] = v.x;
+        im[e] = v.y;
+      }
+      simt::sync_block();
+      fft_tile<T, NT>(re, im, p.lg2, 1, 1, 0, tb.tw2, true);
+      const unsigned k1 = bitrev(unsigned(r), p.lg1);
+      for (int e = simt::tid(); e < p.M2; e += NT) {
+        const cpx<T> w = tb.twM[((long long)k1 * e) & (p.M - 1)];
+        row[e] = cmulc(cpx<T>{re[e], im[e]}, w);
+      }
+    } else {
+      for (int e = simt::tid(); e < p.M2; e += NT) row[e] = cpx<T>{re[e], im[e]};
+    }
+    simt::sync_block();
+  }
+}
+
+// ---- pass 3: columns inverse ---------------------------------------------------------------------
+template <typename T, int NT, int TC, class Storer>
+PAL_DEV void colpass_inv_body(BluePlan p, BlueTables<T> tb, Storer store, long long n_tr, const cpx<T>* buf,
+                              char* smem) {
+  const int tc = p.M2 < TC ? p.M2 : TC;
+  const int tiles = p.M2 / tc;
+  T* re = reinterpret_cast<T*>(smem);
+  T* im = re + p.M1 * tc;
+  const T inv_m = T(1) / T(p.M);
+  for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks()) {
+    const long long t = u / tiles;
+    const int j20 = int(u % tiles) * tc;
+    const cpx<T>* in = buf + t * p.M;
+    for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
+      const int r = e / tc, c = e % tc;
+      const cpx<T> v = in[(long long)r * p.M2 + j20 + c];
+      re[e] = v.x;
+      im[e] = v.y;
+    }
+    simt::sync_block();
+    fft_tile<T, NT>(re, im, p.lg1, tc, tc, 1, tb.tw1, true);
+    for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
+      const int j1 = e / tc, c = e % tc;
+      store(t, j1 * p.M2 + j20 + c, cpx<T>{re[e] * inv_m, im[e] * inv_m});
+    }
+    simt::sync_block();
+  }
+}
+
+// ---- peak pick over correlation rows in global memory ------------------------------------------
+struct RowPickSmem {
+  PickScratch ps;
+  int out_k[16];
+  double out_gmax, out_peak;
+};
+
+// near-tie audit of an fp32 decision (SURVEY.md hard part 3): any other sample of the extended
+// window within eps of the winner, or a winner within eps of the threshold in force.
+template <typename T, int NT>
+PAL_DEV unsigned tie_audit(const T* c, int n, int c0, int win_half, int dist, int k_best, T h_best, T eps,
+                           unsigned pick_flags, PickScratch* ps) {
+  int lo = 0, hi = n - 1;
+  if (!(pick_flags & PAL_FLAG_FALLBACK_ARGMAX) && win_half >= 0) {
+    lo = c0 - win_half - dist;
+    hi = c0 + win_half + dist;
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > n - 1 ? n - 1 : hi;
+  }
+  int cnt = 0;
+  T s_abs = T(0);
+  for (int k = simt::tid(); k < n; k += NT) {
+    const T v = c[k];
+    s_abs += abs_(v);
+    if (k >= lo && k <= hi && k != k_best && v >= h_best - eps) ++cnt;
+  }
+  cnt = block_sum<int, NT>(cnt, ps->isum);
+  s_abs = block_sum<T, NT>(s_abs, reinterpret_cast<T*>(ps->dsum));
+  unsigned fl = 0;
+  if (cnt > 0 && s_abs != T(0)) fl |= PAL_FLAG_NEAR_TIE;
+  if (!(pick_flags & PAL_FLAG_FALLBACK_ARGMAX) && h_best < s_abs / T(n) + eps) fl |= PAL_FLAG_NEAR_TIE;
+  return fl;
+}
+
+template <typename T, int NT>
+PAL_DEV void pick_rows_body(const T* corr, int n, int c0, long long n_rows, const int* item_list, int win_half,
+                            int dist, int method, float mult, int num_peaks, float eps, unsigned char* pkmap_ws,
+                            int* k_idx, int* k_count, float* peak, float* gmax, unsigned* flags, unsigned extra_flag,
+                            unsigned keep_mask, float* corr_out, char* smem) {
+  RowPickSmem* sm = reinterpret_cast<RowPickSmem*>(smem);
+  unsigned char* pkmap = pkmap_ws + (long long)simt::bid() * ((n + 15) / 16 * 16);
+  for (long long rw = simt::bid(); rw < n_rows; rw += simt::nblocks()) {
+    const long long item = item_list ? item_list[rw] : rw;
+    const T* c = corr + rw * n;
+    T g, pk;
+    T* og = reinterpret_cast<T*>(&sm->out_gmax);
+    T* op = reinterpret_cast<T*>(&sm->out_peak);
+    PickResult pr = peakpick_row<T, NT>(c, n, c0, win_half, dist, method, T(mult), num_peaks, pkmap, &sm->ps,
+                                        sm->out_k, og, op);
+    simt::sync_block();
+    g = *og;
+    pk = *op;
+    const int k0 = sm->out_k[0];
+    unsigned fl = pr.flags | extra_flag;
+    if (eps > 0.f) fl |= tie_audit<T, NT>(c, n, c0, win_half, dist, k0, pk, T(eps), pr.flags, &sm->ps);
+    if (simt::tid() == 0) {
+      for (int t = 0; t < num_peaks; ++t) k_idx[item * num_peaks + t] = (t < pr.count) ? sm->out_k[t] : -1;
+      if (k_count) k_count[item] = pr.count;
+      peak[item] = float(pk);
+      gmax[item] = float(g);
+      flags[item] = (keep_mask ? (flags[item] & keep_mask) : 0u) | fl;
+    }
+    if (corr_out)
+      for (int k = simt::tid(); k < n; k += NT) corr_out[item * n + k] = float(c[k]);
+    simt::sync_block();
+  }
+}
+
+}  // namespace pal

@@ -9,6 +9,7 @@
 
 #include "../../include/pal_b200.h"
 #include "pal_pfa4095.cuh"
+#include "pal_generic_host.cuh"
 
 using namespace pal;
 
@@ -16,6 +17,11 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
+}  // namespace
+namespace palhost {
+std::atomic<unsigned long long>* g_launch_counter = &g_launches;
+}
+namespace {
 int g_prof_stage = 0;
 cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
 struct ProfScope {   // records the caller's events around one stage (pal_profile_hook)
@@ -109,6 +115,55 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 constexpr unsigned kRefineMask = PAL_FLAG_NEAR_TIE | PAL_FLAG_CHAIN | PAL_FLAG_PLATEAU;
 
+// arbitrary-length path (Bluestein): float32 sweep with a near-tie audit, then a float64 sweep
+// over the flagged rows only
+int generic_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, int n1, int n2, const int32_t* pairs_dev,
+                 int32_t P, const pal_tdoa_params* prm, int32_t* k_idx_dev, int32_t* k_count_dev, float* peak_dev,
+                 float* gmax_dev, uint32_t* flags_dev, float* corr_opt_dev, void* ws_dev, size_t ws_bytes,
+                 cudaStream_t stream) {
+  if (B * (int64_t)P > 0x3fffffffLL) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: B*P too large; split the batch");
+  if (reinterpret_cast<uintptr_t>(ws_dev) & 255u) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: ws_dev must be 256-byte aligned");
+  if (n1 + n2 - 1 < 3) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: signals too short (n1+n2-1 < 3)");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  const size_t list_bytes = align_up(size_t(B) * P * sizeof(int), 256) + 256;
+  const size_t rows_bytes = align_up(size_t(B) * P * 2 * sizeof(int), 256);
+  const int n = n1 + n2 - 1;
+  if (ws_bytes < list_bytes + rows_bytes + std::max(palhost::generic_min_bytes<float>(n, M, di.sms),
+                                                   palhost::generic_min_bytes<double>(n, 2, di.sms)))
+    return fail(PAL_ERR_WORKSPACE, "pal_gcc_phat_tdoa: workspace too small");
+  char* ws = static_cast<char*>(ws_dev);
+  int* list = reinterpret_cast<int*>(ws);
+  int* count = reinterpret_cast<int*>(ws + list_bytes - 256);
+  int* rows = reinterpret_cast<int*>(ws + list_bytes);
+  char* region = ws + list_bytes + rows_bytes;
+  const size_t region_bytes = ws_bytes - list_bytes - rows_bytes;
+  palhost::GenericCall c{sig_dev, (long long)B, M, n_samples, n1, n2, pairs_dev, P,
+                         PickParams{prm->win_half, prm->peak_dist, prm->thr_method, prm->thr_mult, prm->num_peaks},
+                         prm->refine ? prm->tie_eps : 0.f, k_idx_dev, k_count_dev, peak_dev, gmax_dev, flags_dev,
+                         corr_opt_dev, stream, di.sms};
+  cudaError_t e = palhost::run_generic<float>(c, region, region_bytes, nullptr, 0, nullptr, 0u, 0u);
+  if (e != cudaSuccess) return cuda_fail(e, "generic float sweep");
+  if (!prm->refine) return PAL_OK;
+  PAL_CUDA(cudaMemsetAsync(count, 0, sizeof(int), stream));
+  const long long n_items = (long long)B * P;
+  k_compact_flagged<<<(unsigned)((n_items + 255) / 256), 256, 0, stream>>>(flags_dev, n_items, 0, PAL_FLAG_NEAR_TIE, list, count);
+  ++g_launches;
+  int h_count = 0;
+  PAL_CUDA(cudaMemcpyAsync(&h_count, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  PAL_CUDA(cudaStreamSynchronize(stream));
+  if (h_count > 0) {
+    palhost::k_rows_of_items<<<(h_count + 255) / 256, 256, 0, stream>>>(list, count, pairs_dev, M, P, rows);
+    ++g_launches;
+    c.eps = 0.f;
+    c.corr_out = nullptr;
+    e = palhost::run_generic<double>(c, region, region_bytes, list, h_count, rows, PAL_FLAG_REFINED, kRefineMask);
+    if (e != cudaSuccess) return cuda_fail(e, "generic float64 sweep");
+  }
+  PAL_CUDA(cudaGetLastError());
+  return PAL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -126,12 +181,24 @@ int pal_profile_hook(int32_t stage, void* start_event, void* stop_event) {
 
 int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, size_t* bytes, size_t* min_bytes) {
   if (B < 0 || M < 2 || P < 1 || n_samples < 1 || !bytes) return fail(PAL_ERR_INVALID, "pal_gcc_phat_workspace: bad argument");
-  if (n_samples != kFrame2048)
-    return fail(PAL_ERR_UNSUPPORTED, "pal_gcc_phat_workspace: only n_samples == 2048 is implemented in this build");
-  const size_t per_frame = align_up(size_t(M) * kSpecSlots * sizeof(cpxf), 256);
   const size_t list = align_up(size_t(B) * P * sizeof(int), 256) + 256;
-  *bytes = per_frame * size_t(B > 0 ? B : 1) + list;
-  if (min_bytes) *min_bytes = per_frame + list;
+  if (n_samples == kFrame2048) {
+    const size_t per_frame = align_up(size_t(M) * kSpecSlots * sizeof(cpxf), 256);
+    *bytes = per_frame * size_t(B > 0 ? B : 1) + list;
+    if (min_bytes) *min_bytes = per_frame + list;
+    return PAL_OK;
+  }
+  // Bluestein path: sized for the longest transform the rows allow (n <= 2*n_samples-1)
+  int sms = 148;
+  DevInfo di;
+  if (device_info(di) == PAL_OK && di.sms > 0) sms = di.sms;
+  const int n = 2 * n_samples - 1;
+  const size_t rows = align_up(size_t(B) * P * 2 * sizeof(int), 256);
+  const size_t dmin = palhost::generic_min_bytes<double>(n, 2, sms);
+  const size_t fmin = palhost::generic_min_bytes<float>(n, M, sms);
+  const size_t ffull = palhost::generic_full_bytes<float>(n, B > 0 ? B : 1, M, P, sms);
+  *bytes = list + rows + std::max(ffull, dmin * 4);
+  if (min_bytes) *min_bytes = list + rows + std::max(fmin, dmin);
   return PAL_OK;
 }
 
@@ -146,8 +213,13 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
     return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: NULL device pointer");
   if (prm->peak_dist < 1) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: peak_dist must be >= 1 (scipy: `distance` must be greater or equal to 1)");
   if (prm->num_peaks < 1 || prm->num_peaks > 16) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: num_peaks must be in 1..16");
-  if (n_samples != kFrame2048)
-    return fail(PAL_ERR_UNSUPPORTED, "pal_gcc_phat_tdoa: only n_samples == 2048 is implemented in this build");
+  const int n1 = prm->len_first > 0 ? prm->len_first : n_samples;
+  const int n2 = prm->len_second > 0 ? prm->len_second : n_samples;
+  if (n1 > n_samples || n2 > n_samples) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: len_first/len_second exceed n_samples");
+  if (n1 != n2 && M != 2) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: unequal lengths need M == 2");
+  if (n_samples != kFrame2048 || n1 != kFrame2048 || n2 != kFrame2048)
+    return generic_tdoa(sig_dev, B, M, n_samples, n1, n2, pairs_dev, P, prm, k_idx_dev, k_count_dev, peak_dev, gmax_dev,
+                        flags_dev, corr_opt_dev, ws_dev, ws_bytes, static_cast<cudaStream_t>(stream_));
   if ((reinterpret_cast<uintptr_t>(sig_dev) & 15u) || (reinterpret_cast<uintptr_t>(ws_dev) & 255u))
     return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: sig_dev must be 16-byte and ws_dev 256-byte aligned");
   if (B * (int64_t)P > 0x7fffffffLL) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: B*P exceeds 2^31-1; split the batch");

@@ -1,0 +1,238 @@
+// pal_generic_host.cuh -- host-side orchestration of the arbitrary-length GCC-PHAT path
+// (Bluestein, pal_bluestein.cuh).  Included by pal_capi.cu only.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+
+#include "pal_bluestein.cuh"
+
+namespace palhost {
+using namespace pal;
+
+extern std::atomic<unsigned long long>* g_launch_counter;
+
+constexpr int kGT = 256;  // threads per block of every generic kernel
+template <typename T> struct ColTile { static constexpr int TC = 16; };
+template <> struct ColTile<double> { static constexpr int TC = 8; };
+
+template <typename T> __global__ void __launch_bounds__(kGT) k_blue_init(BluePlan p, cpx<T>* chirp, cpx<T>* tw1,
+                                                                       cpx<T>* tw2, cpx<T>* twM) {
+  blue_init_tables_body<T>(p, chirp, tw1, tw2, twM);
+}
+template <typename T, class Loader>
+__global__ void __launch_bounds__(kGT) k_colpass_fwd(BluePlan p, BlueTables<T> tb, Loader ld, long long n_tr,
+                                                     const int* n_tr_dev, cpx<T>* buf) {
+  extern __shared__ __align__(128) char smem[];
+  colpass_fwd_body<T, kGT, ColTile<T>::TC, Loader>(p, tb, ld, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
+}
+template <typename T, bool CONV, bool CONJ>
+__global__ void __launch_bounds__(kGT) k_rowpass(BluePlan p, BlueTables<T> tb, long long n_tr, const int* n_tr_dev,
+                                                 cpx<T>* buf) {
+  extern __shared__ __align__(128) char smem[];
+  rowpass_body<T, kGT, CONV, CONJ>(p, tb, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
+}
+template <typename T, class Storer>
+__global__ void __launch_bounds__(kGT) k_colpass_inv(BluePlan p, BlueTables<T> tb, Storer st, long long n_tr,
+                                                     const int* n_tr_dev, const cpx<T>* buf) {
+  extern __shared__ __align__(128) char smem[];
+  colpass_inv_body<T, kGT, ColTile<T>::TC, Storer>(p, tb, st, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
+}
+template <typename T>
+__global__ void __launch_bounds__(kGT) k_pick_rows(const T* corr, int n, int c0, long long n_rows, const int* n_rows_dev,
+                                                   const int* item_list, int win_half, int dist, int method, float mult,
+                                                   int num_peaks, float eps, unsigned char* pkmap_ws, int* k_idx,
+                                                   int* k_count, float* peak, float* gmax, unsigned* flags,
+                                                   unsigned extra_flag, unsigned keep_mask, float* corr_out) {
+  extern __shared__ __align__(128) char smem[];
+  pick_rows_body<T, kGT>(corr, n, c0, n_rows_dev ? (long long)*n_rows_dev : n_rows, item_list, win_half, dist, method,
+                         mult, num_peaks, eps, pkmap_ws, k_idx, k_count, peak, gmax, flags, extra_flag, keep_mask, corr_out, smem);
+}
+// flagged item -> its two channel rows (for the float64 re-evaluation)
+__global__ void k_rows_of_items(const int* item_list, const int* count, const int* pairs, int Mics, int P, int* rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *count) {
+    const int item = item_list[i];
+    const int f = item / P, p = item % P;
+    rows[2 * i] = f * Mics + pairs[2 * p];
+    rows[2 * i + 1] = f * Mics + pairs[2 * p + 1];
+  }
+}
+
+inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
+
+template <typename T> struct GenericLayout {
+  BluePlan p;
+  size_t tables;      // bytes of chirp + tw1 + tw2 + twM + bhat
+  size_t per_tr;      // conv buffer + corr row, per transform in flight
+  size_t per_row;     // one spectrum row
+  GenericLayout(int n) : p(make_blue_plan(n)) {
+    tables = al(sizeof(cpx<T>) * size_t(p.n)) + al(sizeof(cpx<T>) * (p.M1 / 2 + 1)) +
+             al(sizeof(cpx<T>) * (p.M2 / 2 + 1)) + 2 * al(sizeof(cpx<T>) * size_t(p.M));
+    per_tr = al(sizeof(cpx<T>) * size_t(p.M)) + al(sizeof(T) * size_t(p.n));
+    per_row = al(sizeof(cpx<T>) * size_t(p.n));
+  }
+};
+
+struct GenericCall {
+  const float* sig;
+  long long B;
+  int Mics, ld, n1, n2;
+  const int* pairs;
+  int P;
+  PickParams pp;
+  float eps;
+  int* k_idx;
+  int* k_count;
+  float* peak;
+  float* gmax;
+  unsigned* flags;
+  float* corr_out;
+  cudaStream_t stream;
+  int sms;
+};
+
+inline void count_launch(int k = 1) {
+  if (g_launch_counter) g_launch_counter->fetch_add(k);
+}
+
+template <typename T> struct BlueBuffers {
+  cpx<T>*chirp, *tw1, *tw2, *twM, *bhat;
+  BlueTables<T> tb() const { return BlueTables<T>{chirp, tw1, tw2, twM, bhat}; }
+};
+
+template <typename T> inline size_t col_smem(const BluePlan& p) {
+  const int tc = std::min(p.M2, ColTile<T>::TC);
+  return 2 * sizeof(T) * size_t(p.M1) * tc;
+}
+
+// carve the tables out of `base`, fill them, and build the chirp spectrum
+template <typename T> cudaError_t setup_plan(const BluePlan& p, char*& base, BlueBuffers<T>& bb, cudaStream_t s, int sms) {
+  bb.chirp = reinterpret_cast<cpx<T>*>(base); base += al(sizeof(cpx<T>) * size_t(p.n));
+  bb.tw1 = reinterpret_cast<cpx<T>*>(base);   base += al(sizeof(cpx<T>) * (p.M1 / 2 + 1));
+  bb.tw2 = reinterpret_cast<cpx<T>*>(base);   base += al(sizeof(cpx<T>) * (p.M2 / 2 + 1));
+  bb.twM = reinterpret_cast<cpx<T>*>(base);   base += al(sizeof(cpx<T>) * size_t(p.M));
+  bb.bhat = reinterpret_cast<cpx<T>*>(base);  base += al(sizeof(cpx<T>) * size_t(p.M));
+  k_blue_init<T><<<std::min(4 * sms, (p.M + kGT - 1) / kGT), kGT, 0, s>>>(p, bb.chirp, bb.tw1, bb.tw2, bb.twM);
+  const size_t cs = col_smem<T>(p), rs = 2 * sizeof(T) * size_t(p.M2);
+  cudaFuncSetAttribute(k_colpass_fwd<T, LoadBhat<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignal<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_fwd<T, LoadPhat<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_inv<T, StoreSpectrum<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_inv<T, StoreCorr<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
+  k_colpass_fwd<T, LoadBhat<T>><<<std::min(tiles, 8 * sms), kGT, cs, s>>>(p, bb.tb(), LoadBhat<T>{p, bb.chirp}, 1, nullptr,
+                                                                          bb.bhat);
+  k_rowpass<T, false, false><<<std::min(p.M1, 8 * sms), kGT, rs, s>>>(p, bb.tb(), 1, nullptr, bb.bhat);
+  count_launch(3);
+  return cudaGetLastError();
+}
+
+inline int pick_grid(int sms) { return std::max(1, std::min(2 * sms, 1024)); }
+inline size_t pkmap_bytes(int n, int sms) { return al(size_t((n + 15) / 16 * 16) * pick_grid(sms)); }
+
+// smallest / comfortable workspace of one sweep in precision T
+template <typename T> size_t generic_min_bytes(int n, int rows_per_unit, int sms) {
+  GenericLayout<T> L(n);
+  return L.tables + pkmap_bytes(n, sms) + L.per_tr + size_t(rows_per_unit) * L.per_row + 1024;
+}
+template <typename T> size_t generic_full_bytes(int n, long long B, int Mics, int P, int sms) {
+  GenericLayout<T> L(n);
+  const long long tr = std::min<long long>(2048, std::max<long long>(B * P, B * Mics));
+  return L.tables + pkmap_bytes(n, sms) + size_t(tr) * L.per_tr + size_t(B) * Mics * L.per_row + 1024;
+}
+
+// One sweep of the whole batch in precision T.  items: all B*P (list == nullptr) or the
+// `n_list` flagged items of `list` (host-known count), whose channel rows are in `rows_scratch`.
+template <typename T>
+cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const int* list, int n_list, int* rows_scratch,
+                        unsigned extra_flag, unsigned keep_mask) {
+  const int n = c.n1 + c.n2 - 1;
+  GenericLayout<T> L(n);
+  const BluePlan p = L.p;
+  if (ws_bytes < generic_min_bytes<T>(n, list ? 2 : c.Mics, c.sms)) return cudaErrorMemoryAllocation;
+  char* base = ws;
+  BlueBuffers<T> bb;
+  cudaError_t e = setup_plan<T>(p, base, bb, c.stream, c.sms);
+  if (e != cudaSuccess) return e;
+  const int grid_pick = pick_grid(c.sms);
+  unsigned char* pkmap = reinterpret_cast<unsigned char*>(base);
+  base += pkmap_bytes(n, c.sms);
+  size_t rem = ws_bytes - size_t(base - ws);
+  // transforms in flight: a quarter of what is left (at most 2048), the rest holds spectrum rows
+  const long long total_items = list ? n_list : c.B * c.P;
+  const long long min_rows = list ? 2 : c.Mics;
+  long long tr_cap = std::max<long long>(1, std::min<long long>(2048, (long long)((rem / 4) / L.per_tr)));
+  tr_cap = std::min<long long>(tr_cap, std::max<long long>(total_items, list ? 2LL * n_list : c.B * c.Mics));
+  while (tr_cap > 1 && rem < size_t(tr_cap) * L.per_tr + size_t(min_rows) * L.per_row) tr_cap /= 2;
+  cpx<T>* conv = reinterpret_cast<cpx<T>*>(base);
+  base += tr_cap * al(sizeof(cpx<T>) * size_t(p.M));
+  T* corr = reinterpret_cast<T*>(base);
+  base += tr_cap * al(sizeof(T) * size_t(n));
+  rem = ws_bytes - size_t(base - ws);
+  const long long row_cap = (long long)(rem / L.per_row);
+  if (row_cap < min_rows) return cudaErrorMemoryAllocation;
+  cpx<T>* spec = reinterpret_cast<cpx<T>*>(base);
+  // note: conv rows / corr rows / spectrum rows are addressed densely (t * M, t * n), the al()
+  // padding above only makes the regions start aligned
+  const size_t cs = col_smem<T>(p), rs = 2 * sizeof(T) * size_t(p.M2);
+  const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
+  const BlueTables<T> tb = bb.tb();
+  const int c0 = c.n2 - 1;
+
+  auto forward = [&](long long row0, long long nrows, const int* row_list, cpx<T>* spec_out) {
+    for (long long r0 = 0; r0 < nrows; r0 += tr_cap) {
+      const long long nt = std::min(tr_cap, nrows - r0);
+      LoadSignal<T> ld{p, bb.chirp, c.sig + (row_list ? 0 : (row0 + r0) * (long long)c.ld), c.ld,
+                       (row_list || ((row0 + r0) & 1) == 0) ? c.n1 : c.n2, (row_list || ((row0 + r0) & 1) == 0) ? c.n2 : c.n1,
+                       row_list ? row_list + r0 : nullptr};
+      k_colpass_fwd<T, LoadSignal<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+          p, tb, ld, nt, nullptr, conv);
+      k_rowpass<T, true, false><<<(unsigned)std::min<long long>(nt * p.M1, 16LL * c.sms), kGT, rs, c.stream>>>(p, tb, nt, nullptr, conv);
+      StoreSpectrum<T> st{p, bb.chirp, spec_out + r0 * n};
+      k_colpass_inv<T, StoreSpectrum<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+          p, tb, st, nt, nullptr, conv);
+      count_launch(3);
+    }
+  };
+  // items [i0, i0+nitems) of the resident set (frame-major, or flagged-list order when ilist != nullptr);
+  // out0 = global item id of resident item 0 (frame-major mode)
+  auto inverse = [&](long long nitems, const cpx<T>* spec_in, long long out0, const int* ilist) {
+    for (long long i0 = 0; i0 < nitems; i0 += tr_cap) {
+      const long long nt = std::min(tr_cap, nitems - i0);
+      LoadPhat<T> ld{p, bb.chirp, spec_in, c.pairs, c.Mics, c.P, i0, ilist != nullptr};
+      k_colpass_fwd<T, LoadPhat<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+          p, tb, ld, nt, nullptr, conv);
+      k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * p.M1, 16LL * c.sms), kGT, rs, c.stream>>>(p, tb, nt, nullptr, conv);
+      StoreCorr<T> st{p, bb.chirp, corr};
+      k_colpass_inv<T, StoreCorr<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+          p, tb, st, nt, nullptr, conv);
+      const long long o = ilist ? 0 : out0 + i0;
+      k_pick_rows<T><<<(unsigned)std::min<long long>(nt, grid_pick), kGT, sizeof(RowPickSmem), c.stream>>>(
+          corr, n, c0, nt, nullptr, ilist ? ilist + i0 : nullptr, c.pp.win_half, c.pp.dist, c.pp.method, c.pp.mult,
+          c.pp.num_peaks, c.eps, pkmap, c.k_idx + o * c.pp.num_peaks, c.k_count ? c.k_count + o : nullptr, c.peak + o,
+          c.gmax + o, c.flags + o, extra_flag, keep_mask, (c.corr_out && !ilist) ? c.corr_out + o * n : nullptr);
+      count_launch(4);
+    }
+  };
+
+  if (!list) {
+    const long long fchunk = std::max<long long>(1, std::min<long long>(c.B, row_cap / c.Mics));
+    for (long long f0 = 0; f0 < c.B; f0 += fchunk) {
+      const long long nf = std::min(fchunk, c.B - f0);
+      forward(f0 * c.Mics, nf * c.Mics, nullptr, spec);
+      inverse(nf * c.P, spec, f0 * c.P, nullptr);
+    }
+  } else {
+    const long long ichunk = std::max<long long>(1, std::min<long long>(n_list, row_cap / 2));
+    for (long long i0 = 0; i0 < n_list; i0 += ichunk) {
+      const long long ni = std::min<long long>(ichunk, n_list - i0);
+      forward(0, 2 * ni, rows_scratch + 2 * i0, spec);
+      inverse(ni, spec, 0, list + i0);
+    }
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace palhost

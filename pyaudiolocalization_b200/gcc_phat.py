@@ -53,7 +53,7 @@ class TdoaBatch:
     gmax: torch.Tensor       # [B, P] float32, max(corr)   (main.py:223)
     flags: torch.Tensor      # [B, P] int32 (bit field, see _lib.FLAG_*)
     corr: Optional[torch.Tensor]  # [B, P, n1+n2-1] float32 (FFT order) when requested
-    n_samples: int
+    n_samples: int           # n2: lag = k - (n2 - 1)
     fs: float
 
     def lags(self) -> torch.Tensor:
@@ -82,11 +82,14 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
                           return_corr: bool = False, tie_eps: float = 1e-6, refine: bool = True,
                           workspace: Optional[torch.Tensor] = None,
                           max_workspace_bytes: Optional[int] = None,
-                          out: Optional["TdoaBatch"] = None, pairs_dev: Optional[torch.Tensor] = None
-                          ) -> TdoaBatch:
+                          out: Optional["TdoaBatch"] = None, pairs_dev: Optional[torch.Tensor] = None,
+                          lengths: Optional[tuple] = None) -> TdoaBatch:
     """frames: [B, M, N] float32 CUDA tensor.  Same options as utils.get_time_delays_phat
     (utils.py:121-127), applied to every pair of every frame.  Everything stays on the device
-    and on the current CUDA stream; nothing synchronises."""
+    and on the current CUDA stream.  N == 2048 (n = 4095) takes the fused prime-factor kernels
+    and never synchronises; other lengths take the Bluestein path.  `lengths=(n1, n2)` (M == 2
+    only) marks row 0 / row 1 as holding n1 / n2 valid samples (zero beyond), which is how a
+    single pair of unequal signals is expressed."""
     if not (isinstance(frames, torch.Tensor) and frames.is_cuda):
         raise TypeError("frames must be a CUDA tensor (there is no CPU path)")
     if frames.dim() != 3:
@@ -102,9 +105,14 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
             raise ValueError("pair index out of range")
         pairs_dev = torch.from_numpy(pr).to(dev)
     p = pairs_dev.shape[0]
-    prm = _lib.TdoaParams(window_half_width(n, n, fs, max_expected_delay), peak_distance(fs),
+    n1, n2 = (n, n) if lengths is None else (int(lengths[0]), int(lengths[1]))
+    if not (1 <= n1 <= n and 1 <= n2 <= n):
+        raise ValueError("lengths must satisfy 1 <= n1, n2 <= N")
+    if (n1, n2) != (n, n) and m != 2:
+        raise ValueError("lengths=(n1, n2) needs exactly two rows (M == 2)")
+    prm = _lib.TdoaParams(window_half_width(n1, n2, fs, max_expected_delay), peak_distance(fs),
                           _METHODS.get(threshold_method, 0), float(threshold_multiplier), int(num_peaks),
-                          float(tie_eps), 1 if refine else 0)
+                          float(tie_eps), 1 if refine else 0, n1, n2)
     if out is not None:
         k_idx, k_count, peak, gmax, flags, corr = out.k_idx, out.k_count, out.peak, out.gmax, out.flags, out.corr
         if tuple(k_idx.shape) != (b, p, num_peaks) or not all(t.is_contiguous() for t in (k_idx, k_count, peak, gmax, flags)):
@@ -115,7 +123,7 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
         peak = torch.empty((b, p), dtype=torch.float32, device=dev)
         gmax = torch.empty((b, p), dtype=torch.float32, device=dev)
         flags = torch.empty((b, p), dtype=torch.int32, device=dev)
-        corr = torch.empty((b, p, 2 * n - 1), dtype=torch.float32, device=dev) if return_corr else None
+        corr = torch.empty((b, p, n1 + n2 - 1), dtype=torch.float32, device=dev) if return_corr else None
     if workspace is None:
         full, small = workspace_bytes(b, m, n, p)
         want = full if max_workspace_bytes is None else max(small, min(full, int(max_workspace_bytes)))
@@ -132,7 +140,7 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
     # keep the inputs alive until the stream has consumed them
     for t in (frames, pairs_dev, workspace):
         t.record_stream(torch.cuda.current_stream(dev))
-    return TdoaBatch(k_idx, k_count, peak, gmax, flags, corr, n, float(fs))
+    return TdoaBatch(k_idx, k_count, peak, gmax, flags, corr, n2, float(fs))
 
 
 def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_delay: Optional[float] = None,

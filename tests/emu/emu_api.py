@@ -74,3 +74,21 @@ def peakpick_f64(c, c0, win_half, dist, method=0, mult=1.0, num_peaks=1):
     lib().emu_peakpick_f64(_p(c, C.c_double), len(c), c0, win_half, dist, method, C.c_double(mult), num_peaks,
                            _p(out, C.c_int), _p(cnt, C.c_int), _p(fl, C.c_uint))
     return list(out[: cnt[0]]), int(fl[0])
+
+
+def generic_gcc_phat(sig, n1, n2, pairs, win_half, dist, method=0, mult=1.0, num_peaks=1, eps=0.0, use_double=False):
+    """sig: [B, M, ld] float32 rows (zero beyond n1 / n2 for even / odd rows when they differ)."""
+    b, m, ld = sig.shape
+    p = len(pairs)
+    n = n1 + n2 - 1
+    k = np.full((b, p, num_peaks), -7, np.int32)
+    cnt = np.zeros((b, p), np.int32)
+    pk = np.zeros((b, p), np.float32)
+    gm = np.zeros((b, p), np.float32)
+    fl = np.zeros((b, p), np.uint32)
+    corr = np.zeros((b, p, n), np.float32)
+    lib().emu_generic_gcc_phat(int(use_double), _p(sig, C.c_float), C.c_longlong(b), m, ld, n1, n2, _p(pairs, C.c_int), p,
+                               win_half, dist, method, C.c_float(mult), num_peaks, C.c_float(eps), _p(k, C.c_int),
+                               _p(cnt, C.c_int), _p(pk, C.c_float), _p(gm, C.c_float), _p(fl, C.c_uint),
+                               _p(corr, C.c_float))
+    return k, cnt, pk, gm, fl, corr

@@ -79,3 +79,60 @@ void emu_peakpick_f64(const double* c, int n, int c0, int win_half, int dist, in
   });
 }
 }
+
+// ---------------------------------------------------------------- arbitrary-length (Bluestein) path
+#include "pal_bluestein.cuh"
+#include <algorithm>
+
+template <typename T>
+static void emu_generic_impl(const float* sig, long long B, int Mics, int ld, int n1, int n2, const int* pairs, int P,
+                             int win_half, int dist, int method, float mult, int num_peaks, float eps, int* k_idx,
+                             int* k_count, float* peak, float* gmax, unsigned* flags, float* corr_out) {
+  constexpr int NT = 64;
+  constexpr int TC = 4;
+  const int n = n1 + n2 - 1;
+  const BluePlan p = make_blue_plan(n);
+  std::vector<cpx<T>> chirp(n), tw1(p.M1 / 2 + 1), tw2(p.M2 / 2 + 1), twM(p.M), bhat(p.M);
+  simt::launch(2, NT, 16, [&](char*) { blue_init_tables_body<T>(p, chirp.data(), tw1.data(), tw2.data(), twM.data()); });
+  BlueTables<T> tb{chirp.data(), tw1.data(), tw2.data(), twM.data(), bhat.data()};
+  const int tc = std::min(p.M2, TC);
+  const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2);
+  simt::launch(2, NT, cs, [&](char* sm) { colpass_fwd_body<T, NT, TC>(p, tb, LoadBhat<T>{p, chirp.data()}, 1, bhat.data(), sm); });
+  simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, false, false>(p, tb, 1, bhat.data(), sm); });
+  const long long rows = B * Mics, items = B * P;
+  std::vector<cpx<T>> conv(size_t(std::max(rows, items)) * p.M), spec(size_t(rows) * n);
+  std::vector<T> corr(size_t(items) * n);
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_fwd_body<T, NT, TC>(p, tb, LoadSignal<T>{p, chirp.data(), sig, ld, n1, n2, nullptr}, rows, conv.data(), sm);
+  });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, true, false>(p, tb, rows, conv.data(), sm); });
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_inv_body<T, NT, TC>(p, tb, StoreSpectrum<T>{p, chirp.data(), spec.data()}, rows, conv.data(), sm);
+  });
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_fwd_body<T, NT, TC>(p, tb, LoadPhat<T>{p, chirp.data(), spec.data(), pairs, Mics, P, 0, false}, items,
+                                conv.data(), sm);
+  });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, true, true>(p, tb, items, conv.data(), sm); });
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_inv_body<T, NT, TC>(p, tb, StoreCorr<T>{p, chirp.data(), corr.data()}, items, conv.data(), sm);
+  });
+  const int grid = 2;
+  std::vector<unsigned char> pk(size_t(grid) * ((n + 15) / 16 * 16));
+  simt::launch(grid, NT, sizeof(RowPickSmem), [&](char* sm) {
+    pick_rows_body<T, NT>(corr.data(), n, n2 - 1, items, nullptr, win_half, dist, method, mult, num_peaks, eps,
+                          pk.data(), k_idx, k_count, peak, gmax, flags, 0u, 0u, corr_out, sm);
+  });
+}
+
+extern "C" void emu_generic_gcc_phat(int use_double, const float* sig, long long B, int Mics, int ld, int n1, int n2,
+                                     const int* pairs, int P, int win_half, int dist, int method, float mult,
+                                     int num_peaks, float eps, int* k_idx, int* k_count, float* peak, float* gmax,
+                                     unsigned* flags, float* corr_out) {
+  if (use_double)
+    emu_generic_impl<double>(sig, B, Mics, ld, n1, n2, pairs, P, win_half, dist, method, mult, num_peaks, eps, k_idx,
+                             k_count, peak, gmax, flags, corr_out);
+  else
+    emu_generic_impl<float>(sig, B, Mics, ld, n1, n2, pairs, P, win_half, dist, method, mult, num_peaks, eps, k_idx,
+                            k_count, peak, gmax, flags, corr_out);
+}

@@ -20,7 +20,7 @@ def test_library_exports_declared_symbols():
             "pal_profile_hook", "pal_launch_count"} <= set(names)
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.pal_abi_version() == 1
+    assert lib.pal_abi_version() == 2
 
 
 def test_argument_errors_without_gpu():
@@ -31,7 +31,7 @@ def test_argument_errors_without_gpu():
     assert L.pal_gcc_phat_workspace(16, 4, 2048, 6, ctypes.byref(full), ctypes.byref(small)) == 0
     assert full.value >= 16 * 4 * 2080 * 8 and small.value < full.value
     assert L.pal_gcc_phat_workspace(16, 1, 2048, 6, ctypes.byref(full), None) == -1
-    prm = _lib.TdoaParams(800, 0, 0, 1.0, 1, 2e-6, 1)
+    prm = _lib.TdoaParams(800, 0, 0, 1.0, 1, 2e-6, 1, 0, 0)
     rc = L.pal_gcc_phat_tdoa(None, 1, 4, 2048, None, 6, ctypes.byref(prm), None, None, None, None, None, None,
                              None, 0, None)
     assert rc == -1 and b"NULL" in L.pal_last_error()

@@ -119,3 +119,60 @@ def test_chunked_equals_single_pass_and_flag_budget(pal):
         corr = O.phat_correlation(frh[f, i].astype(np.float64), frh[f, j].astype(np.float64))
         want = O.tdoa_pick_restated(corr, 2048, 800, 16)
         assert k[f, p] == want[0], (f, p, k[f, p], want, flags[f, p])
+
+
+# ------------------------------------------------------------------ arbitrary lengths (Bluestein path)
+@pytest.mark.parametrize("n1,n2,m", [(50, 37, 2), (300, 300, 3), (1000, 1000, 2), (4000, 4000, 4), (44100, 44100, 2)])
+def test_generic_lengths_vs_oracle(pal, n1, n2, m):
+    rng = np.random.default_rng(n1 + n2)
+    ld = max(n1, n2)
+    fr = np.zeros((2, m, ld), np.float32)
+    base = rng.standard_normal(ld + 64)
+    for f in range(2):
+        for c in range(m):
+            ln = n1 if c % 2 == 0 else n2
+            d = int(rng.integers(0, 12))
+            fr[f, c, :ln] = base[d:d + ln] + 0.3 * rng.standard_normal(ln)
+    fs = 16000.0 if ld < 10000 else 44100.0
+    med = 0.004
+    res = pal.gcc_phat_tdoa_batched(torch.from_numpy(fr).cuda(), fs, max_expected_delay=med, return_corr=True,
+                                    lengths=(n1, n2) if n1 != n2 else None)
+    td = res.tdoa_seconds()[..., 0]
+    corr = res.corr.cpu().numpy()
+    pairs = pal.all_pairs(m)
+    worst = 0.0
+    for f in range(2):
+        for p, (i, j) in enumerate(pairs):
+            a = fr[f, i, :(n1 if i % 2 == 0 else n2)].astype(np.float64)
+            b = fr[f, j, :(n1 if j % 2 == 0 else n2)].astype(np.float64)
+            want_td, want_corr, _ = O.get_time_delays_phat(a, b, fs, max_expected_delay=med)
+            err = np.abs(corr[f, p] - want_corr).max() / np.abs(want_corr).max()
+            worst = max(worst, err)
+            assert err <= CORR_RTOL, (f, p, err)
+            assert td[f, p] == want_td[0], (f, p, td[f, p], want_td)
+    print(f"n1={n1} n2={n2}: worst corr error {worst:.2e} relative to max|corr|")
+
+
+def test_reference_signature_functions_on_fuzz_rows(pal, golden):
+    """utils.get_time_delays_phat / utils.phat_correlation (reference signatures) reproduce the
+    TDOA lists the unmodified reference produced for the committed fuzz rows."""
+    from pyaudiolocalization_b200 import utils as U
+    meta = golden["fuzz_meta"]
+    methods = ["median", "adaptive", "other"]
+    n_exact = 0
+    for i in range(0, len(meta), 3):
+        n1, n2, fs, mi, mult, med, npk, _ = meta[i]
+        a, b, want = golden[f"fuzz_a{i}"], golden[f"fuzz_b{i}"], golden[f"fuzz_td{i}"]
+        med = None if med < 0 else float(med)
+        td, corr, lags = U.get_time_delays_phat(a, b, fs, num_peaks=int(npk), threshold_method=methods[int(mi)],
+                                                threshold_multiplier=mult, max_expected_delay=med)
+        ref_corr = O.phat_correlation(a, b)
+        assert corr.dtype == np.float64 and corr.shape == ref_corr.shape and lags.shape == ref_corr.shape
+        scale = max(np.abs(ref_corr).max(), 1e-30)
+        assert np.abs(corr - ref_corr).max() <= CORR_RTOL * scale
+        assert isinstance(td, list) and np.array_equal(np.array(td), want), (i, td, want)
+        n_exact += 1
+    assert n_exact >= 50
+    c = U.phat_correlation(golden["fuzz_a1"], golden["fuzz_b1"])
+    r = O.phat_correlation(golden["fuzz_a1"], golden["fuzz_b1"])
+    assert np.abs(c - r).max() <= CORR_RTOL * np.abs(r).max()
