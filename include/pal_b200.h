@@ -102,6 +102,52 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
                       uint32_t* flags_dev, float* corr_opt_dev, void* ws_dev, size_t ws_bytes,
                       void* stream);
 
+/* ---------------------------------------------------------------- stage 1: scene synthesis
+ *
+ * pal_image_sources replaces utils.generate_image_sources_iterative (utils.py:67-106, with
+ * reflect_point_across_plane :29-42, distance :44-48, calculate_attenuation :50-65) for n_scenes
+ * independent scenes: float64, the reference's evaluation order, discovery order, the
+ * 10^-round_decimals de-duplication key and the mean/min pruning rule.
+ *   sources_dev [n_scenes][3] f64; planes_dev [n_planes][4] f64 (a, b, c, d); plane_mat_dev
+ *   [n_planes] index into mat_abs_dev / mat_freq_dev (the 'absorption' / 'freq' table,
+ *   materials.py:2-16); mics_dev [n_mics][3] f64 shared by all scenes (mic_stride = 0) or per
+ *   scene (mic_stride = 3*n_mics doubles).
+ *   out_pos_dev [n_scenes][k_max][3] f64, out_mat_dev [n_scenes][k_max] (material index of the
+ *   LAST reflecting plane, utils.py:101), out_count_dev [n_scenes] (-1: more than k_max images).
+ */
+int pal_image_sources_workspace(int32_t n_planes, int32_t k_max, int64_t n_scenes, size_t* bytes);
+int pal_image_sources(const double* sources_dev, int64_t n_scenes, const double* planes_dev,
+                      const int32_t* plane_mat_dev, int32_t n_planes, const double* mat_abs_dev,
+                      const double* mat_freq_dev, const double* mics_dev, int32_t n_mics,
+                      int64_t mic_stride, int32_t max_order, double frequency, double threshold,
+                      int32_t round_decimals, int32_t k_max, double* out_pos_dev, int32_t* out_mat_dev,
+                      int32_t* out_count_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Per (mic, path) delay [s] and raw attenuation of one scene: main.py:94-116.  Path 0 is the
+ * direct path (material index air_mat, main.py:108), path k the k-th image source.
+ *   tau_dev, gain_dev: [n_mics][n_img + 1] f64 */
+int pal_path_table(const double* source_dev, const double* img_pos_dev, const int32_t* img_mat_dev,
+                   int32_t n_img, const double* mics_dev, int32_t n_mics, const double* mat_abs_dev,
+                   const double* mat_freq_dev, int32_t air_mat, double frequency, double c_sound,
+                   double* tau_dev, double* gain_dev, void* stream);
+
+/* Render one scene: the loop main.py:104-122 (sum over paths of fractional_delay(base, tau) *
+ * gain, signal_processing.py:66-80; trim; normalize_signal :82-86; dynamic_range_compression
+ * :88-94) for all n_mics channels.  N = int((duration + max tau) * fs) is decided by the caller
+ * (main.py:102); base_dev holds the n_base = int(fs*duration) source samples (zero-padded to N
+ * implicitly); n_keep = n_base when trim_to_duration else N.  out_dev [n_mics][n_keep] f32. */
+int pal_render_workspace(int32_t N, int32_t n_mics, size_t* bytes, size_t* min_bytes);
+#define PAL_RENDER_NORMALISE_COMPRESS 1  /* apply main.py:121-122; without it the call is the bare
+                                          sum of fractional_delay() copies (signal_processing.py:66-80) */
+int pal_render_scene(const float* base_dev, int32_t n_base, int32_t N, const double* tau_dev,
+                     const double* gain_dev, int32_t n_mics, int32_t n_paths, double fs, int32_t n_keep,
+                     int32_t flags, float* out_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* In place on n_rows rows of n float32: mode 0 = normalize_signal (signal_processing.py:82-86),
+ * mode 1 = dynamic_range_compression(threshold, epsilon) (signal_processing.py:88-94). */
+int pal_normalise_compress(float* rows_dev, int64_t n_rows, int32_t n, float threshold, float epsilon,
+                           int32_t mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

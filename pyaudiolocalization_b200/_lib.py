@@ -55,6 +55,20 @@ def lib():
     L.pal_gcc_phat_tdoa.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                     C.POINTER(TdoaParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    VP, I32, I64, F64, F32, SZP = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_float, C.POINTER(C.c_size_t)
+    L.pal_image_sources_workspace.restype = C.c_int
+    L.pal_image_sources_workspace.argtypes = [I32, I32, I64, SZP]
+    L.pal_image_sources.restype = C.c_int
+    L.pal_image_sources.argtypes = [VP, I64, VP, VP, I32, VP, VP, VP, I32, I64, I32, F64, F64, I32, I32, VP, VP, VP,
+                                    VP, C.c_size_t, VP]
+    L.pal_path_table.restype = C.c_int
+    L.pal_path_table.argtypes = [VP, VP, VP, I32, VP, I32, VP, VP, I32, F64, F64, VP, VP, VP]
+    L.pal_render_workspace.restype = C.c_int
+    L.pal_render_workspace.argtypes = [I32, I32, SZP, SZP]
+    L.pal_render_scene.restype = C.c_int
+    L.pal_render_scene.argtypes = [VP, I32, I32, VP, VP, I32, I32, F64, I32, I32, VP, VP, C.c_size_t, VP]
+    L.pal_normalise_compress.restype = C.c_int
+    L.pal_normalise_compress.argtypes = [VP, I64, I32, F32, F32, I32, VP]
     if L.pal_abi_version() != PAL_ABI_VERSION:
         raise PalError(f"libpal_b200.so ABI {L.pal_abi_version()} != expected {PAL_ABI_VERSION}; rebuild")
     _lib = L

@@ -10,6 +10,7 @@
 #include "../../include/pal_b200.h"
 #include "pal_pfa4095.cuh"
 #include "pal_generic_host.cuh"
+#include "pal_render_host.cuh"
 
 using namespace pal;
 
@@ -309,6 +310,98 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
     }
     PAL_CUDA(cudaGetLastError());
   }
+  return PAL_OK;
+}
+
+int pal_image_sources_workspace(int32_t n_planes, int32_t k_max, int64_t n_scenes, size_t* bytes) {
+  if (n_planes < 0 || k_max < 1 || n_scenes < 0 || !bytes) return fail(PAL_ERR_INVALID, "pal_image_sources_workspace: bad argument");
+  int sms = 148;
+  DevInfo di;
+  if (device_info(di) == PAL_OK && di.sms > 0) sms = di.sms;
+  *bytes = palhost::image_scratch_per_block(std::max(n_planes, 1), k_max) * size_t(palhost::image_grid(std::max<int64_t>(n_scenes, 1), sms));
+  return PAL_OK;
+}
+
+int pal_image_sources(const double* sources_dev, int64_t n_scenes, const double* planes_dev, const int32_t* plane_mat_dev,
+                      int32_t n_planes, const double* mat_abs_dev, const double* mat_freq_dev, const double* mics_dev,
+                      int32_t n_mics, int64_t mic_stride, int32_t max_order, double frequency, double threshold,
+                      int32_t round_decimals, int32_t k_max, double* out_pos_dev, int32_t* out_mat_dev,
+                      int32_t* out_count_dev, void* ws_dev, size_t ws_bytes, void* stream_) {
+  if (n_scenes < 0 || n_planes < 0 || n_mics < 1 || k_max < 1 || max_order < 0)
+    return fail(PAL_ERR_INVALID, "pal_image_sources: bad size argument");
+  if (n_scenes == 0) return PAL_OK;
+  if (!sources_dev || !mics_dev || !out_pos_dev || !out_mat_dev || !out_count_dev || !ws_dev ||
+      (n_planes > 0 && (!planes_dev || !plane_mat_dev || !mat_abs_dev || !mat_freq_dev)))
+    return fail(PAL_ERR_INVALID, "pal_image_sources: NULL device pointer");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  const size_t per_block = palhost::image_scratch_per_block(std::max(n_planes, 1), k_max);
+  const int grid = palhost::image_grid(n_scenes, di.sms);
+  if (ws_bytes < per_block * size_t(grid)) return fail(PAL_ERR_WORKSPACE, "pal_image_sources: workspace too small");
+  double scale = 1.0;
+  for (int i = 0; i < round_decimals; ++i) scale *= 10.0;
+  for (int i = 0; i > round_decimals; --i) scale /= 10.0;
+  ImgParams ip{n_planes, n_mics, max_order, k_max, frequency, threshold, scale};
+  palhost::k_image_sources<<<grid, palhost::kImgThreads, 64 * sizeof(int), static_cast<cudaStream_t>(stream_)>>>(
+      ip, sources_dev, n_scenes, planes_dev, plane_mat_dev, mat_abs_dev, mat_freq_dev, mics_dev, mic_stride, out_pos_dev,
+      out_mat_dev, out_count_dev, static_cast<char*>(ws_dev), per_block);
+  ++g_launches;
+  PAL_CUDA(cudaGetLastError());
+  return PAL_OK;
+}
+
+int pal_path_table(const double* source_dev, const double* img_pos_dev, const int32_t* img_mat_dev, int32_t n_img,
+                   const double* mics_dev, int32_t n_mics, const double* mat_abs_dev, const double* mat_freq_dev,
+                   int32_t air_mat, double frequency, double c_sound, double* tau_dev, double* gain_dev, void* stream_) {
+  if (n_img < 0 || n_mics < 1 || !source_dev || !mics_dev || !mat_abs_dev || !mat_freq_dev || !tau_dev || !gain_dev ||
+      (n_img > 0 && (!img_pos_dev || !img_mat_dev)))
+    return fail(PAL_ERR_INVALID, "pal_path_table: bad argument");
+  const long long total = (long long)n_mics * (n_img + 1);
+  palhost::k_path_table<<<(unsigned)((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream_)>>>(
+      source_dev, img_pos_dev, img_mat_dev, n_img, mics_dev, n_mics, mat_abs_dev, mat_freq_dev, air_mat, frequency, c_sound,
+      tau_dev, gain_dev);
+  ++g_launches;
+  PAL_CUDA(cudaGetLastError());
+  return PAL_OK;
+}
+
+int pal_render_workspace(int32_t N, int32_t n_mics, size_t* bytes, size_t* min_bytes) {
+  if (N < 2 || n_mics < 1 || !bytes) return fail(PAL_ERR_INVALID, "pal_render_workspace: bad argument");
+  *bytes = palhost::render_full_bytes(N, n_mics);
+  if (min_bytes) *min_bytes = palhost::render_min_bytes(N, n_mics);
+  return PAL_OK;
+}
+
+int pal_render_scene(const float* base_dev, int32_t n_base, int32_t N, const double* tau_dev, const double* gain_dev,
+                     int32_t n_mics, int32_t n_paths, double fs, int32_t n_keep, int32_t flags, float* out_dev,
+                     void* ws_dev, size_t ws_bytes, void* stream_) {
+  if (!base_dev || !tau_dev || !gain_dev || !out_dev || !ws_dev) return fail(PAL_ERR_INVALID, "pal_render_scene: NULL device pointer");
+  if (n_base < 1 || N < n_base || n_mics < 1 || n_paths < 1 || n_keep < 1 || n_keep > N)
+    return fail(PAL_ERR_INVALID, "pal_render_scene: need 1 <= n_base <= N, 1 <= n_keep <= N, n_mics, n_paths >= 1");
+  if (int(0.01 * N) < 1)
+    return fail(PAL_ERR_INVALID, "pal_render_scene: N < 100 (the reference's fade window of int(0.01*N) samples is empty and numpy cannot broadcast it)");
+  if (reinterpret_cast<uintptr_t>(ws_dev) & 255u) return fail(PAL_ERR_INVALID, "pal_render_scene: ws_dev must be 256-byte aligned");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (ws_bytes < palhost::render_min_bytes(N, n_mics)) return fail(PAL_ERR_WORKSPACE, "pal_render_scene: workspace too small");
+  cudaError_t e = palhost::render_scene(base_dev, n_base, N, tau_dev, gain_dev, n_mics, n_paths, fs, n_keep,
+                                        (flags & PAL_RENDER_NORMALISE_COMPRESS) != 0, out_dev, static_cast<char*>(ws_dev),
+                                        ws_bytes, static_cast<cudaStream_t>(stream_), di.sms);
+  if (e != cudaSuccess) return cuda_fail(e, "pal_render_scene");
+  return PAL_OK;
+}
+
+int pal_normalise_compress(float* rows_dev, int64_t n_rows, int32_t n, float threshold, float epsilon, int32_t mode,
+                           void* stream_) {
+  if (n_rows < 0 || n < 1 || (n_rows > 0 && !rows_dev) || (mode != 0 && mode != 1))
+    return fail(PAL_ERR_INVALID, "pal_normalise_compress: bad argument");
+  if (n_rows == 0) return PAL_OK;
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  palhost::k_normalise_compress<<<(unsigned)std::min<long long>(n_rows, 8LL * di.sms), palhost::kGT, 64,
+                                  static_cast<cudaStream_t>(stream_)>>>(rows_dev, n_rows, n, threshold, epsilon, mode == 1);
+  ++g_launches;
+  PAL_CUDA(cudaGetLastError());
   return PAL_OK;
 }
 

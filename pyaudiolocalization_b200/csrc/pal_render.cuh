@@ -1,0 +1,307 @@
+// pal_render.cuh -- stage 1 of the hot path: image sources and the multipath renderer.
+//
+//   image_sources_body   utils.py:67-106 (+ :29-65)  breadth-first image sources, one block per scene
+//   path_table_body      main.py:94-116              per (mic, path) delay and gain
+//   transfer_body        main.py:104-118 + signal_processing.py:66-73: because every delayed copy shares one
+//                        FFT and one fade window, sum_k a_k * fractional_delay(x, tau_k) equals
+//                        w * irfft(rfft(x, 2N) * H), H[m] = sum_k a_k exp(-j 2 pi m tau_k fs / (2N));
+//                        this kernel accumulates H for a tile of bins (no atomics) and multiplies by X
+//   LoadHermitian / StoreRender   the length-2N inverse DFT runs through the Bluestein kernels
+//   normalise_compress_body       main.py:119-122, signal_processing.py:82-94
+#pragma once
+#include "pal_bluestein.cuh"
+
+namespace pal {
+
+// ------------------------------------------------------------------ image sources
+#if PAL_GPU
+PAL_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }   // no FMA contraction: the reference
+PAL_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }   // evaluates with python scalars
+PAL_DEV double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+PAL_DEV long long round_key(double x, double scale) { return __double2ll_rn(__dmul_rn(x, scale)); }
+#else
+inline double dmul(double a, double b) { volatile double r = a * b; return r; }
+inline double dadd(double a, double b) { volatile double r = a + b; return r; }
+inline double ddiv(double a, double b) { volatile double r = a / b; return r; }
+inline long long round_key(double x, double scale) { return (long long)std::nearbyint(dmul(x, scale)); }
+#endif
+
+struct ImgParams {
+  int n_planes, n_mics, max_order, k_max;
+  double frequency, threshold, round_scale;
+};
+
+// utils.py:50-65 for one distance
+PAL_DEV double attenuation(double d, double absorption, double freq_factor, double frequency) {
+  d = d < 0.1 ? 0.1 : d;
+  return (1.0 / d) * exp(-freq_factor * frequency * d) * exp(-absorption * d);
+}
+
+// One block per scene (grid-stride).  Scratch per BLOCK: cand_pos[cmax][3] f64, cand_key[cmax][3] i64,
+// cand_ok[cmax] i32 with cmax = k_max * n_planes; keys[k_max+1][3] i64.
+// Output per scene: pos[k_max][3], mat[k_max] (plane material id), count (or -1 on overflow).
+template <int NT>
+PAL_DEV void image_sources_body(ImgParams ip, const double* sources, long long n_scenes, const double* planes,
+                                const int* plane_mat, const double* mat_abs, const double* mat_freq,
+                                const double* mics, long long mic_stride /* 0: shared array */, double* out_pos,
+                                int* out_mat, int* out_count, char* scratch_all, size_t scratch_per_block,
+                                char* smem_raw) {
+  int* sh = reinterpret_cast<int*>(smem_raw);   // [0] running offset, [1..NT/32] warp sums
+  const int tid = simt::tid();
+  const int cmax = ip.k_max * ip.n_planes;
+  char* sc = scratch_all + size_t(simt::bid()) * scratch_per_block;
+  double* cand_pos = reinterpret_cast<double*>(sc);
+  long long* cand_key = reinterpret_cast<long long*>(cand_pos + size_t(cmax) * 3);
+  long long* keys = cand_key + size_t(cmax) * 3;
+  int* cand_ok = reinterpret_cast<int*>(keys + size_t(ip.k_max + 1) * 3);
+  for (long long s = simt::bid(); s < n_scenes; s += simt::nblocks()) {
+    const double* src = sources + s * 3;
+    const double* mic = mics + s * mic_stride;
+    double* pos = out_pos + s * ip.k_max * 3;
+    int* mat = out_mat + s * ip.k_max;
+    if (tid < 3) keys[tid] = round_key(src[tid], ip.round_scale);      // the source itself is "seen"
+    simt::sync_block();
+    int n_img = 0, lvl0 = -1, lvl1 = 0;    // frontier = images [lvl0, lvl1); lvl0 == -1: the source
+    bool overflow = false;
+    for (int order = 1; order <= ip.max_order; ++order) {
+      const int nf = (lvl0 < 0) ? 1 : (lvl1 - lvl0);
+      const int nc = nf * ip.n_planes;
+      if (nc == 0) break;
+      // 1. candidates: reflect, key, prune test (utils.py:89-99)
+      for (int c = tid; c < nc; c += NT) {
+        const int par = c / ip.n_planes, pl = c % ip.n_planes;
+        const double* p = (lvl0 < 0) ? src : pos + size_t(lvl0 + par) * 3;
+        const double a = planes[pl * 4], b = planes[pl * 4 + 1], cc = planes[pl * 4 + 2], d = planes[pl * 4 + 3];
+        const double den = dadd(dadd(dmul(a, a), dmul(b, b)), dmul(cc, cc));
+        const double num = dadd(dadd(dadd(dmul(a, p[0]), dmul(b, p[1])), dmul(cc, p[2])), d);
+        const double f = ddiv(dmul(2.0, num), den);
+        const double x = dadd(p[0], -dmul(a, f)), y = dadd(p[1], -dmul(b, f)), z = dadd(p[2], -dmul(cc, f));
+        cand_pos[c * 3] = x; cand_pos[c * 3 + 1] = y; cand_pos[c * 3 + 2] = z;
+        cand_key[c * 3] = round_key(x, ip.round_scale);
+        cand_key[c * 3 + 1] = round_key(y, ip.round_scale);
+        cand_key[c * 3 + 2] = round_key(z, ip.round_scale);
+        const int m = plane_mat[pl];
+        double sum = 0.0, mn = 1e300;
+        for (int q = 0; q < ip.n_mics; ++q) {
+          const double dx = x - mic[q * 3], dy = y - mic[q * 3 + 1], dz = z - mic[q * 3 + 2];
+          const double att = attenuation(sqrt(dx * dx + dy * dy + dz * dz), mat_abs[m], mat_freq[m], ip.frequency);
+          sum += att;
+          mn = att < mn ? att : mn;
+        }
+        cand_ok[c] = (sum / ip.n_mics > ip.threshold && mn > ip.threshold / 2) ? 1 : 0;
+      }
+      simt::sync_block();
+      // 2. a passing candidate is new iff its key is neither among the seen keys (source + accepted
+      //    images of earlier levels) nor carried by an EARLIER PASSING candidate of this level
+      //    (failed candidates are not added to `seen`, utils.py:99-100)
+      for (int c = tid; c < nc; c += NT) {
+        if (!cand_ok[c]) continue;
+        const long long k0 = cand_key[c * 3], k1 = cand_key[c * 3 + 1], k2 = cand_key[c * 3 + 2];
+        bool dup = false;
+        for (int j = 0; j <= n_img && !dup; ++j) dup = keys[j * 3] == k0 && keys[j * 3 + 1] == k1 && keys[j * 3 + 2] == k2;
+        for (int j = 0; j < c && !dup; ++j)
+          dup = cand_ok[j] && cand_key[j * 3] == k0 && cand_key[j * 3 + 1] == k1 && cand_key[j * 3 + 2] == k2;
+        if (dup) cand_ok[c] = 2;    // 2 = passing duplicate (keeps masking later twins, but is not accepted)
+      }
+      simt::sync_block();
+      // 3. append the accepted candidates in candidate order (block-wide exclusive scan)
+      if (tid == 0) sh[0] = n_img;
+      simt::sync_block();
+      for (int c0 = 0; c0 < nc; c0 += NT) {
+        const int c = c0 + tid;
+        const int acc = (c < nc && cand_ok[c] == 1) ? 1 : 0;
+        int incl = acc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = simt::shfl(incl, simt::lane() - o);
+          if (simt::lane() >= o) incl += v;
+        }
+        if (simt::lane() == 31) sh[1 + simt::warp()] = incl;
+        simt::sync_block();
+        int woff = 0;
+        for (int w = 0; w < simt::warp(); ++w) woff += sh[1 + w];
+        int tot = 0;
+        for (int w = 0; w < NT / 32; ++w) tot += sh[1 + w];
+        const int base = sh[0];
+        const int slot = base + woff + incl - acc;
+        if (acc) {
+          if (slot < ip.k_max) {
+            pos[slot * 3] = cand_pos[c * 3]; pos[slot * 3 + 1] = cand_pos[c * 3 + 1]; pos[slot * 3 + 2] = cand_pos[c * 3 + 2];
+            mat[slot] = plane_mat[c % ip.n_planes];
+            keys[(slot + 1) * 3] = cand_key[c * 3]; keys[(slot + 1) * 3 + 1] = cand_key[c * 3 + 1];
+            keys[(slot + 1) * 3 + 2] = cand_key[c * 3 + 2];
+          }
+        }
+        simt::sync_block();
+        if (tid == 0) sh[0] = base + tot;
+        simt::sync_block();
+      }
+      const int new_total = sh[0];
+      simt::sync_block();
+      if (new_total > ip.k_max) { overflow = true; break; }
+      lvl0 = n_img;
+      lvl1 = new_total;
+      n_img = new_total;
+      if (lvl1 == lvl0) break;
+    }
+    if (tid == 0) out_count[s] = overflow ? -1 : n_img;
+    simt::sync_block();
+  }
+}
+
+// ------------------------------------------------------------------ path table
+// thread per (mic, path) of one scene; path 0 = direct (material 'air', main.py:108), path k = image
+// k-1.  tau [M][K1] f64 seconds; gain [M][K1] f64 RAW attenuation evaluated like the reference
+// (utils.py:50-65; it may be 1e-38, denormal or exactly 0 -- the renderer divides by the per-mic
+// maximum in float64 before anything is rounded to fp32, and a zero maximum yields a zero row).
+PAL_DEV void path_table_body(const double* src, const double* img_pos, const int* img_mat, int n_img,
+                             const double* mics, int n_mics, const double* mat_abs, const double* mat_freq,
+                             int air_mat, double frequency, double c_sound, double* tau, double* gain) {
+  const int k1 = n_img + 1;
+  const long long i = (long long)simt::bid() * simt::nthreads() + simt::tid();
+  if (i >= (long long)n_mics * k1) return;
+  const int m = int(i / k1), k = int(i % k1);
+  const double* p = (k == 0) ? src : img_pos + size_t(k - 1) * 3;
+  const int mat = (k == 0) ? air_mat : img_mat[k - 1];
+  const double dx = p[0] - mics[m * 3], dy = p[1] - mics[m * 3 + 1], dz = p[2] - mics[m * 3 + 2];
+  const double d = sqrt(dx * dx + dy * dy + dz * dz);
+  tau[i] = d / c_sound;
+  gain[i] = attenuation(d, mat_abs[mat], mat_freq[mat], frequency);
+}
+
+// ------------------------------------------------------------------ transfer function x spectrum
+// G[mic][m] = X[m] * sum_k g_k exp(-j 2 pi m tau_k fs / (2N)),  m = 0..N   (bin N: real part only,
+// sum_k g_k cos(pi fs tau_k), because the reference's fftfreq labels it -fs/2 and keeps .real)
+// One block per (mic, tile of NT*J bins); each thread owns bins m0 + t + NT*j and advances its
+// phasor by a per-path rotation of NT bins; phases are reduced mod 1 in float64 before any
+// single-precision trigonometry (SURVEY.md hard part 6).
+template <int NT, int J>
+PAL_DEV void transfer_body(const cpxf* X, int N, const double* tau, const double* gain, int k1, int n_mics,
+                           double fs, cpxf* G, char* smem_raw) {
+  float* s_gain = reinterpret_cast<float*>(smem_raw);         // [k1]
+  cpxf* s_rot = reinterpret_cast<cpxf*>(s_gain + ((k1 + 3) & ~3));   // [k1] rotation by NT bins
+  double* s_delta = reinterpret_cast<double*>(s_rot + k1);   // [k1] turns per bin
+  const int tid = simt::tid();
+  const int nbins = N + 1;
+  const int tiles = (nbins + NT * J - 1) / (NT * J);
+  for (long long u = simt::bid(); u < (long long)n_mics * tiles; u += simt::nblocks()) {
+    const int mic = int(u / tiles);
+    const int m0 = int(u % tiles) * NT * J;
+    const double* tk = tau + size_t(mic) * k1;
+    const double* gk = gain + size_t(mic) * k1;
+    double gmx = 0.0;
+    for (int k = 0; k < k1; ++k) gmx = gk[k] > gmx ? gk[k] : gmx;        // small k1, L1-resident
+    for (int k = tid; k < k1; k += NT) {
+      const double delta = tk[k] * fs / (2.0 * N);
+      s_delta[k] = delta;
+      s_gain[k] = (gmx > 0.0) ? float(gk[k] / gmx) : 0.f;
+      double fr = delta * NT;
+      fr -= floor(fr);
+      float sn, cs;
+      sincospi_<float>(2.0 * fr, sn, cs);
+      s_rot[k] = cpxf{cs, -sn};
+    }
+    simt::sync_block();
+    float ar[J], ai[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) { ar[j] = 0.f; ai[j] = 0.f; }
+    const int mt = m0 + tid;
+    for (int k = 0; k < k1; ++k) {
+      double fr = s_delta[k] * double(mt);
+      fr -= floor(fr);
+      float sn, cs;
+      sincospi_<float>(2.0 * fr, sn, cs);
+      float zr = cs, zi = -sn;
+      const float g = s_gain[k];
+      const cpxf r = s_rot[k];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        ar[j] = fmaf(g, zr, ar[j]);
+        ai[j] = fmaf(g, zi, ai[j]);
+        const float nr = fmaf(zr, r.x, -(zi * r.y));
+        zi = fmaf(zr, r.y, zi * r.x);
+        zr = nr;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int m = mt + NT * j;
+      if (m < nbins) {
+        const cpxf x = X[m];
+        cpxf o{fmaf(x.x, ar[j], -(x.y * ai[j])), fmaf(x.x, ai[j], x.y * ar[j])};
+        if (m == N) {   // Nyquist bin: X[N] is real, H = sum g cos(pi fs tau)
+          float h = 0.f;
+          for (int k = 0; k < k1; ++k) {
+            double fr = 0.5 * fs * tk[k];
+            fr -= floor(fr);
+            float sn, cs;
+            sincospi_<float>(2.0 * fr, sn, cs);
+            h = fmaf(s_gain[k], cs, h);
+          }
+          o = cpxf{x.x * h, 0.f};
+        }
+        G[size_t(mic) * nbins + m] = o;
+      }
+    }
+    simt::sync_block();
+  }
+}
+
+// ------------------------------------------------------------------ Bluestein loader / storer
+// inverse DFT of length 2N of the Hermitian extension of G[row][0..N]
+template <typename T> struct LoadHermitian {
+  BluePlan p;              // p.n == 2N
+  const cpx<T>* chirp;
+  const cpxf* G;           // [rows][N+1]
+  int N;
+  PAL_DEV cpx<T> operator()(long long t, int k) const {
+    if (k >= p.n) return cpx<T>{T(0), T(0)};
+    const cpxf g = (k <= N) ? G[t * (N + 1) + k] : G[t * (N + 1) + (p.n - k)];
+    const cpx<T> v{T(g.x), (k <= N) ? T(g.y) : T(-g.y)};
+    return cmulc(v, chirp[k]);      // inverse transform: conjugate chirp
+  }
+};
+// y[t] = Re(conv[t] * conj(chirp[t])) / (2N) * fade[t], t < n_keep   (signal_processing.py:72-79)
+template <typename T> struct StoreRender {
+  BluePlan p;
+  const cpx<T>* chirp;
+  float* out;              // [rows][n_keep]
+  int N, n_keep, fade;
+  PAL_DEV void operator()(long long t, int j, cpx<T> y) const {
+    if (j >= n_keep) return;
+    const cpx<T> w = chirp[j];
+    T v = fma_(y.x, w.x, y.y * w.y) / T(p.n);
+    if (j < fade) v *= (fade > 1) ? T(j) / T(fade - 1) : T(0);                      // np.linspace(0, 1, fade)
+    if (j >= N - fade) v *= (fade > 1) ? T(N - 1 - j) / T(fade - 1) : T(1);         // np.linspace(1, 0, fade)
+    out[t * n_keep + j] = float(v);
+  }
+};
+
+// ------------------------------------------------------------------ normalise + log compressor
+// one block per row, in place: x / max|x| ; sign(x) * log1p(|x|/0.8 + 1e-8) / log1p(1.25 + 1e-8)
+template <int NT> PAL_DEV void normalise_compress_body(float* rows, long long n_rows, int n, float threshold,
+                                                       float epsilon, bool compress, char* smem_raw) {
+  float* sh = reinterpret_cast<float*>(smem_raw);
+  for (long long r = simt::bid(); r < n_rows; r += simt::nblocks()) {
+    float* x = rows + r * n;
+    float mx = 0.f;
+    for (int i = simt::tid(); i < n; i += NT) mx = fmaxf(mx, fabsf(x[i]));
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, simt::shfl_xor(mx, m));
+    if (simt::lane() == 0) sh[simt::warp()] = mx;
+    simt::sync_block();
+    mx = 0.f;
+    for (int w = 0; w < NT / 32; ++w) mx = fmaxf(mx, sh[w]);
+    simt::sync_block();
+    if (mx > 0.f) {
+      const float denom = log1pf(1.0f / threshold + epsilon);
+      for (int i = simt::tid(); i < n; i += NT) {
+        const float v = x[i] / mx;
+        const float c = compress ? log1pf(fabsf(v) / threshold + epsilon) / denom : fabsf(v);
+        x[i] = (v > 0.f) ? c : ((v < 0.f) ? -c : 0.f);
+      }
+    }
+  }
+}
+
+}  // namespace pal

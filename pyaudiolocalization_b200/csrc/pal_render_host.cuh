@@ -1,0 +1,104 @@
+// pal_render_host.cuh -- host-side orchestration of stage 1 (image sources, multipath renderer).
+// Included by pal_capi.cu only.
+#pragma once
+#include "pal_generic_host.cuh"
+#include "pal_render.cuh"
+
+namespace palhost {
+
+constexpr int kImgThreads = 128;
+constexpr int kXferJ = 16;
+
+__global__ void __launch_bounds__(kImgThreads)
+    k_image_sources(ImgParams ip, const double* sources, long long n_scenes, const double* planes, const int* plane_mat,
+                    const double* mat_abs, const double* mat_freq, const double* mics, long long mic_stride,
+                    double* out_pos, int* out_mat, int* out_count, char* scratch, size_t per_block) {
+  extern __shared__ __align__(16) char smem[];
+  image_sources_body<kImgThreads>(ip, sources, n_scenes, planes, plane_mat, mat_abs, mat_freq, mics, mic_stride, out_pos,
+                                  out_mat, out_count, scratch, per_block, smem);
+}
+__global__ void k_path_table(const double* src, const double* img_pos, const int* img_mat, int n_img, const double* mics,
+                             int n_mics, const double* mat_abs, const double* mat_freq, int air_mat, double frequency,
+                             double c_sound, double* tau, double* gain) {
+  path_table_body(src, img_pos, img_mat, n_img, mics, n_mics, mat_abs, mat_freq, air_mat, frequency, c_sound, tau, gain);
+}
+__global__ void __launch_bounds__(kGT) k_transfer(const cpxf* X, int N, const double* tau, const double* gain, int k1,
+                                                  int n_mics, double fs, cpxf* G) {
+  extern __shared__ __align__(16) char smem[];
+  transfer_body<kGT, kXferJ>(X, N, tau, gain, k1, n_mics, fs, G, smem);
+}
+__global__ void __launch_bounds__(kGT) k_normalise_compress(float* rows, long long n_rows, int n, float thr, float eps,
+                                                            bool compress) {
+  extern __shared__ __align__(16) char smem[];
+  normalise_compress_body<kGT>(rows, n_rows, n, thr, eps, compress, smem);
+}
+
+inline size_t image_scratch_per_block(int n_planes, int k_max) {
+  const size_t cmax = size_t(k_max) * n_planes;
+  return al(cmax * 3 * 8 * 2 + size_t(k_max + 1) * 3 * 8 + cmax * 4 + 64);
+}
+inline int image_grid(long long n_scenes, int sms) { return (int)std::min<long long>(n_scenes, 8LL * sms); }
+
+// workspace of one rendered scene: tables(2N) + X[2N] + G[M][N+1] + conv buffers
+inline size_t render_min_bytes(int N, int n_mics) {
+  GenericLayout<float> L(2 * N);
+  return L.tables + al(sizeof(cpxf) * size_t(2 * N)) + al(sizeof(cpxf) * size_t(n_mics) * (N + 1)) +
+         al(sizeof(cpxf) * size_t(L.p.M)) + 1024;
+}
+inline size_t render_full_bytes(int N, int n_mics) {
+  GenericLayout<float> L(2 * N);
+  return render_min_bytes(N, n_mics) + size_t(std::max(0, n_mics - 1)) * al(sizeof(cpxf) * size_t(L.p.M));
+}
+
+inline cudaError_t render_scene(const float* base, int n_base, int N, const double* tau, const double* gain, int n_mics,
+                                int k1, double fs, int n_keep, bool normalise, float* out, char* ws, size_t ws_bytes,
+                                cudaStream_t s, int sms) {
+  using T = float;
+  if (ws_bytes < render_min_bytes(N, n_mics)) return cudaErrorMemoryAllocation;
+  GenericLayout<T> L(2 * N);
+  const BluePlan p = L.p;
+  char* b = ws;
+  BlueBuffers<T> bb;
+  cudaError_t e = setup_plan<T>(p, b, bb, s, sms);
+  if (e != cudaSuccess) return e;
+  cpxf* X = reinterpret_cast<cpxf*>(b);
+  b += al(sizeof(cpxf) * size_t(2 * N));
+  cpxf* G = reinterpret_cast<cpxf*>(b);
+  b += al(sizeof(cpxf) * size_t(n_mics) * (N + 1));
+  const size_t conv_one = al(sizeof(cpxf) * size_t(p.M));
+  const long long tr_cap = std::max<long long>(1, std::min<long long>(n_mics, (long long)((ws_bytes - size_t(b - ws)) / conv_one)));
+  cpxf* conv = reinterpret_cast<cpxf*>(b);
+  const size_t cs = col_smem<T>(p), rs = 2 * sizeof(T) * size_t(p.M2);
+  const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
+  const BlueTables<T> tb = bb.tb();
+  cudaFuncSetAttribute(k_colpass_fwd<T, LoadHermitian<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_inv<T, StoreRender<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  // X = fft(base zero-padded, 2N)                                      (signal_processing.py:69)
+  k_colpass_fwd<T, LoadSignal<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(
+      p, tb, LoadSignal<T>{p, bb.chirp, base, n_base, n_base, n_base, nullptr}, 1, nullptr, conv);
+  k_rowpass<T, true, false><<<std::min(p.M1, 16 * sms), kGT, rs, s>>>(p, tb, 1, nullptr, conv);
+  k_colpass_inv<T, StoreSpectrum<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(p, tb, StoreSpectrum<T>{p, bb.chirp, X}, 1, nullptr, conv);
+  // G = X * H                                                          (main.py:104-118)
+  const int xtiles = (N + 1 + kGT * kXferJ - 1) / (kGT * kXferJ);
+  const size_t ts = 4 * size_t((k1 + 3) & ~3) + 16 * size_t(k1) + 16;
+  if (ts > 48 * 1024) cudaFuncSetAttribute(k_transfer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts);
+  k_transfer<<<(unsigned)std::min<long long>((long long)n_mics * xtiles, 32LL * sms), kGT, ts, s>>>(X, N, tau, gain, k1, n_mics, fs, G);
+  count_launch(4);
+  const int fade = int(0.01 * N);
+  for (long long r0 = 0; r0 < n_mics; r0 += tr_cap) {
+    const long long nt = std::min<long long>(tr_cap, n_mics - r0);
+    k_colpass_fwd<T, LoadHermitian<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * sms), kGT, cs, s>>>(
+        p, tb, LoadHermitian<T>{p, bb.chirp, G + size_t(r0) * (N + 1), N}, nt, nullptr, conv);
+    k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * p.M1, 16LL * sms), kGT, rs, s>>>(p, tb, nt, nullptr, conv);
+    k_colpass_inv<T, StoreRender<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * sms), kGT, cs, s>>>(
+        p, tb, StoreRender<T>{p, bb.chirp, out + size_t(r0) * n_keep, N, n_keep, fade}, nt, nullptr, conv);
+    count_launch(3);
+  }
+  if (normalise) {
+    k_normalise_compress<<<(unsigned)std::min<long long>(n_mics, 8LL * sms), kGT, 64, s>>>(out, n_mics, n_keep, 0.8f, 1e-8f, true);
+    count_launch(1);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace palhost

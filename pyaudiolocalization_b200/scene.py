@@ -1,0 +1,142 @@
+"""Stage 1 on the GPU: image sources (utils.py:67-106) and the multipath renderer
+(main.py:66-124), host side of pal_image_sources / pal_path_table / pal_render_scene."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise RuntimeError("pyaudiolocalization_b200 needs a CUDA device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ws(nbytes, dev):
+    t = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
+    p = (t.data_ptr() + 255) // 256 * 256
+    return t, p, t.numel() - (p - t.data_ptr())
+
+
+class MaterialTable:
+    """material_properties dict (materials.py:2-16) as index-addressed device arrays."""
+
+    def __init__(self, mats: Dict[str, Any], dev):
+        self.names = list(mats.keys())
+        for n in self.names:
+            if 'absorption' not in mats[n] or 'freq' not in mats[n]:
+                raise ValueError(f"Absorptions- oder Frequenzeigenschaft für Material '{n}' fehlt.")
+        self.index = {n: i for i, n in enumerate(self.names)}
+        self.absorption = torch.tensor([float(mats[n]['absorption']) for n in self.names], dtype=torch.float64, device=dev)
+        self.freq = torch.tensor([float(mats[n]['freq']) for n in self.names], dtype=torch.float64, device=dev)
+
+
+def image_sources_batched(sources, planes: Sequence[Dict[str, Any]], max_order: int, frequency: float,
+                          material_properties: Dict[str, Any], mic_positions, absorption_threshold: float = 0.01,
+                          round_decimals: int = 6, k_max: Optional[int] = None
+                          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, MaterialTable]:
+    """Image sources of many scenes at once.  sources [B, 3]; mic_positions [M, 3] (shared) or
+    [B, M, 3].  Returns device tensors (pos [B, K, 3] f64, mat [B, K] i32, count [B] i32) in the
+    reference's discovery order, plus the material table that decodes `mat`."""
+    dev = _dev()
+    src = torch.as_tensor(np.asarray(sources, dtype=np.float64).reshape(-1, 3)).to(dev)
+    b = src.shape[0]
+    mics_np = np.asarray(mic_positions, dtype=np.float64)
+    per_scene = mics_np.ndim == 3
+    mics = torch.as_tensor(np.ascontiguousarray(mics_np)).to(dev)
+    n_mics = mics_np.shape[-2]
+    table = MaterialTable(material_properties, dev)
+    planes = list(planes or [])
+    pl = np.zeros((max(len(planes), 1), 4), np.float64)
+    pm = np.zeros(max(len(planes), 1), np.int32)
+    for i, p in enumerate(planes):
+        a, bb, c, d = [float(v) for v in p['plane']]
+        if a * a + bb * bb + c * c == 0:
+            raise ValueError("Ungültige Ebene: a^2 + b^2 + c^2 ist 0.")
+        mat = p.get('material', 'air')
+        if mat not in table.index:
+            raise ValueError(f"Material '{mat}' ist nicht definiert. Bitte zum Dictionary hinzufügen.")
+        pl[i] = (a, bb, c, d)
+        pm[i] = table.index[mat]
+    planes_dev = torch.as_tensor(pl).to(dev)
+    pm_dev = torch.as_tensor(pm).to(dev)
+    if k_max is None:
+        # number of distinct images is bounded by sum_o P*(P-1)^(o-1); cap the allocation
+        bound, lvl = 0, len(planes)
+        for _ in range(max_order):
+            bound += lvl
+            lvl *= max(len(planes) - 1, 1)
+            if bound > 4096:
+                break
+        k_max = int(max(1, min(bound, 4096)))
+    pos = torch.zeros((b, k_max, 3), dtype=torch.float64, device=dev)
+    mat = torch.zeros((b, k_max), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((b,), dtype=torch.int32, device=dev)
+    need = C.c_size_t(0)
+    L = _lib.lib()
+    _lib.check(L.pal_image_sources_workspace(len(planes), k_max, b, C.byref(need)), "pal_image_sources_workspace")
+    ws, wp, wl = _ws(need.value, dev)
+    rc = L.pal_image_sources(src.data_ptr(), b, planes_dev.data_ptr(), pm_dev.data_ptr(), len(planes),
+                             table.absorption.data_ptr(), table.freq.data_ptr(), mics.data_ptr(), n_mics,
+                             3 * n_mics if per_scene else 0, int(max_order), float(frequency),
+                             float(absorption_threshold), int(round_decimals), k_max, pos.data_ptr(), mat.data_ptr(),
+                             cnt.data_ptr(), wp, wl, _stream(dev))
+    _lib.check(rc, "pal_image_sources")
+    return pos, mat, cnt, table
+
+
+def render_scene(base_signal, source_pos, img_pos: torch.Tensor, img_mat: torch.Tensor, n_img: int, mic_positions,
+                 fs: float, c: float, duration: float, freq: float, table: MaterialTable,
+                 trim_to_duration: bool = True, normalise: bool = True) -> torch.Tensor:
+    """main.py:94-122 for one scene; returns a [M, n_keep] float32 CUDA tensor."""
+    dev = _dev()
+    L = _lib.lib()
+    if 'air' not in table.index:
+        raise KeyError('air')                      # main.py:108 looks up material_properties['air']
+    mics = torch.as_tensor(np.ascontiguousarray(np.asarray(mic_positions, dtype=np.float64).reshape(-1, 3))).to(dev)
+    src = torch.as_tensor(np.asarray(source_pos, dtype=np.float64).reshape(3)).to(dev)
+    m = mics.shape[0]
+    k1 = int(n_img) + 1
+    tau = torch.empty((m, k1), dtype=torch.float64, device=dev)
+    gain = torch.empty((m, k1), dtype=torch.float64, device=dev)
+    _lib.check(L.pal_path_table(src.data_ptr(), img_pos.data_ptr() if n_img else None,
+                                img_mat.data_ptr() if n_img else None, int(n_img), mics.data_ptr(), m,
+                                table.absorption.data_ptr(), table.freq.data_ptr(), table.index['air'], float(freq),
+                                float(c), tau.data_ptr(), gain.data_ptr(), _stream(dev)), "pal_path_table")
+    base = torch.as_tensor(np.ascontiguousarray(np.asarray(base_signal, dtype=np.float32))).to(dev) \
+        if not isinstance(base_signal, torch.Tensor) else base_signal.to(dev, torch.float32).contiguous()
+    n_base = base.numel()
+    max_delay = float(tau.max().item())                         # main.py:94-101 (one small read-back)
+    total = int((duration + max_delay) * fs)                    # main.py:102
+    if total < n_base:
+        raise ValueError("negative dimensions are not allowed")  # np.pad with a negative width
+    if int(0.01 * total) < 1:
+        raise ValueError("operands could not be broadcast together")   # empty fade window, signal_processing.py:78
+    n_keep = min(int(duration * fs), total) if trim_to_duration else total
+    out = torch.empty((m, n_keep), dtype=torch.float32, device=dev)
+    full, small = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(L.pal_render_workspace(total, m, C.byref(full), C.byref(small)), "pal_render_workspace")
+    ws, wp, wl = _ws(full.value, dev)
+    _lib.check(L.pal_render_scene(base.data_ptr(), n_base, total, tau.data_ptr(), gain.data_ptr(), m, k1, float(fs),
+                                  n_keep, 1 if normalise else 0, out.data_ptr(), wp, wl, _stream(dev)),
+               "pal_render_scene")
+    for t in (base, tau, gain, ws, mics, src):
+        t.record_stream(torch.cuda.current_stream(dev))
+    return out
+
+
+def normalise_compress(x: torch.Tensor, threshold: float = 0.8, epsilon: float = 1e-8, compress: bool = True):
+    """In place on the rows of a float32 CUDA tensor [R, n]."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    _lib.check(_lib.lib().pal_normalise_compress(x.data_ptr(), x.shape[0], x.shape[1], float(threshold), float(epsilon),
+                                                 1 if compress else 0, _stream(x.device)), "pal_normalise_compress")
+    return x

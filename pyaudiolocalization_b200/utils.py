@@ -105,3 +105,25 @@ def get_time_delays_phat(sig1: np.ndarray, sig2: np.ndarray, fs: float, num_peak
     time_lags = np.arange(-(n2 - 1), n1) / fs          # scipy.signal.correlation_lags(n1, n2, 'full') / fs
     corr = res.corr[0, 0].double().cpu().numpy()
     return list(time_lags[k]), corr, time_lags
+
+
+def generate_image_sources_iterative(source, planes, max_order: int, frequency: float,
+                                     material_properties: Dict[str, Any], mic_positions,
+                                     absorption_threshold: float = 0.01, round_decimals: int = 6
+                                     ) -> List[Dict[str, Any]]:
+    """utils.py:67-106 -- list of {'source': ndarray[3], 'material': str} in discovery order,
+    computed by one thread block on the device (float64, the reference's evaluation order)."""
+    from . import scene as _s
+    if max_order < 1 or not planes:
+        return []
+    k_max = None
+    while True:
+        pos, mat, cnt, table = _s.image_sources_batched([source], planes, max_order, frequency, material_properties,
+                                                        mic_positions, absorption_threshold, round_decimals, k_max)
+        n = int(cnt[0].item())
+        if n >= 0:
+            break
+        k_max = pos.shape[1] * 4            # more images than the first allocation: retry larger
+    p = pos[0, :n].cpu().numpy()
+    m = mat[0, :n].cpu().numpy()
+    return [{'source': p[i].copy(), 'material': table.names[int(m[i])]} for i in range(n)]

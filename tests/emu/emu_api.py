@@ -92,3 +92,51 @@ def generic_gcc_phat(sig, n1, n2, pairs, win_half, dist, method=0, mult=1.0, num
                                _p(cnt, C.c_int), _p(pk, C.c_float), _p(gm, C.c_float), _p(fl, C.c_uint),
                                _p(corr, C.c_float))
     return k, cnt, pk, gm, fl, corr
+
+
+def _pd(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def image_sources(sources, planes, plane_mat, mat_abs, mat_freq, mics, max_order, frequency, threshold, k_max,
+                  round_scale=1e6):
+    sources = np.ascontiguousarray(sources, np.float64).reshape(-1, 3)
+    planes = np.ascontiguousarray(planes, np.float64).reshape(-1, 4)
+    mics = np.ascontiguousarray(mics, np.float64).reshape(-1, 3)
+    plane_mat = np.ascontiguousarray(plane_mat, np.int32)
+    mat_abs = np.ascontiguousarray(mat_abs, np.float64)
+    mat_freq = np.ascontiguousarray(mat_freq, np.float64)
+    b = len(sources)
+    pos = np.zeros((b, k_max, 3), np.float64)
+    mat = np.zeros((b, k_max), np.int32)
+    cnt = np.zeros(b, np.int32)
+    lib().emu_image_sources(_pd(sources), C.c_longlong(b), _pd(planes), _p(plane_mat, C.c_int), len(planes), _pd(mat_abs),
+                            _pd(mat_freq), _pd(mics), len(mics), max_order, C.c_double(frequency), C.c_double(threshold),
+                            C.c_double(round_scale), k_max, _pd(pos), _p(mat, C.c_int), _p(cnt, C.c_int))
+    return pos, mat, cnt
+
+
+def path_table(src, img_pos, img_mat, mics, mat_abs, mat_freq, air_mat, frequency, c_sound):
+    src = np.ascontiguousarray(src, np.float64)
+    img_pos = np.ascontiguousarray(img_pos, np.float64).reshape(-1, 3)
+    img_mat = np.ascontiguousarray(img_mat, np.int32)
+    mics = np.ascontiguousarray(mics, np.float64).reshape(-1, 3)
+    k1 = len(img_pos) + 1
+    tau = np.zeros((len(mics), k1))
+    gain = np.zeros((len(mics), k1))
+    lib().emu_path_table(_pd(src), _pd(img_pos if len(img_pos) else np.zeros((1, 3))), _p(img_mat if len(img_mat) else np.zeros(1, np.int32), C.c_int),
+                         len(img_pos), _pd(mics), len(mics), _pd(np.ascontiguousarray(mat_abs, np.float64)),
+                         _pd(np.ascontiguousarray(mat_freq, np.float64)), air_mat, C.c_double(frequency),
+                         C.c_double(c_sound), _pd(tau), _pd(gain))
+    return tau, gain
+
+
+def render_scene(base, total, tau, gain, fs, n_keep):
+    base = np.ascontiguousarray(base, np.float32)
+    tau = np.ascontiguousarray(tau, np.float64)
+    gain = np.ascontiguousarray(gain, np.float64)
+    m, k1 = tau.shape
+    out = np.zeros((m, n_keep), np.float32)
+    lib().emu_render_scene(_p(base, C.c_float), len(base), total, _pd(tau), _pd(gain), m, k1, C.c_double(fs), n_keep,
+                           _p(out, C.c_float))
+    return out

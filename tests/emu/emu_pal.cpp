@@ -136,3 +136,65 @@ extern "C" void emu_generic_gcc_phat(int use_double, const float* sig, long long
     emu_generic_impl<float>(sig, B, Mics, ld, n1, n2, pairs, P, win_half, dist, method, mult, num_peaks, eps, k_idx,
                             k_count, peak, gmax, flags, corr_out);
 }
+
+// ---------------------------------------------------------------- stage 1: image sources + renderer
+#include "pal_render.cuh"
+
+extern "C" void emu_image_sources(const double* sources, long long n_scenes, const double* planes, const int* plane_mat,
+                                  int n_planes, const double* mat_abs, const double* mat_freq, const double* mics,
+                                  int n_mics, int max_order, double frequency, double threshold, double round_scale,
+                                  int k_max, double* out_pos, int* out_mat, int* out_count) {
+  constexpr int NT = 64;
+  ImgParams ip{n_planes, n_mics, max_order, k_max, frequency, threshold, round_scale};
+  const int cmax = k_max * n_planes;
+  const size_t per_block = size_t(cmax) * 3 * 8 * 2 + size_t(k_max + 1) * 3 * 8 + size_t(cmax) * 4 + 64;
+  const int grid = 2;
+  std::vector<char> scratch(per_block * grid);
+  simt::launch(grid, NT, 64 * sizeof(int), [&](char* sm) {
+    image_sources_body<NT>(ip, sources, n_scenes, planes, plane_mat, mat_abs, mat_freq, mics, 0, out_pos, out_mat,
+                           out_count, scratch.data(), per_block, sm);
+  });
+}
+
+extern "C" void emu_path_table(const double* src, const double* img_pos, const int* img_mat, int n_img, const double* mics,
+                               int n_mics, const double* mat_abs, const double* mat_freq, int air_mat, double frequency,
+                               double c_sound, double* tau, double* gain) {
+  const int total = n_mics * (n_img + 1);
+  simt::launch((total + 63) / 64, 64, 16, [&](char*) {
+    path_table_body(src, img_pos, img_mat, n_img, mics, n_mics, mat_abs, mat_freq, air_mat, frequency, c_sound, tau, gain);
+  });
+}
+
+extern "C" void emu_render_scene(const float* base, int n_base, int N, const double* tau, const double* gain, int n_mics,
+                                 int k1, double fs, int n_keep, float* out) {
+  using T = float;
+  constexpr int NT = 64, TC = 4, J = 4;
+  const BluePlan p = make_blue_plan(2 * N);
+  std::vector<cpx<T>> chirp(p.n), tw1(p.M1 / 2 + 1), tw2(p.M2 / 2 + 1), twM(p.M), bhat(p.M);
+  simt::launch(2, NT, 16, [&](char*) { blue_init_tables_body<T>(p, chirp.data(), tw1.data(), tw2.data(), twM.data()); });
+  BlueTables<T> tb{chirp.data(), tw1.data(), tw2.data(), twM.data(), bhat.data()};
+  const int tc = std::min(p.M2, TC);
+  const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2);
+  simt::launch(2, NT, cs, [&](char* sm) { colpass_fwd_body<T, NT, TC>(p, tb, LoadBhat<T>{p, chirp.data()}, 1, bhat.data(), sm); });
+  simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, false, false>(p, tb, 1, bhat.data(), sm); });
+  std::vector<cpx<T>> conv(size_t(n_mics) * p.M), X(p.n);
+  std::vector<cpxf> G(size_t(n_mics) * (N + 1));
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_fwd_body<T, NT, TC>(p, tb, LoadSignal<T>{p, chirp.data(), base, n_base, n_base, n_base, nullptr}, 1, conv.data(), sm);
+  });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, true, false>(p, tb, 1, conv.data(), sm); });
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_inv_body<T, NT, TC>(p, tb, StoreSpectrum<T>{p, chirp.data(), X.data()}, 1, conv.data(), sm);
+  });
+  const size_t ts = 4 * ((k1 + 3) & ~3) + 16 * size_t(k1) + 16;
+  simt::launch(3, NT, ts, [&](char* sm) { transfer_body<NT, J>(X.data(), N, tau, gain, k1, n_mics, fs, G.data(), sm); });
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_fwd_body<T, NT, TC>(p, tb, LoadHermitian<T>{p, chirp.data(), G.data(), N}, n_mics, conv.data(), sm);
+  });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, true, true>(p, tb, n_mics, conv.data(), sm); });
+  const int fade = int(0.01 * N);
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_inv_body<T, NT, TC>(p, tb, StoreRender<T>{p, chirp.data(), out, N, n_keep, fade}, n_mics, conv.data(), sm);
+  });
+  simt::launch(2, NT, 64, [&](char* sm) { normalise_compress_body<NT>(out, n_mics, n_keep, 0.8f, 1e-8f, true, sm); });
+}

@@ -1,0 +1,118 @@
+"""GPU parity tests of stage 1 (image sources + multipath renderer) through the C ABI.
+Bars: image-source positions bit-exact (float64); rendered signals within 1e-5 absolute."""
+import numpy as np
+import pytest
+
+from oracle import pal_oracle as O
+from tests.golden.make_golden import CUSTOM_MATERIALS, shoebox
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RENDER_ATOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pal():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pyaudiolocalization_b200 as p
+    return p
+
+
+def test_image_sources_golden(pal, golden):
+    from pyaudiolocalization_b200 import utils as U
+    mics, src = golden["img_mics"], golden["img_src"]
+    counts = [len(U.generate_image_sources_iterative(src, shoebox(6, 5, 3), o, 1000.0, CUSTOM_MATERIALS, mics, -1.0))
+              for o in range(1, 7)]
+    assert counts == list(golden["img_counts_thr_neg1"]) == [6, 24, 62, 128, 230, 376]
+    im = U.generate_image_sources_iterative(src, shoebox(6, 5, 3), 3, 1000.0, CUSTOM_MATERIALS, mics, 0.01)
+    assert np.array_equal(np.array([i["source"] for i in im]), golden["img_pos_o3"])
+    names = sorted(CUSTOM_MATERIALS)
+    assert [names.index(i["material"]) for i in im] == list(golden["img_mat_o3"])
+    # README example 1: the stock materials prune every reflection (SURVEY headline fact 5)
+    from pyaudiolocalization_b200.materials import material_properties as stock
+    cfg1 = U.generate_image_sources_iterative([0.5, 0.5, 0.5],
+                                              [{'plane': [1, 0, 0, -5], 'material': 'wood'},
+                                               {'plane': [0, 1, 0, -5], 'material': 'metal'},
+                                               {'plane': [0, 0, 1, -5], 'material': 'wood'}], 3, 1000, stock,
+                                              np.eye(4, 3, k=-1), 0.01)
+    assert cfg1 == []
+    with pytest.raises(ValueError):
+        U.generate_image_sources_iterative(src, [{'plane': [0, 0, 0, 1], 'material': 'wood'}], 1, 1000.0,
+                                           CUSTOM_MATERIALS, mics)
+    with pytest.raises(ValueError):
+        U.generate_image_sources_iterative(src, [{'plane': [1, 0, 0, 1], 'material': 'unobtainium'}], 1, 1000.0,
+                                           CUSTOM_MATERIALS, mics)
+
+
+def test_image_sources_batched_vs_oracle(pal):
+    from pyaudiolocalization_b200 import scene
+    rng = np.random.default_rng(3)
+    mics = rng.uniform([1, 1, 0.5], [5, 4, 2.5], size=(6, 3))
+    srcs = rng.uniform([0.5, 0.5, 0.3], [5.5, 4.5, 2.7], size=(9, 3))
+    pos, mat, cnt, table = scene.image_sources_batched(srcs, shoebox(6, 5, 3), 4, 800.0, CUSTOM_MATERIALS, mics, 0.02)
+    pos, mat, cnt = pos.cpu().numpy(), mat.cpu().numpy(), cnt.cpu().numpy()
+    for s in range(len(srcs)):
+        im = O.generate_image_sources_iterative(srcs[s], shoebox(6, 5, 3), 4, 800.0, CUSTOM_MATERIALS, mics, 0.02)
+        assert cnt[s] == len(im)
+        assert np.array_equal(pos[s, :cnt[s]], np.array([i["source"] for i in im]).reshape(-1, 3))
+        assert [table.names[m] for m in mat[s, :cnt[s]]] == [i["material"] for i in im]
+
+
+def test_render_golden_and_fractional_delay(pal, golden):
+    from pyaudiolocalization_b200 import main as M, signal_processing as SP
+    fs = 16000.0
+    mics, src = golden["img_mics"][:4], golden["img_src"]
+    sig = M.simulate_signals_with_multipath(src, mics, fs, 343.62, duration=0.25, signal_type="chirp", freq=500,
+                                            reflective_planes=shoebox(6, 5, 3), material_properties=CUSTOM_MATERIALS,
+                                            max_reflections=2, absorption_threshold=0.01)
+    assert isinstance(sig, list) and len(sig) == 4 and sig[0].dtype == np.float64
+    err = np.abs(np.array(sig) - golden["render_o2_4mics"]).max()
+    print("render max abs error vs reference:", err)
+    assert err <= RENDER_ATOL
+    fd = SP.fractional_delay(np.pad(golden["chirp_16k_025_500"], (0, 300)), 0.00731, fs)
+    assert np.abs(fd - golden["frac_delay"]).max() <= RENDER_ATOL
+    dc = SP.dynamic_range_compression(golden["compress_in"].copy())
+    assert np.abs(dc - golden["compress_out"]).max() <= RENDER_ATOL
+    x = golden["compress_in"]
+    assert np.abs(SP.normalize_signal(x) - x / np.abs(x).max()).max() <= 1e-6
+    assert np.array_equal(SP.normalize_signal(np.zeros(16)), np.zeros(16))
+
+
+@pytest.mark.parametrize("order,fs,dur", [(3, 16000.0, 0.25), (1, 44100.0, 0.2), (0, 8000.0, 0.5)])
+def test_render_vs_oracle(pal, order, fs, dur):
+    from pyaudiolocalization_b200 import main as M
+    rng = np.random.default_rng(int(fs) + order)
+    mics = rng.uniform([1, 1, 0.5], [5, 4, 2.5], size=(5, 3))
+    src = rng.uniform([0.5, 0.5, 0.3], [5.5, 4.5, 2.7], size=3)
+    kw = dict(duration=dur, signal_type="chirp", freq=700, reflective_planes=shoebox(6, 5, 3),
+              material_properties=CUSTOM_MATERIALS, max_reflections=order, absorption_threshold=0.01)
+    got = np.array(M.simulate_signals_with_multipath(src, mics, fs, 343.62, **kw))
+    want = np.array(O.simulate_signals_with_multipath(src, mics, fs, 343.62, **kw))
+    assert got.shape == want.shape
+    err = np.abs(got - want).max()
+    print(f"order {order} fs {fs}: render max abs error {err:.2e}")
+    assert err <= RENDER_ATOL
+
+
+def test_render_stock_materials_tiny_gains(pal):
+    """README example 1 geometry: raw gains are 2.8e-38 and every reflection is pruned; the four
+    channels are identical and must still come out normalised (relative gains, float64 ratio)."""
+    from pyaudiolocalization_b200 import main as M
+    from pyaudiolocalization_b200.materials import material_properties as stock
+    cfg = M.config
+    kw = dict(duration=0.1, signal_type="sine", freq=1000, reflective_planes=cfg["reflective_planes"],
+              material_properties=stock, max_reflections=3, absorption_threshold=0.01)
+    got = np.array(M.simulate_signals_with_multipath(cfg["source_position"], np.array(cfg["mic_positions"]), 44100,
+                                                     343.62, **kw))
+    want = np.array(O.simulate_signals_with_multipath(cfg["source_position"], np.array(cfg["mic_positions"]), 44100,
+                                                      343.62, **kw))
+    assert np.abs(got - want).max() <= RENDER_ATOL
+    assert np.abs(got).max() == pytest.approx(1.0, abs=1e-6)
+    # a source so far away that the reference's gain underflows to exactly 0 -> all-zero channels
+    far = np.array(M.simulate_signals_with_multipath([900.0, 0, 0], np.array(cfg["mic_positions"]), 8000, 343.62,
+                                                     duration=0.05, signal_type="sine", freq=1000,
+                                                     reflective_planes=[], material_properties=stock,
+                                                     max_reflections=0))
+    assert np.array_equal(far, np.zeros_like(far))
