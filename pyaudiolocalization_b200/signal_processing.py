@@ -94,3 +94,6 @@ def dynamic_range_compression(signal: np.ndarray, threshold: float = 0.8, epsilo
     if x.size == 0:
         raise ValueError("zero-size array to reduction operation maximum which has no identity")
     return _s.normalise_compress(r, threshold, epsilon, compress=True)[0].double().cpu().numpy().reshape(x.shape)
+
+
+from .host_solver import noise_reduction  # noqa: E402,F401  (signal_processing.py:109-138, host side)

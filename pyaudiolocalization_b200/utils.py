@@ -127,3 +127,10 @@ def generate_image_sources_iterative(source, planes, max_order: int, frequency: 
     p = pos[0, :n].cpu().numpy()
     m = mat[0, :n].cpu().numpy()
     return [{'source': p[i].copy(), 'material': table.names[int(m[i])]} for i in range(n)]
+
+
+# Host-side helpers of the reference's `utils` namespace (unchanged algorithms, see host_solver.py)
+from .host_solver import (bootstrap_significance, compute_cross_correlation_metrics,  # noqa: E402,F401
+                          compute_peak_to_peak_ratio, compute_snr, compute_weights,
+                          determine_optimal_number_of_clusters, dynamic_bounds_extended, equations,
+                          heuristic_initialization_adaptive, read_audio_files, synchronize_signals_improved)

@@ -116,3 +116,53 @@ def test_render_stock_materials_tiny_gains(pal):
                                                      reflective_planes=[], material_properties=stock,
                                                      max_reflections=0))
     assert np.array_equal(far, np.zeros_like(far))
+
+
+def test_localize_sound_source_end_to_end(pal):
+    """Whole `localize_sound_source(config)` call (reference signature) against the oracle chain:
+    oracle renderer -> the same host sync / band-pass -> oracle pair loop -> the same host solver."""
+    import logging
+    from pyaudiolocalization_b200 import host_solver as H, main as M, materials
+    logging.getLogger().setLevel(logging.ERROR)
+    rng = np.random.default_rng(21)
+    mics = rng.uniform([1, 1, 0.5], [5, 4, 2.5], size=(5, 3))
+    cfg = {"fs": 16000, "duration": 0.25, "celsius": 20, "humidity": 50, "mic_positions": mics.tolist(),
+           "source_position": [2.3, 3.3, 1.2], "signal_type": "chirp", "freq": 500,
+           "reflective_planes": shoebox(6, 5, 3),
+           "localization": {"max_reflections": 2, "absorption_threshold": 0.01, "max_expected_delay": 0.02,
+                            "analyze_correlation": False, "visualize_correlation": True}}
+    saved = dict(materials.material_properties)
+    materials.material_properties.clear()
+    materials.material_properties.update(CUSTOM_MATERIALS)       # the reference reads this shared dict (main.py:135)
+    try:
+        out = M.localize_sound_source(cfg, use_simulation=True, show_plots=False)
+    finally:
+        materials.material_properties.clear()
+        materials.material_properties.update(saved)
+    c = O.speed_of_sound(20, 50)
+    sig = O.simulate_signals_with_multipath(cfg["source_position"], mics, 16000, c, duration=0.25, signal_type="chirp",
+                                            freq=500, reflective_planes=shoebox(6, 5, 3),
+                                            material_properties=CUSTOM_MATERIALS, max_reflections=2,
+                                            absorption_threshold=0.01)
+    sig = [H.noise_reduction(s, 16000) for s in H.synchronize_signals_improved(sig, 16000)]
+    tds, pairs, cm = O.pair_loop(sig, 16000, max_expected_delay=0.02)
+    want = H.solve_position(mics, pairs, tds, c, {}, False, "kmeans", 0.001, 2)
+    assert set(out) == {"estimated_position", "actual_position", "mic_positions", "correlation_metrics",
+                        "correlation_matrix", "calibration_data"}
+    assert np.allclose(out["estimated_position"], np.array(want), atol=1e-6), (out["estimated_position"], want)
+    assert np.abs(out["correlation_matrix"] - cm).max() <= 1e-4 * np.abs(cm).max()
+    assert out["correlation_metrics"] is None and out["actual_position"] == cfg["source_position"]
+
+
+def test_bootstrap_significance_on_gpu(pal):
+    """utils.bootstrap_significance: the 1000 permuted correlations run as one GPU batch; the
+    reference RNG is unseeded, so parity is statistical (same seed -> same permutations here)."""
+    from pyaudiolocalization_b200 import host_solver as H
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal(600)
+    b = np.roll(a, 3) + 0.1 * rng.standard_normal(600)
+    np.random.seed(123)
+    got = H.bootstrap_significance(a, b, 16000.0, num_bootstrap=64)
+    np.random.seed(123)
+    peaks = [np.max(O.phat_correlation(a, np.random.permutation(b))) for _ in range(64)]
+    assert got == pytest.approx(np.percentile(peaks, 95), rel=1e-4)
