@@ -93,24 +93,6 @@ template <typename T> PAL_DEV void phat_bin(T ar, T ai, T br, T bi, T inv_n, T& 
   rr = xr * sc;
   ri = xi * sc;
 }
-// fp32 hot-path flavour: MUFU.SQRT + MUFU.RCP (about 1 ulp each) instead of the branchy IEEE
-// sqrt/divide sequences; only the MAGNITUDE of the weight is affected (2e-7 relative), never
-// the phase, so the correlation moves far less than the 1e-4 tolerance.
-PAL_DEV void phat_bin_fast(float ar, float ai, float br, float bi, float inv_n, float& rr, float& ri) {
-#if PAL_GPU
-  const float xr = fmaf(ar, br, ai * bi);
-  const float xi = fmaf(ai, br, -(ar * bi));
-  float mag, rcp;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(xr, xr, xi * xi)));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(mag + 1e-10f));
-  const float sc = inv_n * rcp;
-  rr = xr * sc;
-  ri = xi * sc;
-#else
-  phat_bin<float>(ar, ai, br, bi, inv_n, rr, ri);
-#endif
-}
-
 // ---------------------------------------------------------------- forward kernel
 // grid: one block per (frame, channel pair).  sig: [B][M][2048] float32.
 // spec: [B][M][65][32] complex64 -- S[e(r,q)] with e = (2080 r + 2016 q) mod 4095.
@@ -257,26 +239,43 @@ PAL_DEV void pair4095_exact_body(const float* sig, const cpxf* spec, const int* 
 }
 
 // ---------------------------------------------------------------- fast pair kernel (warp per pair)
+// All complex arithmetic is packed (re, im) f32x2 (FFMA2 / FADD2 / FMUL2, pal_simt.h): half the
+// issue slots of scalar code.  The correlation row is kept UNSCALED (n * corr): the 1/n of the
+// inverse DFT is applied only to the two values that leave the kernel.
+//
 // Per-warp shared memory: the phase-A -> phase-B exchange Y[r][kq] (r < 32 by Hermitian symmetry),
 // later overwritten by the 4095-sample correlation row the peak pick scans.
 struct alignas(16) FastWarpSmem {
   union {
     struct {
-      cpxf ya[32 * 33];   // Y[r][kq], kq = 1..32  -> column kq-1
-      cpxf yb[32 * 33];   // Y[r][kq], kq = 33..64 -> column kq-33
-      cpxf y0[32];        // Y[r][0]
+      f2 ya[32 * 33];   // Y[r][kq], kq = 1..32  -> column kq-1
+      f2 yb[32 * 33];   // Y[r][kq], kq = 33..64 -> column kq-33
+      f2 y0[32];        // Y[r][0]
     } y;
     float corr[4096];
   };
-  cpxf lx[64];            // exchange of the odd column kq = 0 (DFT-7 -> DFT-9)
+  f2 lx[64];            // exchange of the odd column kq = 0 (DFT-7 -> DFT-9)
 };
 
 constexpr float kNegBig = -3.0e38f;
 
-// (k mod 4095) for 0 <= k < 8190 in two integer instructions (unsigned min trick)
-PAL_DEV int wrap4095(int k) {
-  const unsigned a = unsigned(k), b = unsigned(k - kN4095);
-  return int(a < b ? a : b);
+// PHAT weighting of one cross-spectrum bin a * conj(b) / (|a * conj(b)| + 1e-10)  (utils.py:116-117),
+// 8 issue slots: FMUL2, FFMA2 (swizzled operand), FMUL, FFMA, MUFU.SQRT, FADD, MUFU.RCP, FMUL2.
+// The approximate sqrt / reciprocal (about 1 ulp each) touch only the MAGNITUDE of the weight
+// (2e-7 relative), never the phase, so the correlation moves far less than the 1e-4 tolerance.
+PAL_DEV f2 phat_bin_p(f2 a, f2 b) {
+  const f2 t = f2_mul(a, f2_bcast(f2_lo(b)));                                    // (ar br, ai br)
+  const f2 x = f2_fma(f2_make(f2_hi(a), -f2_lo(a)), f2_bcast(f2_hi(b)), t);      // + (ai bi, -ar bi)
+  const float xr = f2_lo(x), xi = f2_hi(x);
+  const float m2 = fmaf(xr, xr, xi * xi);
+#if PAL_GPU
+  float mag, rcp;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(m2));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(mag + 1e-10f));
+#else
+  const float rcp = 1.0f / (std::sqrt(m2) + 1e-10f);
+#endif
+  return f2_mul(x, f2_bcast(rcp));
 }
 
 // Careful scan of the window (strict local maxima, runner-up, equal neighbours).  Only used when
@@ -316,6 +315,10 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
   const int lane = simt::lane();
   FastWarpSmem* sm = reinterpret_cast<FastWarpSmem*>(smem_raw) + simt::warp();
   const float inv_n = 1.0f / float(kN4095);
+  const float eps_s = eps * float(kN4095);       // tolerance in the unscaled row
+  // mean|c| <= rms(c) <= 1/sqrt(n) by Parseval (|R| <= 1 after PHAT); in the unscaled row: sqrt(n).
+  // A winner above this bound is above mean|c| whatever the row looks like (utils.py:155,166).
+  const float mean_bound = 64.0f;                // sqrt(4095) = 63.99 rounded up
   const int c0 = kFrame2048 - 1;
   int lo = 1, hi = kN4095 - 2;
   if (win_half >= 0) {
@@ -327,105 +330,100 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
   // window split into 16-byte groups [g_lo, g_hi) plus at most 3 + 3 edge samples
   const int g_lo = (lo + 3) & ~3;
   const int g_hi = (hi + 1) & ~3;
+  // scatter bases: output k = (63 kq + 65 kr) mod 4095 of columns kq = lane+1 and lane+33;
+  // p?w are the same bases pre-wrapped by -4095 so that every store is [base + immediate]
+  const int b0 = 63 * (lane + 1);
+  float* const p1 = sm->corr + b0;
+  float* const p1w = p1 - kN4095;
+  float* const p2 = p1 + 63 * 32;
+  float* const p2w = p2 - kN4095;
 
   for (long long base = (long long)simt::bid() * WARPS; base < n_items; base += (long long)simt::nblocks() * WARPS) {
     const long long item = base + simt::warp();
     const bool active = item < n_items;
     if (PHASE_SYNC) simt::sync_block();
     if (!PHASE_SYNC && !active) break;
-    float s_abs = 0.f, gm = kNegBig;
+    float gm = kNegBig;
     if (active) {
       const long long frame = item / P;
       const int p = int(item % P);
       const int mi = pairs[2 * p], mj = pairs[2 * p + 1];
-      const cpxf* si = spec + (frame * M + mi) * kSpecSlots + lane;
-      const cpxf* sj = spec + (frame * M + mj) * kSpecSlots + lane;
+      const f2* si = reinterpret_cast<const f2*>(spec + (frame * M + mi) * kSpecSlots) + lane;
+      const f2* sj = reinterpret_cast<const f2*>(spec + (frame * M + mj) * kSpecSlots) + lane;
 
       // ---- phase A: lane r owns elements e(r, q), q = 0..64: PHAT, then DFT-65 over q ------
-      float zr[65], zi[65];
+      f2 z[65];
 #pragma unroll
-      for (int q = 0; q < 65; ++q) {
-        const cpxf a = si[q * 32], b = sj[q * 32];
-        phat_bin_fast(a.x, a.y, b.x, b.y, inv_n, zr[q], zi[q]);
-      }
-      dft_pfa2<5, 13, +1, float>(zr, zi);
+      for (int q = 0; q < 65; ++q) z[q] = phat_bin_p(si[q * 32], sj[q * 32]);
+      dft_pfa2_p<5, 13, +1>(z);
 #pragma unroll
       for (int s = 0; s < 65; ++s) {
         const int kq = P65::out_index(s);
-        const cpxf v{zr[s], zi[s]};
-        if (kq == 0) sm->y.y0[lane] = v;
-        else if (kq <= 32) sm->y.ya[lane * 33 + (kq - 1)] = v;
-        else sm->y.yb[lane * 33 + (kq - 33)] = v;
+        if (kq == 0) sm->y.y0[lane] = z[s];
+        else if (kq <= 32) sm->y.ya[lane * 33 + (kq - 1)] = z[s];
+        else sm->y.yb[lane * 33 + (kq - 33)] = z[s];
       }
     }
     if (PHASE_SYNC) simt::sync_block(); else simt::sync_warp();
 
     if (active) {
       // ---- phase B: lane l owns output columns kq = l+1 (real part) and l+33 (imaginary part)
-      float wr[63], wi[63];
+      // of ONE complex DFT-63: w[r] = Y[r][l+1] + i Y[r][l+33], with Y[63-r][kq] = conj(Y[r][65-kq])
+      f2 w[63];
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
-        const cpxf a = sm->y.ya[r * 33 + lane], b = sm->y.yb[r * 33 + lane];
+        const f2 a = sm->y.ya[r * 33 + lane], b = sm->y.yb[r * 33 + lane];
         if (r == 0) {
-          wr[0] = a.x;
-          wi[0] = b.x;
+          w[0] = f2_make(f2_lo(a), f2_lo(b));
         } else {
-          wr[r] = a.x - b.y;       wi[r] = a.y + b.x;
-          wr[63 - r] = a.x + b.y;  wi[63 - r] = b.x - a.y;
+          w[r] = f2_add(a, f2_muli(b));                   // (a.x - b.y, a.y + b.x)
+          w[63 - r] = f2_add(f2_conj(a), f2_swap(b));     // (a.x + b.y, b.x - a.y)
         }
       }
       // odd column kq = 0: nine DFT-7 on lanes 0..8 now, seven DFT-9 on lanes 0..6 below
-      float tr[7], ti[7];
+      f2 t7[7];
       if (lane < 9) {
 #pragma unroll
         for (int a = 0; a < 7; ++a) {
           const int r = (a * P63::UA + lane * P63::UB) % 63;
-          const cpxf v = sm->y.y0[r < 32 ? r : 63 - r];
-          tr[a] = v.x;
-          ti[a] = (r == 0) ? 0.f : (r < 32 ? v.y : -v.y);
+          const f2 v = sm->y.y0[r < 32 ? r : 63 - r];
+          t7[a] = f2_make(f2_lo(v), (r == 0) ? 0.f : (r < 32 ? f2_hi(v) : -f2_hi(v)));
         }
       }
       simt::sync_warp();            // every read of Y is done: the union now holds the correlation row
       if (lane < 9) {
-        dft_odd<7, +1, float>(tr, ti);
+        dft_odd_p<7, +1>(t7);
 #pragma unroll
-        for (int a = 0; a < 7; ++a) sm->lx[(a * P63::UA + lane * P63::UB) % 63] = cpxf{tr[a], ti[a]};
+        for (int a = 0; a < 7; ++a) sm->lx[(a * P63::UA + lane * P63::UB) % 63] = t7[a];
       }
-      dft_pfa2<7, 9, +1, float>(wr, wi);
-      // scatter to natural order: k = (65 kr + 63 kq) mod 4095; consecutive lanes are 63 floats
-      // apart -> conflict-free.  sum|c| and max(c) are taken from the registers on the way.
-      const int b0 = 63 * (lane + 1);
-      float sa0 = 0.f, sa1 = 0.f, g0 = kNegBig, g1 = kNegBig;
+      dft_pfa2_p<7, 9, +1>(w);
+      // scatter to natural order: consecutive lanes are 63 floats apart -> conflict-free.  Whether
+      // (63 kq + 65 kr) wraps past 4095 is known at compile time for half of the stores; max(c) is
+      // taken from the registers on the way (FMNMX3).
 #pragma unroll
       for (int s = 0; s < 63; ++s) {
         const int kr = P63::out_index(s);
-        const int k1 = wrap4095(b0 + 65 * kr);
-        const int k2 = wrap4095(b0 + 65 * kr + 63 * 32);
-        sm->corr[k1] = wr[s];
-        sm->corr[k2] = wi[s];
-        sa0 += fabsf(wr[s]);
-        sa1 += fabsf(wi[s]);
-        g0 = fmaxf(g0, wr[s]);
-        g1 = fmaxf(g1, wi[s]);
+        const int c = 65 * kr;
+        const float vr = f2_lo(w[s]), vi = f2_hi(w[s]);
+        if (kr <= 31) p1[c] = vr;
+        else ((b0 + c >= kN4095) ? p1w : p1)[c] = vr;
+        if (kr == 0) p2[c] = vi;
+        else if (kr >= 32) p2w[c] = vi;
+        else ((b0 + 63 * 32 + c >= kN4095) ? p2w : p2)[c] = vi;
+        gm = fmaxf(gm, fmaxf(vr, vi));
       }
-      s_abs = sa0 + sa1;
-      gm = fmaxf(g0, g1);
       simt::sync_warp();
       if (lane < 7) {
-        float ur[9], ui[9];
+        f2 u[9];
 #pragma unroll
-        for (int b = 0; b < 9; ++b) {
-          const cpxf v = sm->lx[(lane * P63::UA + b * P63::UB) % 63];
-          ur[b] = v.x;
-          ui[b] = v.y;
-        }
-        dft_odd<9, +1, float>(ur, ui);
+        for (int b = 0; b < 9; ++b) u[b] = sm->lx[(lane * P63::UA + b * P63::UB) % 63];
+        dft_odd_p<9, +1>(u);
 #pragma unroll
         for (int b = 0; b < 9; ++b) {
           const int kr = (9 * lane + 7 * b) % 63;
-          sm->corr[(65 * kr) % kN4095] = ur[b];
-          s_abs += fabsf(ur[b]);
-          gm = fmaxf(gm, ur[b]);
+          const float v = f2_lo(u[b]);
+          sm->corr[(65 * kr) % kN4095] = v;
+          gm = fmaxf(gm, v);
         }
       }
     }
@@ -436,12 +434,10 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
     const float* c = sm->corr;
     if (WRITE_CORR) {
       float* dst = corr_out + item * kN4095;
-      for (int k = lane; k < kN4095; k += 32) dst[k] = c[k];
+      for (int k = lane; k < kN4095; k += 32) dst[k] = c[k] * inv_n;
     }
-    s_abs = warp_sum(s_abs);
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) gm = fmaxf(gm, simt::shfl_xor(gm, m));
-    const float mean_abs = s_abs * inv_n;
 
     // largest and second largest SAMPLE of the window (vectorised, no neighbour tests): the
     // largest one is the answer whenever it is a strict local maximum, which is then verified
@@ -486,17 +482,17 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
     unsigned fl = 0;
     int kbest;
     float hbest;
-    if (bi >= 0 && bv >= mean_abs + eps) {
+    if (bi >= 0 && bv >= mean_bound + eps_s) {
       kbest = bi;
       hbest = bv;
-      if (cand2 >= bv - eps) fl |= PAL_FLAG_NEAR_TIE;
-      if (pl >= bv - eps) fl |= PAL_FLAG_PLATEAU;
+      if (cand2 >= bv - eps_s) fl |= PAL_FLAG_NEAR_TIE;
+      if (pl >= bv - eps_s) fl |= PAL_FLAG_PLATEAU;
       // anything within `dist` samples that is as high as the winner (up to eps) needs the
       // full greedy resolution of the distance rule -> exact kernel
       bool hit = false;
       for (int o = -dist + lane; o <= dist; o += 32) {
         const int q = bi + o;
-        if (o != 0 && q >= 0 && q < kN4095 && c[q] >= bv - eps) hit = true;
+        if (o != 0 && q >= 0 && q < kN4095 && c[q] >= bv - eps_s) hit = true;
       }
       if (simt::ballot(hit)) fl |= PAL_FLAG_CHAIN;
     } else if (bi >= 0) {
@@ -508,10 +504,12 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
       // no local maximum in the window: unbounded first argmax (utils.py:168-172)
       int gi = 0x7fffffff;
       int near = 0;
+      bool nonzero = false;
       for (int k = lane; k < kN4095; k += 32) {
         const float v = c[k];
         if (v == gm && k < gi) gi = k;
-        if (v >= gm - eps) ++near;
+        if (v >= gm - eps_s) ++near;
+        nonzero |= (v != 0.f);
       }
 #pragma unroll
       for (int m = 16; m >= 1; m >>= 1) {
@@ -522,14 +520,14 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
       kbest = gi;
       hbest = gm;
       fl |= PAL_FLAG_FALLBACK_ARGMAX;
-      const bool all_zero = (s_abs == 0.f);
+      const bool all_zero = simt::ballot(nonzero) == 0u;
       if (near > 1 && !all_zero) fl |= PAL_FLAG_NEAR_TIE;
       if (pl > kNegBig && !all_zero) fl |= PAL_FLAG_PLATEAU;
     }
     if (lane == 0) {
       k_idx[item] = kbest;
-      peak[item] = hbest;
-      gmax[item] = gm;
+      peak[item] = hbest * inv_n;
+      gmax[item] = gm * inv_n;
       flags[item] = fl;
     }
     if (!PHASE_SYNC) simt::sync_warp();   // the next item overwrites the union

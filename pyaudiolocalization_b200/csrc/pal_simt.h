@@ -85,6 +85,19 @@ PAL_DEV void mbar_wait(mbar_t* b, unsigned parity) {
 }
 }  // namespace simt
 
+// ---- packed pair of fp32 values (Blackwell FFMA2 / FADD2 / FMUL2: fma.rn.f32x2 & co, sm_100+).
+// One issue slot does two fp32 operations; ptxas folds half swaps / per-half negations of an
+// operand (f2_make(-hi, lo) ...) and scalar broadcasts into operand modifiers, so a complex
+// number carried as (re, im) in one aligned register pair costs nothing extra for *i, conj.
+struct f2 { unsigned long long v; };
+PAL_DEV f2 f2_make(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+PAL_DEV float f2_lo(f2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); return lo; }
+PAL_DEV float f2_hi(f2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); return hi; }
+PAL_DEV f2 f2_add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+PAL_DEV f2 f2_sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+PAL_DEV f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+PAL_DEV f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+
 PAL_DEV float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 PAL_DEV double fma_(double a, double b, double c) { return fma(a, b, c); }
 PAL_DEV float sqrt_(float a) { return sqrtf(a); }
@@ -200,6 +213,15 @@ template <class F> inline void launch(int grid, int block, size_t smem_bytes, F 
 }
 }  // namespace simt
 
+struct alignas(8) f2 { float lo, hi; };
+inline f2 f2_make(float lo, float hi) { return f2{lo, hi}; }
+inline float f2_lo(f2 a) { return a.lo; }
+inline float f2_hi(f2 a) { return a.hi; }
+inline f2 f2_add(f2 a, f2 b) { return f2{a.lo + b.lo, a.hi + b.hi}; }
+inline f2 f2_sub(f2 a, f2 b) { return f2{a.lo - b.lo, a.hi - b.hi}; }
+inline f2 f2_mul(f2 a, f2 b) { return f2{a.lo * b.lo, a.hi * b.hi}; }
+inline f2 f2_fma(f2 a, f2 b, f2 c) { return f2{std::fmaf(a.lo, b.lo, c.lo), std::fmaf(a.hi, b.hi, c.hi)}; }
+
 inline float fma_(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline double fma_(double a, double b, double c) { return std::fma(a, b, c); }
 inline float sqrt_(float a) { return std::sqrt(a); }
@@ -211,5 +233,11 @@ inline double max_(double a, double b) { return std::fmax(a, b); }
 inline float min_(float a, float b) { return std::fmin(a, b); }
 inline double min_(double a, double b) { return std::fmin(a, b); }
 #endif
+
+// helpers common to both builds: complex numbers as (re, im) pairs
+PAL_DEV f2 f2_bcast(float c) { return f2_make(c, c); }
+PAL_DEV f2 f2_muli(f2 a) { return f2_make(-f2_hi(a), f2_lo(a)); }     // i * a
+PAL_DEV f2 f2_conj(f2 a) { return f2_make(f2_lo(a), -f2_hi(a)); }
+PAL_DEV f2 f2_swap(f2 a) { return f2_make(f2_hi(a), f2_lo(a)); }
 
 }  // namespace pal

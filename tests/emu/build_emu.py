@@ -14,7 +14,7 @@ def build(force=False):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in srcs):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-DPAL_EMU", "-x", "c++", "-I", CSRC,
+    cmd = ["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-DPAL_EMU", "-fno-strict-aliasing", "-x", "c++", "-I", CSRC,
            os.path.join(HERE, "emu_pal.cpp"), "-o", OUT, "-lpthread"]
     subprocess.run(cmd, check=True)
     return OUT
