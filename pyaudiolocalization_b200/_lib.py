@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpal_b200.so")
+LIB_PATH = os.environ.get("PAL_B200_LIB") or os.path.join(_PKG, "libpal_b200.so")   # env override: tuning experiments only
 
 PAL_ABI_VERSION = 2
 

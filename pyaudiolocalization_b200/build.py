@@ -9,7 +9,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 ROOT = os.path.dirname(PKG)
-LIB = os.path.join(PKG, "libpal_b200.so")
+LIB = os.environ.get("PAL_B200_LIB") or os.path.join(PKG, "libpal_b200.so")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -25,7 +25,8 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in sources()):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", CSRC, "-I", os.path.join(ROOT, "include"),
+    extra = os.environ.get("PAL_NVCC_EXTRA", "").split()      # tuning experiments only
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", CSRC, "-I", os.path.join(ROOT, "include"),
                                  os.path.join(CSRC, "pal_capi.cu"), "-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr

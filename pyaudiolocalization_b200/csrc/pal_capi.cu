@@ -50,32 +50,28 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 constexpr int kFwdThreads = 256;
-constexpr int kFastWarps = 8;
+#ifndef PAL_FAST_WARPS
+#define PAL_FAST_WARPS 8
+#endif
+constexpr int kFastWarps = PAL_FAST_WARPS;   // warps (= mic pairs in flight) per CTA of the fused pair kernel
 constexpr int kExactThreads = 256;
-// tuning switch (read once from the environment): PAL_PHASE_SYNC=1 makes the warps of a block
-// walk the unrolled phases together (block barriers) instead of drifting apart.  Measured on
-// B200: 7 % slower than free-running warps (profiles/), hence off by default.
-bool phase_sync_enabled() {
-  static const bool on = [] {
-    const char* e = std::getenv("PAL_PHASE_SYNC");
-    return e && e[0] == '1';
-  }();
-  return on;
-}
-
 __global__ void __launch_bounds__(kFwdThreads) k_fwd4095(const float* __restrict__ sig, int M, long long units,
                                                        cpxf* __restrict__ spec) {
   extern __shared__ __align__(128) char smem[];
   fwd4095_body<kFwdThreads>(sig, M, units, spec, smem);
 }
 
-template <bool WRITE_CORR, bool kPhaseSync>
+template <bool WRITE_CORR>
+#ifdef PAL_FAST_MAXNREG   // tuning experiment
+__global__ void __launch_bounds__(kFastWarps * 32, 1) __maxnreg__(PAL_FAST_MAXNREG)
+#else
 __global__ void __launch_bounds__(kFastWarps * 32, 1)
+#endif
     k_pair4095_fast(const cpxf* __restrict__ spec, const int* __restrict__ pairs, int M, int P, long long n_items,
                     int win_half, int dist, float eps, int* __restrict__ k_idx, float* __restrict__ peak,
                     float* __restrict__ gmax, unsigned* __restrict__ flags, float* __restrict__ corr_out) {
   extern __shared__ __align__(128) char smem[];
-  pair4095_fast_body<kFastWarps, WRITE_CORR, kPhaseSync>(spec, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax,
+  pair4095_fast_body<kFastWarps, WRITE_CORR>(spec, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax,
                                              flags, corr_out, smem);
 }
 
@@ -240,12 +236,13 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
 
   const PickParams pp{prm->win_half, prm->peak_dist, prm->thr_method, prm->thr_mult, prm->num_peaks};
   const size_t fwd_smem = sizeof(FwdSmem);
-  const size_t fast_smem = kFastWarps * sizeof(FastWarpSmem);
+#ifndef PAL_FAST_SMEM_PAD   // tuning experiment: shrink the L1 carve-out
+#define PAL_FAST_SMEM_PAD 0
+#endif
+  const size_t fast_smem = kFastWarps * sizeof(FastWarpSmem) + PAL_FAST_SMEM_PAD;
   const size_t exd_smem = sizeof(ExactSmem<double>);
-  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_exact<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exd_smem));
   PAL_CUDA(cudaFuncSetAttribute(k_fwd4095, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
 
@@ -280,8 +277,7 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
       float* corr = corr_opt_dev ? corr_opt_dev + item0 * kN4095 : nullptr;
       {
         ProfScope ps(2, stream);
-        auto kern = corr ? (phase_sync_enabled() ? k_pair4095_fast<true, true> : k_pair4095_fast<true, false>)
-                         : (phase_sync_enabled() ? k_pair4095_fast<false, true> : k_pair4095_fast<false, false>);
+        auto kern = corr ? k_pair4095_fast<true> : k_pair4095_fast<false>;
         kern<<<gp, kFastWarps * 32, fast_smem, stream>>>(spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist,
                                                          prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
                                                          gmax_dev + item0, flags_dev + item0, corr);

@@ -13,6 +13,9 @@
 // 4095 = 5*7*9*13 = 63*65: the transform is a Good-Thomas prime-factor DFT -- no twiddle
 // multiplications between stages (pal_dft_small.h).
 #pragma once
+#ifndef PAL_STAGGER
+#define PAL_STAGGER 6000   // cycles, see pair4095_fast_body
+#endif
 #include "pal_dft_small.h"
 #include "pal_peakpick.cuh"
 
@@ -304,9 +307,42 @@ PAL_DEV void window_scan_slow(const float* c, int lo, int hi, int lane, float& b
   }
 }
 
-// PHASE_SYNC: the warps of a block walk through the (large, fully unrolled) phases together,
-// separated by block barriers, so that one instruction-cache fill serves all of them.
-template <int WARPS, bool WRITE_CORR, bool PHASE_SYNC>
+// warp-wide max in ONE instruction (Blackwell CREDUX.MAX.F32 / .S32, redux.sync, sm_100a)
+PAL_DEV float warp_max_f32(float v) {
+#if PAL_GPU
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+#else
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, simt::shfl_xor(v, m));
+  return v;
+#endif
+}
+PAL_DEV int warp_max_s32(int v) {
+#if PAL_GPU
+  int r;
+  asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+#else
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) { const int o = simt::shfl_xor(v, m); v = o > v ? o : v; }
+  return v;
+#endif
+}
+
+// Bins of the NEXT pair whose spectra are fetched into registers before the peak pick of the current
+// pair starts (the pick needs few registers and ~2000 cycles: it hides the L2 latency completely).
+#ifndef PAL_PREFETCH_BINS
+#define PAL_PREFETCH_BINS 8
+#endif
+#ifndef PAL_L1_PREFETCH_BINS
+#define PAL_L1_PREFETCH_BINS 8    // = kPrefetchBins: off (measured: no gain on B200, profiles/)
+#endif
+constexpr int kPrefetchBins = PAL_PREFETCH_BINS;        // multiple of 4
+constexpr int kL1PrefetchBins = PAL_L1_PREFETCH_BINS;   // bins [kPrefetchBins, kL1PrefetchBins) go to L1 only
+
+template <int WARPS, bool WRITE_CORR>
 PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P, long long n_items,
                                 int win_half, int dist, float eps, int* k_idx, float* peak, float* gmax,
                                 unsigned* flags, float* corr_out, char* smem_raw) {
@@ -338,23 +374,41 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
   float* const p2 = p1 + 63 * 32;
   float* const p2w = p2 - kN4095;
 
-  for (long long base = (long long)simt::bid() * WARPS; base < n_items; base += (long long)simt::nblocks() * WARPS) {
-    const long long item = base + simt::warp();
-    const bool active = item < n_items;
-    if (PHASE_SYNC) simt::sync_block();
-    if (!PHASE_SYNC && !active) break;
-    float gm = kNegBig;
-    if (active) {
-      const long long frame = item / P;
-      const int p = int(item % P);
-      const int mi = pairs[2 * p], mj = pairs[2 * p + 1];
-      const f2* si = reinterpret_cast<const f2*>(spec + (frame * M + mi) * kSpecSlots) + lane;
-      const f2* sj = reinterpret_cast<const f2*>(spec + (frame * M + mj) * kSpecSlots) + lane;
+  const long long stride = (long long)simt::nblocks() * WARPS;
+  long long item = (long long)simt::bid() * WARPS + simt::warp();
+  if (item >= n_items) return;
+#if PAL_GPU && PAL_STAGGER > 0
+  // De-phase the two warps that share an SM sub-partition (warp w and w + WARPS/2) once, at kernel
+  // start.  Measured on B200: 7 % faster at 16384 frames (bursts to L2 no longer line up); the
+  // amount does not matter (profiles/).
+  if (simt::warp() >= WARPS / 2) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)(PAL_STAGGER)) {}
+  }
+#endif
 
+  // spectrum rows of the current pair, and the first kPrefetchBins bins of both in registers
+  const f2* si;
+  const f2* sj;
+  f2 pa[kPrefetchBins], pb[kPrefetchBins];
+  {
+    const long long frame = item / P;
+    const int p = int(item % P);
+    si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
+    sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
+#pragma unroll
+    for (int q = 0; q < kPrefetchBins; ++q) { pa[q] = si[q * 32]; pb[q] = sj[q * 32]; }
+  }
+
+  for (;;) {
+    float gm = kNegBig;
+    {
       // ---- phase A: lane r owns elements e(r, q), q = 0..64: PHAT, then DFT-65 over q ------
       f2 z[65];
 #pragma unroll
-      for (int q = 0; q < 65; ++q) z[q] = phat_bin_p(si[q * 32], sj[q * 32]);
+      for (int q = 0; q < 65; ++q)
+        z[q] = (q < kPrefetchBins) ? phat_bin_p(pa[q < kPrefetchBins ? q : 0], pb[q < kPrefetchBins ? q : 0])
+                                   : phat_bin_p(si[q * 32], sj[q * 32]);
       dft_pfa2_p<5, 13, +1>(z);
 #pragma unroll
       for (int s = 0; s < 65; ++s) {
@@ -364,11 +418,11 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
         else sm->y.yb[lane * 33 + (kq - 33)] = z[s];
       }
     }
-    if (PHASE_SYNC) simt::sync_block(); else simt::sync_warp();
-
-    if (active) {
+    simt::sync_warp();
+    {
       // ---- phase B: lane l owns output columns kq = l+1 (real part) and l+33 (imaginary part)
-      // of ONE complex DFT-63: w[r] = Y[r][l+1] + i Y[r][l+33], with Y[63-r][kq] = conj(Y[r][65-kq])
+      // of ONE complex DFT-63: w[r] = Y[r][l+1] + i Y[r][l+33]; every column is Hermitian in r
+      // (Y[63-r][kq] = conj(Y[r][kq])), so only r < 32 was computed in phase A
       f2 w[63];
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
@@ -427,8 +481,27 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
         }
       }
     }
-    if (PHASE_SYNC) simt::sync_block(); else simt::sync_warp();
-    if (!active) continue;
+    // ---- fetch the first bins of the NEXT pair while this one is being picked -----------------
+    const long long next = item + stride;
+    const bool has_next = next < n_items;
+    if (has_next) {
+      const long long frame = next / P;
+      const int p = int(next % P);
+      si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
+      sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
+#pragma unroll
+      for (int q = 0; q < kPrefetchBins; ++q) { pa[q] = si[q * 32]; pb[q] = sj[q * 32]; }
+#if PAL_GPU
+      // ... and pull the following bins into L1 (CCTL.PF1, no registers): 32 lanes x 32-byte sectors
+      // per instruction = 4 bins of one row
+#pragma unroll
+      for (int t = kPrefetchBins / 4; t < kL1PrefetchBins / 4; ++t) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(si - lane) + (t * 32 + lane) * 32));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(sj - lane) + (t * 32 + lane) * 32));
+      }
+#endif
+    }
+    simt::sync_warp();
 
     // ---- peak pick (num_peaks = 1), utils.py:140-181 in the reduced form ----------------
     const float* c = sm->corr;
@@ -436,8 +509,7 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
       float* dst = corr_out + item * kN4095;
       for (int k = lane; k < kN4095; k += 32) dst[k] = c[k] * inv_n;
     }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) gm = fmaxf(gm, simt::shfl_xor(gm, m));
+    gm = warp_max_f32(gm);
 
     // largest and second largest SAMPLE of the window (vectorised, no neighbour tests): the
     // largest one is the answer whenever it is a strict local maximum, which is then verified
@@ -445,39 +517,34 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
     int gsel = -1;
     for (int g = g_lo + 4 * lane; g < g_hi; g += 128) {
       const float4 v = *reinterpret_cast<const float4*>(c + g);
-      const float before = b1;
-      b2 = fmaxf(b2, fminf(b1, v.x)); b1 = fmaxf(b1, v.x);
-      b2 = fmaxf(b2, fminf(b1, v.y)); b1 = fmaxf(b1, v.y);
-      b2 = fmaxf(b2, fminf(b1, v.z)); b1 = fmaxf(b1, v.z);
-      b2 = fmaxf(b2, fminf(b1, v.w)); b1 = fmaxf(b1, v.w);
-      if (b1 > before) gsel = g;
+      const float m01 = fmaxf(v.x, v.y), n01 = fminf(v.x, v.y);
+      const float m23 = fmaxf(v.z, v.w), n23 = fminf(v.z, v.w);
+      const float m = fmaxf(m01, m23);
+      const float s4 = fmaxf(fminf(m01, m23), fmaxf(n01, n23));     // second largest of the four
+      b2 = fmaxf(b2, fmaxf(fminf(b1, m), s4));
+      if (m > b1) gsel = g;
+      b1 = fmaxf(b1, m);
+    }
+    int ksel = -1;
+    if (gsel >= 0) {
+      const float4 v = *reinterpret_cast<const float4*>(c + gsel);
+      ksel = gsel + ((v.w == b1) ? 3 : (v.z == b1) ? 2 : (v.y == b1) ? 1 : 0);
     }
     if (lane < 6) {                      // the <= 3 + 3 samples outside the aligned groups
       const int k = (lane < 3) ? lo + lane : g_hi + (lane - 3);
       const bool ok = (lane < 3) ? (k < g_lo && k <= hi) : (k <= hi && g_hi >= g_lo);
       if (ok) {
         const float v = c[k];
-        const float before = b1;
-        b2 = fmaxf(b2, fminf(b1, v)); b1 = fmaxf(b1, v);
-        if (b1 > before) gsel = k | 0x40000000;    // tagged: a single sample, not a group
+        b2 = fmaxf(b2, fminf(b1, v));
+        if (v > b1) ksel = k;
+        b1 = fmaxf(b1, v);
       }
     }
-    float bv = b1;
-    int bi = gsel;
-    warp_argmax<true>(bv, bi);
-    float cand2 = (gsel == bi) ? b2 : b1;
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) cand2 = fmaxf(cand2, simt::shfl_xor(cand2, m));
+    float bv = warp_max_f32(b1);
+    int bi = warp_max_s32((b1 == bv) ? ksel : -1);
+    float cand2 = warp_max_f32((ksel == bi) ? b2 : b1);
     float pl = kNegBig;
-    if (bi >= 0) {
-      if (bi & 0x40000000) {
-        bi &= 0x3fffffff;
-      } else {
-        const float4 v = *reinterpret_cast<const float4*>(c + bi);
-        bi += (v.w == bv) ? 3 : (v.z == bv) ? 2 : (v.y == bv) ? 1 : 0;
-      }
-      if (!(c[bi - 1] < bv && bv > c[bi + 1])) window_scan_slow(c, lo, hi, lane, bv, bi, cand2, pl);
-    }
+    if (bi >= 0 && !(c[bi - 1] < bv && bv > c[bi + 1])) window_scan_slow(c, lo, hi, lane, bv, bi, cand2, pl);
 
     unsigned fl = 0;
     int kbest;
@@ -487,14 +554,17 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
       hbest = bv;
       if (cand2 >= bv - eps_s) fl |= PAL_FLAG_NEAR_TIE;
       if (pl >= bv - eps_s) fl |= PAL_FLAG_PLATEAU;
-      // anything within `dist` samples that is as high as the winner (up to eps) needs the
-      // full greedy resolution of the distance rule -> exact kernel
-      bool hit = false;
-      for (int o = -dist + lane; o <= dist; o += 32) {
-        const int q = bi + o;
-        if (o != 0 && q >= 0 && q < kN4095 && c[q] >= bv - eps_s) hit = true;
+      // Anything within `dist` samples that is as high as the winner (up to eps) needs the full
+      // greedy resolution of the distance rule -> exact kernel.  Samples inside the window are
+      // already covered by cand2; only a winner close to a window edge has neighbours outside.
+      if (bi - dist < lo || bi + dist > hi) {
+        bool hit = false;
+        for (int o = -dist + lane; o <= dist; o += 32) {
+          const int q = bi + o;
+          if (o != 0 && q >= 0 && q < kN4095 && c[q] >= bv - eps_s) hit = true;
+        }
+        if (simt::ballot(hit)) fl |= PAL_FLAG_CHAIN;
       }
-      if (simt::ballot(hit)) fl |= PAL_FLAG_CHAIN;
     } else if (bi >= 0) {
       // winner not clearly above mean|c|: the median / fallback logic decides -> exact kernel
       kbest = bi;
@@ -530,7 +600,9 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
       gmax[item] = gm * inv_n;
       flags[item] = fl;
     }
-    if (!PHASE_SYNC) simt::sync_warp();   // the next item overwrites the union
+    if (!has_next) break;
+    item = next;
+    simt::sync_warp();   // the next item overwrites the union
   }
 }
 

@@ -20,18 +20,11 @@ void emu_pair4095_fast(const float* spec, const int* pairs, int M, int P, long l
   constexpr int W = 2;
   const cpxf* sp = reinterpret_cast<const cpxf*>(spec);
   simt::launch(grid, 32 * W, W * sizeof(FastWarpSmem), [&](char* smem) {
-    if (corr_out && phase_sync)
-      pair4095_fast_body<W, true, true>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags,
-                                        corr_out, smem);
-    else if (corr_out)
-      pair4095_fast_body<W, true, false>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags,
-                                         corr_out, smem);
-    else if (phase_sync)
-      pair4095_fast_body<W, false, true>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags,
-                                         corr_out, smem);
+    (void)phase_sync;
+    if (corr_out)
+      pair4095_fast_body<W, true>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
     else
-      pair4095_fast_body<W, false, false>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags,
-                                          corr_out, smem);
+      pair4095_fast_body<W, false>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
   });
 }
 
