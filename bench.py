@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=16384, help="frames per GPU per step (cfg3: 16384)")
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU reference arm")
-    ap.add_argument("--e2e-chunk", type=int, default=1024)
+    ap.add_argument("--e2e-chunk", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PAL_ABI_VERSION 2
+#define PAL_ABI_VERSION 3
 
 /* error codes */
 #define PAL_OK 0
@@ -101,6 +101,12 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
                       int32_t* k_idx_dev, int32_t* k_count_dev, float* peak_dev, float* gmax_dev,
                       uint32_t* flags_dev, float* corr_opt_dev, void* ws_dev, size_t ws_bytes,
                       void* stream);
+
+/* time_lags[k] of utils.py:141-142 for every selected peak: out[i] = (double)(k_idx[i] - (n_second - 1)) / fs
+ * with an IEEE round-to-nearest float64 division, i.e. bit-identical to numpy's int64 / float64;
+ * NaN where k_idx[i] < 0 (padding).  k_idx_dev / out_dev: `count` elements. */
+int pal_tdoa_seconds(const int32_t* k_idx_dev, int64_t count, int32_t n_second, double fs, double* out_dev,
+                     void* stream);
 
 /* ---------------------------------------------------------------- stage 1: scene synthesis
  *

@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PAL_B200_LIB") or os.path.join(_PKG, "libpal_b200.so")   # env override: tuning experiments only
 
-PAL_ABI_VERSION = 2
+PAL_ABI_VERSION = 3
 
 # per-row flag bits (include/pal_b200.h)
 FLAG_NEAR_TIE = 1
@@ -55,6 +55,8 @@ def lib():
     L.pal_gcc_phat_tdoa.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                     C.POINTER(TdoaParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pal_tdoa_seconds.restype = C.c_int
+    L.pal_tdoa_seconds.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
     VP, I32, I64, F64, F32, SZP = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_float, C.POINTER(C.c_size_t)
     L.pal_image_sources_workspace.restype = C.c_int
     L.pal_image_sources_workspace.argtypes = [I32, I32, I64, SZP]

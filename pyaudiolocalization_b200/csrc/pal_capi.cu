@@ -98,6 +98,14 @@ __global__ void k_fill_count(int* k_count, long long n) {
   if (i < n) k_count[i] = 1;
 }
 
+__global__ void k_tdoa_seconds(const int* __restrict__ k_idx, long long n, int c0, double fs, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int k = k_idx[i];
+    out[i] = (k < 0) ? __longlong_as_double(0x7ff8000000000000LL) : __ddiv_rn(double(k - c0), fs);
+  }
+}
+
 struct DevInfo {
   int sms = 0;
   int dev = -1;
@@ -306,6 +314,17 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
     }
     PAL_CUDA(cudaGetLastError());
   }
+  return PAL_OK;
+}
+
+int pal_tdoa_seconds(const int32_t* k_idx_dev, int64_t count, int32_t n_second, double fs, double* out_dev, void* stream_) {
+  if (count < 0 || n_second < 1 || !(fs > 0.0) || (count > 0 && (!k_idx_dev || !out_dev)))
+    return fail(PAL_ERR_INVALID, "pal_tdoa_seconds: bad argument");
+  if (count == 0) return PAL_OK;
+  k_tdoa_seconds<<<(unsigned)((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(k_idx_dev, count, n_second - 1, fs,
+                                                                                                   out_dev);
+  ++g_launches;
+  PAL_CUDA(cudaGetLastError());
   return PAL_OK;
 }
 

@@ -143,12 +143,26 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
     return TdoaBatch(k_idx, k_count, peak, gmax, flags, corr, n2, float(fs))
 
 
+def tdoa_seconds_device(k_idx: torch.Tensor, n_second: int, fs: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """time_lags[k] = (k - (n2 - 1)) / fs in float64 ON THE DEVICE (pal_tdoa_seconds): the same IEEE
+    division numpy performs in utils.py:141-142, so the result is bit-identical; NaN for padding."""
+    k_idx = k_idx.contiguous()
+    if out is None:
+        out = torch.empty(k_idx.shape, dtype=torch.float64, device=k_idx.device)
+    with torch.cuda.device(k_idx.device):
+        rc = _lib.lib().pal_tdoa_seconds(k_idx.data_ptr(), k_idx.numel(), int(n_second), float(fs), out.data_ptr(),
+                                         torch.cuda.current_stream(k_idx.device).cuda_stream)
+    _lib.check(rc, "pal_tdoa_seconds")
+    return out
+
+
 def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_delay: Optional[float] = None,
-                            chunk_frames: int = 1024, device=None, **kw) -> dict:
+                            chunk_frames: int = 256, device=None, **kw) -> dict:
     """End-to-end call with HOST buffers: frames_host [B, M, N] float32 on the CPU (pinned memory
-    makes the copies asynchronous).  Frames are streamed to the device in chunks on a copy
-    stream while the previous chunk is processed on a compute stream; the integer lag indices
-    and max(corr) come back to pinned host memory.  Returns numpy arrays."""
+    makes the copies asynchronous).  Three streams form a pipeline over chunks of frames: host->device
+    copy of chunk c+1, kernels of chunk c, device->host copy of the results of chunk c-1 (lag
+    indices, max(corr) and the float64 TDOA seconds, all derived on the device).  Returns numpy
+    arrays backed by pinned memory."""
     if frames_host.is_cuda:
         raise TypeError("frames_host must live in host memory")
     if kw.get("return_corr"):
@@ -169,10 +183,14 @@ def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_d
                     torch.empty((b, p), dtype=torch.float32, device=dev),
                     torch.empty((b, p), dtype=torch.float32, device=dev),
                     torch.empty((b, p), dtype=torch.int32, device=dev), None, n, float(fs))
-    copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    td_dev = torch.empty((b, p, num_peaks), dtype=torch.float64, device=dev)
+    k_host = torch.empty(res.k_idx.shape, dtype=torch.int32, pin_memory=True)
+    g_host = torch.empty(res.gmax.shape, dtype=torch.float32, pin_memory=True)
+    td_host = torch.empty(td_dev.shape, dtype=torch.float64, pin_memory=True)
+    copy_s, comp_s, back_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     cur = torch.cuda.current_stream(dev)
-    copy_s.wait_stream(cur)
-    comp_s.wait_stream(cur)
+    for s_ in (copy_s, comp_s, back_s):
+        s_.wait_stream(cur)
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     for c, f0 in enumerate(range(0, b, chunk)):
@@ -190,15 +208,17 @@ def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_d
             gcc_phat_tdoa_batched(bufs[sl][:nb], fs, max_expected_delay, workspace=ws, out=view,
                                   pairs_dev=pairs_dev, **kw)
             consumed[sl].record(comp_s)
-    with torch.cuda.stream(comp_s):
-        k_host = torch.empty(res.k_idx.shape, dtype=torch.int32, pin_memory=True)
-        g_host = torch.empty(res.gmax.shape, dtype=torch.float32, pin_memory=True)
-        k_host.copy_(res.k_idx, non_blocking=True)
-        g_host.copy_(res.gmax, non_blocking=True)
-    comp_s.synchronize()
+            tdoa_seconds_device(res.k_idx[f0:f0 + nb], n, fs, out=td_dev[f0:f0 + nb])
+            done = torch.cuda.Event()
+            done.record(comp_s)
+        with torch.cuda.stream(back_s):
+            back_s.wait_event(done)
+            k_host[f0:f0 + nb].copy_(res.k_idx[f0:f0 + nb], non_blocking=True)
+            g_host[f0:f0 + nb].copy_(res.gmax[f0:f0 + nb], non_blocking=True)
+            td_host[f0:f0 + nb].copy_(td_dev[f0:f0 + nb], non_blocking=True)
+    back_s.synchronize()
     cur.wait_stream(comp_s)
-    k = k_host.numpy()
-    td = (k.astype(np.int64) - (n - 1)) / float(fs)
-    td[k < 0] = np.nan
-    return {"k_idx": k, "tdoa": td, "gmax": g_host.numpy(), "h2d_bytes": int(frames_host.numel() * 4),
-            "d2h_bytes": int(k_host.numel() * 4 + g_host.numel() * 4)}
+    cur.wait_stream(copy_s)
+    return {"k_idx": k_host.numpy(), "tdoa": td_host.numpy(), "gmax": g_host.numpy(),
+            "h2d_bytes": int(frames_host.numel() * 4),
+            "d2h_bytes": int(k_host.numel() * 4 + g_host.numel() * 4 + td_host.numel() * 8)}

@@ -176,3 +176,22 @@ def test_reference_signature_functions_on_fuzz_rows(pal, golden):
     c = U.phat_correlation(golden["fuzz_a1"], golden["fuzz_b1"])
     r = O.phat_correlation(golden["fuzz_a1"], golden["fuzz_b1"])
     assert np.abs(c - r).max() <= CORR_RTOL * np.abs(r).max()
+
+
+def test_host_streaming_entry_point_matches_device_path(pal):
+    """gcc_phat_tdoa_from_host (pinned host frames -> chunked H2D / kernels / D2H pipeline) must return
+    exactly what the device-resident call returns; the float64 TDOA seconds derived on the device
+    (pal_tdoa_seconds) must be bit-identical to numpy's int64 / float64 (utils.py:141-142)."""
+    from pyaudiolocalization_b200 import synth
+    from pyaudiolocalization_b200.gcc_phat import gcc_phat_tdoa_from_host
+    fr = synth.cfg3_frames(37, mics=5, seed=21)
+    ref = pal.gcc_phat_tdoa_batched(fr, 16000.0, 0.05)
+    host = torch.empty(fr.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(fr)
+    torch.cuda.synchronize()
+    for chunk in (8, 37, 64):
+        r = gcc_phat_tdoa_from_host(host, 16000.0, 0.05, chunk_frames=chunk)
+        assert np.array_equal(r["k_idx"], ref.k_idx.cpu().numpy())
+        assert np.array_equal(r["gmax"], ref.gmax.cpu().numpy())
+        assert r["tdoa"].dtype == np.float64 and np.array_equal(r["tdoa"], ref.tdoa_seconds())
+        assert r["h2d_bytes"] == fr.numel() * 4
