@@ -175,17 +175,35 @@ def run_gpu_arm(args):
     full, _ = pal.gcc_phat.workspace_bytes(frames_n, MICS, NS, PAIRS)
     ws = torch.empty(full + 256, dtype=torch.uint8, device=dev)
     pairs_dev = torch.from_numpy(pal.all_pairs(MICS)).to(dev)
-    out = pal.TdoaBatch(torch.empty((frames_n, PAIRS, 1), dtype=torch.int32, device=dev),
-                        torch.empty((frames_n, PAIRS), dtype=torch.int32, device=dev),
-                        torch.empty((frames_n, PAIRS), dtype=torch.float32, device=dev),
-                        torch.empty((frames_n, PAIRS), dtype=torch.float32, device=dev),
-                        torch.empty((frames_n, PAIRS), dtype=torch.int32, device=dev), None, NS, FS)
-    gathered = torch.empty((world, frames_n, PAIRS, 1), dtype=torch.int32, device=dev) if world > 1 else None
+    def new_out():
+        return pal.TdoaBatch(torch.empty((frames_n, PAIRS, 1), dtype=torch.int32, device=dev),
+                             torch.empty((frames_n, PAIRS), dtype=torch.int32, device=dev),
+                             torch.empty((frames_n, PAIRS), dtype=torch.float32, device=dev),
+                             torch.empty((frames_n, PAIRS), dtype=torch.float32, device=dev),
+                             torch.empty((frames_n, PAIRS), dtype=torch.int32, device=dev), None, NS, FS)
+    # Results are double-buffered so that the NCCL all-gather of step i (asynchronous, on NCCL's own
+    # stream) overlaps the kernels of step i+1: a rank never idles inside a step waiting for a slower
+    # peer; every gather has completed before the timed region ends.
+    outs = [new_out(), new_out()] if world > 1 else [new_out()]
+    out = outs[0]
+    gathered = [torch.empty((world, frames_n, PAIRS, 1), dtype=torch.int32, device=dev) for _ in outs] if world > 1 else None
+    works = [None, None]
+    step_no = [0]
 
     def step():
-        pal.gcc_phat_tdoa_batched(frames, FS, MED, workspace=ws, out=out, pairs_dev=pairs_dev)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out.k_idx)
+        s = step_no[0] % len(outs)
+        step_no[0] += 1
+        if works[s] is not None:
+            works[s].wait()
+        pal.gcc_phat_tdoa_batched(frames, FS, MED, workspace=ws, out=outs[s], pairs_dev=pairs_dev)
+        if world > 1 and not args.no_gather:
+            works[s] = dist.all_gather_into_tensor(gathered[s], outs[s].k_idx, async_op=True)
+
+    def drain():
+        for s in range(len(works)):
+            if works[s] is not None:
+                works[s].wait()
+                works[s] = None
 
     def barrier():
         if world > 1:
@@ -199,6 +217,7 @@ def run_gpu_arm(args):
 
     for _ in range(args.warmup):
         step()
+    drain()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -209,6 +228,7 @@ def run_gpu_arm(args):
     t0.record()
     for _ in range(args.steps):
         step()
+    drain()
     t1.record()
     barrier()
     ms = t0.elapsed_time(t1)
@@ -219,6 +239,7 @@ def run_gpu_arm(args):
         reps = []
         for _ in range(max(2, min(args.steps, 5))):
             step()
+            drain()
             torch.cuda.synchronize()
             reps.append(ks.elapsed_time(ke))
         kernel_ms.append(float(np.mean(reps)))
@@ -228,6 +249,8 @@ def run_gpu_arm(args):
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+    if world > 1 and not args.no_gather:   # sharded + gathered lags of the last step: this rank's slice must be its own result
+        assert torch.equal(gathered[(step_no[0] - 1) % 2][rank], outs[(step_no[0] - 1) % 2].k_idx)
     flags = out.flags
     refined_frac = float(((flags & 8) != 0).float().mean().item())
 
@@ -305,6 +328,11 @@ def run_gpu_arm(args):
 
 
 def main():
+    # The contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner)
+    # are sent to stderr for the duration of the run.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -315,6 +343,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostic only: skip the NCCL all-gather (invalid as a result)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1,0 +1,127 @@
+"""Secondary measurements on the other BASELINE.json configurations (the bench.py line is cfg3).
+Each prints one JSON line; sizes are bounded sub-samples of the named configuration.
+
+    python tools/bench_configs.py [cfg2 cfg4 cfg5 img] [--small]
+"""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import pyaudiolocalization_b200 as pal
+from pyaudiolocalization_b200 import main as pmain, scene
+from pyaudiolocalization_b200.signal_processing import generate_signal
+
+MATS = {"air": {"absorption": 0.01, "freq": 1e-6}, "wood": {"absorption": 0.05, "freq": 1e-5},
+        "metal": {"absorption": 0.1, "freq": 2e-5}, "glass": {"absorption": 0.07, "freq": 1.5e-5}}
+
+
+def shoebox(lx, ly, lz):
+    m = ["wood", "metal", "glass", "wood", "wood", "metal"]
+    pl = [[1, 0, 0, 0], [1, 0, 0, -lx], [0, 1, 0, 0], [0, 1, 0, -ly], [0, 0, 1, 0], [0, 0, 1, -lz]]
+    return [{"plane": p, "material": mm} for p, mm in zip(pl, m)]
+
+
+def timed(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t) / reps
+
+
+def stage2(name, B, M, N, fs, med, seed):
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    base = torch.as_tensor(generate_signal("chirp", fs, N / fs, 1000.0 if fs > 20000 else 500.0)[:N], dtype=torch.float32, device="cuda")
+    d = torch.randint(0, 64, (B, M), generator=g, device="cuda")
+    idx = torch.arange(N, device="cuda")[None, None, :] - d[:, :, None]
+    fr = torch.where(idx >= 0, base[idx.clamp(min=0)], torch.zeros((), device="cuda"))
+    fr = fr + 0.05 * torch.randn((B, M, N), generator=g, device="cuda")
+    P = M * (M - 1) // 2
+    full, small = pal.gcc_phat.workspace_bytes(B, M, N, P)
+    ws = torch.empty(min(full, 8 << 30) + 256, dtype=torch.uint8, device="cuda")
+    sec = timed(lambda: pal.gcc_phat_tdoa_batched(fr, fs, med, workspace=ws), reps=2)
+    r = pal.gcc_phat_tdoa_batched(fr, fs, med, workspace=ws)
+    refined = float(((r.flags & 8) != 0).float().mean().item())
+    alg = 20 * M * N + 16 * P * N + 16 * P
+    print(json.dumps({"config": name, "stage": "gcc_phat_tdoa", "units": B, "mics": M, "samples": N, "n_fft": 2 * N - 1,
+                      "ms": sec * 1e3, "scenes_per_s": B / sec, "pair_corr_per_s": B * P / sec,
+                      "algorithmic_GBps": alg * B / sec / 1e9, "refined_row_fraction": refined}), flush=True)
+
+
+def cfg4(small):
+    rng0, rng1 = np.random.default_rng(0), np.random.default_rng(1)
+    mics = rng0.uniform([1, 1, 0.5], [5, 4, 2.5], size=(64, 3))
+    srcs = rng1.uniform([0.5, 0.5, 0.3], [5.5, 4.5, 2.7], size=(1024, 3))
+    planes = shoebox(6, 5, 3)
+    n_src = 2 if small else 4
+    t0 = time.perf_counter()
+    outs = []
+    for s in range(n_src):
+        outs.append(pmain.simulate_signals_device(srcs[s], mics, 48000, 343.62, 1.0, "chirp", 1000, planes, MATS, 6, 0.01))
+    torch.cuda.synchronize()
+    first = time.perf_counter() - t0
+    sec = timed(lambda: pmain.simulate_signals_device(srcs[0], mics, 48000, 343.62, 1.0, "chirp", 1000, planes, MATS, 6, 0.01), reps=2, warm=0)
+    print(json.dumps({"config": "cfg4", "stage": "render (image sources + path table + transfer + inverse DFT + normalise/compress)",
+                      "mics": 64, "order": 6, "fs": 48000, "ms_per_source": sec * 1e3, "sources_per_s": 1 / sec,
+                      "rendered_samples_per_s": 64 * 48000 / sec, "first_call_ms": first * 1e3 / n_src}), flush=True)
+    fr = outs[0][None].contiguous()           # [1, 64, 48000]
+    P = 64 * 63 // 2
+    sec = timed(lambda: pal.gcc_phat_tdoa_batched(fr, 48000.0, 0.05), reps=1)
+    print(json.dumps({"config": "cfg4", "stage": "gcc_phat_tdoa", "units": 1, "mics": 64, "samples": 48000, "n_fft": 95999,
+                      "ms": sec * 1e3, "pair_corr_per_s": P / sec}), flush=True)
+
+
+def cfg5_render(small):
+    rng = np.random.default_rng(5000)
+    n_sc = 8 if small else 32
+    scenes = []
+    for _ in range(n_sc):
+        dims = rng.uniform([3, 3, 2.5], [10, 8, 4])
+        mics = rng.uniform([0.3, 0.3, 0.3], dims - 0.3, size=(8, 3))
+        src = rng.uniform([0.3, 0.3, 0.3], dims - 0.3)
+        scenes.append((dims, mics, src))
+
+    def run():
+        for dims, mics, src in scenes:
+            pmain.simulate_signals_device(src, mics, 16000, 343.62, 0.25, "chirp", 500, shoebox(*dims), MATS, 3, 0.01)
+    sec = timed(run, reps=2)
+    print(json.dumps({"config": "cfg5", "stage": "render", "mics": 8, "order": 3, "fs": 16000, "scenes": n_sc,
+                      "ms_per_scene": sec * 1e3 / n_sc, "scenes_per_s": n_sc / sec}), flush=True)
+
+
+def img(small):
+    rng = np.random.default_rng(1)
+    mics = np.random.default_rng(0).uniform([1, 1, 0.5], [5, 4, 2.5], size=(64, 3))
+    srcs = rng.uniform([0.5, 0.5, 0.3], [5.5, 4.5, 2.7], size=(1024, 3))
+    sec = timed(lambda: scene.image_sources_batched(srcs, shoebox(6, 5, 3), 6, 1000.0, MATS, mics, 0.01), reps=2)
+    pos, mat, cnt, _ = scene.image_sources_batched(srcs, shoebox(6, 5, 3), 6, 1000.0, MATS, mics, 0.01)
+    print(json.dumps({"config": "cfg4", "stage": "image_sources", "scenes": 1024, "order": 6, "mics": 64, "ms": sec * 1e3,
+                      "scenes_per_s": 1024 / sec, "mean_images": float(cnt.float().mean().item())}), flush=True)
+    n = 16384 if small else 65536
+    mics8 = np.random.default_rng(2).uniform([0.3, 0.3, 0.3], [2.7, 2.7, 2.2], size=(8, 3))
+    srcs = np.random.default_rng(3).uniform([0.3, 0.3, 0.3], [2.7, 2.7, 2.2], size=(n, 3))
+    sec = timed(lambda: scene.image_sources_batched(srcs, shoebox(3, 3, 2.5), 3, 500.0, MATS, mics8, 0.01), reps=2)
+    print(json.dumps({"config": "cfg5", "stage": "image_sources", "scenes": n, "order": 3, "mics": 8, "ms": sec * 1e3,
+                      "scenes_per_s": n / sec}), flush=True)
+
+
+if __name__ == "__main__":
+    args = [a for a in sys.argv[1:] if not a.startswith("--")] or ["img", "cfg5", "cfg2", "cfg4"]
+    small = "--small" in sys.argv
+    for a in args:
+        if a == "cfg2":
+            stage2("cfg2", 64 if small else 256, 4, 44100, 44100.0, 0.05, 2000)
+        elif a == "cfg5":
+            stage2("cfg5", 1024 if small else 8192, 8, 4000, 16000.0, 0.05, 5000)
+            cfg5_render(small)
+        elif a == "cfg4":
+            cfg4(small)
+        elif a == "img":
+            img(small)
