@@ -114,7 +114,8 @@ int pal_tdoa_seconds(const int32_t* k_idx_dev, int64_t count, int32_t n_second, 
  * reflect_point_across_plane :29-42, distance :44-48, calculate_attenuation :50-65) for n_scenes
  * independent scenes: float64, the reference's evaluation order, discovery order, the
  * 10^-round_decimals de-duplication key and the mean/min pruning rule.
- *   sources_dev [n_scenes][3] f64; planes_dev [n_planes][4] f64 (a, b, c, d); plane_mat_dev
+ *   sources_dev [n_scenes][3] f64; planes_dev [n_planes][4] f64 (a, b, c, d), shared by all scenes
+ *   (plane_stride = 0) or per scene (plane_stride = 4*n_planes doubles); plane_mat_dev
  *   [n_planes] index into mat_abs_dev / mat_freq_dev (the 'absorption' / 'freq' table,
  *   materials.py:2-16); mics_dev [n_mics][3] f64 shared by all scenes (mic_stride = 0) or per
  *   scene (mic_stride = 3*n_mics doubles).
@@ -122,7 +123,7 @@ int pal_tdoa_seconds(const int32_t* k_idx_dev, int64_t count, int32_t n_second, 
  *   LAST reflecting plane, utils.py:101), out_count_dev [n_scenes] (-1: more than k_max images).
  */
 int pal_image_sources_workspace(int32_t n_planes, int32_t k_max, int64_t n_scenes, size_t* bytes);
-int pal_image_sources(const double* sources_dev, int64_t n_scenes, const double* planes_dev,
+int pal_image_sources(const double* sources_dev, int64_t n_scenes, const double* planes_dev, int64_t plane_stride,
                       const int32_t* plane_mat_dev, int32_t n_planes, const double* mat_abs_dev,
                       const double* mat_freq_dev, const double* mics_dev, int32_t n_mics,
                       int64_t mic_stride, int32_t max_order, double frequency, double threshold,
@@ -148,6 +149,25 @@ int pal_render_workspace(int32_t N, int32_t n_mics, size_t* bytes, size_t* min_b
 int pal_render_scene(const float* base_dev, int32_t n_base, int32_t N, const double* tau_dev,
                      const double* gain_dev, int32_t n_mics, int32_t n_paths, double fs, int32_t n_keep,
                      int32_t flags, float* out_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Batched forms for many scenes (BASELINE cfg4 / cfg5).  pal_path_table_batched fills, for every scene s,
+ * tau/gain [s][mic][k_stride] (k_stride >= k_max + 1; path 0 direct, path k image k-1 of
+ * pal_image_sources' output), path_count[s] = images + 1 (0 if the image list overflowed) and
+ * max_tau[s] = the largest delay of the scene, from which the caller forms N = int((duration + max_tau) * fs)
+ * exactly as main.py:94-102 does.  Scenes that share N are then rendered together by pal_render_scenes:
+ * scene_index_dev [n_bucket_scenes] lists them (NULL = all scenes 0..n-1); out_dev is the whole batch
+ * [scenes][n_mics][n_keep] and only the listed scenes' rows are written (not normalised: apply
+ * pal_normalise_compress to the batch afterwards, main.py:121-122). */
+int pal_path_table_batched(const double* sources_dev, const double* img_pos_dev, const int32_t* img_mat_dev,
+                           const int32_t* img_count_dev, int64_t n_scenes, int32_t k_max, const double* mics_dev,
+                           int32_t n_mics, int64_t mic_stride, const double* mat_abs_dev, const double* mat_freq_dev,
+                           int32_t air_mat, double frequency, double c_sound, int32_t k_stride, double* tau_dev,
+                           double* gain_dev, int32_t* path_count_dev, double* max_tau_dev, void* stream);
+int pal_render_scenes_workspace(int32_t N, int64_t n_rows, size_t* bytes, size_t* min_bytes);
+int pal_render_scenes(const float* base_dev, int32_t n_base, int32_t N, const double* tau_dev, const double* gain_dev,
+                      const int32_t* path_count_dev, int32_t k_stride, const int64_t* scene_index_dev,
+                      int64_t n_bucket_scenes, int32_t n_mics, double fs, int32_t n_keep, float* out_dev, void* ws_dev,
+                      size_t ws_bytes, void* stream);
 
 /* In place on n_rows rows of n float32: mode 0 = normalize_signal (signal_processing.py:82-86),
  * mode 1 = dynamic_range_compression(threshold, epsilon) (signal_processing.py:88-94). */

@@ -61,8 +61,14 @@ def lib():
     L.pal_image_sources_workspace.restype = C.c_int
     L.pal_image_sources_workspace.argtypes = [I32, I32, I64, SZP]
     L.pal_image_sources.restype = C.c_int
-    L.pal_image_sources.argtypes = [VP, I64, VP, VP, I32, VP, VP, VP, I32, I64, I32, F64, F64, I32, I32, VP, VP, VP,
+    L.pal_image_sources.argtypes = [VP, I64, VP, I64, VP, I32, VP, VP, VP, I32, I64, I32, F64, F64, I32, I32, VP, VP, VP,
                                     VP, C.c_size_t, VP]
+    L.pal_path_table_batched.restype = C.c_int
+    L.pal_path_table_batched.argtypes = [VP, VP, VP, VP, I64, I32, VP, I32, I64, VP, VP, I32, F64, F64, I32, VP, VP, VP, VP, VP]
+    L.pal_render_scenes_workspace.restype = C.c_int
+    L.pal_render_scenes_workspace.argtypes = [I32, I64, SZP, SZP]
+    L.pal_render_scenes.restype = C.c_int
+    L.pal_render_scenes.argtypes = [VP, I32, I32, VP, VP, VP, I32, VP, I64, I32, F64, I32, VP, VP, C.c_size_t, VP]
     L.pal_path_table.restype = C.c_int
     L.pal_path_table.argtypes = [VP, VP, VP, I32, VP, I32, VP, VP, I32, F64, F64, VP, VP, VP]
     L.pal_render_workspace.restype = C.c_int

@@ -337,8 +337,8 @@ int pal_image_sources_workspace(int32_t n_planes, int32_t k_max, int64_t n_scene
   return PAL_OK;
 }
 
-int pal_image_sources(const double* sources_dev, int64_t n_scenes, const double* planes_dev, const int32_t* plane_mat_dev,
-                      int32_t n_planes, const double* mat_abs_dev, const double* mat_freq_dev, const double* mics_dev,
+int pal_image_sources(const double* sources_dev, int64_t n_scenes, const double* planes_dev, int64_t plane_stride,
+                      const int32_t* plane_mat_dev, int32_t n_planes, const double* mat_abs_dev, const double* mat_freq_dev, const double* mics_dev,
                       int32_t n_mics, int64_t mic_stride, int32_t max_order, double frequency, double threshold,
                       int32_t round_decimals, int32_t k_max, double* out_pos_dev, int32_t* out_mat_dev,
                       int32_t* out_count_dev, void* ws_dev, size_t ws_bytes, void* stream_) {
@@ -358,7 +358,7 @@ int pal_image_sources(const double* sources_dev, int64_t n_scenes, const double*
   for (int i = 0; i > round_decimals; --i) scale /= 10.0;
   ImgParams ip{n_planes, n_mics, max_order, k_max, frequency, threshold, scale};
   palhost::k_image_sources<<<grid, palhost::kImgThreads, 64 * sizeof(int), static_cast<cudaStream_t>(stream_)>>>(
-      ip, sources_dev, n_scenes, planes_dev, plane_mat_dev, mat_abs_dev, mat_freq_dev, mics_dev, mic_stride, out_pos_dev,
+      ip, sources_dev, n_scenes, planes_dev, plane_stride, plane_mat_dev, mat_abs_dev, mat_freq_dev, mics_dev, mic_stride, out_pos_dev,
       out_mat_dev, out_count_dev, static_cast<char*>(ws_dev), per_block);
   ++g_launches;
   PAL_CUDA(cudaGetLastError());
@@ -399,10 +399,60 @@ int pal_render_scene(const float* base_dev, int32_t n_base, int32_t N, const dou
   DevInfo di;
   if (int rc = device_info(di)) return rc;
   if (ws_bytes < palhost::render_min_bytes(N, n_mics)) return fail(PAL_ERR_WORKSPACE, "pal_render_scene: workspace too small");
-  cudaError_t e = palhost::render_scene(base_dev, n_base, N, tau_dev, gain_dev, n_mics, n_paths, fs, n_keep,
-                                        (flags & PAL_RENDER_NORMALISE_COMPRESS) != 0, out_dev, static_cast<char*>(ws_dev),
-                                        ws_bytes, static_cast<cudaStream_t>(stream_), di.sms);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const RenderRows rr{tau_dev, gain_dev, nullptr, nullptr, n_paths, n_mics};
+  cudaError_t e = palhost::render_rows(base_dev, n_base, N, rr, n_mics, fs, n_keep, out_dev, static_cast<char*>(ws_dev), ws_bytes,
+                                       st, di.sms);
+  if (e == cudaSuccess && (flags & PAL_RENDER_NORMALISE_COMPRESS)) e = palhost::normalise_rows(out_dev, n_mics, n_keep, st, di.sms);
   if (e != cudaSuccess) return cuda_fail(e, "pal_render_scene");
+  return PAL_OK;
+}
+
+int pal_path_table_batched(const double* sources_dev, const double* img_pos_dev, const int32_t* img_mat_dev,
+                           const int32_t* img_count_dev, int64_t n_scenes, int32_t k_max, const double* mics_dev,
+                           int32_t n_mics, int64_t mic_stride, const double* mat_abs_dev, const double* mat_freq_dev,
+                           int32_t air_mat, double frequency, double c_sound, int32_t k_stride, double* tau_dev,
+                           double* gain_dev, int32_t* path_count_dev, double* max_tau_dev, void* stream_) {
+  if (n_scenes < 0 || k_max < 1 || n_mics < 1 || k_stride < k_max + 1)
+    return fail(PAL_ERR_INVALID, "pal_path_table_batched: need n_scenes >= 0, k_max >= 1, n_mics >= 1, k_stride >= k_max + 1");
+  if (n_scenes == 0) return PAL_OK;
+  if (!sources_dev || !img_pos_dev || !img_mat_dev || !img_count_dev || !mics_dev || !mat_abs_dev || !mat_freq_dev || !tau_dev ||
+      !gain_dev || !path_count_dev || !max_tau_dev)
+    return fail(PAL_ERR_INVALID, "pal_path_table_batched: NULL device pointer");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  palhost::k_path_table_batched<<<(unsigned)std::min<long long>(n_scenes, 16LL * di.sms), 128, 64, static_cast<cudaStream_t>(stream_)>>>(
+      sources_dev, img_pos_dev, img_mat_dev, img_count_dev, n_scenes, k_max, mics_dev, n_mics, mic_stride, mat_abs_dev,
+      mat_freq_dev, air_mat, frequency, c_sound, k_stride, tau_dev, gain_dev, path_count_dev, max_tau_dev);
+  ++g_launches;
+  PAL_CUDA(cudaGetLastError());
+  return PAL_OK;
+}
+
+int pal_render_scenes_workspace(int32_t N, int64_t n_rows, size_t* bytes, size_t* min_bytes) {
+  if (N < 2 || n_rows < 1 || !bytes) return fail(PAL_ERR_INVALID, "pal_render_scenes_workspace: bad argument");
+  *bytes = palhost::render_full_bytes(N, n_rows);
+  if (min_bytes) *min_bytes = palhost::render_min_bytes(N, 1);
+  return PAL_OK;
+}
+
+int pal_render_scenes(const float* base_dev, int32_t n_base, int32_t N, const double* tau_dev, const double* gain_dev,
+                      const int32_t* path_count_dev, int32_t k_stride, const int64_t* scene_index_dev, int64_t n_bucket_scenes,
+                      int32_t n_mics, double fs, int32_t n_keep, float* out_dev, void* ws_dev, size_t ws_bytes, void* stream_) {
+  if (!base_dev || !tau_dev || !gain_dev || !path_count_dev || !out_dev || !ws_dev)
+    return fail(PAL_ERR_INVALID, "pal_render_scenes: NULL device pointer");
+  if (n_base < 1 || N < n_base || n_mics < 1 || k_stride < 1 || n_keep < 1 || n_keep > N || n_bucket_scenes < 0)
+    return fail(PAL_ERR_INVALID, "pal_render_scenes: need 1 <= n_base <= N, 1 <= n_keep <= N, n_mics, k_stride >= 1");
+  if (int(0.01 * N) < 1) return fail(PAL_ERR_INVALID, "pal_render_scenes: N < 100 (empty fade window, signal_processing.py:74-79)");
+  if (reinterpret_cast<uintptr_t>(ws_dev) & 255u) return fail(PAL_ERR_INVALID, "pal_render_scenes: ws_dev must be 256-byte aligned");
+  if (n_bucket_scenes == 0) return PAL_OK;
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (ws_bytes < palhost::render_min_bytes(N, 1)) return fail(PAL_ERR_WORKSPACE, "pal_render_scenes: workspace too small");
+  const RenderRows rr{tau_dev, gain_dev, path_count_dev, reinterpret_cast<const long long*>(scene_index_dev), k_stride, n_mics};
+  cudaError_t e = palhost::render_rows(base_dev, n_base, N, rr, n_bucket_scenes * n_mics, fs, n_keep, out_dev,
+                                       static_cast<char*>(ws_dev), ws_bytes, static_cast<cudaStream_t>(stream_), di.sms);
+  if (e != cudaSuccess) return cuda_fail(e, "pal_render_scenes");
   return PAL_OK;
 }
 

@@ -403,19 +403,37 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
   for (;;) {
     float gm = kNegBig;
     {
-      // ---- phase A: lane r owns elements e(r, q), q = 0..64: PHAT, then DFT-65 over q ------
+      // ---- phase A: lane r owns elements e(r, q), q = 0..64: PHAT, then DFT-65 over q as a 5 x 13
+      // prime-factor transform.  Pass 1 consumes the bins five at a time (PHAT + DFT-5), pass 2
+      // stores each DFT-13 group as soon as it is done, so loads, MUFU work and shared-memory
+      // stores are spread over the arithmetic instead of arriving in bursts.
       f2 z[65];
 #pragma unroll
-      for (int q = 0; q < 65; ++q)
-        z[q] = (q < kPrefetchBins) ? phat_bin_p(pa[q < kPrefetchBins ? q : 0], pb[q < kPrefetchBins ? q : 0])
-                                   : phat_bin_p(si[q * 32], sj[q * 32]);
-      dft_pfa2_p<5, 13, +1>(z);
+      for (int b = 0; b < 13; ++b) {
+        f2 t[5];
 #pragma unroll
-      for (int s = 0; s < 65; ++s) {
-        const int kq = P65::out_index(s);
-        if (kq == 0) sm->y.y0[lane] = z[s];
-        else if (kq <= 32) sm->y.ya[lane * 33 + (kq - 1)] = z[s];
-        else sm->y.yb[lane * 33 + (kq - 33)] = z[s];
+        for (int a = 0; a < 5; ++a) {
+          const int q = P65::slot(a, b);
+          t[a] = (q < kPrefetchBins) ? phat_bin_p(pa[q < kPrefetchBins ? q : 0], pb[q < kPrefetchBins ? q : 0])
+                                     : phat_bin_p(si[q * 32], sj[q * 32]);
+        }
+        dft_odd_p<5, +1>(t);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) z[P65::slot(a, b)] = t[a];
+      }
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+        f2 t[13];
+#pragma unroll
+        for (int b = 0; b < 13; ++b) t[b] = z[P65::slot(a, b)];
+        dft_odd_p<13, +1>(t);
+#pragma unroll
+        for (int b = 0; b < 13; ++b) {
+          const int kq = P65::out_index(P65::slot(a, b));
+          if (kq == 0) sm->y.y0[lane] = t[b];
+          else if (kq <= 32) sm->y.ya[lane * 33 + (kq - 1)] = t[b];
+          else sm->y.yb[lane * 33 + (kq - 33)] = t[b];
+        }
       }
     }
     simt::sync_warp();
@@ -450,21 +468,37 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
 #pragma unroll
         for (int a = 0; a < 7; ++a) sm->lx[(a * P63::UA + lane * P63::UB) % 63] = t7[a];
       }
-      dft_pfa2_p<7, 9, +1>(w);
-      // scatter to natural order: consecutive lanes are 63 floats apart -> conflict-free.  Whether
+      // DFT-63 as a 7 x 9 prime-factor transform; each DFT-9 group is scattered to natural order as
+      // soon as it is done: consecutive lanes are 63 floats apart -> conflict-free.  Whether
       // (63 kq + 65 kr) wraps past 4095 is known at compile time for half of the stores; max(c) is
       // taken from the registers on the way (FMNMX3).
 #pragma unroll
-      for (int s = 0; s < 63; ++s) {
-        const int kr = P63::out_index(s);
-        const int c = 65 * kr;
-        const float vr = f2_lo(w[s]), vi = f2_hi(w[s]);
-        if (kr <= 31) p1[c] = vr;
-        else ((b0 + c >= kN4095) ? p1w : p1)[c] = vr;
-        if (kr == 0) p2[c] = vi;
-        else if (kr >= 32) p2w[c] = vi;
-        else ((b0 + 63 * 32 + c >= kN4095) ? p2w : p2)[c] = vi;
-        gm = fmaxf(gm, fmaxf(vr, vi));
+      for (int b = 0; b < 9; ++b) {
+        f2 t[7];
+#pragma unroll
+        for (int a = 0; a < 7; ++a) t[a] = w[P63::slot(a, b)];
+        dft_odd_p<7, +1>(t);
+#pragma unroll
+        for (int a = 0; a < 7; ++a) w[P63::slot(a, b)] = t[a];
+      }
+#pragma unroll
+      for (int a = 0; a < 7; ++a) {
+        f2 t[9];
+#pragma unroll
+        for (int b = 0; b < 9; ++b) t[b] = w[P63::slot(a, b)];
+        dft_odd_p<9, +1>(t);
+#pragma unroll
+        for (int b = 0; b < 9; ++b) {
+          const int kr = P63::out_index(P63::slot(a, b));
+          const int c = 65 * kr;
+          const float vr = f2_lo(t[b]), vi = f2_hi(t[b]);
+          if (kr <= 31) p1[c] = vr;
+          else ((b0 + c >= kN4095) ? p1w : p1)[c] = vr;
+          if (kr == 0) p2[c] = vi;
+          else if (kr >= 32) p2w[c] = vi;
+          else ((b0 + 63 * 32 + c >= kN4095) ? p2w : p2)[c] = vi;
+          gm = fmaxf(gm, fmaxf(vr, vi));
+        }
       }
       simt::sync_warp();
       if (lane < 7) {

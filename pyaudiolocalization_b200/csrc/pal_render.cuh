@@ -41,8 +41,8 @@ PAL_DEV double attenuation(double d, double absorption, double freq_factor, doub
 // cand_ok[cmax] i32 with cmax = k_max * n_planes; keys[k_max+1][3] i64.
 // Output per scene: pos[k_max][3], mat[k_max] (plane material id), count (or -1 on overflow).
 template <int NT>
-PAL_DEV void image_sources_body(ImgParams ip, const double* sources, long long n_scenes, const double* planes,
-                                const int* plane_mat, const double* mat_abs, const double* mat_freq,
+PAL_DEV void image_sources_body(ImgParams ip, const double* sources, long long n_scenes, const double* planes_all,
+                                long long plane_stride /* 0: shared planes */, const int* plane_mat, const double* mat_abs, const double* mat_freq,
                                 const double* mics, long long mic_stride /* 0: shared array */, double* out_pos,
                                 int* out_mat, int* out_count, char* scratch_all, size_t scratch_per_block,
                                 char* smem_raw) {
@@ -57,6 +57,7 @@ PAL_DEV void image_sources_body(ImgParams ip, const double* sources, long long n
   for (long long s = simt::bid(); s < n_scenes; s += simt::nblocks()) {
     const double* src = sources + s * 3;
     const double* mic = mics + s * mic_stride;
+    const double* planes = planes_all + s * plane_stride;
     double* pos = out_pos + s * ip.k_max * 3;
     int* mat = out_mat + s * ip.k_max;
     if (tid < 3) keys[tid] = round_key(src[tid], ip.round_scale);      // the source itself is "seen"
@@ -169,6 +170,67 @@ PAL_DEV void path_table_body(const double* src, const double* img_pos, const int
   gain[i] = attenuation(d, mat_abs[mat], mat_freq[mat], frequency);
 }
 
+// Batched form: one block per scene (grid-stride).  tau / gain [S][M][k_stride] with k_stride >= count+1,
+// path_count[s] = img_count[s] + 1 (0 when the image list overflowed), max_tau[s] = max over mics and
+// paths of the delay (main.py:94-101), reduced inside the block -- no atomics.
+template <int NT>
+PAL_DEV void path_table_batched_body(const double* sources, const double* img_pos, const int* img_mat,
+                                     const int* img_count, long long n_scenes, int k_max, const double* mics,
+                                     int n_mics, long long mic_stride, const double* mat_abs, const double* mat_freq,
+                                     int air_mat, double frequency, double c_sound, int k_stride, double* tau,
+                                     double* gain, int* path_count, double* max_tau, char* smem_raw) {
+  double* sh = reinterpret_cast<double*>(smem_raw);   // [NT/32]
+  for (long long s = simt::bid(); s < n_scenes; s += simt::nblocks()) {
+    const int cnt = img_count[s];
+    const int k1 = (cnt < 0) ? 0 : cnt + 1;
+    const double* src = sources + s * 3;
+    const double* mic = mics + s * mic_stride;
+    double mx = 0.0;
+    for (int i = simt::tid(); i < n_mics * k1; i += NT) {
+      const int m = i / k1, k = i % k1;
+      const double* p = (k == 0) ? src : img_pos + (size_t(s) * k_max + (k - 1)) * 3;
+      const int mat = (k == 0) ? air_mat : img_mat[size_t(s) * k_max + (k - 1)];
+      const double dx = p[0] - mic[m * 3], dy = p[1] - mic[m * 3 + 1], dz = p[2] - mic[m * 3 + 2];
+      const double d = sqrt(dx * dx + dy * dy + dz * dz);
+      const double t = d / c_sound;
+      const size_t o = (size_t(s) * n_mics + m) * k_stride + k;
+      tau[o] = t;
+      gain[o] = attenuation(d, mat_abs[mat], mat_freq[mat], frequency);
+      mx = t > mx ? t : mx;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const double o = simt::shfl_xor(mx, m);
+      mx = o > mx ? o : mx;
+    }
+    if (simt::lane() == 0) sh[simt::warp()] = mx;
+    simt::sync_block();
+    if (simt::tid() == 0) {
+      double r = 0.0;
+      for (int w = 0; w < NT / 32; ++w) r = sh[w] > r ? sh[w] : r;
+      max_tau[s] = r;
+      path_count[s] = k1;
+    }
+    simt::sync_block();
+  }
+}
+
+// Which (scene, mic) a renderer row is, and where its path list lives.  A "local" row is a row of
+// the bucket being rendered (scenes that share the transform length N); scene_index maps bucket
+// scenes to scenes of the batch.
+struct RenderRows {
+  const double* tau;             // [scenes][n_mics][k_stride]
+  const double* gain;
+  const int* path_count;         // [scenes] paths per row (direct + images); nullptr: k_stride for all
+  const long long* scene_index;  // [bucket scenes] -> scene; nullptr: identity
+  int k_stride, n_mics;
+  PAL_DEV long long global_row(long long local_row) const {
+    const long long sl = local_row / n_mics;
+    return (scene_index ? scene_index[sl] : sl) * n_mics + local_row % n_mics;
+  }
+  PAL_DEV int paths(long long global_row_) const { return path_count ? path_count[global_row_ / n_mics] : k_stride; }
+};
+
 // ------------------------------------------------------------------ transfer function x spectrum
 // G[mic][m] = X[m] * sum_k g_k exp(-j 2 pi m tau_k fs / (2N)),  m = 0..N   (bin N: real part only,
 // sum_k g_k cos(pi fs tau_k), because the reference's fftfreq labels it -fs/2 and keeps .real)
@@ -176,19 +238,22 @@ PAL_DEV void path_table_body(const double* src, const double* img_pos, const int
 // phasor by a per-path rotation of NT bins; phases are reduced mod 1 in float64 before any
 // single-precision trigonometry (SURVEY.md hard part 6).
 template <int NT, int J>
-PAL_DEV void transfer_body(const cpxf* X, int N, const double* tau, const double* gain, int k1, int n_mics,
-                           double fs, cpxf* G, char* smem_raw) {
+PAL_DEV void transfer_body(const cpxf* X, int N, RenderRows rr, long long row0, long long n_rows, double fs, cpxf* G,
+                           char* smem_raw) {
+  const int kcap = rr.k_stride;
   float* s_gain = reinterpret_cast<float*>(smem_raw);         // [k1]
-  cpxf* s_rot = reinterpret_cast<cpxf*>(s_gain + ((k1 + 3) & ~3));   // [k1] rotation by NT bins
-  double* s_delta = reinterpret_cast<double*>(s_rot + k1);   // [k1] turns per bin
+  cpxf* s_rot = reinterpret_cast<cpxf*>(s_gain + ((kcap + 3) & ~3));   // [k1] rotation by NT bins
+  double* s_delta = reinterpret_cast<double*>(s_rot + kcap);   // [k1] turns per bin
   const int tid = simt::tid();
   const int nbins = N + 1;
   const int tiles = (nbins + NT * J - 1) / (NT * J);
-  for (long long u = simt::bid(); u < (long long)n_mics * tiles; u += simt::nblocks()) {
-    const int mic = int(u / tiles);
+  for (long long u = simt::bid(); u < n_rows * tiles; u += simt::nblocks()) {
+    const long long lrow = u / tiles;                       // row of this chunk
+    const long long grow = rr.global_row(row0 + lrow);
+    const int k1 = rr.paths(grow);
     const int m0 = int(u % tiles) * NT * J;
-    const double* tk = tau + size_t(mic) * k1;
-    const double* gk = gain + size_t(mic) * k1;
+    const double* tk = rr.tau + size_t(grow) * rr.k_stride;
+    const double* gk = rr.gain + size_t(grow) * rr.k_stride;
     double gmx = 0.0;
     for (int k = 0; k < k1; ++k) gmx = gk[k] > gmx ? gk[k] : gmx;        // small k1, L1-resident
     for (int k = tid; k < k1; k += NT) {
@@ -240,7 +305,7 @@ PAL_DEV void transfer_body(const cpxf* X, int N, const double* tau, const double
           }
           o = cpxf{x.x * h, 0.f};
         }
-        G[size_t(mic) * nbins + m] = o;
+        G[size_t(lrow) * nbins + m] = o;
       }
     }
     simt::sync_block();
@@ -265,15 +330,17 @@ template <typename T> struct LoadHermitian {
 template <typename T> struct StoreRender {
   BluePlan p;
   const cpx<T>* chirp;
-  float* out;              // [rows][n_keep]
+  float* out;              // [all rows][n_keep]
   int N, n_keep, fade;
+  RenderRows rr;           // chunk-local transform t -> output row rr.global_row(row0 + t)
+  long long row0;
   PAL_DEV void operator()(long long t, int j, cpx<T> y) const {
     if (j >= n_keep) return;
     const cpx<T> w = chirp[j];
     T v = fma_(y.x, w.x, y.y * w.y) / T(p.n);
     if (j < fade) v *= (fade > 1) ? T(j) / T(fade - 1) : T(0);                      // np.linspace(0, 1, fade)
     if (j >= N - fade) v *= (fade > 1) ? T(N - 1 - j) / T(fade - 1) : T(1);         // np.linspace(1, 0, fade)
-    out[t * n_keep + j] = float(v);
+    out[rr.global_row(row0 + t) * n_keep + j] = float(v);
   }
 };
 

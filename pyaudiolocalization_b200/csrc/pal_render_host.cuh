@@ -10,11 +10,12 @@ constexpr int kImgThreads = 128;
 constexpr int kXferJ = 16;
 
 __global__ void __launch_bounds__(kImgThreads)
-    k_image_sources(ImgParams ip, const double* sources, long long n_scenes, const double* planes, const int* plane_mat,
+    k_image_sources(ImgParams ip, const double* sources, long long n_scenes, const double* planes, long long plane_stride,
+                    const int* plane_mat,
                     const double* mat_abs, const double* mat_freq, const double* mics, long long mic_stride,
                     double* out_pos, int* out_mat, int* out_count, char* scratch, size_t per_block) {
   extern __shared__ __align__(16) char smem[];
-  image_sources_body<kImgThreads>(ip, sources, n_scenes, planes, plane_mat, mat_abs, mat_freq, mics, mic_stride, out_pos,
+  image_sources_body<kImgThreads>(ip, sources, n_scenes, planes, plane_stride, plane_mat, mat_abs, mat_freq, mics, mic_stride, out_pos,
                                   out_mat, out_count, scratch, per_block, smem);
 }
 __global__ void k_path_table(const double* src, const double* img_pos, const int* img_mat, int n_img, const double* mics,
@@ -22,10 +23,20 @@ __global__ void k_path_table(const double* src, const double* img_pos, const int
                              double c_sound, double* tau, double* gain) {
   path_table_body(src, img_pos, img_mat, n_img, mics, n_mics, mat_abs, mat_freq, air_mat, frequency, c_sound, tau, gain);
 }
-__global__ void __launch_bounds__(kGT) k_transfer(const cpxf* X, int N, const double* tau, const double* gain, int k1,
-                                                  int n_mics, double fs, cpxf* G) {
+__global__ void __launch_bounds__(kGT) k_transfer(const cpxf* X, int N, RenderRows rr, long long row0, long long n_rows,
+                                                  double fs, cpxf* G) {
   extern __shared__ __align__(16) char smem[];
-  transfer_body<kGT, kXferJ>(X, N, tau, gain, k1, n_mics, fs, G, smem);
+  transfer_body<kGT, kXferJ>(X, N, rr, row0, n_rows, fs, G, smem);
+}
+__global__ void __launch_bounds__(128) k_path_table_batched(const double* sources, const double* img_pos, const int* img_mat,
+                                                            const int* img_count, long long n_scenes, int k_max,
+                                                            const double* mics, int n_mics, long long mic_stride,
+                                                            const double* mat_abs, const double* mat_freq, int air_mat,
+                                                            double frequency, double c_sound, int k_stride, double* tau,
+                                                            double* gain, int* path_count, double* max_tau) {
+  extern __shared__ __align__(16) char smem[];
+  path_table_batched_body<128>(sources, img_pos, img_mat, img_count, n_scenes, k_max, mics, n_mics, mic_stride, mat_abs,
+                               mat_freq, air_mat, frequency, c_sound, k_stride, tau, gain, path_count, max_tau, smem);
 }
 __global__ void __launch_bounds__(kGT) k_normalise_compress(float* rows, long long n_rows, int n, float thr, float eps,
                                                             bool compress) {
@@ -39,22 +50,27 @@ inline size_t image_scratch_per_block(int n_planes, int k_max) {
 }
 inline int image_grid(long long n_scenes, int sms) { return (int)std::min<long long>(n_scenes, 8LL * sms); }
 
-// workspace of one rendered scene: tables(2N) + X[2N] + G[M][N+1] + conv buffers
-inline size_t render_min_bytes(int N, int n_mics) {
+// workspace of a render call over `rows` (scene, mic) rows of transform length 2N:
+// tables(2N) + X[2N] + per row in flight: G[N+1] + one convolution buffer
+inline size_t render_row_bytes(int N) {
   GenericLayout<float> L(2 * N);
-  return L.tables + al(sizeof(cpxf) * size_t(2 * N)) + al(sizeof(cpxf) * size_t(n_mics) * (N + 1)) +
-         al(sizeof(cpxf) * size_t(L.p.M)) + 1024;
+  return al(sizeof(cpxf) * size_t(N + 1)) + al(sizeof(cpxf) * size_t(L.p.M));
 }
-inline size_t render_full_bytes(int N, int n_mics) {
+inline size_t render_fixed_bytes(int N) {
   GenericLayout<float> L(2 * N);
-  return render_min_bytes(N, n_mics) + size_t(std::max(0, n_mics - 1)) * al(sizeof(cpxf) * size_t(L.p.M));
+  return L.tables + al(sizeof(cpxf) * size_t(2 * N)) + 1024;
+}
+inline size_t render_min_bytes(int N, int /*n_mics*/) { return render_fixed_bytes(N) + render_row_bytes(N); }
+inline size_t render_full_bytes(int N, long long rows) {
+  return render_fixed_bytes(N) + size_t(std::min<long long>(rows, 4096)) * render_row_bytes(N);
 }
 
-inline cudaError_t render_scene(const float* base, int n_base, int N, const double* tau, const double* gain, int n_mics,
-                                int k1, double fs, int n_keep, bool normalise, float* out, char* ws, size_t ws_bytes,
-                                cudaStream_t s, int sms) {
+// Render `n_rows` rows (bucket-local order, see RenderRows) of transform length 2N into `out`
+// (row r of the batch at out + r * n_keep).  No normalisation here.
+inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows rr, long long n_rows, double fs, int n_keep,
+                               float* out, char* ws, size_t ws_bytes, cudaStream_t s, int sms) {
   using T = float;
-  if (ws_bytes < render_min_bytes(N, n_mics)) return cudaErrorMemoryAllocation;
+  if (ws_bytes < render_min_bytes(N, 1)) return cudaErrorMemoryAllocation;
   GenericLayout<T> L(2 * N);
   const BluePlan p = L.p;
   char* b = ws;
@@ -63,11 +79,11 @@ inline cudaError_t render_scene(const float* base, int n_base, int N, const doub
   if (e != cudaSuccess) return e;
   cpxf* X = reinterpret_cast<cpxf*>(b);
   b += al(sizeof(cpxf) * size_t(2 * N));
-  cpxf* G = reinterpret_cast<cpxf*>(b);
-  b += al(sizeof(cpxf) * size_t(n_mics) * (N + 1));
-  const size_t conv_one = al(sizeof(cpxf) * size_t(p.M));
-  const long long tr_cap = std::max<long long>(1, std::min<long long>(n_mics, (long long)((ws_bytes - size_t(b - ws)) / conv_one)));
-  cpxf* conv = reinterpret_cast<cpxf*>(b);
+  const size_t g_one = al(sizeof(cpxf) * size_t(N + 1)), conv_one = al(sizeof(cpxf) * size_t(p.M));
+  const long long cap = std::max<long long>(1, std::min<long long>(n_rows, (long long)((ws_bytes - size_t(b - ws)) / (g_one + conv_one))));
+  cpxf* G = reinterpret_cast<cpxf*>(b);          // rows addressed densely: G[t * (N+1)]
+  b += size_t(cap) * g_one;
+  cpxf* conv = reinterpret_cast<cpxf*>(b);       // conv[t * M]
   const size_t cs = col_smem<T>(p), rs = 2 * sizeof(T) * size_t(p.M2);
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   const BlueTables<T> tb = bb.tb();
@@ -78,26 +94,29 @@ inline cudaError_t render_scene(const float* base, int n_base, int N, const doub
       p, tb, LoadSignal<T>{p, bb.chirp, base, n_base, n_base, n_base, nullptr}, 1, nullptr, conv);
   k_rowpass<T, true, false><<<std::min(p.M1, 16 * sms), kGT, rs, s>>>(p, tb, 1, nullptr, conv);
   k_colpass_inv<T, StoreSpectrum<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(p, tb, StoreSpectrum<T>{p, bb.chirp, X}, 1, nullptr, conv);
-  // G = X * H                                                          (main.py:104-118)
+  count_launch(3);
   const int xtiles = (N + 1 + kGT * kXferJ - 1) / (kGT * kXferJ);
-  const size_t ts = 4 * size_t((k1 + 3) & ~3) + 16 * size_t(k1) + 16;
+  const int kcap = rr.k_stride;
+  const size_t ts = 4 * size_t((kcap + 3) & ~3) + 16 * size_t(kcap) + 16;
   if (ts > 48 * 1024) cudaFuncSetAttribute(k_transfer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts);
-  k_transfer<<<(unsigned)std::min<long long>((long long)n_mics * xtiles, 32LL * sms), kGT, ts, s>>>(X, N, tau, gain, k1, n_mics, fs, G);
-  count_launch(4);
   const int fade = int(0.01 * N);
-  for (long long r0 = 0; r0 < n_mics; r0 += tr_cap) {
-    const long long nt = std::min<long long>(tr_cap, n_mics - r0);
+  for (long long r0 = 0; r0 < n_rows; r0 += cap) {
+    const long long nt = std::min<long long>(cap, n_rows - r0);
+    // G = X * H                                                        (main.py:104-118)
+    k_transfer<<<(unsigned)std::min<long long>(nt * xtiles, 32LL * sms), kGT, ts, s>>>(X, N, rr, r0, nt, fs, G);
     k_colpass_fwd<T, LoadHermitian<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * sms), kGT, cs, s>>>(
-        p, tb, LoadHermitian<T>{p, bb.chirp, G + size_t(r0) * (N + 1), N}, nt, nullptr, conv);
+        p, tb, LoadHermitian<T>{p, bb.chirp, G, N}, nt, nullptr, conv);
     k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * p.M1, 16LL * sms), kGT, rs, s>>>(p, tb, nt, nullptr, conv);
     k_colpass_inv<T, StoreRender<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * sms), kGT, cs, s>>>(
-        p, tb, StoreRender<T>{p, bb.chirp, out + size_t(r0) * n_keep, N, n_keep, fade}, nt, nullptr, conv);
-    count_launch(3);
+        p, tb, StoreRender<T>{p, bb.chirp, out, N, n_keep, fade, rr, r0}, nt, nullptr, conv);
+    count_launch(4);
   }
-  if (normalise) {
-    k_normalise_compress<<<(unsigned)std::min<long long>(n_mics, 8LL * sms), kGT, 64, s>>>(out, n_mics, n_keep, 0.8f, 1e-8f, true);
-    count_launch(1);
-  }
+  return cudaGetLastError();
+}
+
+inline cudaError_t normalise_rows(float* out, long long n_rows, int n_keep, cudaStream_t s, int sms) {
+  k_normalise_compress<<<(unsigned)std::min<long long>(n_rows, 8LL * sms), kGT, 64, s>>>(out, n_rows, n_keep, 0.8f, 1e-8f, true);
+  count_launch(1);
   return cudaGetLastError();
 }
 

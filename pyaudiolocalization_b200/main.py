@@ -67,6 +67,36 @@ def simulate_signals_device(source_pos, mic_positions, fs, c, duration=1.0, sign
                            trim_to_duration=trim_to_duration)
 
 
+def simulate_scenes_batched(source_positions, mic_positions, fs, c, duration=1.0, signal_type='sine', freq=1000,
+                            reflective_planes=None, material_properties=None, max_reflections=2,
+                            absorption_threshold=0.01, trim_to_duration=True, base_signal=None) -> torch.Tensor:
+    """simulate_signals_with_multipath (main.py:66-124) for MANY source positions / scenes in one go:
+    source_positions [S, 3]; mic_positions [M, 3] (shared array) or [S, M, 3]; reflective_planes one
+    list (shared room) or a list of S lists (one room per scene, same plane count and materials).
+    Returns a [S, M, n] float32 tensor on the device.  Image sources, path tables, transfer
+    functions, inverse transforms and the normalise / compress epilogue all run batched."""
+    base = generate_signal(signal_type, fs, duration, freq) if base_signal is None else base_signal
+    mats = material_properties
+    planes = list(reflective_planes or [])
+    srcs = np.asarray(source_positions, dtype=np.float64).reshape(-1, 3)
+    dev = _s._dev()
+    if max_reflections >= 1 and planes:
+        k_max = None
+        while True:
+            pos, mat, cnt, table = _s.image_sources_batched(srcs, planes, max_reflections, freq, mats, mic_positions,
+                                                            absorption_threshold, 6, k_max)
+            if not bool((cnt < 0).any().item()):
+                break
+            k_max = pos.shape[1] * 4
+    else:
+        table = _s.MaterialTable(mats, dev)
+        pos = torch.zeros((len(srcs), 1, 3), dtype=torch.float64, device=dev)
+        mat = torch.zeros((len(srcs), 1), dtype=torch.int32, device=dev)
+        cnt = torch.zeros((len(srcs),), dtype=torch.int32, device=dev)
+    return _s.render_scenes_batched(base, srcs, pos, mat, cnt, mic_positions, fs, c, duration, freq, table,
+                                    trim_to_duration=trim_to_duration)
+
+
 def simulate_signals_with_multipath(source_pos, mic_positions, fs, c, duration=1.0, signal_type='sine', freq=1000,
                                     reflective_planes=None, material_properties=None, max_reflections=2,
                                     absorption_threshold=0.01, trim_to_duration=True):

@@ -56,17 +56,30 @@ def image_sources_batched(sources, planes: Sequence[Dict[str, Any]], max_order: 
     n_mics = mics_np.shape[-2]
     table = MaterialTable(material_properties, dev)
     planes = list(planes or [])
-    pl = np.zeros((max(len(planes), 1), 4), np.float64)
-    pm = np.zeros(max(len(planes), 1), np.int32)
-    for i, p in enumerate(planes):
-        a, bb, c, d = [float(v) for v in p['plane']]
-        if a * a + bb * bb + c * c == 0:
-            raise ValueError("Ungültige Ebene: a^2 + b^2 + c^2 ist 0.")
-        mat = p.get('material', 'air')
-        if mat not in table.index:
-            raise ValueError(f"Material '{mat}' ist nicht definiert. Bitte zum Dictionary hinzufügen.")
-        pl[i] = (a, bb, c, d)
-        pm[i] = table.index[mat]
+    # planes: one list shared by all scenes, or (per-scene geometry) a list of B such lists that
+    # agree in the number of planes and in their materials
+    per_scene_planes = bool(planes) and isinstance(planes[0], (list, tuple))
+    plane_sets = planes if per_scene_planes else [planes]
+    if per_scene_planes and len(plane_sets) != b:
+        raise ValueError("per-scene planes: need one plane list per source")
+    n_pl = len(plane_sets[0])
+    pl = np.zeros((len(plane_sets), max(n_pl, 1), 4), np.float64)
+    pm = np.zeros(max(n_pl, 1), np.int32)
+    for si_, pls in enumerate(plane_sets):
+        if len(pls) != n_pl:
+            raise ValueError("per-scene planes: every scene needs the same number of planes")
+        for i, p in enumerate(pls):
+            a, bb, c, d = [float(v) for v in p['plane']]
+            if a * a + bb * bb + c * c == 0:
+                raise ValueError("Ungültige Ebene: a^2 + b^2 + c^2 ist 0.")
+            mat = p.get('material', 'air')
+            if mat not in table.index:
+                raise ValueError(f"Material '{mat}' ist nicht definiert. Bitte zum Dictionary hinzufügen.")
+            if si_ and table.index[mat] != pm[i]:
+                raise ValueError("per-scene planes: plane materials must agree between scenes")
+            pl[si_, i] = (a, bb, c, d)
+            pm[i] = table.index[mat]
+    planes = plane_sets[0]
     planes_dev = torch.as_tensor(pl).to(dev)
     pm_dev = torch.as_tensor(pm).to(dev)
     if k_max is None:
@@ -85,7 +98,8 @@ def image_sources_batched(sources, planes: Sequence[Dict[str, Any]], max_order: 
     L = _lib.lib()
     _lib.check(L.pal_image_sources_workspace(len(planes), k_max, b, C.byref(need)), "pal_image_sources_workspace")
     ws, wp, wl = _ws(need.value, dev)
-    rc = L.pal_image_sources(src.data_ptr(), b, planes_dev.data_ptr(), pm_dev.data_ptr(), len(planes),
+    rc = L.pal_image_sources(src.data_ptr(), b, planes_dev.data_ptr(), 4 * max(n_pl, 1) if per_scene_planes else 0,
+                             pm_dev.data_ptr(), len(planes),
                              table.absorption.data_ptr(), table.freq.data_ptr(), mics.data_ptr(), n_mics,
                              3 * n_mics if per_scene else 0, int(max_order), float(frequency),
                              float(absorption_threshold), int(round_decimals), k_max, pos.data_ptr(), mat.data_ptr(),
@@ -130,6 +144,74 @@ def render_scene(base_signal, source_pos, img_pos: torch.Tensor, img_mat: torch.
                                   n_keep, 1 if normalise else 0, out.data_ptr(), wp, wl, _stream(dev)),
                "pal_render_scene")
     for t in (base, tau, gain, ws, mics, src):
+        t.record_stream(torch.cuda.current_stream(dev))
+    return out
+
+
+def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: torch.Tensor, img_count: torch.Tensor,
+                          mic_positions, fs: float, c: float, duration: float, freq: float, table: MaterialTable,
+                          trim_to_duration: bool = True, normalise: bool = True,
+                          max_workspace_bytes: int = 4 << 30) -> torch.Tensor:
+    """main.py:94-122 for MANY scenes that share fs / duration / base signal: sources [S, 3],
+    img_pos [S, K, 3], img_mat [S, K], img_count [S] (output of image_sources_batched),
+    mic_positions [M, 3] or [S, M, 3].  Returns [S, M, n_keep] float32 on the device.
+
+    The transform length N = int((duration + max delay) * fs) (main.py:102) differs from scene to
+    scene; delays are computed for all scenes in one launch, N is formed on the host in float64
+    exactly like the reference (one small read-back), and scenes that share N are rendered together."""
+    dev = _dev()
+    L = _lib.lib()
+    if 'air' not in table.index:
+        raise KeyError('air')
+    src = torch.as_tensor(np.asarray(sources, dtype=np.float64).reshape(-1, 3)).to(dev)
+    s_n = src.shape[0]
+    mics_np = np.asarray(mic_positions, dtype=np.float64)
+    per_scene = mics_np.ndim == 3
+    mics = torch.as_tensor(np.ascontiguousarray(mics_np)).to(dev)
+    m = mics_np.shape[-2]
+    k_max = int(img_pos.shape[1])
+    if (img_count < 0).any().item():
+        raise RuntimeError("image_sources_batched overflowed k_max for some scene; call it again with a larger k_max")
+    k_stride = k_max + 1
+    tau = torch.empty((s_n, m, k_stride), dtype=torch.float64, device=dev)
+    gain = torch.empty((s_n, m, k_stride), dtype=torch.float64, device=dev)
+    pcount = torch.empty((s_n,), dtype=torch.int32, device=dev)
+    max_tau = torch.empty((s_n,), dtype=torch.float64, device=dev)
+    _lib.check(L.pal_path_table_batched(src.data_ptr(), img_pos.data_ptr(), img_mat.data_ptr(), img_count.data_ptr(), s_n,
+                                        k_max, mics.data_ptr(), m, 3 * m if per_scene else 0, table.absorption.data_ptr(),
+                                        table.freq.data_ptr(), table.index['air'], float(freq), float(c), k_stride,
+                                        tau.data_ptr(), gain.data_ptr(), pcount.data_ptr(), max_tau.data_ptr(),
+                                        _stream(dev)), "pal_path_table_batched")
+    base = torch.as_tensor(np.ascontiguousarray(np.asarray(base_signal, dtype=np.float32))).to(dev) \
+        if not isinstance(base_signal, torch.Tensor) else base_signal.to(dev, torch.float32).contiguous()
+    n_base = base.numel()
+    totals = ((duration + max_tau.cpu().numpy()) * fs).astype(np.int64)          # main.py:102, float64 then int()
+    if (totals < n_base).any():
+        raise ValueError("negative dimensions are not allowed")
+    if (np.floor(0.01 * totals) < 1).any():
+        raise ValueError("operands could not be broadcast together")
+    n_dur = int(duration * fs)
+    if not trim_to_duration and len(np.unique(totals)) > 1:
+        raise ValueError("trim_to_duration=False gives rows of different length; render such scenes one by one")
+    n_keep = min(n_dur, int(totals.min())) if trim_to_duration else int(totals[0])
+    out = torch.empty((s_n, m, n_keep), dtype=torch.float32, device=dev)
+    order = np.argsort(totals, kind="stable")
+    uniq, starts = np.unique(totals[order], return_index=True)
+    idx_dev = torch.as_tensor(order.astype(np.int64)).to(dev)
+    need, small = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(L.pal_render_scenes_workspace(int(uniq.max()), int(s_n) * m, C.byref(need), C.byref(small)),
+               "pal_render_scenes_workspace")
+    ws, wp, wl = _ws(max(small.value, min(need.value, int(max_workspace_bytes))), dev)
+    bounds = list(starts) + [len(order)]
+    for bi, total in enumerate(uniq):
+        lo, hi = int(bounds[bi]), int(bounds[bi + 1])
+        _lib.check(L.pal_render_scenes(base.data_ptr(), n_base, int(total), tau.data_ptr(), gain.data_ptr(), pcount.data_ptr(),
+                                       k_stride, idx_dev.data_ptr() + 8 * lo, hi - lo, m, float(fs), n_keep, out.data_ptr(),
+                                       wp, wl, _stream(dev)), "pal_render_scenes")
+    if normalise:
+        _lib.check(L.pal_normalise_compress(out.data_ptr(), s_n * m, n_keep, 0.8, 1e-8, 1, _stream(dev)),
+                   "pal_normalise_compress")
+    for t in (base, tau, gain, pcount, ws, mics, src, idx_dev):
         t.record_stream(torch.cuda.current_stream(dev))
     return out
 

@@ -140,3 +140,23 @@ def render_scene(base, total, tau, gain, fs, n_keep):
     lib().emu_render_scene(_p(base, C.c_float), len(base), total, _pd(tau), _pd(gain), m, k1, C.c_double(fs), n_keep,
                            _p(out, C.c_float))
     return out
+
+
+def path_table_batched(sources, img_pos, img_mat, img_count, mics, mat_abs, mat_freq, air_mat, frequency, c_sound):
+    """sources [S,3], img_pos [S,K,3], img_mat [S,K], img_count [S]; mics [M,3] shared."""
+    sources = np.ascontiguousarray(sources, np.float64).reshape(-1, 3)
+    img_pos = np.ascontiguousarray(img_pos, np.float64)
+    img_mat = np.ascontiguousarray(img_mat, np.int32)
+    img_count = np.ascontiguousarray(img_count, np.int32)
+    mics = np.ascontiguousarray(mics, np.float64).reshape(-1, 3)
+    s, k = img_mat.shape
+    ks = k + 1
+    tau = np.zeros((s, len(mics), ks))
+    gain = np.zeros((s, len(mics), ks))
+    cnt = np.zeros(s, np.int32)
+    mx = np.zeros(s)
+    lib().emu_path_table_batched(_pd(sources), _pd(img_pos), _p(img_mat, C.c_int), _p(img_count, C.c_int), C.c_longlong(s), k,
+                                 _pd(mics), len(mics), C.c_longlong(0), _pd(np.ascontiguousarray(mat_abs, np.float64)),
+                                 _pd(np.ascontiguousarray(mat_freq, np.float64)), air_mat, C.c_double(frequency),
+                                 C.c_double(c_sound), ks, _pd(tau), _pd(gain), _p(cnt, C.c_int), _pd(mx))
+    return tau, gain, cnt, mx

@@ -144,7 +144,7 @@ extern "C" void emu_image_sources(const double* sources, long long n_scenes, con
   const int grid = 2;
   std::vector<char> scratch(per_block * grid);
   simt::launch(grid, NT, 64 * sizeof(int), [&](char* sm) {
-    image_sources_body<NT>(ip, sources, n_scenes, planes, plane_mat, mat_abs, mat_freq, mics, 0, out_pos, out_mat,
+    image_sources_body<NT>(ip, sources, n_scenes, planes, 0, plane_mat, mat_abs, mat_freq, mics, 0, out_pos, out_mat,
                            out_count, scratch.data(), per_block, sm);
   });
 }
@@ -180,14 +180,27 @@ extern "C" void emu_render_scene(const float* base, int n_base, int N, const dou
     colpass_inv_body<T, NT, TC>(p, tb, StoreSpectrum<T>{p, chirp.data(), X.data()}, 1, conv.data(), sm);
   });
   const size_t ts = 4 * ((k1 + 3) & ~3) + 16 * size_t(k1) + 16;
-  simt::launch(3, NT, ts, [&](char* sm) { transfer_body<NT, J>(X.data(), N, tau, gain, k1, n_mics, fs, G.data(), sm); });
+  const RenderRows rr{tau, gain, nullptr, nullptr, k1, n_mics};
+  simt::launch(3, NT, ts, [&](char* sm) { transfer_body<NT, J>(X.data(), N, rr, 0, n_mics, fs, G.data(), sm); });
   simt::launch(3, NT, cs, [&](char* sm) {
     colpass_fwd_body<T, NT, TC>(p, tb, LoadHermitian<T>{p, chirp.data(), G.data(), N}, n_mics, conv.data(), sm);
   });
   simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, true, true>(p, tb, n_mics, conv.data(), sm); });
   const int fade = int(0.01 * N);
   simt::launch(3, NT, cs, [&](char* sm) {
-    colpass_inv_body<T, NT, TC>(p, tb, StoreRender<T>{p, chirp.data(), out, N, n_keep, fade}, n_mics, conv.data(), sm);
+    colpass_inv_body<T, NT, TC>(p, tb, StoreRender<T>{p, chirp.data(), out, N, n_keep, fade, rr, 0}, n_mics, conv.data(), sm);
   });
   simt::launch(2, NT, 64, [&](char* sm) { normalise_compress_body<NT>(out, n_mics, n_keep, 0.8f, 1e-8f, true, sm); });
+}
+
+extern "C" void emu_path_table_batched(const double* sources, const double* img_pos, const int* img_mat, const int* img_count,
+                                       long long n_scenes, int k_max, const double* mics, int n_mics, long long mic_stride,
+                                       const double* mat_abs, const double* mat_freq, int air_mat, double frequency,
+                                       double c_sound, int k_stride, double* tau, double* gain, int* path_count,
+                                       double* max_tau) {
+  constexpr int NT = 64;
+  simt::launch(2, NT, 64, [&](char* sm) {
+    path_table_batched_body<NT>(sources, img_pos, img_mat, img_count, n_scenes, k_max, mics, n_mics, mic_stride, mat_abs,
+                                mat_freq, air_mat, frequency, c_sound, k_stride, tau, gain, path_count, max_tau, sm);
+  });
 }

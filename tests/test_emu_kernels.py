@@ -114,3 +114,29 @@ def test_peakpick_plateaus_and_chains():
         want = O.tdoa_pick_restated(c, n2, w, d, 2)
         got, _ = E.peakpick_f64(c, n2 - 1, w, d, 0, 1.0, 2)
         assert got == want, (trial, got, want)
+
+
+def test_path_table_batched_matches_per_scene():
+    """Batched delay / gain table (one block per scene, in-block max reduction) against the per-scene
+    kernel and the oracle restatement of main.py:94-116."""
+    from oracle import pal_oracle as O
+    from tests.golden.make_golden import CUSTOM_MATERIALS, shoebox
+    rng = np.random.default_rng(3)
+    mics = rng.uniform([1, 1, 0.5], [5, 4, 2.5], size=(4, 3))
+    srcs = rng.uniform([0.5, 0.5, 0.3], [5.5, 4.5, 2.7], size=(3, 3))
+    names = list(CUSTOM_MATERIALS)
+    mat_abs = [CUSTOM_MATERIALS[n]["absorption"] for n in names]
+    mat_freq = [CUSTOM_MATERIALS[n]["freq"] for n in names]
+    planes = shoebox(6, 5, 3)
+    pl = [p["plane"] for p in planes]
+    pm = [names.index(p["material"]) for p in planes]
+    pos, mat, cnt = E.image_sources(srcs, pl, pm, mat_abs, mat_freq, mics, 2, 700.0, 0.01, 64)
+    tau, gain, pc, mx = E.path_table_batched(srcs, pos, mat, cnt, mics, mat_abs, mat_freq, names.index("air"), 700.0, 343.62)
+    for s in range(3):
+        k = int(cnt[s])
+        assert pc[s] == k + 1
+        t1, g1 = E.path_table(srcs[s], pos[s, :k], mat[s, :k], mics, mat_abs, mat_freq, names.index("air"), 700.0, 343.62)
+        assert np.array_equal(tau[s, :, :k + 1], t1) and np.array_equal(gain[s, :, :k + 1], g1)
+        assert mx[s] == t1.max()
+        imgs = O.generate_image_sources_iterative(srcs[s], planes, 2, 700.0, CUSTOM_MATERIALS, mics, 0.01)
+        assert len(imgs) == k

@@ -169,3 +169,41 @@ def test_bootstrap_significance_on_gpu(pal):
     np.random.seed(123)
     peaks = [np.max(O.phat_correlation(a, np.random.permutation(b))) for _ in range(64)]
     assert got == pytest.approx(np.percentile(peaks, 95), rel=1e-4)
+
+
+def test_batched_scenes_match_per_scene_render_and_oracle(pal):
+    """simulate_scenes_batched: many scenes (different rooms -> different transform lengths N, bucketed
+    by N) in one call must equal the per-scene drop-in bit for bit and the oracle within 1e-5."""
+    from pyaudiolocalization_b200 import main as M
+    rng = np.random.default_rng(5000)
+    n_sc = 7
+    rooms, mics, srcs = [], [], []
+    for _ in range(n_sc):
+        dims = rng.uniform([3, 3, 2.5], [10, 8, 4])
+        rooms.append(shoebox(*dims))
+        mics.append(rng.uniform([0.3, 0.3, 0.3], dims - 0.3, size=(4, 3)))
+        srcs.append(rng.uniform([0.3, 0.3, 0.3], dims - 0.3))
+    kw = dict(duration=0.25, signal_type="chirp", freq=500, material_properties=CUSTOM_MATERIALS, max_reflections=3,
+              absorption_threshold=0.01)
+    got = M.simulate_scenes_batched(np.array(srcs), np.array(mics), 16000, 343.62, reflective_planes=rooms, **kw).cpu().numpy()
+    assert got.shape == (n_sc, 4, 4000)
+    for s in range(n_sc):
+        one = M.simulate_signals_device(srcs[s], mics[s], 16000, 343.62, reflective_planes=rooms[s], **kw).cpu().numpy()
+        assert np.array_equal(got[s], one), s
+    for s in (0, 3):
+        want = np.array(O.simulate_signals_with_multipath(srcs[s], mics[s], 16000, 343.62, reflective_planes=rooms[s], **kw))
+        assert np.abs(got[s] - want).max() <= RENDER_ATOL
+
+
+def test_batched_scenes_shared_room(pal):
+    """Shared room and microphones, many source positions (BASELINE cfg4 shape, scaled down)."""
+    from pyaudiolocalization_b200 import main as M
+    rng = np.random.default_rng(1)
+    mics = np.random.default_rng(0).uniform([1, 1, 0.5], [5, 4, 2.5], size=(6, 3))
+    srcs = rng.uniform([0.5, 0.5, 0.3], [5.5, 4.5, 2.7], size=(5, 3))
+    kw = dict(duration=0.1, signal_type="chirp", freq=1000, reflective_planes=shoebox(6, 5, 3),
+              material_properties=CUSTOM_MATERIALS, max_reflections=4, absorption_threshold=0.01)
+    got = M.simulate_scenes_batched(srcs, mics, 48000, 343.62, **kw).cpu().numpy()
+    for s in (0, 4):
+        want = np.array(O.simulate_signals_with_multipath(srcs[s], mics, 48000, 343.62, **kw))
+        assert np.abs(got[s] - want).max() <= RENDER_ATOL

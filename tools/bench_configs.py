@@ -60,40 +60,43 @@ def cfg4(small):
     mics = rng0.uniform([1, 1, 0.5], [5, 4, 2.5], size=(64, 3))
     srcs = rng1.uniform([0.5, 0.5, 0.3], [5.5, 4.5, 2.7], size=(1024, 3))
     planes = shoebox(6, 5, 3)
-    n_src = 2 if small else 4
-    t0 = time.perf_counter()
-    outs = []
-    for s in range(n_src):
-        outs.append(pmain.simulate_signals_device(srcs[s], mics, 48000, 343.62, 1.0, "chirp", 1000, planes, MATS, 6, 0.01))
-    torch.cuda.synchronize()
-    first = time.perf_counter() - t0
-    sec = timed(lambda: pmain.simulate_signals_device(srcs[0], mics, 48000, 343.62, 1.0, "chirp", 1000, planes, MATS, 6, 0.01), reps=2, warm=0)
+    n_src = 8 if small else 64
+    sec1 = timed(lambda: pmain.simulate_signals_device(srcs[0], mics, 48000, 343.62, 1.0, "chirp", 1000, planes, MATS, 6, 0.01), reps=2)
+    sec = timed(lambda: pmain.simulate_scenes_batched(srcs[:n_src], mics, 48000, 343.62, 1.0, "chirp", 1000, planes, MATS, 6, 0.01), reps=2)
     print(json.dumps({"config": "cfg4", "stage": "render (image sources + path table + transfer + inverse DFT + normalise/compress)",
-                      "mics": 64, "order": 6, "fs": 48000, "ms_per_source": sec * 1e3, "sources_per_s": 1 / sec,
-                      "rendered_samples_per_s": 64 * 48000 / sec, "first_call_ms": first * 1e3 / n_src}), flush=True)
-    fr = outs[0][None].contiguous()           # [1, 64, 48000]
+                      "mics": 64, "order": 6, "fs": 48000, "sources": n_src, "batched_ms": sec * 1e3,
+                      "sources_per_s_batched": n_src / sec, "sources_per_s_per_scene_api": 1 / sec1,
+                      "rendered_samples_per_s": n_src * 64 * 48000 / sec}), flush=True)
+    fr = pmain.simulate_scenes_batched(srcs[:2], mics, 48000, 343.62, 1.0, "chirp", 1000, planes, MATS, 6, 0.01)
     P = 64 * 63 // 2
     sec = timed(lambda: pal.gcc_phat_tdoa_batched(fr, 48000.0, 0.05), reps=1)
-    print(json.dumps({"config": "cfg4", "stage": "gcc_phat_tdoa", "units": 1, "mics": 64, "samples": 48000, "n_fft": 95999,
-                      "ms": sec * 1e3, "pair_corr_per_s": P / sec}), flush=True)
+    print(json.dumps({"config": "cfg4", "stage": "gcc_phat_tdoa", "units": 2, "mics": 64, "samples": 48000, "n_fft": 95999,
+                      "ms": sec * 1e3, "pair_corr_per_s": 2 * P / sec}), flush=True)
 
 
 def cfg5_render(small):
     rng = np.random.default_rng(5000)
-    n_sc = 8 if small else 32
-    scenes = []
+    n_sc = 256 if small else 4096
+    rooms, micl, srcl = [], [], []
     for _ in range(n_sc):
         dims = rng.uniform([3, 3, 2.5], [10, 8, 4])
-        mics = rng.uniform([0.3, 0.3, 0.3], dims - 0.3, size=(8, 3))
-        src = rng.uniform([0.3, 0.3, 0.3], dims - 0.3)
-        scenes.append((dims, mics, src))
+        rooms.append(shoebox(*dims))
+        micl.append(rng.uniform([0.3, 0.3, 0.3], dims - 0.3, size=(8, 3)))
+        srcl.append(rng.uniform([0.3, 0.3, 0.3], dims - 0.3))
+    micl, srcl = np.array(micl), np.array(srcl)
 
-    def run():
-        for dims, mics, src in scenes:
-            pmain.simulate_signals_device(src, mics, 16000, 343.62, 0.25, "chirp", 500, shoebox(*dims), MATS, 3, 0.01)
-    sec = timed(run, reps=2)
+    def per_scene():
+        for s in range(16):
+            pmain.simulate_signals_device(srcl[s], micl[s], 16000, 343.62, 0.25, "chirp", 500, rooms[s], MATS, 3, 0.01)
+    sec1 = timed(per_scene, reps=2) / 16
+    sec = timed(lambda: pmain.simulate_scenes_batched(srcl, micl, 16000, 343.62, 0.25, "chirp", 500, rooms, MATS, 3, 0.01), reps=2)
     print(json.dumps({"config": "cfg5", "stage": "render", "mics": 8, "order": 3, "fs": 16000, "scenes": n_sc,
-                      "ms_per_scene": sec * 1e3 / n_sc, "scenes_per_s": n_sc / sec}), flush=True)
+                      "batched_ms": sec * 1e3, "scenes_per_s_batched": n_sc / sec, "scenes_per_s_per_scene_api": 1 / sec1}), flush=True)
+    sig = pmain.simulate_scenes_batched(srcl, micl, 16000, 343.62, 0.25, "chirp", 500, rooms, MATS, 3, 0.01)
+    P = 28
+    sec2 = timed(lambda: pal.gcc_phat_tdoa_batched(sig, 16000.0, 0.05), reps=2)
+    print(json.dumps({"config": "cfg5", "stage": "render -> gcc_phat_tdoa (rendered scenes fed to stage 2)", "scenes": n_sc,
+                      "gcc_ms": sec2 * 1e3, "scenes_per_s_gcc": n_sc / sec2, "scenes_per_s_both": n_sc / (sec + sec2)}), flush=True)
 
 
 def img(small):
