@@ -279,39 +279,52 @@ PAL_DEV void colpass_fwd_body(BluePlan p, BlueTables<T> tb, Loader load, long lo
 }
 
 // ---- pass 2: rows: forward FFT, (x chirp spectrum, inverse FFT, conj twiddle) ------------------
-// work unit = (transform t, row r).  CONV=false stops after the forward FFT (plan set-up).
-template <typename T, int NT, bool CONV, bool CONJ_BHAT>
+// work unit = (transform t, tile of TR adjacent rows r).  The TR rows are contiguous in global memory
+// (TR * M2 complex); in shared memory element e of row c sits at e * (TR + 1) + c, i.e. the rows
+// are interleaved (and padded) so that the butterflies of one stage touch consecutive banks.
+// CONV=false stops after the forward FFT (plan set-up).
+template <typename T, int NT, int TR, bool CONV, bool CONJ_BHAT>
 PAL_DEV void rowpass_body(BluePlan p, BlueTables<T> tb, long long n_tr, cpx<T>* buf, char* smem) {
+  const int tr = p.M1 < TR ? p.M1 : TR;
+  const int tiles = p.M1 / tr;
+  const int ld = tr + 1;
   T* re = reinterpret_cast<T*>(smem);
-  T* im = re + p.M2;
-  for (long long u = simt::bid(); u < n_tr * p.M1; u += simt::nblocks()) {
-    const long long t = u / p.M1;
-    const int r = int(u % p.M1);
-    cpx<T>* row = buf + t * p.M + (long long)r * p.M2;
-    for (int e = simt::tid(); e < p.M2; e += NT) {
-      const cpx<T> v = row[e];
-      re[e] = v.x;
-      im[e] = v.y;
+  T* im = re + p.M2 * ld;
+  for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks()) {
+    const long long t = u / tiles;
+    const int r0 = int(u % tiles) * tr;
+    cpx<T>* rows = buf + t * p.M + (long long)r0 * p.M2;
+    for (int x = simt::tid(); x < tr * p.M2; x += NT) {
+      const int c = x / p.M2, e = x % p.M2;
+      const cpx<T> v = rows[x];
+      re[e * ld + c] = v.x;
+      im[e * ld + c] = v.y;
     }
     simt::sync_block();
-    fft_tile<T, NT>(re, im, p.lg2, 1, 1, 0, tb.tw2, false);
+    fft_tile<T, NT>(re, im, p.lg2, tr, ld, 1, tb.tw2, false);
     if (CONV) {
-      const cpx<T>* bh = tb.bhat + (long long)r * p.M2;
-      for (int e = simt::tid(); e < p.M2; e += NT) {
-        const cpx<T> b = bh[e];
-        const cpx<T> v = CONJ_BHAT ? cmulc(cpx<T>{re[e], im[e]}, b) : cmul(cpx<T>{re[e], im[e]}, b);
-        re[e] = v.x;
-        im[e] = v.y;
+      const cpx<T>* bh = tb.bhat + (long long)r0 * p.M2;
+      for (int x = simt::tid(); x < tr * p.M2; x += NT) {
+        const int c = x / p.M2, e = x % p.M2;
+        const cpx<T> b = bh[x];
+        const cpx<T> a{re[e * ld + c], im[e * ld + c]};
+        const cpx<T> v = CONJ_BHAT ? cmulc(a, b) : cmul(a, b);
+        re[e * ld + c] = v.x;
+        im[e * ld + c] = v.y;
       }
       simt::sync_block();
-      fft_tile<T, NT>(re, im, p.lg2, 1, 1, 0, tb.tw2, true);
-      const unsigned k1 = bitrev(unsigned(r), p.lg1);
-      for (int e = simt::tid(); e < p.M2; e += NT) {
+      fft_tile<T, NT>(re, im, p.lg2, tr, ld, 1, tb.tw2, true);
+      for (int x = simt::tid(); x < tr * p.M2; x += NT) {
+        const int c = x / p.M2, e = x % p.M2;
+        const unsigned k1 = bitrev(unsigned(r0 + c), p.lg1);
         const cpx<T> w = tb.twM[((long long)k1 * e) & (p.M - 1)];
-        row[e] = cmulc(cpx<T>{re[e], im[e]}, w);
+        rows[x] = cmulc(cpx<T>{re[e * ld + c], im[e * ld + c]}, w);
       }
     } else {
-      for (int e = simt::tid(); e < p.M2; e += NT) row[e] = cpx<T>{re[e], im[e]};
+      for (int x = simt::tid(); x < tr * p.M2; x += NT) {
+        const int c = x / p.M2, e = x % p.M2;
+        rows[x] = cpx<T>{re[e * ld + c], im[e * ld + c]};
+      }
     }
     simt::sync_block();
   }

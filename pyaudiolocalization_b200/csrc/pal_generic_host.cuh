@@ -14,8 +14,8 @@ using namespace pal;
 extern std::atomic<unsigned long long>* g_launch_counter;
 
 constexpr int kGT = 256;  // threads per block of every generic kernel
-template <typename T> struct ColTile { static constexpr int TC = 16; };
-template <> struct ColTile<double> { static constexpr int TC = 8; };
+template <typename T> struct ColTile { static constexpr int TC = 16; static constexpr int TR = 16; };
+template <> struct ColTile<double> { static constexpr int TC = 8; static constexpr int TR = 8; };
 
 template <typename T> __global__ void __launch_bounds__(kGT) k_blue_init(BluePlan p, cpx<T>* chirp, cpx<T>* tw1,
                                                                        cpx<T>* tw2, cpx<T>* twM) {
@@ -31,7 +31,7 @@ template <typename T, bool CONV, bool CONJ>
 __global__ void __launch_bounds__(kGT) k_rowpass(BluePlan p, BlueTables<T> tb, long long n_tr, const int* n_tr_dev,
                                                  cpx<T>* buf) {
   extern __shared__ __align__(128) char smem[];
-  rowpass_body<T, kGT, CONV, CONJ>(p, tb, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
+  rowpass_body<T, kGT, ColTile<T>::TR, CONV, CONJ>(p, tb, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
 }
 template <typename T, class Storer>
 __global__ void __launch_bounds__(kGT) k_colpass_inv(BluePlan p, BlueTables<T> tb, Storer st, long long n_tr,
@@ -102,6 +102,11 @@ template <typename T> struct BlueBuffers {
   BlueTables<T> tb() const { return BlueTables<T>{chirp, tw1, tw2, twM, bhat}; }
 };
 
+template <typename T> inline size_t row_smem(const BluePlan& p) {
+  const int tr = std::min(p.M1, ColTile<T>::TR);
+  return 2 * sizeof(T) * size_t(p.M2) * (tr + 1);
+}
+template <typename T> inline int row_units(const BluePlan& p) { return p.M1 / std::min(p.M1, ColTile<T>::TR); }
 template <typename T> inline size_t col_smem(const BluePlan& p) {
   const int tc = std::min(p.M2, ColTile<T>::TC);
   return 2 * sizeof(T) * size_t(p.M1) * tc;
@@ -115,7 +120,7 @@ template <typename T> cudaError_t setup_plan(const BluePlan& p, char*& base, Blu
   bb.twM = reinterpret_cast<cpx<T>*>(base);   base += al(sizeof(cpx<T>) * size_t(p.M));
   bb.bhat = reinterpret_cast<cpx<T>*>(base);  base += al(sizeof(cpx<T>) * size_t(p.M));
   k_blue_init<T><<<std::min(4 * sms, (p.M + kGT - 1) / kGT), kGT, 0, s>>>(p, bb.chirp, bb.tw1, bb.tw2, bb.twM);
-  const size_t cs = col_smem<T>(p), rs = 2 * sizeof(T) * size_t(p.M2);
+  const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadBhat<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignal<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadPhat<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
@@ -124,7 +129,10 @@ template <typename T> cudaError_t setup_plan(const BluePlan& p, char*& base, Blu
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   k_colpass_fwd<T, LoadBhat<T>><<<std::min(tiles, 8 * sms), kGT, cs, s>>>(p, bb.tb(), LoadBhat<T>{p, bb.chirp}, 1, nullptr,
                                                                           bb.bhat);
-  k_rowpass<T, false, false><<<std::min(p.M1, 8 * sms), kGT, rs, s>>>(p, bb.tb(), 1, nullptr, bb.bhat);
+  cudaFuncSetAttribute(k_rowpass<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
+  cudaFuncSetAttribute(k_rowpass<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
+  cudaFuncSetAttribute(k_rowpass<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
+  k_rowpass<T, false, false><<<std::min(row_units<T>(p), 8 * sms), kGT, rs, s>>>(p, bb.tb(), 1, nullptr, bb.bhat);
   count_launch(3);
   return cudaGetLastError();
 }
@@ -176,7 +184,7 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   cpx<T>* spec = reinterpret_cast<cpx<T>*>(base);
   // note: conv rows / corr rows / spectrum rows are addressed densely (t * M, t * n), the al()
   // padding above only makes the regions start aligned
-  const size_t cs = col_smem<T>(p), rs = 2 * sizeof(T) * size_t(p.M2);
+  const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   const BlueTables<T> tb = bb.tb();
   const int c0 = c.n2 - 1;
@@ -189,7 +197,7 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
                        row_list ? row_list + r0 : nullptr};
       k_colpass_fwd<T, LoadSignal<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, ld, nt, nullptr, conv);
-      k_rowpass<T, true, false><<<(unsigned)std::min<long long>(nt * p.M1, 16LL * c.sms), kGT, rs, c.stream>>>(p, tb, nt, nullptr, conv);
+      k_rowpass<T, true, false><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * c.sms), kGT, rs, c.stream>>>(p, tb, nt, nullptr, conv);
       StoreSpectrum<T> st{p, bb.chirp, spec_out + r0 * n};
       k_colpass_inv<T, StoreSpectrum<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, st, nt, nullptr, conv);
@@ -204,7 +212,7 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
       LoadPhat<T> ld{p, bb.chirp, spec_in, c.pairs, c.Mics, c.P, i0, ilist != nullptr};
       k_colpass_fwd<T, LoadPhat<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, ld, nt, nullptr, conv);
-      k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * p.M1, 16LL * c.sms), kGT, rs, c.stream>>>(p, tb, nt, nullptr, conv);
+      k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * c.sms), kGT, rs, c.stream>>>(p, tb, nt, nullptr, conv);
       StoreCorr<T> st{p, bb.chirp, corr};
       k_colpass_inv<T, StoreCorr<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, st, nt, nullptr, conv);

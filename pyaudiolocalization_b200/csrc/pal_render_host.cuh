@@ -84,7 +84,7 @@ inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows 
   cpxf* G = reinterpret_cast<cpxf*>(b);          // rows addressed densely: G[t * (N+1)]
   b += size_t(cap) * g_one;
   cpxf* conv = reinterpret_cast<cpxf*>(b);       // conv[t * M]
-  const size_t cs = col_smem<T>(p), rs = 2 * sizeof(T) * size_t(p.M2);
+  const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   const BlueTables<T> tb = bb.tb();
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadHermitian<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
@@ -92,7 +92,7 @@ inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows 
   // X = fft(base zero-padded, 2N)                                      (signal_processing.py:69)
   k_colpass_fwd<T, LoadSignal<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(
       p, tb, LoadSignal<T>{p, bb.chirp, base, n_base, n_base, n_base, nullptr}, 1, nullptr, conv);
-  k_rowpass<T, true, false><<<std::min(p.M1, 16 * sms), kGT, rs, s>>>(p, tb, 1, nullptr, conv);
+  k_rowpass<T, true, false><<<std::min(row_units<T>(p), 16 * sms), kGT, rs, s>>>(p, tb, 1, nullptr, conv);
   k_colpass_inv<T, StoreSpectrum<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(p, tb, StoreSpectrum<T>{p, bb.chirp, X}, 1, nullptr, conv);
   count_launch(3);
   const int xtiles = (N + 1 + kGT * kXferJ - 1) / (kGT * kXferJ);
@@ -106,7 +106,7 @@ inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows 
     k_transfer<<<(unsigned)std::min<long long>(nt * xtiles, 32LL * sms), kGT, ts, s>>>(X, N, rr, r0, nt, fs, G);
     k_colpass_fwd<T, LoadHermitian<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * sms), kGT, cs, s>>>(
         p, tb, LoadHermitian<T>{p, bb.chirp, G, N}, nt, nullptr, conv);
-    k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * p.M1, 16LL * sms), kGT, rs, s>>>(p, tb, nt, nullptr, conv);
+    k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * sms), kGT, rs, s>>>(p, tb, nt, nullptr, conv);
     k_colpass_inv<T, StoreRender<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * sms), kGT, cs, s>>>(
         p, tb, StoreRender<T>{p, bb.chirp, out, N, n_keep, fade, rr, r0}, nt, nullptr, conv);
     count_launch(4);

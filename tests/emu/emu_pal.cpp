@@ -89,16 +89,17 @@ static void emu_generic_impl(const float* sig, long long B, int Mics, int ld, in
   simt::launch(2, NT, 16, [&](char*) { blue_init_tables_body<T>(p, chirp.data(), tw1.data(), tw2.data(), twM.data()); });
   BlueTables<T> tb{chirp.data(), tw1.data(), tw2.data(), twM.data(), bhat.data()};
   const int tc = std::min(p.M2, TC);
-  const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2);
+  constexpr int TRW = 4;
+  const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2) * (std::min(p.M1, TRW) + 1);
   simt::launch(2, NT, cs, [&](char* sm) { colpass_fwd_body<T, NT, TC>(p, tb, LoadBhat<T>{p, chirp.data()}, 1, bhat.data(), sm); });
-  simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, false, false>(p, tb, 1, bhat.data(), sm); });
+  simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, false, false>(p, tb, 1, bhat.data(), sm); });
   const long long rows = B * Mics, items = B * P;
   std::vector<cpx<T>> conv(size_t(std::max(rows, items)) * p.M), spec(size_t(rows) * n);
   std::vector<T> corr(size_t(items) * n);
   simt::launch(3, NT, cs, [&](char* sm) {
     colpass_fwd_body<T, NT, TC>(p, tb, LoadSignal<T>{p, chirp.data(), sig, ld, n1, n2, nullptr}, rows, conv.data(), sm);
   });
-  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, true, false>(p, tb, rows, conv.data(), sm); });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, false>(p, tb, rows, conv.data(), sm); });
   simt::launch(3, NT, cs, [&](char* sm) {
     colpass_inv_body<T, NT, TC>(p, tb, StoreSpectrum<T>{p, chirp.data(), spec.data()}, rows, conv.data(), sm);
   });
@@ -106,7 +107,7 @@ static void emu_generic_impl(const float* sig, long long B, int Mics, int ld, in
     colpass_fwd_body<T, NT, TC>(p, tb, LoadPhat<T>{p, chirp.data(), spec.data(), pairs, Mics, P, 0, false}, items,
                                 conv.data(), sm);
   });
-  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, true, true>(p, tb, items, conv.data(), sm); });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, true>(p, tb, items, conv.data(), sm); });
   simt::launch(3, NT, cs, [&](char* sm) {
     colpass_inv_body<T, NT, TC>(p, tb, StoreCorr<T>{p, chirp.data(), corr.data()}, items, conv.data(), sm);
   });
@@ -167,15 +168,16 @@ extern "C" void emu_render_scene(const float* base, int n_base, int N, const dou
   simt::launch(2, NT, 16, [&](char*) { blue_init_tables_body<T>(p, chirp.data(), tw1.data(), tw2.data(), twM.data()); });
   BlueTables<T> tb{chirp.data(), tw1.data(), tw2.data(), twM.data(), bhat.data()};
   const int tc = std::min(p.M2, TC);
-  const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2);
+  constexpr int TRW = 4;
+  const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2) * (std::min(p.M1, TRW) + 1);
   simt::launch(2, NT, cs, [&](char* sm) { colpass_fwd_body<T, NT, TC>(p, tb, LoadBhat<T>{p, chirp.data()}, 1, bhat.data(), sm); });
-  simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, false, false>(p, tb, 1, bhat.data(), sm); });
+  simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, false, false>(p, tb, 1, bhat.data(), sm); });
   std::vector<cpx<T>> conv(size_t(n_mics) * p.M), X(p.n);
   std::vector<cpxf> G(size_t(n_mics) * (N + 1));
   simt::launch(3, NT, cs, [&](char* sm) {
     colpass_fwd_body<T, NT, TC>(p, tb, LoadSignal<T>{p, chirp.data(), base, n_base, n_base, n_base, nullptr}, 1, conv.data(), sm);
   });
-  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, true, false>(p, tb, 1, conv.data(), sm); });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, false>(p, tb, 1, conv.data(), sm); });
   simt::launch(3, NT, cs, [&](char* sm) {
     colpass_inv_body<T, NT, TC>(p, tb, StoreSpectrum<T>{p, chirp.data(), X.data()}, 1, conv.data(), sm);
   });
@@ -185,7 +187,7 @@ extern "C" void emu_render_scene(const float* base, int n_base, int N, const dou
   simt::launch(3, NT, cs, [&](char* sm) {
     colpass_fwd_body<T, NT, TC>(p, tb, LoadHermitian<T>{p, chirp.data(), G.data(), N}, n_mics, conv.data(), sm);
   });
-  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, true, true>(p, tb, n_mics, conv.data(), sm); });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, true>(p, tb, n_mics, conv.data(), sm); });
   const int fade = int(0.01 * N);
   simt::launch(3, NT, cs, [&](char* sm) {
     colpass_inv_body<T, NT, TC>(p, tb, StoreRender<T>{p, chirp.data(), out, N, n_keep, fade, rr, 0}, n_mics, conv.data(), sm);

@@ -140,3 +140,45 @@ def test_path_table_batched_matches_per_scene():
         assert mx[s] == t1.max()
         imgs = O.generate_image_sources_iterative(srcs[s], planes, 2, 700.0, CUSTOM_MATERIALS, mics, 0.01)
         assert len(imgs) == k
+
+
+@pytest.mark.parametrize("n1,n2,use_double", [(300, 300, False), (257, 190, False), (140, 333, True), (64, 64, True)])
+def test_generic_bluestein_path_vs_oracle(n1, n2, use_double):
+    """Arbitrary-length GCC-PHAT (Bluestein over tiled two-pass FFTs) against the reference algorithm:
+    float64 sweep bit-exact on the chosen lag, float32 sweep within 1e-4 on the correlation."""
+    rng = np.random.default_rng(n1 * 1000 + n2)
+    x = rng.standard_normal(max(n1, n2) + 40)
+    a = x[7:7 + n1] + 0.1 * rng.standard_normal(n1)
+    b = x[:n2] + 0.1 * rng.standard_normal(n2)
+    ld = max(n1, n2)
+    sig = np.zeros((1, 2, ld), np.float32)
+    sig[0, 0, :n1] = a
+    sig[0, 1, :n2] = b
+    fs, med = 8000.0, 0.01
+    want_td, want_corr, _ = O.get_time_delays_phat(sig[0, 0, :n1].astype(np.float64), sig[0, 1, :n2].astype(np.float64), fs,
+                                                   max_expected_delay=med)
+    wh = O.window_half_width(n1, n2, fs, med)
+    k, _, _, _, _, corr = E.generic_gcc_phat(sig, n1, n2, np.array([[0, 1]], np.int32), wh, O.peak_distance(fs),
+                                              use_double=use_double)
+    assert np.abs(corr[0, 0] - want_corr).max() <= 1e-4 * np.abs(want_corr).max()
+    if use_double:
+        assert O.tdoa_from_index(int(k[0, 0, 0]), n2, fs) == want_td[0]
+
+
+def test_render_scene_emulation_vs_oracle():
+    """Renderer kernels (transfer function, Hermitian Bluestein inverse, fade / trim, normalise +
+    compress) on the host emulation against the oracle port of main.py:66-124."""
+    from tests.golden.make_golden import CUSTOM_MATERIALS, shoebox
+    rng = np.random.default_rng(9)
+    mics = rng.uniform([1, 1, 0.5], [5, 4, 2.5], size=(3, 3))
+    src = rng.uniform([0.5, 0.5, 0.3], [5.5, 4.5, 2.7], size=3)
+    fs, dur, freq, c = 8000.0, 0.05, 600.0, 343.62
+    planes = shoebox(6, 5, 3)
+    imgs = O.generate_image_sources_iterative(src, planes, 1, freq, CUSTOM_MATERIALS, mics, 0.01)
+    tau, gain, total = O.path_table_restated(src, imgs, mics, fs, c, dur, freq, CUSTOM_MATERIALS)
+    base = O.generate_signal("chirp", fs, dur, freq)
+    got = E.render_scene(base, total, tau, gain, fs, int(dur * fs))
+    want = np.array(O.simulate_signals_with_multipath(src, mics, fs, c, duration=dur, signal_type="chirp", freq=freq,
+                                                      reflective_planes=planes, material_properties=CUSTOM_MATERIALS,
+                                                      max_reflections=1, absorption_threshold=0.01))
+    assert np.abs(got - want).max() <= 1e-5
