@@ -119,36 +119,89 @@ PAL_DEV void blue_init_tables_body(BluePlan p, cpx<T>* chirp, cpx<T>* tw1, cpx<T
 // Element (l, c) of the tile sits at l*sl + c*sc.  L = 1 << lg points along l, TC independent
 // transforms along c.  Forward: decimation in frequency, natural in -> bit-reversed out.
 // Inverse: decimation in time with conjugate twiddles, bit-reversed in -> natural out (unscaled).
+// One radix-2 butterfly of either flavour on register values.
+template <typename T> PAL_DEV void bfly_dif(T& ur, T& ui, T& vr, T& vi, cpx<T> w) {   // (u, v) -> (u + v, (u - v) w)
+  const T sr = ur + vr, si = ui + vi;
+  const T dr = ur - vr, di = ui - vi;
+  ur = sr; ui = si;
+  vr = fma_(dr, w.x, -(di * w.y));
+  vi = fma_(dr, w.y, di * w.x);
+}
+template <typename T> PAL_DEV void bfly_dit(T& ur, T& ui, T& vr, T& vi, cpx<T> w) {   // (u, v) -> (u + v conj(w), u - v conj(w))
+  const T tr = fma_(vr, w.x, vi * w.y);
+  const T ti = fma_(vi, w.x, -(vr * w.y));
+  vr = ur - tr; vi = ui - ti;
+  ur = ur + tr; ui = ui + ti;
+}
+
+// Two radix-2 stages are fused into one radix-4 step held in registers (half the block barriers and
+// half the shared-memory traffic); an odd log2 length ends (forward) or starts (inverse) with a
+// single radix-2 stage.
 template <typename T, int NT>
-PAL_DEV void fft_tile(T* re, T* im, int lg, int TC, int sl, int sc, const cpx<T>* tw, bool inverse) {
+PAL_DEV void fft_tile(T* re, T* im, int lg, int TC /* power of two */, int sl, int sc, const cpx<T>* tw, bool inverse) {
   const int L = 1 << lg;
-  const int nb = (L >> 1) * TC;
-  for (int st = 0; st < lg; ++st) {
-    const int hl = inverse ? st : (lg - 1 - st);     // log2(half)
-    const int half = 1 << hl;
-    const int tws = lg - 1 - hl;                     // twiddle stride = L / (2*half)
-    for (int t = simt::tid(); t < nb; t += NT) {
-      const int c = t % TC;
-      const int b = t / TC;
-      const int i = b & (half - 1);
-      const int p = ((b >> hl) << (hl + 1)) + i;
-      const int ap = p * sl + c * sc, aq = (p + half) * sl + c * sc;
-      const cpx<T> w = tw[i << tws];
-      const T ur = re[ap], ui = im[ap], vr = re[aq], vi = im[aq];
-      if (!inverse) {
-        re[ap] = ur + vr;
-        im[ap] = ui + vi;
-        const T dr = ur - vr, di = ui - vi;
-        re[aq] = fma_(dr, w.x, -(di * w.y));
-        im[aq] = fma_(dr, w.y, di * w.x);
-      } else {
-        const T tr = fma_(vr, w.x, vi * w.y);        // v * conj(w)
-        const T ti = fma_(vi, w.x, -(vr * w.y));
-        re[ap] = ur + tr;
-        im[ap] = ui + ti;
-        re[aq] = ur - tr;
-        im[aq] = ui - ti;
+  const int lgc = ilog2(TC);
+  int st = 0;
+  while (st < lg) {
+    const bool pair = (lg - st) >= 2 && !(inverse && (lg & 1) && st == 0);
+    if (!pair) {
+      const int hl = inverse ? st : (lg - 1 - st);     // log2(half)
+      const int half = 1 << hl;
+      const int tws = lg - 1 - hl;                     // twiddle stride = L / (2*half)
+      const int nb = (L >> 1) * TC;
+      for (int t = simt::tid(); t < nb; t += NT) {
+        const int c = t & (TC - 1);
+        const int b = t >> lgc;
+        const int i = b & (half - 1);
+        const int p = ((b >> hl) << (hl + 1)) + i;
+        const int ap = p * sl + c * sc, aq = ap + half * sl;
+        const cpx<T> w = tw[i << tws];
+        T ur = re[ap], ui = im[ap], vr = re[aq], vi = im[aq];
+        if (!inverse) bfly_dif(ur, ui, vr, vi, w); else bfly_dit(ur, ui, vr, vi, w);
+        re[ap] = ur; im[ap] = ui; re[aq] = vr; im[aq] = vi;
       }
+      st += 1;
+    } else {
+      // forward: stages with half = H then H/2 (H = 1 << hl); inverse: half = h then 2h (h = 1 << hl)
+      const int nq = (L >> 2) * TC;
+      if (!inverse) {
+        const int hl = lg - 1 - st;                    // first stage: half = 1 << hl
+        const int q = 1 << (hl - 1);                   // quarter
+        const int tws = lg - 1 - hl;
+        for (int t = simt::tid(); t < nq; t += NT) {
+          const int c = t & (TC - 1);
+          const int b = t >> lgc;
+          const int i = b & (q - 1);
+          const int p = ((b >> (hl - 1)) << (hl + 1)) + i;
+          const int a0 = p * sl + c * sc, a1 = a0 + q * sl, a2 = a0 + 2 * q * sl, a3 = a0 + 3 * q * sl;
+          T x0r = re[a0], x0i = im[a0], x1r = re[a1], x1i = im[a1], x2r = re[a2], x2i = im[a2], x3r = re[a3], x3i = im[a3];
+          bfly_dif(x0r, x0i, x2r, x2i, tw[i << tws]);
+          bfly_dif(x1r, x1i, x3r, x3i, tw[(i + q) << tws]);
+          const cpx<T> w2 = tw[i << (tws + 1)];
+          bfly_dif(x0r, x0i, x1r, x1i, w2);
+          bfly_dif(x2r, x2i, x3r, x3i, w2);
+          re[a0] = x0r; im[a0] = x0i; re[a1] = x1r; im[a1] = x1i; re[a2] = x2r; im[a2] = x2i; re[a3] = x3r; im[a3] = x3i;
+        }
+      } else {
+        const int hl = st;                             // first stage: half = h = 1 << hl, second: 2h
+        const int h = 1 << hl;
+        const int tws = lg - 1 - hl;
+        for (int t = simt::tid(); t < nq; t += NT) {
+          const int c = t & (TC - 1);
+          const int b = t >> lgc;
+          const int i = b & (h - 1);
+          const int p = ((b >> hl) << (hl + 2)) + i;
+          const int a0 = p * sl + c * sc, a1 = a0 + h * sl, a2 = a0 + 2 * h * sl, a3 = a0 + 3 * h * sl;
+          T x0r = re[a0], x0i = im[a0], x1r = re[a1], x1i = im[a1], x2r = re[a2], x2i = im[a2], x3r = re[a3], x3i = im[a3];
+          const cpx<T> w1 = tw[i << tws];
+          bfly_dit(x0r, x0i, x1r, x1i, w1);
+          bfly_dit(x2r, x2i, x3r, x3i, w1);
+          bfly_dit(x0r, x0i, x2r, x2i, tw[i << (tws - 1)]);
+          bfly_dit(x1r, x1i, x3r, x3i, tw[(i + h) << (tws - 1)]);
+          re[a0] = x0r; im[a0] = x0i; re[a1] = x1r; im[a1] = x1i; re[a2] = x2r; im[a2] = x2i; re[a3] = x3r; im[a3] = x3i;
+        }
+      }
+      st += 2;
     }
     simt::sync_block();
   }
@@ -252,6 +305,7 @@ template <typename T> struct StoreRaw {           // the chirp spectrum itself (
 template <typename T, int NT, int TC, class Loader>
 PAL_DEV void colpass_fwd_body(BluePlan p, BlueTables<T> tb, Loader load, long long n_tr, cpx<T>* buf, char* smem) {
   const int tc = p.M2 < TC ? p.M2 : TC;
+  const int lgt = ilog2(tc);
   const int tiles = p.M2 / tc;
   T* re = reinterpret_cast<T*>(smem);
   T* im = re + p.M1 * tc;
@@ -259,7 +313,7 @@ PAL_DEV void colpass_fwd_body(BluePlan p, BlueTables<T> tb, Loader load, long lo
     const long long t = u / tiles;
     const int j20 = int(u % tiles) * tc;
     for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
-      const int j1 = e / tc, c = e % tc;
+      const int j1 = e >> lgt, c = e & (tc - 1);
       const cpx<T> a = load(t, j1 * p.M2 + j20 + c);
       re[e] = a.x;
       im[e] = a.y;
@@ -268,7 +322,7 @@ PAL_DEV void colpass_fwd_body(BluePlan p, BlueTables<T> tb, Loader load, long lo
     fft_tile<T, NT>(re, im, p.lg1, tc, tc, 1, tb.tw1, false);
     cpx<T>* out = buf + t * p.M;
     for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
-      const int r = e / tc, c = e % tc;
+      const int r = e >> lgt, c = e & (tc - 1);
       const unsigned k1 = bitrev(unsigned(r), p.lg1);
       const int j2 = j20 + c;
       const cpx<T> w = tb.twM[((long long)k1 * j2) & (p.M - 1)];
@@ -295,7 +349,7 @@ PAL_DEV void rowpass_body(BluePlan p, BlueTables<T> tb, long long n_tr, cpx<T>* 
     const int r0 = int(u % tiles) * tr;
     cpx<T>* rows = buf + t * p.M + (long long)r0 * p.M2;
     for (int x = simt::tid(); x < tr * p.M2; x += NT) {
-      const int c = x / p.M2, e = x % p.M2;
+      const int c = x >> p.lg2, e = x & (p.M2 - 1);
       const cpx<T> v = rows[x];
       re[e * ld + c] = v.x;
       im[e * ld + c] = v.y;
@@ -305,7 +359,7 @@ PAL_DEV void rowpass_body(BluePlan p, BlueTables<T> tb, long long n_tr, cpx<T>* 
     if (CONV) {
       const cpx<T>* bh = tb.bhat + (long long)r0 * p.M2;
       for (int x = simt::tid(); x < tr * p.M2; x += NT) {
-        const int c = x / p.M2, e = x % p.M2;
+        const int c = x >> p.lg2, e = x & (p.M2 - 1);
         const cpx<T> b = bh[x];
         const cpx<T> a{re[e * ld + c], im[e * ld + c]};
         const cpx<T> v = CONJ_BHAT ? cmulc(a, b) : cmul(a, b);
@@ -315,14 +369,14 @@ PAL_DEV void rowpass_body(BluePlan p, BlueTables<T> tb, long long n_tr, cpx<T>* 
       simt::sync_block();
       fft_tile<T, NT>(re, im, p.lg2, tr, ld, 1, tb.tw2, true);
       for (int x = simt::tid(); x < tr * p.M2; x += NT) {
-        const int c = x / p.M2, e = x % p.M2;
+        const int c = x >> p.lg2, e = x & (p.M2 - 1);
         const unsigned k1 = bitrev(unsigned(r0 + c), p.lg1);
         const cpx<T> w = tb.twM[((long long)k1 * e) & (p.M - 1)];
         rows[x] = cmulc(cpx<T>{re[e * ld + c], im[e * ld + c]}, w);
       }
     } else {
       for (int x = simt::tid(); x < tr * p.M2; x += NT) {
-        const int c = x / p.M2, e = x % p.M2;
+        const int c = x >> p.lg2, e = x & (p.M2 - 1);
         rows[x] = cpx<T>{re[e * ld + c], im[e * ld + c]};
       }
     }
@@ -335,6 +389,7 @@ template <typename T, int NT, int TC, class Storer>
 PAL_DEV void colpass_inv_body(BluePlan p, BlueTables<T> tb, Storer store, long long n_tr, const cpx<T>* buf,
                               char* smem) {
   const int tc = p.M2 < TC ? p.M2 : TC;
+  const int lgt = ilog2(tc);
   const int tiles = p.M2 / tc;
   T* re = reinterpret_cast<T*>(smem);
   T* im = re + p.M1 * tc;
@@ -344,7 +399,7 @@ PAL_DEV void colpass_inv_body(BluePlan p, BlueTables<T> tb, Storer store, long l
     const int j20 = int(u % tiles) * tc;
     const cpx<T>* in = buf + t * p.M;
     for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
-      const int r = e / tc, c = e % tc;
+      const int r = e >> lgt, c = e & (tc - 1);
       const cpx<T> v = in[(long long)r * p.M2 + j20 + c];
       re[e] = v.x;
       im[e] = v.y;
@@ -352,7 +407,7 @@ PAL_DEV void colpass_inv_body(BluePlan p, BlueTables<T> tb, Storer store, long l
     simt::sync_block();
     fft_tile<T, NT>(re, im, p.lg1, tc, tc, 1, tb.tw1, true);
     for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
-      const int j1 = e / tc, c = e % tc;
+      const int j1 = e >> lgt, c = e & (tc - 1);
       store(t, j1 * p.M2 + j20 + c, cpx<T>{re[e] * inv_m, im[e] * inv_m});
     }
     simt::sync_block();

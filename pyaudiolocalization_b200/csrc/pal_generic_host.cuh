@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include "pal_bluestein.cuh"
 
@@ -61,6 +62,13 @@ __global__ void k_rows_of_items(const int* item_list, const int* count, const in
 }
 
 inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
+inline long long conv_chunk_bytes() {
+  static const long long v = [] {
+    const char* e = std::getenv("PAL_CONV_CHUNK_MB");     // tuning switch
+    return (long long)(e ? std::max(1, atoi(e)) : 1 << 20) << 20;   // default: no cap (measured: larger launches win)
+  }();
+  return v;
+}
 
 template <typename T> struct GenericLayout {
   BluePlan p;
@@ -172,6 +180,8 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   const long long total_items = list ? n_list : c.B * c.P;
   const long long min_rows = list ? 2 : c.Mics;
   long long tr_cap = std::max<long long>(1, std::min<long long>(2048, (long long)((rem / 4) / L.per_tr)));
+  // optional cap on the convolution buffers of one chunk (PAL_CONV_CHUNK_MB; L2-sized chunks measured slower)
+  tr_cap = std::max<long long>(1, std::min<long long>(tr_cap, conv_chunk_bytes() / (long long)(sizeof(cpx<T>) * size_t(p.M))));
   tr_cap = std::min<long long>(tr_cap, std::max<long long>(total_items, list ? 2LL * n_list : c.B * c.Mics));
   while (tr_cap > 1 && rem < size_t(tr_cap) * L.per_tr + size_t(min_rows) * L.per_row) tr_cap /= 2;
   cpx<T>* conv = reinterpret_cast<cpx<T>*>(base);

@@ -80,7 +80,8 @@ inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows 
   cpxf* X = reinterpret_cast<cpxf*>(b);
   b += al(sizeof(cpxf) * size_t(2 * N));
   const size_t g_one = al(sizeof(cpxf) * size_t(N + 1)), conv_one = al(sizeof(cpxf) * size_t(p.M));
-  const long long cap = std::max<long long>(1, std::min<long long>(n_rows, (long long)((ws_bytes - size_t(b - ws)) / (g_one + conv_one))));
+  long long cap = std::max<long long>(1, std::min<long long>(n_rows, (long long)((ws_bytes - size_t(b - ws)) / (g_one + conv_one))));
+  cap = std::max<long long>(1, std::min<long long>(cap, conv_chunk_bytes() / (long long)conv_one));   // chunk stays in L2
   cpxf* G = reinterpret_cast<cpxf*>(b);          // rows addressed densely: G[t * (N+1)]
   b += size_t(cap) * g_one;
   cpxf* conv = reinterpret_cast<cpxf*>(b);       // conv[t * M]
