@@ -260,13 +260,14 @@ def run_gpu_arm(args):
         host = torch.empty((frames_n, MICS, NS), dtype=torch.float32, pin_memory=True)
         host.copy_(frames)
         torch.cuda.synchronize()
-        r = pal.gcc_phat.gcc_phat_tdoa_from_host(host, FS, MED, chunk_frames=args.e2e_chunk)   # warm-up
+        out_host = pal.gcc_phat.alloc_host_outputs(frames_n, PAIRS)      # pinned result buffers, re-used every step
+        r = pal.gcc_phat.gcc_phat_tdoa_from_host(host, FS, MED, chunk_frames=args.e2e_chunk, out_host=out_host)   # warm-up
         assert np.array_equal(r["k_idx"], out.k_idx.cpu().numpy())
         barrier()
         e_steps = max(1, min(args.steps, 3))
         w0 = time.perf_counter()
         for _ in range(e_steps):
-            r = pal.gcc_phat.gcc_phat_tdoa_from_host(host, FS, MED, chunk_frames=args.e2e_chunk)
+            r = pal.gcc_phat.gcc_phat_tdoa_from_host(host, FS, MED, chunk_frames=args.e2e_chunk, out_host=out_host)
         barrier()
         e_sec = (time.perf_counter() - w0) / e_steps
         if world > 1:
@@ -287,6 +288,13 @@ def run_gpu_arm(args):
     except OSError:
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    traffic, traffic_src = None, None
+    try:   # DRAM bytes of the pair kernel from the committed ncu --set full capture, scaled to this launch size
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+        traffic = float(tj["dram_bytes_per_frame"]) * frames_n
+        traffic_src = tj["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     ms_step = ms / args.steps
     value = world * frames_n * PAIRS / (ms_step * 1e-3)
     achieved = ALG_BYTES_PER_FRAME * frames_n / (kernel_ms[1] * 1e-3) / 1e9
@@ -312,7 +320,9 @@ def run_gpu_arm(args):
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": None,
+                     "frac": achieved / peak_gbs, "traffic": traffic,
+                     "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "traffic_source": traffic_src,
                      "kernel": "k_pair4095_fast (fused cross-spectrum + PHAT + inverse DFT-4095 + peak pick)",
                      "kernel_ms": kernel_ms[1], "forward_ms": kernel_ms[0], "refine_ms": kernel_ms[2],
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",

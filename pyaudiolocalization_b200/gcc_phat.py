@@ -156,8 +156,16 @@ def tdoa_seconds_device(k_idx: torch.Tensor, n_second: int, fs: float, out: Opti
     return out
 
 
+def alloc_host_outputs(b: int, p: int, num_peaks: int = 1) -> dict:
+    """Pinned host buffers for gcc_phat_tdoa_from_host(out_host=...).  Pinning memory is slow (tens of
+    milliseconds per 100 MB), so a caller that processes batch after batch allocates them once."""
+    return {"k_idx": torch.empty((b, p, num_peaks), dtype=torch.int32, pin_memory=True),
+            "gmax": torch.empty((b, p), dtype=torch.float32, pin_memory=True),
+            "tdoa": torch.empty((b, p, num_peaks), dtype=torch.float64, pin_memory=True)}
+
+
 def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_delay: Optional[float] = None,
-                            chunk_frames: int = 256, device=None, **kw) -> dict:
+                            chunk_frames: int = 256, device=None, out_host: Optional[dict] = None, **kw) -> dict:
     """End-to-end call with HOST buffers: frames_host [B, M, N] float32 on the CPU (pinned memory
     makes the copies asynchronous).  Three streams form a pipeline over chunks of frames: host->device
     copy of chunk c+1, kernels of chunk c, device->host copy of the results of chunk c-1 (lag
@@ -184,9 +192,11 @@ def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_d
                     torch.empty((b, p), dtype=torch.float32, device=dev),
                     torch.empty((b, p), dtype=torch.int32, device=dev), None, n, float(fs))
     td_dev = torch.empty((b, p, num_peaks), dtype=torch.float64, device=dev)
-    k_host = torch.empty(res.k_idx.shape, dtype=torch.int32, pin_memory=True)
-    g_host = torch.empty(res.gmax.shape, dtype=torch.float32, pin_memory=True)
-    td_host = torch.empty(td_dev.shape, dtype=torch.float64, pin_memory=True)
+    if out_host is None:
+        out_host = alloc_host_outputs(b, p, num_peaks)
+    k_host, g_host, td_host = out_host["k_idx"], out_host["gmax"], out_host["tdoa"]
+    if tuple(k_host.shape) != (b, p, num_peaks) or tuple(g_host.shape) != (b, p) or tuple(td_host.shape) != (b, p, num_peaks):
+        raise ValueError("out_host buffers do not match [B, P, num_peaks] / [B, P]")
     copy_s, comp_s, back_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     cur = torch.cuda.current_stream(dev)
     for s_ in (copy_s, comp_s, back_s):
