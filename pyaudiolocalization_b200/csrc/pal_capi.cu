@@ -275,7 +275,7 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
     const float* sig = sig_dev + f0 * M * kFrame2048;
     {
       const long long units = (long long)nb * ((M + 1) / 2);
-      const int gf = (int)std::min<long long>(units, (long long)di.sms * 6);
+      const int gf = (int)std::min<long long>(units, (long long)di.sms * 4);   // 48 KB of shared memory per CTA: 4 CTAs per SM
       {
         ProfScope ps(1, stream);
         k_fwd4095<<<gf, kFwdThreads, fwd_smem, stream>>>(sig, M, units, spec);

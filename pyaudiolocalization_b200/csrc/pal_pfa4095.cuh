@@ -99,11 +99,38 @@ template <typename T> PAL_DEV void phat_bin(T ar, T ai, T br, T bi, T inv_n, T& 
 // ---------------------------------------------------------------- forward kernel
 // grid: one block per (frame, channel pair).  sig: [B][M][2048] float32.
 // spec: [B][M][65][32] complex64 -- S[e(r,q)] with e = (2080 r + 2016 q) mod 4095.
-struct FwdSmem {
-  float re[4096];
-  float im[4096];
+// Packed f32x2 arithmetic: the two real channels of a pair travel as (re, im) of one complex
+// sequence, one 64-bit shared-memory access and one FFMA2/FADD2 per complex operation.
+struct alignas(16) FwdSmem {
+  float stage[2][kFrame2048];   // TMA landing zone: the two raw frames
+  f2 z[4096];                   // the complex sequence, transformed in place
   mbar_t bar;
 };
+
+// in-place PFA stage on packed complex data; FIRST: gather the inputs from the raw frames instead
+// (z[k] = x0[k] + i x1[k] for k < 2048, zero beyond)
+template <int F, int NT, bool FIRST> PAL_DEV void pfa_stage_p(f2* z, const float* x0, const float* x1, bool two) {
+  constexpr int U = pfa_u(F);
+  for (int g = simt::tid(); g < kN4095 / F; g += NT) {
+    f2 x[F];
+    int idx = F * g;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      if (FIRST) x[j] = (idx < kFrame2048) ? f2_make(x0[idx], two ? x1[idx] : 0.f) : f2_make(0.f, 0.f);
+      else x[j] = z[idx];
+      idx += U;
+      if (idx >= kN4095) idx -= kN4095;
+    }
+    dft_odd_p<F, -1>(x);
+    idx = F * g;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      z[idx] = x[j];
+      idx += U;
+      if (idx >= kN4095) idx -= kN4095;
+    }
+  }
+}
 
 template <int NT>
 PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil(M/2) */, cpxf* spec, char* smem_raw) {
@@ -118,31 +145,38 @@ PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil
     const int ch0 = 2 * int(unit % cpairs);
     const bool two = (ch0 + 1) < M;
     const float* row0 = sig + (frame * M + ch0) * kFrame2048;
-    // TMA bulk load of the signal frame(s): two contiguous 8 KB rows straight into the re/im planes
+    // TMA bulk load of the signal frame(s): two contiguous 8 KB rows
     if (tid == 0) {
       simt::fence_async_smem();
       simt::mbar_expect_tx(&sm->bar, two ? 2u * kFrame2048 * 4u : kFrame2048 * 4u);
-      simt::bulk_g2s(sm->re, row0, kFrame2048 * 4u, &sm->bar);
-      if (two) simt::bulk_g2s(sm->im, row0 + kFrame2048, kFrame2048 * 4u, &sm->bar);
+      simt::bulk_g2s(sm->stage[0], row0, kFrame2048 * 4u, &sm->bar);
+      if (two) simt::bulk_g2s(sm->stage[1], row0 + kFrame2048, kFrame2048 * 4u, &sm->bar);
     }
-    for (int k = kFrame2048 + tid; k < 4096; k += NT) { sm->re[k] = 0.f; sm->im[k] = 0.f; }
-    if (!two)
-      for (int k = tid; k < kFrame2048; k += NT) sm->im[k] = 0.f;
     simt::mbar_wait(&sm->bar, parity);
     parity ^= 1u;
+    pfa_stage_p<13, NT, true>(sm->z, sm->stage[0], sm->stage[1], two);
     simt::sync_block();
-    pfa4095_inplace<-1, float, NT>(sm->re, sm->im);
-    cpxf* o0 = spec + (frame * M + ch0) * kSpecSlots;
-    cpxf* o1 = o0 + kSpecSlots;
+    pfa_stage_p<9, NT, false>(sm->z, nullptr, nullptr, two);
+    simt::sync_block();
+    pfa_stage_p<7, NT, false>(sm->z, nullptr, nullptr, two);
+    simt::sync_block();
+    pfa_stage_p<5, NT, false>(sm->z, nullptr, nullptr, two);
+    simt::sync_block();
+    f2* o0 = reinterpret_cast<f2*>(spec + (frame * M + ch0) * kSpecSlots);
+    f2* o1 = o0 + kSpecSlots;
     for (int o = tid; o < kSpecSlots; o += NT) {
       const int q = o >> 5, r = o & 31;
       const int e = Idx4095::elem(r, q);
       const int L = Pfa4095::loc(e);
       const int L2 = (L == 0) ? 0 : kN4095 - L;
-      float s1r, s1i, s2r, s2i;
-      split_two_real(sm->re[L], sm->im[L], sm->re[L2], sm->im[L2], s1r, s1i, s2r, s2i);
-      o0[o] = cpxf{s1r, s1i};
-      if (two) o1[o] = cpxf{s2r, s2i};
+      // Z = DFT(x1 + i x2): S1[e] = (Z[e] + conj(Z[n-e])) / 2, S2[e] = (Z[e] - conj(Z[n-e])) / (2i)
+      const f2 zl = sm->z[L], zm = f2_conj(sm->z[L2]);
+      const f2 half = f2_bcast(0.5f);
+      o0[o] = f2_mul(f2_add(zl, zm), half);
+      if (two) {
+        const f2 d = f2_mul(f2_sub(zl, zm), half);       // i * S2
+        o1[o] = f2_make(f2_hi(d), -f2_lo(d));             // S2 = -i * d
+      }
     }
     simt::sync_block();
   }
