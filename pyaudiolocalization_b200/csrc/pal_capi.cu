@@ -75,6 +75,28 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1)
                                              flags, corr_out, smem);
 }
 
+#ifndef PAL_TMEM_WARPS
+#define PAL_TMEM_WARPS 12
+#endif
+constexpr int kTmemWarps = PAL_TMEM_WARPS;   // warps per CTA of the TMEM-assisted pair kernel (3 per scheduler)
+template <bool WRITE_CORR>
+__global__ void __launch_bounds__(kTmemWarps * 32, 1)
+    k_pair4095_tmem(const cpxf* __restrict__ spec, const int* __restrict__ pairs, int M, int P, long long n_items,
+                    int win_half, int dist, float eps, int* __restrict__ k_idx, float* __restrict__ peak,
+                    float* __restrict__ gmax, unsigned* __restrict__ flags, float* __restrict__ corr_out) {
+  extern __shared__ __align__(128) char smem[];
+  pair4095_tmem_body<kTmemWarps, WRITE_CORR>(spec, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax, flags,
+                                             corr_out, smem);
+}
+// which fused pair kernel runs (read once): PAL_PAIR_KERNEL=regs | tmem
+bool use_tmem_kernel() {
+  static const bool on = [] {
+    const char* e = std::getenv("PAL_PAIR_KERNEL");
+    return e ? (e[0] == 't') : false;
+  }();
+  return on;
+}
+
 template <typename T, bool FROM_SPECTRA>
 __global__ void __launch_bounds__(kExactThreads, 1)
     k_pair4095_exact(const float* __restrict__ sig, const cpxf* __restrict__ spec, const int* __restrict__ pairs,
@@ -251,6 +273,9 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
   const size_t exd_smem = sizeof(ExactSmem<double>);
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+  const size_t tmem_smem = kTmemWarps * sizeof(FastWarpSmem) + 16;
+  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_tmem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmem_smem));
+  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_tmem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmem_smem));
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_exact<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exd_smem));
   PAL_CUDA(cudaFuncSetAttribute(k_fwd4095, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
 
@@ -285,10 +310,18 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
       float* corr = corr_opt_dev ? corr_opt_dev + item0 * kN4095 : nullptr;
       {
         ProfScope ps(2, stream);
-        auto kern = corr ? k_pair4095_fast<true> : k_pair4095_fast<false>;
-        kern<<<gp, kFastWarps * 32, fast_smem, stream>>>(spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist,
-                                                         prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
-                                                         gmax_dev + item0, flags_dev + item0, corr);
+        if (use_tmem_kernel()) {
+          const int gt = (int)std::min<long long>((n_items + kTmemWarps - 1) / kTmemWarps, (long long)di.sms);
+          auto kern = corr ? k_pair4095_tmem<true> : k_pair4095_tmem<false>;
+          kern<<<gt, kTmemWarps * 32, tmem_smem, stream>>>(spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist,
+                                                           prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
+                                                           gmax_dev + item0, flags_dev + item0, corr);
+        } else {
+          auto kern = corr ? k_pair4095_fast<true> : k_pair4095_fast<false>;
+          kern<<<gp, kFastWarps * 32, fast_smem, stream>>>(spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist,
+                                                           prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
+                                                           gmax_dev + item0, flags_dev + item0, corr);
+        }
       }
       ++g_launches;
       if (prm->refine) {

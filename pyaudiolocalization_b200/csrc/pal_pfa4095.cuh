@@ -365,6 +365,136 @@ PAL_DEV int warp_max_s32(int v) {
 #endif
 }
 
+// Everything the peak pick of the fast kernels needs besides the row itself.
+struct FastPick {
+  int lo, hi, g_lo, g_hi, dist;
+  float eps_s, mean_bound, inv_n;
+};
+PAL_DEV FastPick make_fast_pick(int win_half, int dist, float eps) {
+  FastPick k;
+  k.inv_n = 1.0f / float(kN4095);
+  k.eps_s = eps * float(kN4095);       // tolerance in the unscaled row
+  // mean|c| <= rms(c) <= 1/sqrt(n) by Parseval (|R| <= 1 after PHAT); in the unscaled row: sqrt(n).
+  // A winner above this bound is above mean|c| whatever the row looks like (utils.py:155,166).
+  k.mean_bound = 64.0f;                // sqrt(4095) = 63.99 rounded up
+  const int c0 = kFrame2048 - 1;
+  k.lo = 1; k.hi = kN4095 - 2;
+  if (win_half >= 0) {
+    k.lo = (c0 - win_half > 1) ? c0 - win_half : 1;
+    k.hi = (c0 + win_half < kN4095 - 2) ? c0 + win_half : kN4095 - 2;
+  } else if (win_half < -1) {
+    k.lo = 1; k.hi = 0;
+  }
+  // window split into 16-byte groups [g_lo, g_hi) plus at most 3 + 3 edge samples
+  k.g_lo = (k.lo + 3) & ~3;
+  k.g_hi = (k.hi + 1) & ~3;
+  k.dist = dist;
+  return k;
+}
+
+// Peak pick (num_peaks = 1) of one unscaled correlation row in shared memory by one warp.
+template <bool WRITE_CORR>
+PAL_DEV void fast_pick_row(const float* c, long long item, float gm, int lane, const FastPick& pk, int* k_idx, float* peak,
+                           float* gmax, unsigned* flags, float* corr_out) {
+  const int lo = pk.lo, hi = pk.hi, g_lo = pk.g_lo, g_hi = pk.g_hi, dist = pk.dist;
+  const float eps_s = pk.eps_s, mean_bound = pk.mean_bound, inv_n = pk.inv_n;
+  if (WRITE_CORR) {
+    float* dst = corr_out + item * kN4095;
+    for (int k = lane; k < kN4095; k += 32) dst[k] = c[k] * inv_n;
+  }
+  gm = warp_max_f32(gm);
+
+  // largest and second largest SAMPLE of the window (vectorised, no neighbour tests): the
+  // largest one is the answer whenever it is a strict local maximum, which is then verified
+  float b1 = kNegBig, b2 = kNegBig;
+  int gsel = -1;
+  for (int g = g_lo + 4 * lane; g < g_hi; g += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(c + g);
+    const float m01 = fmaxf(v.x, v.y), n01 = fminf(v.x, v.y);
+    const float m23 = fmaxf(v.z, v.w), n23 = fminf(v.z, v.w);
+    const float m = fmaxf(m01, m23);
+    const float s4 = fmaxf(fminf(m01, m23), fmaxf(n01, n23));     // second largest of the four
+    b2 = fmaxf(b2, fmaxf(fminf(b1, m), s4));
+    if (m > b1) gsel = g;
+    b1 = fmaxf(b1, m);
+  }
+  int ksel = -1;
+  if (gsel >= 0) {
+    const float4 v = *reinterpret_cast<const float4*>(c + gsel);
+    ksel = gsel + ((v.w == b1) ? 3 : (v.z == b1) ? 2 : (v.y == b1) ? 1 : 0);
+  }
+  if (lane < 6) {                      // the <= 3 + 3 samples outside the aligned groups
+    const int k = (lane < 3) ? lo + lane : g_hi + (lane - 3);
+    const bool ok = (lane < 3) ? (k < g_lo && k <= hi) : (k <= hi && g_hi >= g_lo);
+    if (ok) {
+      const float v = c[k];
+      b2 = fmaxf(b2, fminf(b1, v));
+      if (v > b1) ksel = k;
+      b1 = fmaxf(b1, v);
+    }
+  }
+  float bv = warp_max_f32(b1);
+  int bi = warp_max_s32((b1 == bv) ? ksel : -1);
+  float cand2 = warp_max_f32((ksel == bi) ? b2 : b1);
+  float pl = kNegBig;
+  if (bi >= 0 && !(c[bi - 1] < bv && bv > c[bi + 1])) window_scan_slow(c, lo, hi, lane, bv, bi, cand2, pl);
+
+  unsigned fl = 0;
+  int kbest;
+  float hbest;
+  if (bi >= 0 && bv >= mean_bound + eps_s) {
+    kbest = bi;
+    hbest = bv;
+    if (cand2 >= bv - eps_s) fl |= PAL_FLAG_NEAR_TIE;
+    if (pl >= bv - eps_s) fl |= PAL_FLAG_PLATEAU;
+    // Anything within `dist` samples that is as high as the winner (up to eps) needs the full
+    // greedy resolution of the distance rule -> exact kernel.  Samples inside the window are
+    // already covered by cand2; only a winner close to a window edge has neighbours outside.
+    if (bi - dist < lo || bi + dist > hi) {
+      bool hit = false;
+      for (int o = -dist + lane; o <= dist; o += 32) {
+        const int q = bi + o;
+        if (o != 0 && q >= 0 && q < kN4095 && c[q] >= bv - eps_s) hit = true;
+      }
+      if (simt::ballot(hit)) fl |= PAL_FLAG_CHAIN;
+    }
+  } else if (bi >= 0) {
+    // winner not clearly above mean|c|: the median / fallback logic decides -> exact kernel
+    kbest = bi;
+    hbest = bv;
+    fl |= PAL_FLAG_NEAR_TIE;
+  } else {
+    // no local maximum in the window: unbounded first argmax (utils.py:168-172)
+    int gi = 0x7fffffff;
+    int near = 0;
+    bool nonzero = false;
+    for (int k = lane; k < kN4095; k += 32) {
+      const float v = c[k];
+      if (v == gm && k < gi) gi = k;
+      if (v >= gm - eps_s) ++near;
+      nonzero |= (v != 0.f);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const int og = simt::shfl_xor(gi, m);
+      gi = og < gi ? og : gi;
+      near += simt::shfl_xor(near, m);
+    }
+    kbest = gi;
+    hbest = gm;
+    fl |= PAL_FLAG_FALLBACK_ARGMAX;
+    const bool all_zero = simt::ballot(nonzero) == 0u;
+    if (near > 1 && !all_zero) fl |= PAL_FLAG_NEAR_TIE;
+    if (pl > kNegBig && !all_zero) fl |= PAL_FLAG_PLATEAU;
+  }
+  if (lane == 0) {
+    k_idx[item] = kbest;
+    peak[item] = hbest * inv_n;
+    gmax[item] = gm * inv_n;
+    flags[item] = fl;
+  }
+}
+
 // Bins of the NEXT pair whose spectra are fetched into registers before the peak pick of the current
 // pair starts (the pick needs few registers and ~2000 cycles: it hides the L2 latency completely).
 #ifndef PAL_PREFETCH_BINS
@@ -384,22 +514,7 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
   using P63 = Pfa2<7, 9>;
   const int lane = simt::lane();
   FastWarpSmem* sm = reinterpret_cast<FastWarpSmem*>(smem_raw) + simt::warp();
-  const float inv_n = 1.0f / float(kN4095);
-  const float eps_s = eps * float(kN4095);       // tolerance in the unscaled row
-  // mean|c| <= rms(c) <= 1/sqrt(n) by Parseval (|R| <= 1 after PHAT); in the unscaled row: sqrt(n).
-  // A winner above this bound is above mean|c| whatever the row looks like (utils.py:155,166).
-  const float mean_bound = 64.0f;                // sqrt(4095) = 63.99 rounded up
-  const int c0 = kFrame2048 - 1;
-  int lo = 1, hi = kN4095 - 2;
-  if (win_half >= 0) {
-    lo = (c0 - win_half > 1) ? c0 - win_half : 1;
-    hi = (c0 + win_half < kN4095 - 2) ? c0 + win_half : kN4095 - 2;
-  } else if (win_half < -1) {
-    lo = 1; hi = 0;
-  }
-  // window split into 16-byte groups [g_lo, g_hi) plus at most 3 + 3 edge samples
-  const int g_lo = (lo + 3) & ~3;
-  const int g_hi = (hi + 1) & ~3;
+  const FastPick pk = make_fast_pick(win_half, dist, eps);
   // scatter bases: output k = (63 kq + 65 kr) mod 4095 of columns kq = lane+1 and lane+33;
   // p?w are the same bases pre-wrapped by -4095 so that every store is [base + immediate]
   const int b0 = 63 * (lane + 1);
@@ -572,106 +687,244 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
     simt::sync_warp();
 
     // ---- peak pick (num_peaks = 1), utils.py:140-181 in the reduced form ----------------
-    const float* c = sm->corr;
-    if (WRITE_CORR) {
-      float* dst = corr_out + item * kN4095;
-      for (int k = lane; k < kN4095; k += 32) dst[k] = c[k] * inv_n;
-    }
-    gm = warp_max_f32(gm);
-
-    // largest and second largest SAMPLE of the window (vectorised, no neighbour tests): the
-    // largest one is the answer whenever it is a strict local maximum, which is then verified
-    float b1 = kNegBig, b2 = kNegBig;
-    int gsel = -1;
-    for (int g = g_lo + 4 * lane; g < g_hi; g += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(c + g);
-      const float m01 = fmaxf(v.x, v.y), n01 = fminf(v.x, v.y);
-      const float m23 = fmaxf(v.z, v.w), n23 = fminf(v.z, v.w);
-      const float m = fmaxf(m01, m23);
-      const float s4 = fmaxf(fminf(m01, m23), fmaxf(n01, n23));     // second largest of the four
-      b2 = fmaxf(b2, fmaxf(fminf(b1, m), s4));
-      if (m > b1) gsel = g;
-      b1 = fmaxf(b1, m);
-    }
-    int ksel = -1;
-    if (gsel >= 0) {
-      const float4 v = *reinterpret_cast<const float4*>(c + gsel);
-      ksel = gsel + ((v.w == b1) ? 3 : (v.z == b1) ? 2 : (v.y == b1) ? 1 : 0);
-    }
-    if (lane < 6) {                      // the <= 3 + 3 samples outside the aligned groups
-      const int k = (lane < 3) ? lo + lane : g_hi + (lane - 3);
-      const bool ok = (lane < 3) ? (k < g_lo && k <= hi) : (k <= hi && g_hi >= g_lo);
-      if (ok) {
-        const float v = c[k];
-        b2 = fmaxf(b2, fminf(b1, v));
-        if (v > b1) ksel = k;
-        b1 = fmaxf(b1, v);
-      }
-    }
-    float bv = warp_max_f32(b1);
-    int bi = warp_max_s32((b1 == bv) ? ksel : -1);
-    float cand2 = warp_max_f32((ksel == bi) ? b2 : b1);
-    float pl = kNegBig;
-    if (bi >= 0 && !(c[bi - 1] < bv && bv > c[bi + 1])) window_scan_slow(c, lo, hi, lane, bv, bi, cand2, pl);
-
-    unsigned fl = 0;
-    int kbest;
-    float hbest;
-    if (bi >= 0 && bv >= mean_bound + eps_s) {
-      kbest = bi;
-      hbest = bv;
-      if (cand2 >= bv - eps_s) fl |= PAL_FLAG_NEAR_TIE;
-      if (pl >= bv - eps_s) fl |= PAL_FLAG_PLATEAU;
-      // Anything within `dist` samples that is as high as the winner (up to eps) needs the full
-      // greedy resolution of the distance rule -> exact kernel.  Samples inside the window are
-      // already covered by cand2; only a winner close to a window edge has neighbours outside.
-      if (bi - dist < lo || bi + dist > hi) {
-        bool hit = false;
-        for (int o = -dist + lane; o <= dist; o += 32) {
-          const int q = bi + o;
-          if (o != 0 && q >= 0 && q < kN4095 && c[q] >= bv - eps_s) hit = true;
-        }
-        if (simt::ballot(hit)) fl |= PAL_FLAG_CHAIN;
-      }
-    } else if (bi >= 0) {
-      // winner not clearly above mean|c|: the median / fallback logic decides -> exact kernel
-      kbest = bi;
-      hbest = bv;
-      fl |= PAL_FLAG_NEAR_TIE;
-    } else {
-      // no local maximum in the window: unbounded first argmax (utils.py:168-172)
-      int gi = 0x7fffffff;
-      int near = 0;
-      bool nonzero = false;
-      for (int k = lane; k < kN4095; k += 32) {
-        const float v = c[k];
-        if (v == gm && k < gi) gi = k;
-        if (v >= gm - eps_s) ++near;
-        nonzero |= (v != 0.f);
-      }
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) {
-        const int og = simt::shfl_xor(gi, m);
-        gi = og < gi ? og : gi;
-        near += simt::shfl_xor(near, m);
-      }
-      kbest = gi;
-      hbest = gm;
-      fl |= PAL_FLAG_FALLBACK_ARGMAX;
-      const bool all_zero = simt::ballot(nonzero) == 0u;
-      if (near > 1 && !all_zero) fl |= PAL_FLAG_NEAR_TIE;
-      if (pl > kNegBig && !all_zero) fl |= PAL_FLAG_PLATEAU;
-    }
-    if (lane == 0) {
-      k_idx[item] = kbest;
-      peak[item] = hbest * inv_n;
-      gmax[item] = gm * inv_n;
-      flags[item] = fl;
-    }
+    fast_pick_row<WRITE_CORR>(sm->corr, item, gm, lane, pk, k_idx, peak, gmax, flags, corr_out);
     if (!has_next) break;
     item = next;
     simt::sync_warp();   // the next item overwrites the union
   }
+}
+
+// ---------------------------------------------------------------- fast pair kernel, TMEM-assisted
+// Same algorithm as pair4095_fast_body, but the register tiles between the two passes of each
+// prime-factor transform (65 and 63 complex values per lane) are parked in Tensor Memory
+// (lane-private columns, tcgen05.st / tcgen05.ld) instead of staying in registers.  The working
+// set drops from 255 to <= 168 registers per thread, so 12 warps (3 per scheduler) are resident
+// per SM instead of 8, which is what hides the latency of the exchange / scatter / pick phases.
+// TMEM columns of a warp: [colbase, colbase + 130).
+template <int WARPS> struct TmemPlan {
+  static constexpr int kSlots = (WARPS + 3) / 4;                 // warps per lane quadrant
+  static constexpr int kColsPerWarp = ((512 / kSlots) / 2) * 2;
+  static_assert(kColsPerWarp >= 130, "not enough tensor-memory columns per warp");
+};
+
+template <int WARPS, bool WRITE_CORR>
+PAL_DEV void pair4095_tmem_body(const cpxf* spec, const int* pairs, int M, int P, long long n_items,
+                                int win_half, int dist, float eps, int* k_idx, float* peak, float* gmax,
+                                unsigned* flags, float* corr_out, char* smem_raw) {
+  using P65 = Pfa2<5, 13>;
+  using P63 = Pfa2<7, 9>;
+  const int lane = simt::lane();
+  const int warp = simt::warp();
+  FastWarpSmem* sm = reinterpret_cast<FastWarpSmem*>(smem_raw) + warp;
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(reinterpret_cast<FastWarpSmem*>(smem_raw) + WARPS);
+  if (warp == 0) simt::tmem_alloc512(tmem_slot);
+  simt::tmem_fence_before_sync();
+  simt::sync_block();
+  simt::tmem_fence_after_sync();
+  const unsigned tbase = *tmem_slot;
+  const unsigned tcol = simt::tmem_addr(tbase, warp, (warp >> 2) * TmemPlan<WARPS>::kColsPerWarp);
+
+  const FastPick pk = make_fast_pick(win_half, dist, eps);
+  const int b0 = 63 * (lane + 1);
+  float* const p1 = sm->corr + b0;
+  float* const p1w = p1 - kN4095;
+  float* const p2 = p1 + 63 * 32;
+  float* const p2w = p2 - kN4095;
+
+  const long long stride = (long long)simt::nblocks() * WARPS;
+  long long item = (long long)simt::bid() * WARPS + warp;
+  if (item < n_items) {
+#if PAL_GPU && PAL_STAGGER > 0
+    if (warp >= 4) {   // de-phase the warps that share a scheduler
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)(PAL_STAGGER) * (warp >> 2)) {}
+    }
+#endif
+    // Software pipeline of the spectrum loads: the bins of DFT-5 group b + kLA are requested while
+    // group b is processed (a ring of kLA groups of 5 + 5 complex values in registers); the first
+    // kLA groups of the NEXT pair are requested before the peak pick of the current one.
+    constexpr int kLA = 3;
+    const f2* si;
+    const f2* sj;
+    f2 ra[kLA][5], rb[kLA][5];
+    {
+      const long long frame = item / P;
+      const int p = int(item % P);
+      si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
+      sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
+#pragma unroll
+      for (int g = 0; g < kLA; ++g)
+#pragma unroll
+        for (int a5 = 0; a5 < 5; ++a5) { ra[g][a5] = si[P65::slot(a5, g) * 32]; rb[g][a5] = sj[P65::slot(a5, g) * 32]; }
+    }
+    for (;;) {
+      float gm = kNegBig;
+      // ---- phase A, pass 1: PHAT + DFT-5 over a for every b; result (a, b) parked at column 2 (13 a + b)
+#pragma unroll
+      for (int b = 0; b < 13; ++b) {
+        f2 t[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) t[a] = phat_bin_p(ra[b % kLA][a], rb[b % kLA][a]);
+        if (b + kLA < 13) {
+#pragma unroll
+          for (int a = 0; a < 5; ++a) {
+            ra[b % kLA][a] = si[P65::slot(a, b + kLA) * 32];
+            rb[b % kLA][a] = sj[P65::slot(a, b + kLA) * 32];
+          }
+        }
+        dft_odd_p<5, +1>(t);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+          const f2 one[1] = {t[a]};
+          tmem_st(tcol + 2 * (13 * a + b), one);
+        }
+      }
+      simt::tmem_wait_st();
+      // ---- phase A, pass 2: DFT-13 over b for every a, straight into the exchange tile
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+        f2 t[13];
+        {
+          f2 v8[8], v4[4], v1[1];
+          tmem_ld(tcol + 26 * a, v8);
+          tmem_ld(tcol + 26 * a + 16, v4);
+          tmem_ld(tcol + 26 * a + 24, v1);
+          simt::tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = v8[i];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) t[8 + i] = v4[i];
+          t[12] = v1[0];
+        }
+        dft_odd_p<13, +1>(t);
+#pragma unroll
+        for (int b = 0; b < 13; ++b) {
+          const int kq = P65::out_index(P65::slot(a, b));
+          if (kq == 0) sm->y.y0[lane] = t[b];
+          else if (kq <= 32) sm->y.ya[lane * 33 + (kq - 1)] = t[b];
+          else sm->y.yb[lane * 33 + (kq - 33)] = t[b];
+        }
+      }
+      simt::sync_warp();
+      // ---- phase B, pass 1: the DFT-7 groups b and 9-b together (they share the rows r and 63-r of
+      // the Hermitian columns); result (a, b) parked at column 2 (9 a + b)
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        const int bc = (9 - b) % 9;
+        f2 t1[7], t2[7];
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+          const int s = P63::slot(a, b);
+          const int ac = (7 - a) % 7;                       // slot(ac, bc) == (63 - s) % 63
+          if (s == 0) {
+            const f2 ya = sm->y.ya[lane], yb = sm->y.yb[lane];
+            t1[0] = f2_make(f2_lo(ya), f2_lo(yb));
+          } else if (b != 0 || s < 32) {
+            const int r = s < 32 ? s : 63 - s;
+            const f2 ya = sm->y.ya[r * 33 + lane], yb = sm->y.yb[r * 33 + lane];
+            const f2 wlo = f2_add(ya, f2_muli(yb));                 // w[r]
+            const f2 whi = f2_add(f2_conj(ya), f2_swap(yb));        // w[63 - r]
+            if (b == 0) { t1[a] = wlo; t1[ac] = whi; }              // both partners live in group 0
+            else if (s < 32) { t1[a] = wlo; t2[ac] = whi; }
+            else { t1[a] = whi; t2[ac] = wlo; }
+          }
+        }
+        dft_odd_p<7, +1>(t1);
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+          const f2 one[1] = {t1[a]};
+          tmem_st(tcol + 2 * (9 * a + b), one);
+        }
+        if (b != 0) {
+          dft_odd_p<7, +1>(t2);
+#pragma unroll
+          for (int a = 0; a < 7; ++a) {
+            const f2 one[1] = {t2[a]};
+            tmem_st(tcol + 2 * (9 * a + bc), one);
+          }
+        }
+      }
+      // odd column kq = 0: nine DFT-7 on lanes 0..8 now, seven DFT-9 on lanes 0..6 below
+      f2 t7[7];
+      if (lane < 9) {
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+          const int r = (a * P63::UA + lane * P63::UB) % 63;
+          const f2 v = sm->y.y0[r < 32 ? r : 63 - r];
+          t7[a] = f2_make(f2_lo(v), (r == 0) ? 0.f : (r < 32 ? f2_hi(v) : -f2_hi(v)));
+        }
+      }
+      simt::tmem_wait_st();
+      simt::sync_warp();            // every read of Y is done: the union now holds the correlation row
+      if (lane < 9) {
+        dft_odd_p<7, +1>(t7);
+#pragma unroll
+        for (int a = 0; a < 7; ++a) sm->lx[(a * P63::UA + lane * P63::UB) % 63] = t7[a];
+      }
+      // ---- phase B, pass 2: DFT-9 over b for every a, scattered to natural order
+#pragma unroll
+      for (int a = 0; a < 7; ++a) {
+        f2 t[9];
+        {
+          f2 v8[8], v1[1];
+          tmem_ld(tcol + 18 * a, v8);
+          tmem_ld(tcol + 18 * a + 16, v1);
+          simt::tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = v8[i];
+          t[8] = v1[0];
+        }
+        dft_odd_p<9, +1>(t);
+#pragma unroll
+        for (int b = 0; b < 9; ++b) {
+          const int kr = P63::out_index(P63::slot(a, b));
+          const int c = 65 * kr;
+          const float vr = f2_lo(t[b]), vi = f2_hi(t[b]);
+          if (kr <= 31) p1[c] = vr;
+          else ((b0 + c >= kN4095) ? p1w : p1)[c] = vr;
+          if (kr == 0) p2[c] = vi;
+          else if (kr >= 32) p2w[c] = vi;
+          else ((b0 + 63 * 32 + c >= kN4095) ? p2w : p2)[c] = vi;
+          gm = fmaxf(gm, fmaxf(vr, vi));
+        }
+      }
+      simt::sync_warp();
+      if (lane < 7) {
+        f2 u[9];
+#pragma unroll
+        for (int b = 0; b < 9; ++b) u[b] = sm->lx[(lane * P63::UA + b * P63::UB) % 63];
+        dft_odd_p<9, +1>(u);
+#pragma unroll
+        for (int b = 0; b < 9; ++b) {
+          const int kr = (9 * lane + 7 * b) % 63;
+          const float v = f2_lo(u[b]);
+          sm->corr[(65 * kr) % kN4095] = v;
+          gm = fmaxf(gm, v);
+        }
+      }
+      // ---- fetch the first bins of the NEXT pair while this one is being picked
+      const long long next = item + stride;
+      const bool has_next = next < n_items;
+      if (has_next) {
+        const long long frame = next / P;
+        const int p = int(next % P);
+        si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
+        sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
+#pragma unroll
+        for (int g = 0; g < kLA; ++g)
+#pragma unroll
+          for (int a5 = 0; a5 < 5; ++a5) { ra[g][a5] = si[P65::slot(a5, g) * 32]; rb[g][a5] = sj[P65::slot(a5, g) * 32]; }
+      }
+      simt::sync_warp();
+      fast_pick_row<WRITE_CORR>(sm->corr, item, gm, lane, pk, k_idx, peak, gmax, flags, corr_out);
+      if (!has_next) break;
+      item = next;
+      simt::sync_warp();   // the next item overwrites the union
+    }
+  }
+  simt::tmem_fence_before_sync();
+  simt::sync_block();
+  if (warp == 0) simt::tmem_dealloc512(tbase);
 }
 
 }  // namespace pal

@@ -98,6 +98,53 @@ PAL_DEV f2 f2_sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v)
 PAL_DEV f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 PAL_DEV f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
 
+// ---- Tensor Memory (TMEM, 512 columns x 128 lanes x 32 bit per SM) as LANE-PRIVATE scratch of a SIMT
+// kernel: a warp reads / writes the 32 TMEM lanes of its quadrant (warp % 4), lane i <-> thread i,
+// N consecutive 32-bit columns per instruction (tcgen05.ld / tcgen05.st .32x32b, SASS LDTM / STTM).
+// Used to park register tiles so that more warps fit on an SM (see pair4095_tmem_body).
+namespace simt {
+PAL_DEV void tmem_alloc512(unsigned* smem_slot) {   // one full warp calls this
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(smem_slot)) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+PAL_DEV void tmem_dealloc512(unsigned base) {       // one full warp calls this
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+}
+PAL_DEV void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+PAL_DEV void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+PAL_DEV void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+PAL_DEV void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// address of column `col` in the quadrant of warp `warp`
+PAL_DEV unsigned tmem_addr(unsigned base, int warp, int col) { return base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)col; }
+}  // namespace simt
+PAL_DEV unsigned f2_bits_lo(f2 a) { return (unsigned)(a.v & 0xffffffffull); }
+PAL_DEV unsigned f2_bits_hi(f2 a) { return (unsigned)(a.v >> 32); }
+PAL_DEV f2 f2_from_bits(unsigned lo, unsigned hi) { f2 r; r.v = ((unsigned long long)hi << 32) | lo; return r; }
+// park / fetch N complex values (2N columns)
+PAL_DEV void tmem_st(unsigned ta, const f2 (&v)[1]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(ta), "r"(f2_bits_lo(v[0])), "r"(f2_bits_hi(v[0])) : "memory");
+}
+PAL_DEV void tmem_ld(unsigned ta, f2 (&v)[1]) {
+  unsigned r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(ta) : "memory");
+  v[0] = f2_from_bits(r0, r1);
+}
+PAL_DEV void tmem_ld(unsigned ta, f2 (&v)[4]) {
+  unsigned r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(ta) : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = f2_from_bits(r[2 * i], r[2 * i + 1]);
+}
+PAL_DEV void tmem_ld(unsigned ta, f2 (&v)[8]) {
+  unsigned r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(ta) : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = f2_from_bits(r[2 * i], r[2 * i + 1]);
+}
+
 PAL_DEV float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 PAL_DEV double fma_(double a, double b, double c) { return fma(a, b, c); }
 PAL_DEV float sqrt_(float a) { return sqrtf(a); }
@@ -221,6 +268,24 @@ inline f2 f2_add(f2 a, f2 b) { return f2{a.lo + b.lo, a.hi + b.hi}; }
 inline f2 f2_sub(f2 a, f2 b) { return f2{a.lo - b.lo, a.hi - b.hi}; }
 inline f2 f2_mul(f2 a, f2 b) { return f2{a.lo * b.lo, a.hi * b.hi}; }
 inline f2 f2_fma(f2 a, f2 b, f2 c) { return f2{std::fmaf(a.lo, b.lo, c.lo), std::fmaf(a.hi, b.hi, c.hi)}; }
+
+// TMEM emulation: 512 lane-private columns per thread (thread_local), same call surface
+namespace simt {
+inline thread_local unsigned tmem_cols[512];
+inline void tmem_alloc512(unsigned* smem_slot) { if (lane() == 0) *smem_slot = 0u; }
+inline void tmem_dealloc512(unsigned) {}
+inline void tmem_fence_before_sync() {}
+inline void tmem_fence_after_sync() {}
+inline void tmem_wait_ld() {}
+inline void tmem_wait_st() {}
+inline unsigned tmem_addr(unsigned base, int, int col) { return base + (unsigned)col; }
+}  // namespace simt
+template <int N> inline void tmem_st(unsigned ta, const f2 (&v)[N]) {
+  for (int i = 0; i < N; ++i) { std::memcpy(&simt::tmem_cols[ta + 2 * i], &v[i].lo, 4); std::memcpy(&simt::tmem_cols[ta + 2 * i + 1], &v[i].hi, 4); }
+}
+template <int N> inline void tmem_ld(unsigned ta, f2 (&v)[N]) {
+  for (int i = 0; i < N; ++i) { std::memcpy(&v[i].lo, &simt::tmem_cols[ta + 2 * i], 4); std::memcpy(&v[i].hi, &simt::tmem_cols[ta + 2 * i + 1], 4); }
+}
 
 inline float fma_(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline double fma_(double a, double b, double c) { return std::fma(a, b, c); }

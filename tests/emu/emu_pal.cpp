@@ -19,8 +19,14 @@ void emu_pair4095_fast(const float* spec, const int* pairs, int M, int P, long l
                        int grid, int phase_sync) {
   constexpr int W = 2;
   const cpxf* sp = reinterpret_cast<const cpxf*>(spec);
-  simt::launch(grid, 32 * W, W * sizeof(FastWarpSmem), [&](char* smem) {
-    (void)phase_sync;
+  simt::launch(grid, 32 * W, W * sizeof(FastWarpSmem) + 16, [&](char* smem) {
+    if (phase_sync == 2) {     // TMEM-assisted variant
+      if (corr_out)
+        pair4095_tmem_body<W, true>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
+      else
+        pair4095_tmem_body<W, false>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
+      return;
+    }
     if (corr_out)
       pair4095_fast_body<W, true>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
     else

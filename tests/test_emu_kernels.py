@@ -33,11 +33,12 @@ def test_forward_spectra_layout(frames, spectra):
         assert np.abs(got - want).max() <= 2e-7 * np.abs(want).max() * 8
 
 
+@pytest.mark.parametrize("variant", [0, 2])      # 0: register-resident tiles, 2: tiles parked in (emulated) tensor memory
 @pytest.mark.parametrize("med", [0.05, 0.01, None])
-def test_fast_pair_kernel_vs_oracle(frames, spectra, med):
+def test_fast_pair_kernel_vs_oracle(frames, spectra, med, variant):
     pairs = E.pairs_of(frames.shape[1])
     w = O.window_half_width(2048, 2048, 16000.0, med)
-    k, pk, gm, fl, corr = E.pair_fast(spectra, pairs, w, 16, want_corr=True)
+    k, pk, gm, fl, corr = E.pair_fast(spectra, pairs, w, 16, want_corr=True, phase_sync=variant)
     for p, (i, j) in enumerate(pairs):
         c = O.phat_correlation(frames[0, i].astype(np.float64), frames[0, j].astype(np.float64))
         assert np.abs(corr[0, p] - c).max() <= 1e-4 * np.abs(c).max()
