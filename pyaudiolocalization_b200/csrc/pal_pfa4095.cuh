@@ -513,7 +513,12 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
   using P65 = Pfa2<5, 13>;
   using P63 = Pfa2<7, 9>;
   const int lane = simt::lane();
-  FastWarpSmem* sm = reinterpret_cast<FastWarpSmem*>(smem_raw) + simt::warp();
+#ifdef PAL_UNIFORM_WARP
+  const int warp = simt::shfl(simt::warp(), 0);     // provably warp-uniform (see pair4095_tmem_body)
+#else
+  const int warp = simt::warp();
+#endif
+  FastWarpSmem* sm = reinterpret_cast<FastWarpSmem*>(smem_raw) + warp;
   const FastPick pk = make_fast_pick(win_half, dist, eps);
   // scatter bases: output k = (63 kq + 65 kr) mod 4095 of columns kq = lane+1 and lane+33;
   // p?w are the same bases pre-wrapped by -4095 so that every store is [base + immediate]
@@ -524,13 +529,13 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
   float* const p2w = p2 - kN4095;
 
   const long long stride = (long long)simt::nblocks() * WARPS;
-  long long item = (long long)simt::bid() * WARPS + simt::warp();
+  long long item = (long long)simt::bid() * WARPS + warp;
   if (item >= n_items) return;
 #if PAL_GPU && PAL_STAGGER > 0
   // De-phase the two warps that share an SM sub-partition (warp w and w + WARPS/2) once, at kernel
   // start.  Measured on B200: 7 % faster at 16384 frames (bursts to L2 no longer line up); the
   // amount does not matter (profiles/).
-  if (simt::warp() >= WARPS / 2) {
+  if (warp >= WARPS / 2) {
     const long long t0 = clock64();
     while (clock64() - t0 < (long long)(PAL_STAGGER)) {}
   }
@@ -714,7 +719,10 @@ PAL_DEV void pair4095_tmem_body(const cpxf* spec, const int* pairs, int M, int P
   using P65 = Pfa2<5, 13>;
   using P63 = Pfa2<7, 9>;
   const int lane = simt::lane();
-  const int warp = simt::warp();
+  // The warp index is broadcast from lane 0 so that the compiler can prove it warp-uniform: every
+  // branch on the work item is then a uniform branch, the main loop is convergent code and
+  // descriptors / tensor-memory addresses stay in uniform registers.
+  const int warp = simt::shfl(simt::warp(), 0);
   FastWarpSmem* sm = reinterpret_cast<FastWarpSmem*>(smem_raw) + warp;
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(reinterpret_cast<FastWarpSmem*>(smem_raw) + WARPS);
   if (warp == 0) simt::tmem_alloc512(tmem_slot);
@@ -733,6 +741,12 @@ PAL_DEV void pair4095_tmem_body(const cpxf* spec, const int* pairs, int M, int P
 
   const long long stride = (long long)simt::nblocks() * WARPS;
   long long item = (long long)simt::bid() * WARPS + warp;
+  // The first pair's microphone indices are fetched here, in convergent code, on purpose: it makes
+  // the compiler set up the global-memory descriptor in a uniform register once; if the first global
+  // load sits inside the (formally divergent) block below, every one of the 130 spectrum loads of a
+  // pair pays two extra R2UR instructions.
+  const long long item_c = item < n_items ? item : n_items - 1;
+  const int mi0 = pairs[2 * int(item_c % P)], mj0 = pairs[2 * int(item_c % P) + 1];
   if (item < n_items) {
 #if PAL_GPU && PAL_STAGGER > 0
     if (warp >= 4) {   // de-phase the warps that share a scheduler
@@ -743,15 +757,17 @@ PAL_DEV void pair4095_tmem_body(const cpxf* spec, const int* pairs, int M, int P
     // Software pipeline of the spectrum loads: the bins of DFT-5 group b + kLA are requested while
     // group b is processed (a ring of kLA groups of 5 + 5 complex values in registers); the first
     // kLA groups of the NEXT pair are requested before the peak pick of the current one.
-    constexpr int kLA = 3;
+#ifndef PAL_TMEM_LOOKAHEAD
+#define PAL_TMEM_LOOKAHEAD 3
+#endif
+    constexpr int kLA = PAL_TMEM_LOOKAHEAD;
     const f2* si;
     const f2* sj;
     f2 ra[kLA][5], rb[kLA][5];
     {
       const long long frame = item / P;
-      const int p = int(item % P);
-      si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
-      sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
+      si = reinterpret_cast<const f2*>(spec + (frame * M + mi0) * kSpecSlots) + lane;
+      sj = reinterpret_cast<const f2*>(spec + (frame * M + mj0) * kSpecSlots) + lane;
 #pragma unroll
       for (int g = 0; g < kLA; ++g)
 #pragma unroll
