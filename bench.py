@@ -290,7 +290,7 @@ def run_gpu_arm(args):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     traffic, traffic_src = None, None
     try:   # DRAM bytes of the pair kernel from the committed ncu --set full capture, scaled to this launch size
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1d_traffic.json")))
         traffic = float(tj["dram_bytes_per_frame"]) * frames_n
         traffic_src = tj["source"]
     except (OSError, KeyError, ValueError):
