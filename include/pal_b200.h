@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PAL_ABI_VERSION 3
+#define PAL_ABI_VERSION 4
 
 /* error codes */
 #define PAL_OK 0
@@ -173,6 +173,20 @@ int pal_render_scenes(const float* base_dev, int32_t n_base, int32_t N, const do
  * mode 1 = dynamic_range_compression(threshold, epsilon) (signal_processing.py:88-94). */
 int pal_normalise_compress(float* rows_dev, int64_t n_rows, int32_t n, float threshold, float epsilon,
                            int32_t mode, void* stream);
+
+/* ---------------------------------------------------------------- between the stages: channel filter
+ *
+ * Zero-phase IIR filtering of n_rows channels: scipy.signal.filtfilt(b, a, x) with its defaults (method
+ * "pad", odd extension of padlen = 3 * ntaps samples, lfilter_zi initial conditions), i.e. what
+ * signal_processing.noise_reduction(signal, fs, 'butterworth') (signal_processing.py:124-128) applies to
+ * every channel in main.py:191.  b, a, zi are HOST arrays of ntaps, ntaps, ntaps-1 doubles
+ * (ntaps = max(len(a), len(b)) <= 16, shorter one zero-padded, a[0] == 1, zi = lfilter_zi(b, a)).
+ * x_dev / y_dev: [n_rows][n] float64 (io_f32 == 0) or float32 (io_f32 == 1; the arithmetic is float64
+ * either way); n > padlen.  In float64 the result is bit-identical to scipy on x86 (same operation order,
+ * no FMA contraction).  Workspace: pal_filtfilt_workspace bytes. */
+int pal_filtfilt_workspace(int64_t n_rows, int32_t n, int32_t padlen, size_t* bytes);
+int pal_filtfilt(const void* x_dev, int64_t n_rows, int32_t n, int32_t io_f32, const double* b, const double* a,
+                 const double* zi, int32_t ntaps, int32_t padlen, void* y_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

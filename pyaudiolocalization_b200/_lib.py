@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PAL_B200_LIB") or os.path.join(_PKG, "libpal_b200.so")   # env override: tuning experiments only
 
-PAL_ABI_VERSION = 3
+PAL_ABI_VERSION = 4
 
 # per-row flag bits (include/pal_b200.h)
 FLAG_NEAR_TIE = 1
@@ -77,6 +77,11 @@ def lib():
     L.pal_render_scene.argtypes = [VP, I32, I32, VP, VP, I32, I32, F64, I32, I32, VP, VP, C.c_size_t, VP]
     L.pal_normalise_compress.restype = C.c_int
     L.pal_normalise_compress.argtypes = [VP, I64, I32, F32, F32, I32, VP]
+    L.pal_filtfilt_workspace.restype = C.c_int
+    L.pal_filtfilt_workspace.argtypes = [I64, I32, I32, SZP]
+    L.pal_filtfilt.restype = C.c_int
+    L.pal_filtfilt.argtypes = [VP, I64, I32, I32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), I32, I32,
+                               VP, VP, C.c_size_t, VP]
     if L.pal_abi_version() != PAL_ABI_VERSION:
         raise PalError(f"libpal_b200.so ABI {L.pal_abi_version()} != expected {PAL_ABI_VERSION}; rebuild")
     _lib = L

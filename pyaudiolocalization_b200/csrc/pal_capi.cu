@@ -11,6 +11,7 @@
 #include "pal_pfa4095.cuh"
 #include "pal_generic_host.cuh"
 #include "pal_render_host.cuh"
+#include "pal_filter.cuh"
 
 using namespace pal;
 
@@ -128,6 +129,14 @@ __global__ void k_tdoa_seconds(const int* __restrict__ k_idx, long long n, int c
     const int k = k_idx[i];
     out[i] = (k < 0) ? __longlong_as_double(0x7ff8000000000000LL) : __ddiv_rn(double(k - c0), fs);
   }
+}
+
+constexpr int kFiltThreads = 128;
+template <typename TIO>
+__global__ void __launch_bounds__(kFiltThreads) k_filtfilt(const TIO* __restrict__ x, long long n_rows, int n, FiltParams fp,
+                                                           double* __restrict__ work, TIO* __restrict__ y) {
+  extern __shared__ __align__(16) char smem[];
+  filtfilt_body<TIO, kFiltThreads>(x, n_rows, n, fp, work, y, smem);
 }
 
 struct DevInfo {
@@ -500,6 +509,50 @@ int pal_normalise_compress(float* rows_dev, int64_t n_rows, int32_t n, float thr
   if (int rc = device_info(di)) return rc;
   palhost::k_normalise_compress<<<(unsigned)std::min<long long>(n_rows, 8LL * di.sms), palhost::kGT, 64,
                                   static_cast<cudaStream_t>(stream_)>>>(rows_dev, n_rows, n, threshold, epsilon, mode == 1);
+  ++g_launches;
+  PAL_CUDA(cudaGetLastError());
+  return PAL_OK;
+}
+
+int pal_filtfilt_workspace(int64_t n_rows, int32_t n, int32_t padlen, size_t* bytes) {
+  if (n_rows < 0 || n < 1 || padlen < 0 || !bytes) return fail(PAL_ERR_INVALID, "pal_filtfilt_workspace: bad argument");
+  *bytes = size_t((n_rows + 31) / 32) * size_t(n + 2 * padlen) * 32 * sizeof(double) + 256;
+  return PAL_OK;
+}
+
+int pal_filtfilt(const void* x_dev, int64_t n_rows, int32_t n, int32_t io_f32, const double* b, const double* a,
+                 const double* zi, int32_t ntaps, int32_t padlen, void* y_dev, void* ws_dev, size_t ws_bytes, void* stream_) {
+  if (n_rows < 0 || n < 1 || !b || !a || !zi) return fail(PAL_ERR_INVALID, "pal_filtfilt: bad argument");
+  if (ntaps < 2 || ntaps > kFiltMaxTaps) return fail(PAL_ERR_UNSUPPORTED, "pal_filtfilt: need 2 <= ntaps <= 16");
+  if (padlen < 0 || n <= padlen)
+    return fail(PAL_ERR_INVALID, "pal_filtfilt: The length of the input vector x must be greater than padlen");
+  if (a[0] != 1.0) return fail(PAL_ERR_INVALID, "pal_filtfilt: a[0] must be 1 (normalise b and a by a[0] first)");
+  if (n_rows == 0) return PAL_OK;
+  if (!x_dev || !y_dev || !ws_dev) return fail(PAL_ERR_INVALID, "pal_filtfilt: NULL device pointer");
+  size_t need = 0;
+  pal_filtfilt_workspace(n_rows, n, padlen, &need);
+  if (ws_bytes < need - 256) return fail(PAL_ERR_WORKSPACE, "pal_filtfilt: workspace too small");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  FiltParams fp{};
+  fp.ntaps = ntaps;
+  fp.padlen = padlen;
+  for (int i = 0; i < kFiltMaxTaps; ++i) {
+    fp.b[i] = i < ntaps ? b[i] : 0.0;
+    fp.a[i] = i < ntaps ? a[i] : 0.0;
+    fp.zi[i] = i < ntaps - 1 ? zi[i] : 0.0;
+  }
+  const long long groups = (n_rows + 31) / 32;
+  const int wpb = kFiltThreads / 32;
+  const unsigned grid = (unsigned)std::min<long long>((groups + wpb - 1) / wpb, 16LL * di.sms);
+  const size_t smem = size_t(wpb) * 32 * 33 * sizeof(double);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (io_f32)
+    k_filtfilt<float><<<grid, kFiltThreads, smem, st>>>(static_cast<const float*>(x_dev), n_rows, n, fp, static_cast<double*>(ws_dev),
+                                                        static_cast<float*>(y_dev));
+  else
+    k_filtfilt<double><<<grid, kFiltThreads, smem, st>>>(static_cast<const double*>(x_dev), n_rows, n, fp,
+                                                         static_cast<double*>(ws_dev), static_cast<double*>(y_dev));
   ++g_launches;
   PAL_CUDA(cudaGetLastError());
   return PAL_OK;

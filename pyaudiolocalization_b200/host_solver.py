@@ -80,8 +80,13 @@ def noise_reduction(signal, fs, method='butterworth', lowcut=300, highcut=3400, 
     from scipy.signal import butter, filtfilt, firwin, wiener
     nyq = 0.5 * fs
     if method == 'butterworth':
+        # the Butterworth band-pass of main.py:191 runs on the device (pal_filtfilt): float64,
+        # bit-identical to scipy.signal.filtfilt; the design call below is the reference's own
+        import torch
+        from .filters import filtfilt_batched
         b, a = butter(5, [lowcut / nyq, highcut / nyq], btype='band')
-        return filtfilt(b, a, signal)
+        x = torch.as_tensor(np.ascontiguousarray(np.asarray(signal, dtype=np.float64))).cuda()
+        return filtfilt_batched(x, b, a).cpu().numpy()
     if method == 'fir':
         return filtfilt(firwin(filter_order, [lowcut / nyq, highcut / nyq], pass_zero=False), [1.0], signal)
     if method == 'wiener':

@@ -160,3 +160,15 @@ def path_table_batched(sources, img_pos, img_mat, img_count, mics, mat_abs, mat_
                                  _pd(np.ascontiguousarray(mat_freq, np.float64)), air_mat, C.c_double(frequency),
                                  C.c_double(c_sound), ks, _pd(tau), _pd(gain), _p(cnt, C.c_int), _pd(mx))
     return tau, gain, cnt, mx
+
+
+def filtfilt_f64(x, b, a, zi, padlen):
+    x = np.ascontiguousarray(x, np.float64)
+    rows, n = x.shape
+    nt = max(len(a), len(b))
+    bb = np.zeros(nt); bb[:len(b)] = b
+    aa = np.zeros(nt); aa[:len(a)] = a
+    y = np.zeros_like(x)
+    lib().emu_filtfilt_f64(_pd(x), C.c_longlong(rows), n, _pd(bb), _pd(aa), _pd(np.ascontiguousarray(zi, np.float64)), nt, padlen,
+                           _pd(y))
+    return y

@@ -212,3 +212,22 @@ extern "C" void emu_path_table_batched(const double* sources, const double* img_
                                 mat_freq, air_mat, frequency, c_sound, k_stride, tau, gain, path_count, max_tau, sm);
   });
 }
+
+// ---------------------------------------------------------------- channel filter (filtfilt)
+#include "pal_filter.cuh"
+extern "C" void emu_filtfilt_f64(const double* x, long long n_rows, int n, const double* b, const double* a, const double* zi,
+                                 int ntaps, int padlen, double* y) {
+  constexpr int NT = 64;
+  FiltParams fp{};
+  fp.ntaps = ntaps;
+  fp.padlen = padlen;
+  for (int i = 0; i < kFiltMaxTaps; ++i) {
+    fp.b[i] = i < ntaps ? b[i] : 0.0;
+    fp.a[i] = i < ntaps ? a[i] : 0.0;
+    fp.zi[i] = i < ntaps - 1 ? zi[i] : 0.0;
+  }
+  std::vector<double> work(size_t((n_rows + 31) / 32) * (n + 2 * padlen) * 32);
+  simt::launch(2, NT, size_t(NT / 32) * 32 * 33 * sizeof(double), [&](char* sm) {
+    filtfilt_body<double, NT>(x, n_rows, n, fp, work.data(), y, sm);
+  });
+}

@@ -183,3 +183,17 @@ def test_render_scene_emulation_vs_oracle():
                                                       reflective_planes=planes, material_properties=CUSTOM_MATERIALS,
                                                       max_reflections=1, absorption_threshold=0.01))
     assert np.abs(got - want).max() <= 1e-5
+
+
+@pytest.mark.parametrize("rows,n", [(3, 200), (37, 1000), (1, 2048)])
+def test_filtfilt_bit_exact_vs_scipy(rows, n):
+    """The channel filter kernel (float64, scipy's direct-form-II-transposed update in its own evaluation
+    order) must reproduce scipy.signal.filtfilt bit for bit: the Butterworth band-pass of
+    signal_processing.noise_reduction (order 5, 300-3400 Hz) and a low-order filter."""
+    from scipy.signal import butter, filtfilt, lfilter_zi
+    rng = np.random.default_rng(rows * n)
+    x = rng.standard_normal((rows, n))
+    for (b, a) in (butter(5, [300 / 8000.0, 3400 / 8000.0], btype="band"), butter(2, 0.2)):
+        want = filtfilt(b, a, x, axis=-1)
+        got = E.filtfilt_f64(x, b, a, lfilter_zi(b, a), 3 * max(len(a), len(b)))
+        assert np.array_equal(got, want)

@@ -207,3 +207,24 @@ def test_batched_scenes_shared_room(pal):
     for s in (0, 4):
         want = np.array(O.simulate_signals_with_multipath(srcs[s], mics, 48000, 343.62, **kw))
         assert np.abs(got[s] - want).max() <= RENDER_ATOL
+
+
+def test_channel_filter_bit_exact_vs_scipy(pal):
+    """pal_filtfilt (signal_processing.noise_reduction 'butterworth', main.py:191) in float64 must equal
+    scipy.signal.filtfilt bit for bit; the float32-in/out flavour within one float32 rounding."""
+    from scipy.signal import butter, filtfilt
+    from pyaudiolocalization_b200 import filters, signal_processing as SP
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((70, 3000))
+    b, a = butter(5, [300 / 8000.0, 3400 / 8000.0], btype="band")
+    want = filtfilt(b, a, x, axis=-1)
+    got = filters.filtfilt_batched(torch.from_numpy(x).cuda(), b, a).cpu().numpy()
+    assert np.array_equal(got, want)
+    got32 = filters.filtfilt_batched(torch.from_numpy(x.astype(np.float32)).cuda(), b, a).cpu().numpy()
+    want32 = filtfilt(b, a, x.astype(np.float32).astype(np.float64), axis=-1).astype(np.float32)
+    assert np.array_equal(got32, want32)
+    # the drop-in signature
+    one = SP.noise_reduction(x[0], 16000.0, method="butterworth")
+    assert np.array_equal(one, want[0])
+    with pytest.raises(ValueError):
+        filters.filtfilt_batched(torch.zeros((2, 20), dtype=torch.float64, device="cuda"), b, a)

@@ -115,8 +115,20 @@ def img(small):
                       "scenes_per_s": n / sec}), flush=True)
 
 
+def filt(small):
+    from pyaudiolocalization_b200 import filters
+    frames = 256 if small else 2048
+    fr = pal.synth.cfg3_frames(frames, 32, seed=3000)
+    b, a = filters.design_butter_bandpass(16000.0)
+    sec = timed(lambda: filters.filtfilt_batched(fr, b, a), reps=2)
+    rows = frames * 32
+    print(json.dumps({"config": "cfg3", "stage": "channel filter (noise_reduction butterworth, filtfilt order 5 band-pass, float64 arithmetic)",
+                      "rows": rows, "samples": 2048, "ms": sec * 1e3, "channels_per_s": rows / sec,
+                      "samples_per_s": rows * 2048 / sec, "GBps_io": rows * 2048 * 8 / sec / 1e9}), flush=True)
+
+
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if not a.startswith("--")] or ["img", "cfg5", "cfg2", "cfg4"]
+    args = [a for a in sys.argv[1:] if not a.startswith("--")] or ["img", "cfg5", "cfg2", "cfg4", "filter"]
     small = "--small" in sys.argv
     for a in args:
         if a == "cfg2":
@@ -128,3 +140,5 @@ if __name__ == "__main__":
             cfg4(small)
         elif a == "img":
             img(small)
+        elif a == "filter":
+            filt(small)
