@@ -42,7 +42,7 @@ __all__ = [
     "simulate_signals_with_multipath", "phat_correlation", "get_time_delays_phat",
     "pair_loop", "local_maxima_restated", "select_by_distance_restated",
     "window_half_width", "peak_distance", "tdoa_pick_restated", "tdoa_from_index",
-    "path_table_restated", "render_rows_restated",
+    "path_table_restated", "render_rows_restated", "synchronize_signals_improved",
 ]
 
 # materials.py:2-16 (data table, copied values)
@@ -451,3 +451,51 @@ def render_rows_restated(base: np.ndarray, tau: np.ndarray, gain: np.ndarray, to
         y = y[:n_keep]
         rows.append(dynamic_range_compression(normalize_signal(y)))
     return np.asarray(rows)
+
+
+# --------------------------------------------------------------------------
+# between the stages: utils.py:407-457
+# --------------------------------------------------------------------------
+def synchronize_signals_improved(signals: Sequence[np.ndarray], fs: float,
+                                 use_interpolation: bool = True) -> List[np.ndarray]:
+    """Port of utils.synchronize_signals_improved (utils.py:407-457): same scipy calls in the same
+    order.  Aligns every channel on the highest-energy one by the arg-max of the full
+    cross-correlation, refined on a 5-point cubic spline, and left-pads."""
+    from scipy.interpolate import CubicSpline
+    from scipy.signal import correlate
+    energies = [np.sum(sig ** 2) for sig in signals]                    # :415
+    ref_idx = np.argmax(energies)
+    reference = signals[ref_idx]
+    ref_corr = correlate(reference, reference, mode='full')              # :418
+    ref_peak = np.max(np.abs(ref_corr))
+    shifts = []
+    max_shift_samples = int(fs * 0.05)                                   # :421
+    for idx, sig in enumerate(signals):
+        if idx == ref_idx:
+            shifts.append(0)
+            continue
+        corr = correlate(sig, reference, mode='full')                    # :426
+        peak_index = np.argmax(np.abs(corr))
+        if np.abs(corr[peak_index]) < 0.3 * ref_peak:                    # :428
+            refined_peak = peak_index
+        elif use_interpolation and peak_index > 1 and peak_index < len(corr) - 2:
+            indices = np.arange(peak_index - 2, peak_index + 3)          # :433
+            window_corr = corr[peak_index - 2: peak_index + 3]
+            cs = CubicSpline(indices, window_corr)
+            fine_indices = np.linspace(peak_index - 2, peak_index + 2, 100)
+            fine_vals = cs(fine_indices)
+            refined_peak = fine_indices[np.argmax(np.abs(fine_vals))]
+        else:
+            refined_peak = peak_index
+        base_index = len(reference) - 1                                  # :441
+        shift = refined_peak - base_index
+        if abs(shift) > max_shift_samples:
+            shift = 0
+        shifts.append(shift)
+    min_shift = min(shifts)                                              # :448
+    adjusted = []
+    for sig, shift in zip(signals, shifts):
+        pad_left = max(0, int(round(shift - min_shift)))
+        adjusted.append(np.pad(sig, (pad_left, 0), mode='constant'))
+    max_length = max(len(s) for s in adjusted)
+    return [np.pad(s, (0, max_length - len(s)), mode='constant') for s in adjusted]
