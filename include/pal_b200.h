@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PAL_ABI_VERSION 4
+#define PAL_ABI_VERSION 5
 
 /* error codes */
 #define PAL_OK 0
@@ -187,6 +187,28 @@ int pal_normalise_compress(float* rows_dev, int64_t n_rows, int32_t n, float thr
 int pal_filtfilt_workspace(int64_t n_rows, int32_t n, int32_t padlen, size_t* bytes);
 int pal_filtfilt(const void* x_dev, int64_t n_rows, int32_t n, int32_t io_f32, const double* b, const double* a,
                  const double* zi, int32_t ntaps, int32_t padlen, void* y_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- between the stages: channel alignment
+ *
+ * Front end of utils.synchronize_signals_improved (utils.py:407-457) for n_scenes scenes of n_ch channels
+ * (rows of `ld` float64 samples, lens_dev[scene][ch] of them valid, NULL = all ld):
+ *   ref_idx_dev[scene]        = np.argmax of the channel energies (first maximum)              utils.py:415-416
+ *   for every channel: corr   = scipy.signal.correlate(channel, reference, mode='full')        utils.py:426
+ *   peak_index_dev[scene][ch] = np.argmax(np.abs(corr)) in 'full' order (first maximum)         utils.py:427
+ *   absmax_dev[scene][ch]     = |corr[peak_index]|; the entry of the reference channel itself is ref_peak, :418-419
+ *   win_dev[scene][ch][5]     = corr[peak_index-2 .. peak_index+2] (NaN outside the row): the samples of the
+ *                               cubic spline of utils.py:431-437, which the caller evaluates in float64
+ *   energy_dev[scene][ch]     optional (NULL = not wanted)
+ * All arithmetic is float64 (exact length-(2 ld - 1) transforms).  The library never synchronises. */
+int pal_sync_align_workspace(int64_t n_scenes, int32_t n_ch, int32_t ld, size_t* bytes, size_t* min_bytes);
+int pal_sync_align(const double* sig_dev, int64_t n_scenes, int32_t n_ch, int32_t ld, const int32_t* lens_dev,
+                   int32_t* ref_idx_dev, int32_t* peak_index_dev, double* absmax_dev, double* win_dev,
+                   double* energy_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* The padding of utils.py:448-457 (np.pad): out[row][pad_left[row] + j] = in[row][j] for j < lens[row]
+ * (NULL = ld_in), zero elsewhere; rows of float64 (io_f32 == 0) or float32 (io_f32 == 1). */
+int pal_pad_rows(const void* in_dev, int64_t n_rows, int64_t ld_in, const int32_t* lens_dev, const int32_t* pad_left_dev,
+                 void* out_dev, int64_t ld_out, int32_t io_f32, void* stream);
 
 #ifdef __cplusplus
 }

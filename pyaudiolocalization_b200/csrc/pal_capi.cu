@@ -57,9 +57,9 @@ constexpr int kFwdThreads = 256;
 constexpr int kFastWarps = PAL_FAST_WARPS;   // warps (= mic pairs in flight) per CTA of the fused pair kernel
 constexpr int kExactThreads = 256;
 __global__ void __launch_bounds__(kFwdThreads) k_fwd4095(const float* __restrict__ sig, int M, long long units,
-                                                       cpxf* __restrict__ spec) {
+                                                       cpxf* __restrict__ spec, float* __restrict__ hq) {
   extern __shared__ __align__(128) char smem[];
-  fwd4095_body<kFwdThreads>(sig, M, units, spec, smem);
+  fwd4095_body<kFwdThreads>(sig, M, units, spec, hq, smem);
 }
 
 template <bool WRITE_CORR>
@@ -68,11 +68,12 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1) __maxnreg__(PAL_FAST_MAXNR
 #else
 __global__ void __launch_bounds__(kFastWarps * 32, 1)
 #endif
-    k_pair4095_fast(const cpxf* __restrict__ spec, const int* __restrict__ pairs, int M, int P, long long n_items,
+    k_pair4095_fast(const cpxf* __restrict__ spec, const float* __restrict__ hq, const int* __restrict__ pairs, int M, int P,
+                    long long n_items,
                     int win_half, int dist, float eps, int* __restrict__ k_idx, float* __restrict__ peak,
                     float* __restrict__ gmax, unsigned* __restrict__ flags, float* __restrict__ corr_out) {
   extern __shared__ __align__(128) char smem[];
-  pair4095_fast_body<kFastWarps, WRITE_CORR>(spec, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax,
+  pair4095_fast_body<kFastWarps, WRITE_CORR>(spec, hq, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax,
                                              flags, corr_out, smem);
 }
 
@@ -82,11 +83,12 @@ __global__ void __launch_bounds__(kFastWarps * 32, 1)
 constexpr int kTmemWarps = PAL_TMEM_WARPS;   // warps per CTA of the TMEM-assisted pair kernel (3 per scheduler)
 template <bool WRITE_CORR>
 __global__ void __launch_bounds__(kTmemWarps * 32, 1)
-    k_pair4095_tmem(const cpxf* __restrict__ spec, const int* __restrict__ pairs, int M, int P, long long n_items,
+    k_pair4095_tmem(const cpxf* __restrict__ spec, const float* __restrict__ hq, const int* __restrict__ pairs, int M, int P,
+                    long long n_items,
                     int win_half, int dist, float eps, int* __restrict__ k_idx, float* __restrict__ peak,
                     float* __restrict__ gmax, unsigned* __restrict__ flags, float* __restrict__ corr_out) {
   extern __shared__ __align__(128) char smem[];
-  pair4095_tmem_body<kTmemWarps, WRITE_CORR>(spec, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax, flags,
+  pair4095_tmem_body<kTmemWarps, WRITE_CORR>(spec, hq, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax, flags,
                                              corr_out, smem);
 }
 // Which fused pair kernel runs (read once): PAL_PAIR_KERNEL=tmem (default; 12 warps per SM, register
@@ -222,8 +224,9 @@ int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, s
   const size_t list = align_up(size_t(B) * P * sizeof(int), 256) + 256;
   if (n_samples == kFrame2048) {
     const size_t per_frame = align_up(size_t(M) * kSpecSlots * sizeof(cpxf), 256);
-    *bytes = per_frame * size_t(B > 0 ? B : 1) + list;
-    if (min_bytes) *min_bytes = per_frame + list;
+    const size_t hq_frame = size_t(M) * sizeof(float);     // whitening bound, one float per channel
+    *bytes = (per_frame + hq_frame) * size_t(B > 0 ? B : 1) + list + 256;
+    if (min_bytes) *min_bytes = per_frame + hq_frame + list + 256;
     return PAL_OK;
   }
   // Bluestein path: sized for the longest transform the rows allow (n <= 2*n_samples-1)
@@ -268,12 +271,14 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
 
   const size_t per_frame = align_up(size_t(M) * kSpecSlots * sizeof(cpxf), 256);
   const size_t list_bytes = align_up(size_t(B) * P * sizeof(int), 256) + 256;
-  if (ws_bytes < per_frame + list_bytes) return fail(PAL_ERR_WORKSPACE, "pal_gcc_phat_tdoa: workspace too small");
+  const size_t hq_frame = size_t(M) * sizeof(float);
+  if (ws_bytes < per_frame + hq_frame + list_bytes + 256) return fail(PAL_ERR_WORKSPACE, "pal_gcc_phat_tdoa: workspace too small");
   char* ws = static_cast<char*>(ws_dev);
   int* list = reinterpret_cast<int*>(ws);
   int* count = reinterpret_cast<int*>(ws + list_bytes - 256);
   cpxf* spec = reinterpret_cast<cpxf*>(ws + list_bytes);
-  const int64_t chunk = std::min<int64_t>(B, int64_t((ws_bytes - list_bytes) / per_frame));
+  const int64_t chunk = std::min<int64_t>(B, int64_t((ws_bytes - list_bytes - 256) / (per_frame + hq_frame)));
+  float* hq = reinterpret_cast<float*>(ws + list_bytes + align_up(size_t(chunk) * per_frame, 256));   // [chunk][M]
 
   const PickParams pp{prm->win_half, prm->peak_dist, prm->thr_method, prm->thr_mult, prm->num_peaks};
   const size_t fwd_smem = sizeof(FwdSmem);
@@ -314,7 +319,7 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
       const int gf = (int)std::min<long long>(units, (long long)di.sms * 4);   // 48 KB of shared memory per CTA: 4 CTAs per SM
       {
         ProfScope ps(1, stream);
-        k_fwd4095<<<gf, kFwdThreads, fwd_smem, stream>>>(sig, M, units, spec);
+        k_fwd4095<<<gf, kFwdThreads, fwd_smem, stream>>>(sig, M, units, spec, hq);
       }
       ++g_launches;
       const int gp = (int)std::min<long long>((n_items + kFastWarps - 1) / kFastWarps, (long long)di.sms);
@@ -324,12 +329,12 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
         if (use_tmem_kernel()) {
           const int gt = (int)std::min<long long>((n_items + kTmemWarps - 1) / kTmemWarps, (long long)di.sms);
           auto kern = corr ? k_pair4095_tmem<true> : k_pair4095_tmem<false>;
-          kern<<<gt, kTmemWarps * 32, tmem_smem, stream>>>(spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist,
+          kern<<<gt, kTmemWarps * 32, tmem_smem, stream>>>(spec, hq, pairs_dev, M, P, n_items, pp.win_half, pp.dist,
                                                            prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
                                                            gmax_dev + item0, flags_dev + item0, corr);
         } else {
           auto kern = corr ? k_pair4095_fast<true> : k_pair4095_fast<false>;
-          kern<<<gp, kFastWarps * 32, fast_smem, stream>>>(spec, pairs_dev, M, P, n_items, pp.win_half, pp.dist,
+          kern<<<gp, kFastWarps * 32, fast_smem, stream>>>(spec, hq, pairs_dev, M, P, n_items, pp.win_half, pp.dist,
                                                            prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
                                                            gmax_dev + item0, flags_dev + item0, corr);
         }
@@ -553,6 +558,53 @@ int pal_filtfilt(const void* x_dev, int64_t n_rows, int32_t n, int32_t io_f32, c
   else
     k_filtfilt<double><<<grid, kFiltThreads, smem, st>>>(static_cast<const double*>(x_dev), n_rows, n, fp,
                                                          static_cast<double*>(ws_dev), static_cast<double*>(y_dev));
+  ++g_launches;
+  PAL_CUDA(cudaGetLastError());
+  return PAL_OK;
+}
+
+int pal_sync_align_workspace(int64_t n_scenes, int32_t n_ch, int32_t ld, size_t* bytes, size_t* min_bytes) {
+  if (n_scenes < 0 || n_ch < 1 || ld < 2 || ld > (1 << 28) || !bytes) return fail(PAL_ERR_INVALID, "pal_sync_align_workspace: bad argument");
+  *bytes = palhost::sync_full_bytes<double>(ld, n_scenes, n_ch);
+  if (min_bytes) *min_bytes = palhost::sync_min_bytes<double>(ld, n_ch);
+  return PAL_OK;
+}
+
+int pal_sync_align(const double* sig_dev, int64_t n_scenes, int32_t n_ch, int32_t ld, const int32_t* lens_dev,
+                   int32_t* ref_idx_dev, int32_t* peak_index_dev, double* absmax_dev, double* win_dev,
+                   double* energy_dev, void* ws_dev, size_t ws_bytes, void* stream_) {
+  if (n_scenes < 0 || n_ch < 1 || ld < 2 || ld > (1 << 28)) return fail(PAL_ERR_INVALID, "pal_sync_align: bad size argument");
+  if (n_scenes == 0) return PAL_OK;
+  if (n_scenes * (int64_t)n_ch > 0x3fffffffLL) return fail(PAL_ERR_INVALID, "pal_sync_align: too many rows; split the batch");
+  if (!sig_dev || !ref_idx_dev || !peak_index_dev || !absmax_dev || !win_dev || !ws_dev)
+    return fail(PAL_ERR_INVALID, "pal_sync_align: NULL device pointer");
+  if (reinterpret_cast<uintptr_t>(ws_dev) & 255u) return fail(PAL_ERR_INVALID, "pal_sync_align: ws_dev must be 256-byte aligned");
+  if (ws_bytes < palhost::sync_min_bytes<double>(ld, n_ch)) return fail(PAL_ERR_WORKSPACE, "pal_sync_align: workspace too small");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  palhost::SyncCall c{sig_dev, (long long)n_scenes, n_ch, ld, lens_dev, ref_idx_dev, peak_index_dev, absmax_dev, win_dev,
+                      energy_dev, static_cast<cudaStream_t>(stream_), di.sms};
+  cudaError_t e = palhost::run_sync_align<double>(c, static_cast<char*>(ws_dev), ws_bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "pal_sync_align");
+  return PAL_OK;
+}
+
+int pal_pad_rows(const void* in_dev, int64_t n_rows, int64_t ld_in, const int32_t* lens_dev, const int32_t* pad_left_dev,
+                 void* out_dev, int64_t ld_out, int32_t io_f32, void* stream_) {
+  if (n_rows < 0 || ld_in < 1 || ld_out < 1 || ld_in > 0x7fffffffLL) return fail(PAL_ERR_INVALID, "pal_pad_rows: bad size argument");
+  if (n_rows == 0) return PAL_OK;
+  if (!in_dev || !out_dev || !pad_left_dev) return fail(PAL_ERR_INVALID, "pal_pad_rows: NULL device pointer");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  const long long total = (long long)n_rows * ld_out;
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 32LL * di.sms);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (io_f32)
+    palhost::k_pad_rows<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in_dev), n_rows, ld_in, (int)ld_in, lens_dev,
+                                                     pad_left_dev, static_cast<float*>(out_dev), ld_out);
+  else
+    palhost::k_pad_rows<double><<<grid, 256, 0, st>>>(static_cast<const double*>(in_dev), n_rows, ld_in, (int)ld_in, lens_dev,
+                                                      pad_left_dev, static_cast<double*>(out_dev), ld_out);
   ++g_launches;
   PAL_CUDA(cudaGetLastError());
   return PAL_OK;

@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "pal_bluestein.cuh"
+#include "pal_sync.cuh"
 
 namespace palhost {
 using namespace pal;
@@ -248,6 +249,114 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
       const long long ni = std::min<long long>(ichunk, n_list - i0);
       forward(0, 2 * ni, rows_scratch + 2 * i0, spec);
       inverse(ni, spec, 0, list + i0);
+    }
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- alignment front end (pal_sync.cuh)
+constexpr int kSyncThreads = 256;
+__global__ void __launch_bounds__(kSyncThreads) k_sync_energy(const double* sig, long long n_scenes, int Mics, long long ld,
+                                                              int len, const int* lens, double* energy, int* ref_idx) {
+  extern __shared__ __align__(128) char smem[];
+  sync_energy_body<kSyncThreads>(sig, n_scenes, Mics, ld, len, lens, energy, ref_idx, smem);
+}
+template <typename T>
+__global__ void __launch_bounds__(kSyncThreads) k_sync_pick(const T* corr, int n, long long n_rows, long long item0, int Mics,
+                                                            const int* ref, int len, const int* lens, int* peak_index,
+                                                            double* absmax, double* win) {
+  __shared__ SyncPickSmem sm;
+  sync_pick_body<T, kSyncThreads>(corr, n, n_rows, item0, Mics, ref, len, lens, peak_index, absmax, win,
+                                  reinterpret_cast<char*>(&sm));
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_pad_rows(const T* in, long long n_rows, long long ld_in, int len, const int* lens,
+                                                  const int* pad, T* out, long long ld_out) {
+  pad_rows_body<T>(in, n_rows, ld_in, len, lens, pad, out, ld_out);
+}
+
+struct SyncCall {
+  const double* sig;     // [S][Mics][ld]
+  long long S;
+  int Mics, ld;
+  const int* lens;       // optional [S][Mics]
+  int* ref_idx;          // out [S]
+  int* peak_index;       // out [S][Mics]
+  double* absmax;        // out [S][Mics]
+  double* win;           // out [S][Mics][5]
+  double* energy;        // out [S][Mics] or NULL
+  cudaStream_t stream;
+  int sms;
+};
+template <typename T> size_t sync_min_bytes(int ld, int Mics) {
+  GenericLayout<T> L(2 * ld - 1);
+  return L.tables + L.per_tr + size_t(Mics) * L.per_row + 1024;
+}
+template <typename T> size_t sync_full_bytes(int ld, long long S, int Mics) {
+  GenericLayout<T> L(2 * ld - 1);
+  const long long tr = std::min<long long>(2048, std::max<long long>(1, S * Mics));
+  return L.tables + size_t(tr) * L.per_tr + size_t(std::max<long long>(1, S)) * Mics * L.per_row + 1024;
+}
+
+// energies -> reference channel -> spectra of every channel -> plain cross-correlation with the reference -> arg-max
+template <typename T> cudaError_t run_sync_align(const SyncCall& c, char* ws, size_t ws_bytes) {
+  const int n = 2 * c.ld - 1;
+  GenericLayout<T> L(n);
+  const BluePlan p = L.p;
+  if (ws_bytes < sync_min_bytes<T>(c.ld, c.Mics)) return cudaErrorMemoryAllocation;
+  k_sync_energy<<<(unsigned)std::min<long long>(c.S, 8LL * c.sms), kSyncThreads, sizeof(double) * c.Mics, c.stream>>>(
+      c.sig, c.S, c.Mics, c.ld, c.ld, c.lens, c.energy, c.ref_idx);
+  count_launch();
+  char* base = ws;
+  BlueBuffers<T> bb;
+  cudaError_t e = setup_plan<T>(p, base, bb, c.stream, c.sms);
+  if (e != cudaSuccess) return e;
+  const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
+  cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignalF64<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_fwd<T, LoadCross<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  size_t rem = ws_bytes - size_t(base - ws);
+  long long tr_cap = std::max<long long>(1, std::min<long long>(2048, (long long)((rem / 4) / L.per_tr)));
+  tr_cap = std::min<long long>(tr_cap, c.S * c.Mics);
+  while (tr_cap > 1 && rem < size_t(tr_cap) * L.per_tr + size_t(c.Mics) * L.per_row) tr_cap /= 2;
+  cpx<T>* conv = reinterpret_cast<cpx<T>*>(base);
+  base += tr_cap * al(sizeof(cpx<T>) * size_t(p.M));
+  T* corr = reinterpret_cast<T*>(base);
+  base += tr_cap * al(sizeof(T) * size_t(n));
+  rem = ws_bytes - size_t(base - ws);
+  const long long row_cap = (long long)(rem / L.per_row);
+  if (row_cap < c.Mics) return cudaErrorMemoryAllocation;
+  cpx<T>* spec = reinterpret_cast<cpx<T>*>(base);
+  const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
+  const BlueTables<T> tb = bb.tb();
+  const long long schunk = std::max<long long>(1, std::min<long long>(c.S, row_cap / c.Mics));
+  for (long long s0 = 0; s0 < c.S; s0 += schunk) {
+    const long long ns = std::min(schunk, c.S - s0);
+    const long long nrows = ns * c.Mics;
+    for (long long r0 = 0; r0 < nrows; r0 += tr_cap) {
+      const long long nt = std::min(tr_cap, nrows - r0);
+      LoadSignalF64<T> ld{p, bb.chirp, c.sig, c.ld, c.ld, c.lens, s0 * c.Mics + r0};
+      k_colpass_fwd<T, LoadSignalF64<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+          p, tb, ld, nt, nullptr, conv);
+      k_rowpass<T, true, false><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * c.sms), kGT, rs, c.stream>>>(
+          p, tb, nt, nullptr, conv);
+      StoreSpectrum<T> st{p, bb.chirp, spec + r0 * n};
+      k_colpass_inv<T, StoreSpectrum<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+          p, tb, st, nt, nullptr, conv);
+      count_launch(3);
+    }
+    for (long long i0 = 0; i0 < nrows; i0 += tr_cap) {
+      const long long nt = std::min(tr_cap, nrows - i0);
+      LoadCross<T> ld{p, bb.chirp, spec, c.ref_idx, s0, c.Mics, i0};
+      k_colpass_fwd<T, LoadCross<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+          p, tb, ld, nt, nullptr, conv);
+      k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * c.sms), kGT, rs, c.stream>>>(
+          p, tb, nt, nullptr, conv);
+      StoreCorr<T> st{p, bb.chirp, corr};
+      k_colpass_inv<T, StoreCorr<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+          p, tb, st, nt, nullptr, conv);
+      k_sync_pick<T><<<(unsigned)std::min<long long>(nt, 8LL * c.sms), kSyncThreads, 0, c.stream>>>(
+          corr, n, nt, s0 * c.Mics + i0, c.Mics, c.ref_idx, c.ld, c.lens, c.peak_index, c.absmax, c.win);
+      count_launch(4);
     }
   }
   return cudaGetLastError();

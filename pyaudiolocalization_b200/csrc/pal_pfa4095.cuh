@@ -16,6 +16,9 @@
 #ifndef PAL_STAGGER
 #define PAL_STAGGER 6000   // cycles, see pair4095_fast_body
 #endif
+#ifndef PAL_PREWHITEN
+#define PAL_PREWHITEN 1    // 1: fwd4095 stores unit phasors S/|S| and the pair kernels only multiply (see whiten_bin)
+#endif
 #include "pal_dft_small.h"
 #include "pal_peakpick.cuh"
 
@@ -105,7 +108,34 @@ struct alignas(16) FwdSmem {
   float stage[2][kFrame2048];   // TMA landing zone: the two raw frames
   f2 z[4096];                   // the complex sequence, transformed in place
   mbar_t bar;
+  float red[32];                // per-warp partials of the two whitening bounds (NT <= 512)
 };
+
+// PHAT factorised per CHANNEL instead of per pair.  |Si conj(Sj)| = |Si| |Sj|, so
+//     R / (|R| + 1e-10) = Ui conj(Uj) * g,   U = S / |S|,   g = m / (m + 1e-10),  m = |Si| |Sj|      (utils.py:116-117)
+// and g is 1 to fp32 precision unless a channel is all but silent.  The forward kernel therefore stores the unit
+// phasors U (M normalisations per frame instead of P), the pair kernels multiply two phasors per bin (2 packed
+// instructions instead of 8, no MUFU), and the neglected factor is BOUNDED per row:
+//     |corr_U[k] - corr[k]| <= (1/n) sum_k 1e-10 / m_k <= 1e-10 sqrt(h_i h_j),   h = (1/n) sum_k 1 / |S_k|^2   (Cauchy-Schwarz)
+// h is accumulated here (one float per channel); the pair kernel widens its near-tie margin by the bound and sends
+// the row to the float64 kernel when the bound itself is not negligible (frames quieter than about -69 dBFS).
+// Bins with S == 0 give R == 0 in both forms and are left out of h.
+PAL_DEV f2 whiten_bin(f2 s, float weight, float& hacc) {
+  const float x = f2_lo(s), y = f2_hi(s);
+  const float m2 = fmaf(x, x, y * y);
+  if (m2 > 1e-30f) {
+#if PAL_GPU
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m2));
+#else
+    const float r = 1.0f / std::sqrt(m2);
+#endif
+    hacc = fmaf(weight, r * r, hacc);
+    return f2_mul(s, f2_bcast(r));
+  }
+  if (m2 > 0.f) hacc += weight * 1e30f;     // denormal-range bin: forces the float64 path
+  return f2_make(0.f, 0.f);
+}
 
 // in-place PFA stage on packed complex data; FIRST: gather the inputs from the raw frames instead
 // (z[k] = x0[k] + i x1[k] for k < 2048, zero beyond)
@@ -133,29 +163,36 @@ template <int F, int NT, bool FIRST> PAL_DEV void pfa_stage_p(f2* z, const float
 }
 
 template <int NT>
-PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil(M/2) */, cpxf* spec, char* smem_raw) {
+PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil(M/2) */, cpxf* spec, float* hq /* [B][M] */,
+                          char* smem_raw) {
   FwdSmem* sm = reinterpret_cast<FwdSmem*>(smem_raw);
   const int tid = simt::tid();
   const int cpairs = (M + 1) / 2;
   if (tid == 0) simt::mbar_init(&sm->bar, 1);
   simt::sync_block();
   unsigned parity = 0;
+  // TMA bulk load of the signal frame(s) of one unit: two contiguous 8 KB rows
+  auto request = [&](long long u) {
+    const long long fr = u / cpairs;
+    const int c0 = 2 * int(u % cpairs);
+    const bool both = (c0 + 1) < M;
+    const float* row0 = sig + (fr * M + c0) * kFrame2048;
+    simt::fence_async_smem();
+    simt::mbar_expect_tx(&sm->bar, both ? 2u * kFrame2048 * 4u : kFrame2048 * 4u);
+    simt::bulk_g2s(sm->stage[0], row0, kFrame2048 * 4u, &sm->bar);
+    if (both) simt::bulk_g2s(sm->stage[1], row0 + kFrame2048, kFrame2048 * 4u, &sm->bar);
+  };
+  if (tid == 0 && simt::bid() < n_units) request(simt::bid());
   for (long long unit = simt::bid(); unit < n_units; unit += simt::nblocks()) {
     const long long frame = unit / cpairs;
     const int ch0 = 2 * int(unit % cpairs);
     const bool two = (ch0 + 1) < M;
-    const float* row0 = sig + (frame * M + ch0) * kFrame2048;
-    // TMA bulk load of the signal frame(s): two contiguous 8 KB rows
-    if (tid == 0) {
-      simt::fence_async_smem();
-      simt::mbar_expect_tx(&sm->bar, two ? 2u * kFrame2048 * 4u : kFrame2048 * 4u);
-      simt::bulk_g2s(sm->stage[0], row0, kFrame2048 * 4u, &sm->bar);
-      if (two) simt::bulk_g2s(sm->stage[1], row0 + kFrame2048, kFrame2048 * 4u, &sm->bar);
-    }
     simt::mbar_wait(&sm->bar, parity);
     parity ^= 1u;
     pfa_stage_p<13, NT, true>(sm->z, sm->stage[0], sm->stage[1], two);
     simt::sync_block();
+    // the landing zone is free again: the frames of this block's NEXT unit travel while this one is transformed
+    if (tid == 0 && unit + simt::nblocks() < n_units) request(unit + simt::nblocks());
     pfa_stage_p<9, NT, false>(sm->z, nullptr, nullptr, two);
     simt::sync_block();
     pfa_stage_p<7, NT, false>(sm->z, nullptr, nullptr, two);
@@ -164,6 +201,7 @@ PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil
     simt::sync_block();
     f2* o0 = reinterpret_cast<f2*>(spec + (frame * M + ch0) * kSpecSlots);
     f2* o1 = o0 + kSpecSlots;
+    float h0 = 0.f, h1 = 0.f;
     for (int o = tid; o < kSpecSlots; o += NT) {
       const int q = o >> 5, r = o & 31;
       const int e = Idx4095::elem(r, q);
@@ -172,13 +210,35 @@ PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil
       // Z = DFT(x1 + i x2): S1[e] = (Z[e] + conj(Z[n-e])) / 2, S2[e] = (Z[e] - conj(Z[n-e])) / (2i)
       const f2 zl = sm->z[L], zm = f2_conj(sm->z[L2]);
       const f2 half = f2_bcast(0.5f);
-      o0[o] = f2_mul(f2_add(zl, zm), half);
-      if (two) {
-        const f2 d = f2_mul(f2_sub(zl, zm), half);       // i * S2
-        o1[o] = f2_make(f2_hi(d), -f2_lo(d));             // S2 = -i * d
-      }
+      f2 s0 = f2_mul(f2_add(zl, zm), half);
+      const f2 d = f2_mul(f2_sub(zl, zm), half);          // i * S2
+      f2 s1 = f2_make(f2_hi(d), -f2_lo(d));               // S2 = -i * d
+#if PAL_PREWHITEN
+      // slot (q, r) stands for bins e and n - e when r > 0; row r = 0 holds both members of a conjugate pair
+      const float wgt = r ? 2.f : 1.f;
+      s0 = whiten_bin(s0, wgt, h0);
+      if (two) s1 = whiten_bin(s1, wgt, h1);
+#endif
+      o0[o] = s0;
+      if (two) o1[o] = s1;
     }
+#if PAL_PREWHITEN
+    // both sums in one exchange; the barrier that ends the unit publishes the partials, thread 0 adds them in
+    // warp order (deterministic) before it can reach any barrier of the next unit
+    h0 = warp_sum(h0);
+    h1 = warp_sum(h1);
+    if (simt::lane() == 0) { sm->red[simt::warp()] = h0; sm->red[16 + simt::warp()] = h1; }
+#endif
     simt::sync_block();
+#if PAL_PREWHITEN
+    if (tid == 0) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) { a0 += sm->red[w]; a1 += sm->red[16 + w]; }
+      hq[frame * M + ch0] = a0 * (1.0f / float(kN4095));
+      if (two) hq[frame * M + ch0 + 1] = a1 * (1.0f / float(kN4095));
+    }
+#endif
   }
 }
 
@@ -303,6 +363,9 @@ constexpr float kNegBig = -3.0e38f;
 PAL_DEV f2 phat_bin_p(f2 a, f2 b) {
   const f2 t = f2_mul(a, f2_bcast(f2_lo(b)));                                    // (ar br, ai br)
   const f2 x = f2_fma(f2_make(f2_hi(a), -f2_lo(a)), f2_bcast(f2_hi(b)), t);      // + (ai bi, -ar bi)
+#if PAL_PREWHITEN
+  return x;      // a, b are unit phasors (whiten_bin): the product is the PHAT-weighted bin
+#else
   const float xr = f2_lo(x), xi = f2_hi(x);
   const float m2 = fmaf(xr, xr, xi * xi);
 #if PAL_GPU
@@ -313,6 +376,17 @@ PAL_DEV f2 phat_bin_p(f2 a, f2 b) {
   const float rcp = 1.0f / (std::sqrt(m2) + 1e-10f);
 #endif
   return f2_mul(x, f2_bcast(rcp));
+#endif
+}
+
+// Bound (in the unscaled row, n * corr) on what the factor g neglected by the whitened spectra can move a
+// correlation sample of pair (i, j): n * 1e-10 * sqrt(h_i h_j); see whiten_bin.
+PAL_DEV float whiten_bound(const float* hq, long long row_i, long long row_j) {
+#if PAL_PREWHITEN
+  return (1e-10f * float(kN4095)) * sqrt_(hq[row_i] * hq[row_j]);
+#else
+  return 0.f;
+#endif
 }
 
 // Careful scan of the window (strict local maxima, runner-up, equal neighbours).  Only used when
@@ -394,10 +468,13 @@ PAL_DEV FastPick make_fast_pick(int win_half, int dist, float eps) {
 
 // Peak pick (num_peaks = 1) of one unscaled correlation row in shared memory by one warp.
 template <bool WRITE_CORR>
-PAL_DEV void fast_pick_row(const float* c, long long item, float gm, int lane, const FastPick& pk, int* k_idx, float* peak,
-                           float* gmax, unsigned* flags, float* corr_out) {
+PAL_DEV void fast_pick_row(const float* c, long long item, float gm, int lane, const FastPick& pk, float wbound,
+                           int* k_idx, float* peak, float* gmax, unsigned* flags, float* corr_out) {
   const int lo = pk.lo, hi = pk.hi, g_lo = pk.g_lo, g_hi = pk.g_hi, dist = pk.dist;
-  const float eps_s = pk.eps_s, mean_bound = pk.mean_bound, inv_n = pk.inv_n;
+  // wbound: see whiten_bound.  Small: it widens the near-tie margin.  Not small (or NaN/inf): the row's VALUES
+  // are off by more than the float32 noise -> float64 kernel.
+  const bool quiet = !(wbound <= 2.f * pk.eps_s);
+  const float eps_s = pk.eps_s + (quiet ? 0.f : wbound), mean_bound = pk.mean_bound, inv_n = pk.inv_n;
   if (WRITE_CORR) {
     float* dst = corr_out + item * kN4095;
     for (int k = lane; k < kN4095; k += 32) dst[k] = c[k] * inv_n;
@@ -439,7 +516,7 @@ PAL_DEV void fast_pick_row(const float* c, long long item, float gm, int lane, c
   float pl = kNegBig;
   if (bi >= 0 && !(c[bi - 1] < bv && bv > c[bi + 1])) window_scan_slow(c, lo, hi, lane, bv, bi, cand2, pl);
 
-  unsigned fl = 0;
+  unsigned fl = quiet ? PAL_FLAG_NEAR_TIE : 0u;
   int kbest;
   float hbest;
   if (bi >= 0 && bv >= mean_bound + eps_s) {
@@ -507,7 +584,7 @@ constexpr int kPrefetchBins = PAL_PREFETCH_BINS;        // multiple of 4
 constexpr int kL1PrefetchBins = PAL_L1_PREFETCH_BINS;   // bins [kPrefetchBins, kL1PrefetchBins) go to L1 only
 
 template <int WARPS, bool WRITE_CORR>
-PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P, long long n_items,
+PAL_DEV void pair4095_fast_body(const cpxf* spec, const float* hq, const int* pairs, int M, int P, long long n_items,
                                 int win_half, int dist, float eps, int* k_idx, float* peak, float* gmax,
                                 unsigned* flags, float* corr_out, char* smem_raw) {
   using P65 = Pfa2<5, 13>;
@@ -545,11 +622,13 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
   const f2* si;
   const f2* sj;
   f2 pa[kPrefetchBins], pb[kPrefetchBins];
+  float wb, wb_next = 0.f;     // whiten_bound of the current / next pair
   {
     const long long frame = item / P;
     const int p = int(item % P);
     si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
     sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
+    wb = whiten_bound(hq, frame * M + pairs[2 * p], frame * M + pairs[2 * p + 1]);
 #pragma unroll
     for (int q = 0; q < kPrefetchBins; ++q) { pa[q] = si[q * 32]; pb[q] = sj[q * 32]; }
   }
@@ -677,6 +756,7 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
       const int p = int(next % P);
       si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
       sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
+      wb_next = whiten_bound(hq, frame * M + pairs[2 * p], frame * M + pairs[2 * p + 1]);
 #pragma unroll
       for (int q = 0; q < kPrefetchBins; ++q) { pa[q] = si[q * 32]; pb[q] = sj[q * 32]; }
 #if PAL_GPU
@@ -692,9 +772,10 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const int* pairs, int M, int P
     simt::sync_warp();
 
     // ---- peak pick (num_peaks = 1), utils.py:140-181 in the reduced form ----------------
-    fast_pick_row<WRITE_CORR>(sm->corr, item, gm, lane, pk, k_idx, peak, gmax, flags, corr_out);
+    fast_pick_row<WRITE_CORR>(sm->corr, item, gm, lane, pk, wb, k_idx, peak, gmax, flags, corr_out);
     if (!has_next) break;
     item = next;
+    wb = wb_next;
     simt::sync_warp();   // the next item overwrites the union
   }
 }
@@ -713,7 +794,7 @@ template <int WARPS> struct TmemPlan {
 };
 
 template <int WARPS, bool WRITE_CORR>
-PAL_DEV void pair4095_tmem_body(const cpxf* spec, const int* pairs, int M, int P, long long n_items,
+PAL_DEV void pair4095_tmem_body(const cpxf* spec, const float* hq, const int* pairs, int M, int P, long long n_items,
                                 int win_half, int dist, float eps, int* k_idx, float* peak, float* gmax,
                                 unsigned* flags, float* corr_out, char* smem_raw) {
   using P65 = Pfa2<5, 13>;
@@ -764,10 +845,12 @@ PAL_DEV void pair4095_tmem_body(const cpxf* spec, const int* pairs, int M, int P
     const f2* si;
     const f2* sj;
     f2 ra[kLA][5], rb[kLA][5];
+    float wb, wb_next = 0.f;     // whiten_bound of the current / next pair
     {
       const long long frame = item / P;
       si = reinterpret_cast<const f2*>(spec + (frame * M + mi0) * kSpecSlots) + lane;
       sj = reinterpret_cast<const f2*>(spec + (frame * M + mj0) * kSpecSlots) + lane;
+      wb = whiten_bound(hq, frame * M + mi0, frame * M + mj0);
 #pragma unroll
       for (int g = 0; g < kLA; ++g)
 #pragma unroll
@@ -926,15 +1009,17 @@ PAL_DEV void pair4095_tmem_body(const cpxf* spec, const int* pairs, int M, int P
         const int p = int(next % P);
         si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
         sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
+        wb_next = whiten_bound(hq, frame * M + pairs[2 * p], frame * M + pairs[2 * p + 1]);
 #pragma unroll
         for (int g = 0; g < kLA; ++g)
 #pragma unroll
           for (int a5 = 0; a5 < 5; ++a5) { ra[g][a5] = si[P65::slot(a5, g) * 32]; rb[g][a5] = sj[P65::slot(a5, g) * 32]; }
       }
       simt::sync_warp();
-      fast_pick_row<WRITE_CORR>(sm->corr, item, gm, lane, pk, k_idx, peak, gmax, flags, corr_out);
+      fast_pick_row<WRITE_CORR>(sm->corr, item, gm, lane, pk, wb, k_idx, peak, gmax, flags, corr_out);
       if (!has_next) break;
       item = next;
+      wb = wb_next;
       simt::sync_warp();   // the next item overwrites the union
     }
   }

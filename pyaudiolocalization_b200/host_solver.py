@@ -41,40 +41,6 @@ def read_audio_files(audio_files, expected_fs):
     return out
 
 
-def synchronize_signals_improved(signals, fs, use_interpolation=True):
-    """utils.py:407-457 -- align on the highest-energy channel by full cross-correlation,
-    5-point cubic refinement, left padding."""
-    from scipy.interpolate import CubicSpline
-    from scipy.signal import correlate
-    ref_idx = int(np.argmax([np.sum(s ** 2) for s in signals]))
-    ref = signals[ref_idx]
-    ref_peak = np.max(np.abs(correlate(ref, ref, mode='full')))
-    limit = int(fs * 0.05)
-    shifts = []
-    for idx, sig in enumerate(signals):
-        if idx == ref_idx:
-            shifts.append(0)
-            continue
-        corr = correlate(sig, ref, mode='full')
-        pk = int(np.argmax(np.abs(corr)))
-        refined = pk
-        if np.abs(corr[pk]) < 0.3 * ref_peak:
-            logging.warning(f"Niedriger Korrelationspeak für Signal {idx} während Synchronisation. Setze Shift=0.")
-        elif use_interpolation and 1 < pk < len(corr) - 2:
-            cs = CubicSpline(np.arange(pk - 2, pk + 3), corr[pk - 2:pk + 3])
-            fine = np.linspace(pk - 2, pk + 2, 100)
-            refined = fine[np.argmax(np.abs(cs(fine)))]
-        shift = refined - (len(ref) - 1)
-        if abs(shift) > limit:
-            logging.warning(f"Berechneter Shift ({shift} Samples) für Signal {idx} überschreitet plausiblen Bereich. Setze Shift=0.")
-            shift = 0
-        shifts.append(shift)
-    lo = min(shifts)
-    padded = [np.pad(s, (max(0, int(round(sh - lo))), 0), mode='constant') for s, sh in zip(signals, shifts)]
-    n = max(len(s) for s in padded)
-    return [np.pad(s, (0, n - len(s)), mode='constant') for s in padded]
-
-
 def noise_reduction(signal, fs, method='butterworth', lowcut=300, highcut=3400, filter_order=101):
     """signal_processing.py:109-138."""
     from scipy.signal import butter, filtfilt, firwin, wiener

@@ -2,8 +2,9 @@
 (main.py:66-124) and `localize_sound_source(config, ...)` (main.py:126-333).
 
 The two data-parallel stages run on the GPU (scene synthesis: scene.py; GCC-PHAT / TDOA:
-gcc_phat.py).  Everything the reference keeps in scipy/sklearn on the host -- signal
-synchronisation, band-pass filtering, clustering initialisation, bounded least squares and the
+gcc_phat.py).  The two steps between them run on the GPU too: channel alignment (sync.py, utils.py:407-457) and
+the Butterworth band-pass (filters.py, signal_processing.py:124-128).  What the reference keeps in
+scipy/sklearn for the position solve -- clustering initialisation, bounded least squares and the
 Differential-Evolution fallback -- stays on the host here as well (host_solver.py).
 """
 from __future__ import annotations
@@ -15,6 +16,7 @@ import torch
 
 from . import gcc_phat as _g
 from . import scene as _s
+from . import sync as _sync
 from .materials import material_properties  # noqa: F401
 from .signal_processing import generate_signal
 from .utils import speed_of_sound
@@ -161,7 +163,7 @@ def localize_sound_source(config, calibration_data=None, audio_files=None, use_s
         signals = H.read_audio_files(audio_files, fs)
         logging.info("Echte Audiodaten geladen.")
 
-    signals = H.synchronize_signals_improved(signals, fs)
+    signals = _sync.synchronize_signals_improved(signals, fs)      # utils.py:407-457 on the GPU (sync.py)
     logging.info("Signale synchronisiert.")
     filtered = [H.noise_reduction(sig, fs, method=filter_method) for sig in signals]
     for i in range(len(filtered)):

@@ -133,4 +133,6 @@ def generate_image_sources_iterative(source, planes, max_order: int, frequency: 
 from .host_solver import (bootstrap_significance, compute_cross_correlation_metrics,  # noqa: E402,F401
                           compute_peak_to_peak_ratio, compute_snr, compute_weights,
                           determine_optimal_number_of_clusters, dynamic_bounds_extended, equations,
-                          heuristic_initialization_adaptive, read_audio_files, synchronize_signals_improved)
+                          heuristic_initialization_adaptive, read_audio_files)
+# utils.py:407-457 on the GPU (sync.py)
+from .sync import synchronize_signals_improved  # noqa: E402,F401

@@ -17,3 +17,9 @@ def pytest_configure(config):
 def golden():
     path = os.path.join(ROOT, "tests", "golden", "reference_vectors.npz")
     return np.load(path)
+
+
+@pytest.fixture(scope="session")
+def sync_golden():
+    """utils.synchronize_signals_improved of the unmodified reference (tests/golden/make_golden_sync.py)."""
+    return np.load(os.path.join(ROOT, "tests", "golden", "sync_vectors.npz"))

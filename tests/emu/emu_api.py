@@ -23,11 +23,17 @@ def pairs_of(m):
     return np.array([(i, j) for i in range(m) for j in range(i + 1, m)], dtype=np.int32)
 
 
+class Spectra(np.ndarray):
+    """[B, M, 2080, 2] whitened spectra plus .hq [B, M], the per-channel whitening bound (pal_pfa4095.cuh: whiten_bin)."""
+    hq = None
+
+
 def fwd4095(sig):
     b, m, n = sig.shape
     assert n == 2048 and sig.dtype == np.float32
-    spec = np.zeros((b, m, 2080, 2), np.float32)
-    lib().emu_fwd4095(_p(sig, C.c_float), m, C.c_longlong(b), _p(spec, C.c_float), 2)
+    spec = np.zeros((b, m, 2080, 2), np.float32).view(Spectra)
+    spec.hq = np.zeros((b, m), np.float32)
+    lib().emu_fwd4095(_p(sig, C.c_float), m, C.c_longlong(b), _p(spec, C.c_float), _p(spec.hq, C.c_float), 2)
     return spec
 
 
@@ -39,7 +45,9 @@ def pair_fast(spec, pairs, win_half, dist, eps=2e-6, want_corr=False, phase_sync
     gm = np.zeros((b, p), np.float32)
     fl = np.zeros((b, p), np.uint32)
     corr = np.zeros((b, p, 4095), np.float32) if want_corr else None
-    lib().emu_pair4095_fast(_p(spec, C.c_float), _p(pairs, C.c_int), m, p, C.c_longlong(b), win_half, dist,
+    hq = getattr(spec, "hq", None)
+    hq = np.zeros((b, m), np.float32) if hq is None else np.ascontiguousarray(hq, np.float32)
+    lib().emu_pair4095_fast(_p(spec, C.c_float), _p(hq, C.c_float), _p(pairs, C.c_int), m, p, C.c_longlong(b), win_half, dist,
                             C.c_float(eps), _p(k, C.c_int), _p(pk, C.c_float), _p(gm, C.c_float),
                             _p(fl, C.c_uint), _p(corr, C.c_float), 3, int(phase_sync))
     return k, pk, gm, fl, corr
@@ -172,3 +180,29 @@ def filtfilt_f64(x, b, a, zi, padlen):
     lib().emu_filtfilt_f64(_pd(x), C.c_longlong(rows), n, _pd(bb), _pd(aa), _pd(np.ascontiguousarray(zi, np.float64)), nt, padlen,
                            _pd(y))
     return y
+
+
+def sync_align(sig, lens=None):
+    """sig [S, M, ld] float64 -> ref_idx [S], peak_index [S, M], absmax [S, M], win [S, M, 5], energy [S, M]."""
+    sig = np.ascontiguousarray(sig, np.float64)
+    s, m, ld = sig.shape
+    ln = None if lens is None else np.ascontiguousarray(lens, np.int32)
+    ref = np.zeros(s, np.int32)
+    pk = np.zeros((s, m), np.int32)
+    am = np.zeros((s, m))
+    win = np.zeros((s, m, 5))
+    en = np.zeros((s, m))
+    lib().emu_sync_align(_pd(sig), C.c_longlong(s), m, ld, _p(ln, C.c_int), _p(ref, C.c_int), _p(pk, C.c_int), _pd(am),
+                         _pd(win), _pd(en))
+    return ref, pk, am, win, en
+
+
+def pad_rows_f64(x, pad, ld_out, lens=None):
+    x = np.ascontiguousarray(x, np.float64)
+    rows, ld = x.shape
+    pad = np.ascontiguousarray(pad, np.int32)
+    ln = None if lens is None else np.ascontiguousarray(lens, np.int32)
+    out = np.full((rows, ld_out), np.nan)
+    lib().emu_pad_rows_f64(_pd(x), C.c_longlong(rows), C.c_longlong(ld), _p(ln, C.c_int), _p(pad, C.c_int), _pd(out),
+                           C.c_longlong(ld_out))
+    return out

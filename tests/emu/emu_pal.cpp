@@ -7,14 +7,14 @@ using namespace pal;
 
 extern "C" {
 
-void emu_fwd4095(const float* sig, int M, long long B, float* spec /* [B][M][2080][2] */, int grid) {
+void emu_fwd4095(const float* sig, int M, long long B, float* spec /* [B][M][2080][2] */, float* hq /* [B][M] */, int grid) {
   const long long units = B * ((M + 1) / 2);
   simt::launch(grid, 128, sizeof(FwdSmem), [&](char* smem) {
-    fwd4095_body<128>(sig, M, units, reinterpret_cast<cpxf*>(spec), smem);
+    fwd4095_body<128>(sig, M, units, reinterpret_cast<cpxf*>(spec), hq, smem);
   });
 }
 
-void emu_pair4095_fast(const float* spec, const int* pairs, int M, int P, long long B, int win_half, int dist,
+void emu_pair4095_fast(const float* spec, const float* hq, const int* pairs, int M, int P, long long B, int win_half, int dist,
                        float eps, int* k_idx, float* peak, float* gmax, unsigned* flags, float* corr_out,
                        int grid, int phase_sync) {
   constexpr int W = 2;
@@ -22,15 +22,15 @@ void emu_pair4095_fast(const float* spec, const int* pairs, int M, int P, long l
   simt::launch(grid, 32 * W, W * sizeof(FastWarpSmem) + 16, [&](char* smem) {
     if (phase_sync == 2) {     // TMEM-assisted variant
       if (corr_out)
-        pair4095_tmem_body<W, true>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
+        pair4095_tmem_body<W, true>(sp, hq, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
       else
-        pair4095_tmem_body<W, false>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
+        pair4095_tmem_body<W, false>(sp, hq, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
       return;
     }
     if (corr_out)
-      pair4095_fast_body<W, true>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
+      pair4095_fast_body<W, true>(sp, hq, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
     else
-      pair4095_fast_body<W, false>(sp, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
+      pair4095_fast_body<W, false>(sp, hq, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
   });
 }
 
@@ -230,4 +230,49 @@ extern "C" void emu_filtfilt_f64(const double* x, long long n_rows, int n, const
   simt::launch(2, NT, size_t(NT / 32) * 32 * 33 * sizeof(double), [&](char* sm) {
     filtfilt_body<double, NT>(x, n_rows, n, fp, work.data(), y, sm);
   });
+}
+
+// ---------------------------------------------------------------- channel alignment front end (pal_sync.cuh)
+#include "pal_sync.cuh"
+extern "C" void emu_sync_align(const double* sig, long long S, int Mics, int ld, const int* lens, int* ref_idx,
+                               int* peak_index, double* absmax, double* win, double* energy) {
+  using T = double;
+  constexpr int NT = 64, TC = 4, TRW = 4;
+  const int n = 2 * ld - 1;
+  const BluePlan p = make_blue_plan(n);
+  std::vector<cpx<T>> chirp(n), tw1(p.M1 / 2 + 1), tw2(p.M2 / 2 + 1), twM(p.M), bhat(p.M);
+  simt::launch(2, NT, 16, [&](char*) { blue_init_tables_body<T>(p, chirp.data(), tw1.data(), tw2.data(), twM.data()); });
+  BlueTables<T> tb{chirp.data(), tw1.data(), tw2.data(), twM.data(), bhat.data()};
+  const int tc = std::min(p.M2, TC);
+  const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2) * (std::min(p.M1, TRW) + 1);
+  simt::launch(2, NT, cs, [&](char* sm) { colpass_fwd_body<T, NT, TC>(p, tb, LoadBhat<T>{p, chirp.data()}, 1, bhat.data(), sm); });
+  simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, false, false>(p, tb, 1, bhat.data(), sm); });
+  simt::launch(2, NT, sizeof(double) * Mics, [&](char* sm) {
+    sync_energy_body<NT>(sig, S, Mics, ld, ld, lens, energy, ref_idx, sm);
+  });
+  const long long rows = S * Mics;
+  std::vector<cpx<T>> conv(size_t(rows) * p.M), spec(size_t(rows) * n);
+  std::vector<T> corr(size_t(rows) * n);
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_fwd_body<T, NT, TC>(p, tb, LoadSignalF64<T>{p, chirp.data(), sig, ld, ld, lens, 0}, rows, conv.data(), sm);
+  });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, false>(p, tb, rows, conv.data(), sm); });
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_inv_body<T, NT, TC>(p, tb, StoreSpectrum<T>{p, chirp.data(), spec.data()}, rows, conv.data(), sm);
+  });
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_fwd_body<T, NT, TC>(p, tb, LoadCross<T>{p, chirp.data(), spec.data(), ref_idx, 0, Mics, 0}, rows, conv.data(), sm);
+  });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, true>(p, tb, rows, conv.data(), sm); });
+  simt::launch(3, NT, cs, [&](char* sm) {
+    colpass_inv_body<T, NT, TC>(p, tb, StoreCorr<T>{p, chirp.data(), corr.data()}, rows, conv.data(), sm);
+  });
+  simt::launch(2, NT, sizeof(SyncPickSmem), [&](char* sm) {
+    sync_pick_body<T, NT>(corr.data(), n, rows, 0, Mics, ref_idx, ld, lens, peak_index, absmax, win, sm);
+  });
+}
+
+extern "C" void emu_pad_rows_f64(const double* in, long long n_rows, long long ld_in, const int* lens, const int* pad,
+                                 double* out, long long ld_out) {
+  simt::launch(3, 64, 16, [&](char*) { pad_rows_body<double>(in, n_rows, ld_in, int(ld_in), lens, pad, out, ld_out); });
 }

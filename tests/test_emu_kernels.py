@@ -26,11 +26,37 @@ def spectra(frames):
 
 
 def test_forward_spectra_layout(frames, spectra):
+    """fwd4095 stores the UNIT PHASORS S/|S| of np.fft.fft(sig, 4095) in the [q][r] layout, and per channel
+    h = mean_k 1/|S_k|^2, from which the pair kernel bounds the neglected factor |R|/(|R|+1e-10)."""
     for m in range(frames.shape[1]):
         s = np.fft.fft(frames[0, m].astype(np.float64), N)
         want = np.array([[s[_elem(r, q)] for r in range(32)] for q in range(65)]).reshape(-1)
-        got = spectra[0, m, :, 0] + 1j * spectra[0, m, :, 1]
-        assert np.abs(got - want).max() <= 2e-7 * np.abs(want).max() * 8
+        got = np.asarray(spectra[0, m, :, 0] + 1j * spectra[0, m, :, 1])
+        # phase to ~1e-6 rad (relative to the bin's own magnitude the fp32 transform error is |S|max/|S_k| times 1e-7)
+        assert np.abs(got * np.abs(want) - want).max() <= 2e-7 * np.abs(want).max() * 8
+        assert np.abs(np.abs(got) - 1).max() < 1e-6
+        h = np.mean(1.0 / np.abs(s) ** 2)
+        assert abs(spectra.hq[0, m] - h) <= 1e-3 * h
+
+
+def test_whitening_bound_sends_quiet_frames_to_float64():
+    """Frames so quiet that |R| is not >> 1e-10 (utils.py:117 is not scale invariant): the whitened fast path
+    must flag every row instead of answering, and the bound must dominate the true deviation."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((1, 3, 2048))
+    for scale, expect_flag in ((1.0, False), (1e-2, False), (3e-5, True)):
+        fr = (x * scale).astype(np.float32)
+        sp = E.fwd4095(fr)
+        k, pk, gm, fl, corr = E.pair_fast(sp, E.pairs_of(3), 800, 16, want_corr=True)
+        for p, (i, j) in enumerate(E.pairs_of(3)):
+            c = O.phat_correlation(fr[0, i].astype(np.float64), fr[0, j].astype(np.float64))
+            dev = np.abs(corr[0, p] - c).max()
+            bound = 1e-10 * np.sqrt(float(sp.hq[0, i]) * float(sp.hq[0, j]))
+            assert dev <= bound + 5e-7
+            if expect_flag:
+                assert fl[0, p] & 1
+            else:
+                assert dev < 5e-7
 
 
 @pytest.mark.parametrize("variant", [0, 2])      # 0: register-resident tiles, 2: tiles parked in (emulated) tensor memory
@@ -197,3 +223,51 @@ def test_filtfilt_bit_exact_vs_scipy(rows, n):
         want = filtfilt(b, a, x, axis=-1)
         got = E.filtfilt_f64(x, b, a, lfilter_zi(b, a), 3 * max(len(a), len(b)))
         assert np.array_equal(got, want)
+
+
+def _sync_via_emulation(sigs, fs, use_interpolation=True):
+    """The product's alignment path with the device kernels emulated on the host."""
+    from pyaudiolocalization_b200 import sync as S
+    lens = [len(s) for s in sigs]
+    n = max(lens)
+    host = np.zeros((1, len(sigs), n))
+    for i, s in enumerate(sigs):
+        host[0, i, :lens[i]] = s
+    ref, pk, am, win, en = E.sync_align(host, None if min(lens) == n else np.array([lens], np.int32))
+    pads = S.pads_from_alignment(int(ref[0]), pk[0], am[0], win[0], lens, fs, use_interpolation)
+    n_out = int(max(p + l for p, l in zip(pads, lens)))
+    out = E.pad_rows_f64(host[0], pads, n_out, None if min(lens) == n else np.array(lens, np.int32))
+    return out, dict(ref=int(ref[0]), pk=pk[0], am=am[0], win=win[0], en=en[0], pads=pads)
+
+
+def test_sync_align_emulation_vs_reference_golden(sync_golden):
+    """Alignment kernels (energies, float64 Bluestein cross-correlation, arg-max + spline window, padding)
+    against the UNMODIFIED reference's synchronize_signals_improved: the aligned channels are bit-identical."""
+    from scipy.signal import correlate
+    for c in range(int(sync_golden["n_cases"])):
+        sigs, fs = list(sync_golden[f"in{c}"]), float(sync_golden[f"fs{c}"])
+        out, d = _sync_via_emulation(sigs, fs)
+        assert np.array_equal(out, sync_golden[f"out{c}"])
+        ref = sigs[d["ref"]]
+        assert d["ref"] == int(np.argmax([np.sum(s ** 2) for s in sigs]))
+        for m, s in enumerate(sigs):
+            corr = correlate(s, ref, mode="full")
+            k = int(np.argmax(np.abs(corr)))
+            assert d["pk"][m] == k
+            assert abs(d["am"][m] - abs(corr[k])) <= 1e-12 * abs(corr[k])
+            assert np.abs(d["win"][m] - corr[k - 2:k + 3]).max() <= 1e-11 * abs(corr[k])
+
+
+def test_sync_align_emulation_unequal_lengths_and_edges():
+    """Channels of different lengths (scipy's 'full' index depends on both lengths) and a peak at the edge of
+    the row, against the oracle port."""
+    rng = np.random.default_rng(11)
+    src = rng.standard_normal(700)
+    sigs = [src[20:520] * 1.3, src[5:455] + 0.05 * rng.standard_normal(450), src[33:420], 0.01 * rng.standard_normal(300)]
+    out, d = _sync_via_emulation(sigs, 4000.0)
+    want = O.synchronize_signals_improved([s.copy() for s in sigs], 4000.0)
+    assert np.array_equal(out, np.array(want))
+    # identical channels (BASELINE cfg1: every microphone hears the same signal): first arg-max, no shift
+    same = [src[:256].copy() for _ in range(3)]
+    out2, d2 = _sync_via_emulation(same, 16000.0)
+    assert d2["ref"] == 0 and np.array_equal(out2, np.array(O.synchronize_signals_improved(same, 16000.0)))

@@ -144,7 +144,7 @@ def test_localize_sound_source_end_to_end(pal):
                                             freq=500, reflective_planes=shoebox(6, 5, 3),
                                             material_properties=CUSTOM_MATERIALS, max_reflections=2,
                                             absorption_threshold=0.01)
-    sig = [H.noise_reduction(s, 16000) for s in H.synchronize_signals_improved(sig, 16000)]
+    sig = [H.noise_reduction(s, 16000) for s in O.synchronize_signals_improved(sig, 16000)]
     tds, pairs, cm = O.pair_loop(sig, 16000, max_expected_delay=0.02)
     want = H.solve_position(mics, pairs, tds, c, {}, False, "kmeans", 0.001, 2)
     assert set(out) == {"estimated_position", "actual_position", "mic_positions", "correlation_metrics",
@@ -228,3 +228,32 @@ def test_channel_filter_bit_exact_vs_scipy(pal):
     assert np.array_equal(one, want[0])
     with pytest.raises(ValueError):
         filters.filtfilt_batched(torch.zeros((2, 20), dtype=torch.float64, device="cuda"), b, a)
+
+
+def test_synchronize_signals_vs_reference_golden(pal, sync_golden):
+    """utils.synchronize_signals_improved (utils.py:407-457, main.py:188) on the GPU: pal_sync_align (float64
+    Bluestein cross-correlation with the highest-energy channel, arg-max, spline window) + pal_pad_rows must
+    give the UNMODIFIED reference's aligned channels bit for bit (golden vectors), also with channels of
+    unequal length and for a batch of scenes (against the oracle port)."""
+    from pyaudiolocalization_b200 import sync, utils as U
+    for c in range(int(sync_golden["n_cases"])):
+        got = U.synchronize_signals_improved(list(sync_golden[f"in{c}"]), float(sync_golden[f"fs{c}"]))
+        assert np.array_equal(np.array(got), sync_golden[f"out{c}"])
+    rng = np.random.default_rng(11)
+    src = rng.standard_normal(700)
+    sigs = [src[20:520] * 1.3, src[5:455] + 0.05 * rng.standard_normal(450), src[33:420], 0.01 * rng.standard_normal(300)]
+    want = O.synchronize_signals_improved([s.copy() for s in sigs], 4000.0)
+    got = U.synchronize_signals_improved(sigs, 4000.0)
+    assert len(got) == len(want) and all(np.array_equal(g, w) for g, w in zip(got, want))
+    # batch of scenes, float32 frames on the device (what the renderer produces), 1 s @ 16 kHz
+    s, m, n, fs = 6, 8, 16000, 16000.0
+    base = rng.standard_normal(n + 400)
+    d = rng.integers(0, 300, size=(s, m))
+    frames = np.stack([np.stack([base[300 - d[i, j]:300 - d[i, j] + n] * (1 + 0.05 * j) + 0.2 * rng.standard_normal(n)
+                                 for j in range(m)]) for i in range(s)]).astype(np.float32)
+    out, pads = sync.synchronize_signals_batched(torch.from_numpy(frames).cuda(), fs)
+    out = out.cpu().numpy()
+    assert out.dtype == np.float32
+    for i in range(s):
+        w = np.array(O.synchronize_signals_improved([r.astype(np.float64) for r in frames[i]], fs))
+        assert np.array_equal(out[i, :, :w.shape[1]], w.astype(np.float32)) and not out[i, :, w.shape[1]:].any()

@@ -127,3 +127,11 @@ def test_restated_peak_machinery_vs_scipy():
         if trial % 3:                    # tie order is only defined for distinct heights
             keep = O.select_by_distance_restated(pk, c[pk], dist)
             assert np.array_equal(pk[keep], find_peaks(c, distance=dist)[0])
+
+
+def test_synchronize_port_vs_reference_golden(sync_golden):
+    """oracle.synchronize_signals_improved (port of utils.py:407-457) against the unmodified reference:
+    three scenes incl. an uncorrelated channel (low-peak branch) and fs = 1 kHz."""
+    for c in range(int(sync_golden["n_cases"])):
+        got = O.synchronize_signals_improved(list(sync_golden[f"in{c}"]), float(sync_golden[f"fs{c}"]))
+        assert np.array_equal(np.array(got), sync_golden[f"out{c}"])
