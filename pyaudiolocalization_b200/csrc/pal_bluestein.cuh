@@ -222,55 +222,176 @@ template <typename T> struct LoadBhat {
   }
 };
 
-// forward DFT of one real channel: a[j] = x[j] * chirp[j]          (np.fft.fft(sig, n), utils.py:114-115)
-// transform t = channel row; rows have `ld` floats of which `len` are signal (zero beyond)
-template <typename T> struct LoadSignal {
+// ---- two real sequences per complex transform -----------------------------------------------
+// Every transform of the GCC-PHAT path has a REAL side: the channels are real (forward) and the correlation
+// rows are real (inverse).  Two real sequences therefore share one complex transform, Z = DFT(x1 + i x2):
+//     S1[k] = (Z[k] + conj(Z[n-k])) / 2,      S2[k] = (Z[k] - conj(Z[n-k])) / (2i)
+// and IDFT(R1 + i R2) = corr1 + i corr2 when R1, R2 are Hermitian.  This halves the number of length-M FFTs in
+// both directions.  The spectra are STORED packed (one row Z per channel pair) and unpacked by the PHAT loader,
+// which makes S[n-k] == conj(S[k]) hold bit for bit, so R is exactly Hermitian and the two correlation rows
+// of a packed inverse transform do not leak into each other beyond the rounding of the transform itself.
+template <typename T> PAL_DEV cpx<T> unpack_two_real(const cpx<T>* z, int n, int k, bool second) {
+  const cpx<T> a = z[k], b = z[k == 0 ? 0 : n - k];
+  if (!second) return cpx<T>{T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y)};
+  return cpx<T>{T(0.5) * (a.y + b.y), T(-0.5) * (a.x - b.x)};
+}
+
+// The price of sharing: the rounding residue of the stronger sequence (about 1e-7 of ITS level in float32) lands in the
+// weaker one, and PHAT whitening then amplifies it to full scale.  Every row is therefore brought to unit level before
+// it is packed, by an exact power of two (no rounding): scales[row] = {2^-e, 2^e}, max|x| 2^-e in [0.5, 1); an
+// all-zero row gets {0, 0}, which makes its spectrum exactly zero as in the reference (R = 0, corr = 0) instead of
+// the partner's residue.  The loaders undo the scale where absolute levels matter (the 1e-10 of utils.py:117).
+template <int NT> PAL_DEV void row_scale_body(const float* sig, long long n_rows, long long ld, int len_even, int len_odd,
+                                              float* scales /* [n_rows][2] */, char* smem) {
+  float* sh = reinterpret_cast<float*>(smem);
+  for (long long row = simt::bid(); row < n_rows; row += simt::nblocks()) {
+    const int len = (row & 1) ? len_odd : len_even;
+    const float* x = sig + row * ld;
+    float mx = 0.f;
+    for (int j = simt::tid(); j < len; j += NT) mx = max_(mx, abs_(x[j]));
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) mx = max_(mx, simt::shfl_xor(mx, m));
+    if (simt::lane() == 0) sh[simt::warp()] = mx;
+    simt::sync_block();
+    if (simt::tid() == 0) {
+      for (int w = 0; w < NT / 32; ++w) mx = max_(mx, sh[w]);
+      float sc = 0.f, inv = 0.f;
+      if (mx > 0.f && mx < 3.0e38f) {
+        int e;
+        (void)frexpf(mx, &e);
+        e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        sc = ldexpf(1.f, -e);
+        inv = ldexpf(1.f, e);
+      } else if (mx > 0.f) {
+        sc = inv = 1.f;      // inf / NaN rows: leave them alone
+      }
+      scales[2 * row] = sc;
+      scales[2 * row + 1] = inv;
+    }
+    simt::sync_block();
+  }
+}
+
+// forward DFT of a PAIR of real channels: a[j] = (x1[j] + i x2[j]) * chirp[j]     (np.fft.fft(sig, n), utils.py:114-115)
+// frame-major: packed transform g = t_off + t <-> frame g / CP, channels 2c and 2c+1 (c = g % CP, CP = ceil(Mics/2));
+// list mode: transform g <-> channel rows row_list[2g], row_list[2g+1].  Rows have `ld` floats; even / odd rows
+// hold len_even / len_odd valid samples (n1, n2 of a single unequal pair), zero beyond.
+template <typename T> struct LoadSignal2 {
   BluePlan p;
   const cpx<T>* chirp;
   const float* sig;
   long long ld;
-  int len_even, len_odd;   // valid samples of even / odd rows (n1, n2 of a single unequal pair)
-  const int* row_list;     // optional indirection: transform t -> channel row
+  int Mics, CP;
+  int len_even, len_odd;
+  const int* row_list;
+  long long t_off;
+  const float* scales;     // [all rows][2] from row_scale_body
   PAL_DEV cpx<T> operator()(long long t, int j) const {
-    const long long row = row_list ? row_list[t] : t;
-    const int len = (row & 1) ? len_odd : len_even;
+    if (j >= p.n) return cpx<T>{T(0), T(0)};
+    const long long g = t_off + t;
+    long long ra, rb;
+    if (row_list) {
+      ra = row_list[2 * g];
+      rb = row_list[2 * g + 1];
+    } else {
+      const long long f = g / CP;
+      const int c = int(g - f * CP);
+      ra = f * Mics + 2 * c;
+      rb = (2 * c + 1 < Mics) ? ra + 1 : -1;
+    }
+    const T x = (j < ((ra & 1) ? len_odd : len_even)) ? T(sig[ra * ld + j] * scales[2 * ra]) : T(0);
+    const T y = (rb >= 0 && j < ((rb & 1) ? len_odd : len_even)) ? T(sig[rb * ld + j] * scales[2 * rb]) : T(0);
+    const cpx<T> w = chirp[j];
+    return cpx<T>{fma_(x, w.x, -(y * w.y)), fma_(x, w.y, y * w.x)};
+  }
+};
+
+// forward DFT of ONE real row (the renderer's base signal)
+template <typename T> struct LoadSignal {
+  BluePlan p;
+  const cpx<T>* chirp;
+  const float* sig;
+  int len;
+  PAL_DEV cpx<T> operator()(long long, int j) const {
     if (j >= len) return cpx<T>{T(0), T(0)};
-    const T x = T(sig[row * ld + j]);
+    const T x = T(sig[j]);
     const cpx<T> w = chirp[j];
     return cpx<T>{x * w.x, x * w.y};
   }
 };
 
-// inverse DFT of the PHAT-weighted cross spectrum of pair (i, j) of frame f:
-//   a[k] = R[k] * conj(chirp[k]) / n,  R = Si conj(Sj) / (|Si conj(Sj)| + 1e-10)   (utils.py:116-118)
-template <typename T> struct LoadPhat {
+// PHAT-weighted cross spectrum of one item at bin k, scaled by 1/n:  R = Si conj(Sj) / (|Si conj(Sj)| + 1e-10)   (utils.py:116-117)
+template <typename T> PAL_DEV cpx<T> phat_cross(cpx<T> a, cpx<T> b, T inv_n) {
+  const T xr = fma_(a.x, b.x, a.y * b.y);
+  const T xi = fma_(a.y, b.x, -(a.x * b.y));
+  const T mag = sqrt_(fma_(xr, xr, xi * xi));
+  const T sc = inv_n / (mag + T(1e-10));
+  return cpx<T>{xr * sc, xi * sc};
+}
+
+// inverse DFT of TWO PHAT-weighted cross spectra per transform: a[k] = (R_A[k] + i R_B[k]) * conj(chirp[k]) / n,
+// items A = t_off + 2t, B = A + 1 of the resident set (B absent when A is the last item).
+// frame-major: item it <-> frame it / P, pair it % P, packed spectrum rows frame * CP + mic / 2;
+// list mode (rows2): item it owns packed row it (first channel = its i, second = its j).
+template <typename T> struct LoadPhat2 {
   BluePlan p;
   const cpx<T>* chirp;
-  const cpx<T>* spec;      // spectrum rows of the frames (or flagged items) currently resident
+  const cpx<T>* spec;      // packed spectrum rows of the frames (or flagged items) currently resident
   const int* pairs;        // [P][2]
-  int Mics, P;
-  long long t_off;         // resident item index of transform 0 of this launch
-  bool rows2;              // true: item i owns rows 2i, 2i+1 (flagged-item list); false: frame-major
-  PAL_DEV cpx<T> operator()(long long t, int k) const {
-    if (k >= p.n) return cpx<T>{T(0), T(0)};
-    const long long it = t + t_off;
-    long long ri, rj;
+  int Mics, CP, P;
+  long long t_off;         // resident item index of item A of transform 0
+  long long n_items;       // resident items end here
+  bool rows2;
+  const float* scales;     // [all rows][2] (row_scale_body), indexed by GLOBAL channel row
+  long long frame_base;    // frame-major: global index of resident frame 0
+  const int* row_list;     // list mode: global channel rows of every flagged item ...
+  long long item_base;     // ... and the list position of resident item 0
+  // an item with an all-zero channel: R == 0, the reference's correlation row is exactly zero
+  PAL_DEV bool dead(long long it) const {
+    long long gi, gj;
     if (rows2) {
-      ri = 2 * it;
-      rj = 2 * it + 1;
+      gi = row_list[2 * (item_base + it)];
+      gj = row_list[2 * (item_base + it) + 1];
     } else {
       const long long f = it / P;
-      const int pr = int(it % P);
-      ri = f * Mics + pairs[2 * pr];
-      rj = f * Mics + pairs[2 * pr + 1];
+      const int pr = int(it - f * P);
+      gi = (frame_base + f) * Mics + pairs[2 * pr];
+      gj = (frame_base + f) * Mics + pairs[2 * pr + 1];
     }
-    const cpx<T> a = spec[ri * p.n + k], b = spec[rj * p.n + k];
-    const T xr = fma_(a.x, b.x, a.y * b.y);
-    const T xi = fma_(a.y, b.x, -(a.x * b.y));
-    const T mag = sqrt_(fma_(xr, xr, xi * xi));
-    const T sc = (T(1) / T(p.n)) / (mag + T(1e-10));
-    const cpx<T> w = chirp[k];
-    return cmulc(cpx<T>{xr * sc, xi * sc}, w);
+    return scales[2 * gi] == 0.f || scales[2 * gj] == 0.f;
+  }
+  PAL_DEV cpx<T> one(long long it, int k) const {
+    const cpx<T>*zi, *zj;
+    bool oi, oj;
+    long long gi, gj;
+    if (rows2) {
+      zi = zj = spec + it * p.n;
+      oi = false;
+      oj = true;
+      gi = row_list[2 * (item_base + it)];
+      gj = row_list[2 * (item_base + it) + 1];
+    } else {
+      const long long f = it / P;
+      const int pr = int(it - f * P);
+      const int mi = pairs[2 * pr], mj = pairs[2 * pr + 1];
+      zi = spec + (f * CP + (mi >> 1)) * p.n;
+      zj = spec + (f * CP + (mj >> 1)) * p.n;
+      oi = mi & 1;
+      oj = mj & 1;
+      gi = (frame_base + f) * Mics + mi;
+      gj = (frame_base + f) * Mics + mj;
+    }
+    cpx<T> a = unpack_two_real<T>(zi, p.n, k, oi), b = unpack_two_real<T>(zj, p.n, k, oj);
+    const T ua = T(scales[2 * gi + 1]), ub = T(scales[2 * gj + 1]);     // back to the signal's own level (exact)
+    a.x *= ua; a.y *= ua; b.x *= ub; b.y *= ub;
+    return phat_cross<T>(a, b, T(1) / T(p.n));
+  }
+  PAL_DEV cpx<T> operator()(long long t, int k) const {
+    if (k >= p.n) return cpx<T>{T(0), T(0)};
+    const long long ia = t_off + 2 * t;
+    const cpx<T> ra = one(ia, k);
+    const cpx<T> rb = (ia + 1 < n_items) ? one(ia + 1, k) : cpx<T>{T(0), T(0)};
+    return cmulc(cpx<T>{ra.x - rb.y, ra.y + rb.x}, chirp[k]);
   }
 };
 
@@ -291,6 +412,23 @@ template <typename T> struct StoreCorr {          // corr[t][k] = Re(y[k] * conj
     if (k < p.n) {
       const cpx<T> w = chirp[k];
       corr[t * p.n + k] = fma_(y.x, w.x, y.y * w.y);
+    }
+  }
+};
+// packed inverse: Re -> row 2t, Im -> row 2t+1 of the chunk   (y conj(w) = corr_A + i corr_B)
+template <typename T> struct StoreCorr2 {
+  BluePlan p;
+  const cpx<T>* chirp;
+  T* corr;
+  long long n_rows;        // corr rows of this launch (the last transform may own a single row)
+  LoadPhat2<T> src;        // what was transformed: a dead item's row is written as exact zeros, not as the rounding
+                           // residue of the item it shared the transform with
+  PAL_DEV void operator()(long long t, int k, cpx<T> y) const {
+    if (k < p.n) {
+      const cpx<T> w = chirp[k];
+      const long long ia = src.t_off + 2 * t;
+      corr[(2 * t) * p.n + k] = src.dead(ia) ? T(0) : fma_(y.x, w.x, y.y * w.y);
+      if (2 * t + 1 < n_rows) corr[(2 * t + 1) * p.n + k] = src.dead(ia + 1) ? T(0) : fma_(y.y, w.x, -(y.x * w.y));
     }
   }
 };

@@ -168,20 +168,22 @@ int generic_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, 
   if (int rc = device_info(di)) return rc;
   const size_t list_bytes = align_up(size_t(B) * P * sizeof(int), 256) + 256;
   const size_t rows_bytes = align_up(size_t(B) * P * 2 * sizeof(int), 256);
+  const size_t scale_bytes = align_up(size_t(B) * M * 2 * sizeof(float), 256);
   const int n = n1 + n2 - 1;
-  if (ws_bytes < list_bytes + rows_bytes + std::max(palhost::generic_min_bytes<float>(n, M, di.sms),
+  if (ws_bytes < list_bytes + rows_bytes + scale_bytes + std::max(palhost::generic_min_bytes<float>(n, M, di.sms),
                                                    palhost::generic_min_bytes<double>(n, 2, di.sms)))
     return fail(PAL_ERR_WORKSPACE, "pal_gcc_phat_tdoa: workspace too small");
   char* ws = static_cast<char*>(ws_dev);
   int* list = reinterpret_cast<int*>(ws);
   int* count = reinterpret_cast<int*>(ws + list_bytes - 256);
   int* rows = reinterpret_cast<int*>(ws + list_bytes);
-  char* region = ws + list_bytes + rows_bytes;
-  const size_t region_bytes = ws_bytes - list_bytes - rows_bytes;
+  float* scales = reinterpret_cast<float*>(ws + list_bytes + rows_bytes);
+  char* region = ws + list_bytes + rows_bytes + scale_bytes;
+  const size_t region_bytes = ws_bytes - list_bytes - rows_bytes - scale_bytes;
   palhost::GenericCall c{sig_dev, (long long)B, M, n_samples, n1, n2, pairs_dev, P,
                          PickParams{prm->win_half, prm->peak_dist, prm->thr_method, prm->thr_mult, prm->num_peaks},
                          prm->refine ? prm->tie_eps : 0.f, k_idx_dev, k_count_dev, peak_dev, gmax_dev, flags_dev,
-                         corr_opt_dev, stream, di.sms};
+                         corr_opt_dev, stream, di.sms, scales};
   cudaError_t e = palhost::run_generic<float>(c, region, region_bytes, nullptr, 0, nullptr, 0u, 0u);
   if (e != cudaSuccess) return cuda_fail(e, "generic float sweep");
   if (!prm->refine) return PAL_OK;
@@ -234,7 +236,7 @@ int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, s
   DevInfo di;
   if (device_info(di) == PAL_OK && di.sms > 0) sms = di.sms;
   const int n = 2 * n_samples - 1;
-  const size_t rows = align_up(size_t(B) * P * 2 * sizeof(int), 256);
+  const size_t rows = align_up(size_t(B) * P * 2 * sizeof(int), 256) + align_up(size_t(B > 0 ? B : 1) * M * 2 * sizeof(float), 256);
   const size_t dmin = palhost::generic_min_bytes<double>(n, 2, sms);
   const size_t fmin = palhost::generic_min_bytes<float>(n, M, sms);
   const size_t ffull = palhost::generic_full_bytes<float>(n, B > 0 ? B : 1, M, P, sms);

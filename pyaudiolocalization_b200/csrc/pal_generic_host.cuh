@@ -51,6 +51,11 @@ __global__ void __launch_bounds__(kGT) k_pick_rows(const T* corr, int n, int c0,
   pick_rows_body<T, kGT>(corr, n, c0, n_rows_dev ? (long long)*n_rows_dev : n_rows, item_list, win_half, dist, method,
                          mult, num_peaks, eps, pkmap_ws, k_idx, k_count, peak, gmax, flags, extra_flag, keep_mask, corr_out, smem);
 }
+__global__ void __launch_bounds__(kGT) k_row_scales(const float* sig, long long n_rows, long long ld, int len_even, int len_odd,
+                                                    float* scales) {
+  __shared__ float sh[kGT / 32];
+  row_scale_body<kGT>(sig, n_rows, ld, len_even, len_odd, scales, reinterpret_cast<char*>(sh));
+}
 // flagged item -> its two channel rows (for the float64 re-evaluation)
 __global__ void k_rows_of_items(const int* item_list, const int* count, const int* pairs, int Mics, int P, int* rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -74,12 +79,12 @@ inline long long conv_chunk_bytes() {
 template <typename T> struct GenericLayout {
   BluePlan p;
   size_t tables;      // bytes of chirp + tw1 + tw2 + twM + bhat
-  size_t per_tr;      // conv buffer + corr row, per transform in flight
-  size_t per_row;     // one spectrum row
+  size_t per_tr;      // conv buffer + two corr rows, per (packed) transform in flight
+  size_t per_row;     // one packed spectrum row (two channels)
   GenericLayout(int n) : p(make_blue_plan(n)) {
     tables = al(sizeof(cpx<T>) * size_t(p.n)) + al(sizeof(cpx<T>) * (p.M1 / 2 + 1)) +
              al(sizeof(cpx<T>) * (p.M2 / 2 + 1)) + 2 * al(sizeof(cpx<T>) * size_t(p.M));
-    per_tr = al(sizeof(cpx<T>) * size_t(p.M)) + al(sizeof(T) * size_t(p.n));
+    per_tr = al(sizeof(cpx<T>) * size_t(p.M)) + 2 * al(sizeof(T) * size_t(p.n));   // a packed inverse yields two rows
     per_row = al(sizeof(cpx<T>) * size_t(p.n));
   }
 };
@@ -100,6 +105,7 @@ struct GenericCall {
   float* corr_out;
   cudaStream_t stream;
   int sms;
+  float* scales;     // [B * Mics][2] per-row power-of-two normalisation (filled by the first sweep, reused by the float64 one)
 };
 
 inline void count_launch(int k = 1) {
@@ -132,7 +138,9 @@ template <typename T> cudaError_t setup_plan(const BluePlan& p, char*& base, Blu
   const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadBhat<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignal<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  cudaFuncSetAttribute(k_colpass_fwd<T, LoadPhat<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignal2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_fwd<T, LoadPhat2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_inv<T, StoreCorr2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_inv<T, StoreSpectrum<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_inv<T, StoreCorr<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
@@ -162,12 +170,16 @@ template <typename T> size_t generic_full_bytes(int n, long long B, int Mics, in
 
 // One sweep of the whole batch in precision T.  items: all B*P (list == nullptr) or the
 // `n_list` flagged items of `list` (host-known count), whose channel rows are in `rows_scratch`.
+// Two real sequences share every complex transform (pal_bluestein.cuh): the channels of a frame are
+// transformed in pairs (CP = ceil(Mics/2) packed spectrum rows per frame; in list mode the two channels of
+// an item form one row), and every inverse transform yields the correlation rows of two items.
 template <typename T>
 cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const int* list, int n_list, int* rows_scratch,
                         unsigned extra_flag, unsigned keep_mask) {
   const int n = c.n1 + c.n2 - 1;
   GenericLayout<T> L(n);
   const BluePlan p = L.p;
+  const int CP = (c.Mics + 1) / 2;
   if (ws_bytes < generic_min_bytes<T>(n, list ? 2 : c.Mics, c.sms)) return cudaErrorMemoryAllocation;
   char* base = ws;
   BlueBuffers<T> bb;
@@ -177,18 +189,18 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   unsigned char* pkmap = reinterpret_cast<unsigned char*>(base);
   base += pkmap_bytes(n, c.sms);
   size_t rem = ws_bytes - size_t(base - ws);
-  // transforms in flight: a quarter of what is left (at most 2048), the rest holds spectrum rows
+  // packed transforms in flight: a quarter of what is left (at most 2048), the rest holds spectrum rows
   const long long total_items = list ? n_list : c.B * c.P;
-  const long long min_rows = list ? 2 : c.Mics;
+  const long long min_rows = list ? 1 : CP;
   long long tr_cap = std::max<long long>(1, std::min<long long>(2048, (long long)((rem / 4) / L.per_tr)));
   // optional cap on the convolution buffers of one chunk (PAL_CONV_CHUNK_MB; L2-sized chunks measured slower)
   tr_cap = std::max<long long>(1, std::min<long long>(tr_cap, conv_chunk_bytes() / (long long)(sizeof(cpx<T>) * size_t(p.M))));
-  tr_cap = std::min<long long>(tr_cap, std::max<long long>(total_items, list ? 2LL * n_list : c.B * c.Mics));
+  tr_cap = std::min<long long>(tr_cap, std::max<long long>((total_items + 1) / 2, list ? (long long)n_list : c.B * CP));
   while (tr_cap > 1 && rem < size_t(tr_cap) * L.per_tr + size_t(min_rows) * L.per_row) tr_cap /= 2;
   cpx<T>* conv = reinterpret_cast<cpx<T>*>(base);
   base += tr_cap * al(sizeof(cpx<T>) * size_t(p.M));
   T* corr = reinterpret_cast<T*>(base);
-  base += tr_cap * al(sizeof(T) * size_t(n));
+  base += 2 * tr_cap * al(sizeof(T) * size_t(n));
   rem = ws_bytes - size_t(base - ws);
   const long long row_cap = (long long)(rem / L.per_row);
   if (row_cap < min_rows) return cudaErrorMemoryAllocation;
@@ -199,14 +211,18 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   const BlueTables<T> tb = bb.tb();
   const int c0 = c.n2 - 1;
+  if (!list) {
+    k_row_scales<<<(unsigned)std::min<long long>(c.B * c.Mics, 16LL * c.sms), kGT, 0, c.stream>>>(c.sig, c.B * c.Mics, c.ld, c.n1,
+                                                                                                c.n2, c.scales);
+    count_launch();
+  }
 
-  auto forward = [&](long long row0, long long nrows, const int* row_list, cpx<T>* spec_out) {
-    for (long long r0 = 0; r0 < nrows; r0 += tr_cap) {
-      const long long nt = std::min(tr_cap, nrows - r0);
-      LoadSignal<T> ld{p, bb.chirp, c.sig + (row_list ? 0 : (row0 + r0) * (long long)c.ld), c.ld,
-                       (row_list || ((row0 + r0) & 1) == 0) ? c.n1 : c.n2, (row_list || ((row0 + r0) & 1) == 0) ? c.n2 : c.n1,
-                       row_list ? row_list + r0 : nullptr};
-      k_colpass_fwd<T, LoadSignal<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+  // packed forward transforms g0 .. g0+ntr-1 (global packed index; list mode: flagged-item index) -> spec_out rows 0..
+  auto forward = [&](long long g0, long long ntr, const int* row_list, cpx<T>* spec_out) {
+    for (long long r0 = 0; r0 < ntr; r0 += tr_cap) {
+      const long long nt = std::min(tr_cap, ntr - r0);
+      LoadSignal2<T> ld{p, bb.chirp, c.sig, c.ld, c.Mics, CP, c.n1, c.n2, row_list, g0 + r0, c.scales};
+      k_colpass_fwd<T, LoadSignal2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, ld, nt, nullptr, conv);
       k_rowpass<T, true, false><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * c.sms), kGT, rs, c.stream>>>(p, tb, nt, nullptr, conv);
       StoreSpectrum<T> st{p, bb.chirp, spec_out + r0 * n};
@@ -215,21 +231,22 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
       count_launch(3);
     }
   };
-  // items [i0, i0+nitems) of the resident set (frame-major, or flagged-list order when ilist != nullptr);
+  // items [0, nitems) of the resident set (frame-major, or flagged-list order when ilist != nullptr);
   // out0 = global item id of resident item 0 (frame-major mode)
-  auto inverse = [&](long long nitems, const cpx<T>* spec_in, long long out0, const int* ilist) {
-    for (long long i0 = 0; i0 < nitems; i0 += tr_cap) {
-      const long long nt = std::min(tr_cap, nitems - i0);
-      LoadPhat<T> ld{p, bb.chirp, spec_in, c.pairs, c.Mics, c.P, i0, ilist != nullptr};
-      k_colpass_fwd<T, LoadPhat<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+  auto inverse = [&](long long nitems, const cpx<T>* spec_in, long long out0, const int* ilist, long long frame0, long long list0) {
+    for (long long i0 = 0; i0 < nitems; i0 += 2 * tr_cap) {
+      const long long ni = std::min(2 * tr_cap, nitems - i0);
+      const long long nt = (ni + 1) / 2;
+      LoadPhat2<T> ld{p, bb.chirp, spec_in, c.pairs, c.Mics, CP, c.P, i0, nitems, ilist != nullptr, c.scales, frame0, rows_scratch, list0};
+      k_colpass_fwd<T, LoadPhat2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, ld, nt, nullptr, conv);
       k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * c.sms), kGT, rs, c.stream>>>(p, tb, nt, nullptr, conv);
-      StoreCorr<T> st{p, bb.chirp, corr};
-      k_colpass_inv<T, StoreCorr<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+      StoreCorr2<T> st{p, bb.chirp, corr, ni, ld};
+      k_colpass_inv<T, StoreCorr2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, st, nt, nullptr, conv);
       const long long o = ilist ? 0 : out0 + i0;
-      k_pick_rows<T><<<(unsigned)std::min<long long>(nt, grid_pick), kGT, sizeof(RowPickSmem), c.stream>>>(
-          corr, n, c0, nt, nullptr, ilist ? ilist + i0 : nullptr, c.pp.win_half, c.pp.dist, c.pp.method, c.pp.mult,
+      k_pick_rows<T><<<(unsigned)std::min<long long>(ni, grid_pick), kGT, sizeof(RowPickSmem), c.stream>>>(
+          corr, n, c0, ni, nullptr, ilist ? ilist + i0 : nullptr, c.pp.win_half, c.pp.dist, c.pp.method, c.pp.mult,
           c.pp.num_peaks, c.eps, pkmap, c.k_idx + o * c.pp.num_peaks, c.k_count ? c.k_count + o : nullptr, c.peak + o,
           c.gmax + o, c.flags + o, extra_flag, keep_mask, (c.corr_out && !ilist) ? c.corr_out + o * n : nullptr);
       count_launch(4);
@@ -237,18 +254,19 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   };
 
   if (!list) {
-    const long long fchunk = std::max<long long>(1, std::min<long long>(c.B, row_cap / c.Mics));
+    const long long fchunk = std::max<long long>(1, std::min<long long>(c.B, row_cap / CP));
     for (long long f0 = 0; f0 < c.B; f0 += fchunk) {
       const long long nf = std::min(fchunk, c.B - f0);
-      forward(f0 * c.Mics, nf * c.Mics, nullptr, spec);
-      inverse(nf * c.P, spec, f0 * c.P, nullptr);
+      forward(f0 * CP, nf * CP, nullptr, spec);
+      // the resident spectra start at frame f0: item ids handed to the loader are relative to it
+      inverse(nf * c.P, spec, f0 * c.P, nullptr, f0, 0);
     }
   } else {
-    const long long ichunk = std::max<long long>(1, std::min<long long>(n_list, row_cap / 2));
+    const long long ichunk = std::max<long long>(1, std::min<long long>(n_list, row_cap));
     for (long long i0 = 0; i0 < n_list; i0 += ichunk) {
       const long long ni = std::min<long long>(ichunk, n_list - i0);
-      forward(0, 2 * ni, rows_scratch + 2 * i0, spec);
-      inverse(ni, spec, 0, list + i0);
+      forward(i0, ni, rows_scratch, spec);
+      inverse(ni, spec, 0, list + i0, 0, i0);
     }
   }
   return cudaGetLastError();

@@ -109,7 +109,25 @@ struct alignas(16) FwdSmem {
   f2 z[4096];                   // the complex sequence, transformed in place
   mbar_t bar;
   float red[32];                // per-warp partials of the two whitening bounds (NT <= 512)
+  float lvl[32];                // per-warp partials of the two channel levels max|x|
 };
+
+// Exact power-of-two normalisation of a channel to unit level before two channels are packed into one complex
+// transform: the rounding residue of the stronger channel (1e-7 of ITS level) would otherwise drown a much weaker
+// partner once PHAT whitening brings every bin to unit magnitude.  An all-zero channel gets scale 0 and its spectrum
+// is stored as exact zeros, as in the reference (R = 0, corr = 0), instead of the partner's residue.
+PAL_DEV void level_scale(float mx, float& sc, float& inv) {
+  sc = inv = 0.f;
+  if (mx > 0.f && mx < 3.0e38f) {
+    int e;
+    (void)frexpf(mx, &e);
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    sc = ldexpf(1.f, -e);
+    inv = ldexpf(1.f, e);
+  } else if (mx > 0.f) {
+    sc = inv = 1.f;
+  }
+}
 
 // PHAT factorised per CHANNEL instead of per pair.  |Si conj(Sj)| = |Si| |Sj|, so
 //     R / (|R| + 1e-10) = Ui conj(Uj) * g,   U = S / |S|,   g = m / (m + 1e-10),  m = |Si| |Sj|      (utils.py:116-117)
@@ -139,14 +157,14 @@ PAL_DEV f2 whiten_bin(f2 s, float weight, float& hacc) {
 
 // in-place PFA stage on packed complex data; FIRST: gather the inputs from the raw frames instead
 // (z[k] = x0[k] + i x1[k] for k < 2048, zero beyond)
-template <int F, int NT, bool FIRST> PAL_DEV void pfa_stage_p(f2* z, const float* x0, const float* x1, bool two) {
+template <int F, int NT, bool FIRST> PAL_DEV void pfa_stage_p(f2* z, const float* x0, const float* x1, bool two, f2 sc01) {
   constexpr int U = pfa_u(F);
   for (int g = simt::tid(); g < kN4095 / F; g += NT) {
     f2 x[F];
     int idx = F * g;
 #pragma unroll
     for (int j = 0; j < F; ++j) {
-      if (FIRST) x[j] = (idx < kFrame2048) ? f2_make(x0[idx], two ? x1[idx] : 0.f) : f2_make(0.f, 0.f);
+      if (FIRST) x[j] = (idx < kFrame2048) ? f2_mul(f2_make(x0[idx], two ? x1[idx] : 0.f), sc01) : f2_make(0.f, 0.f);
       else x[j] = z[idx];
       idx += U;
       if (idx >= kN4095) idx -= kN4095;
@@ -189,15 +207,39 @@ PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil
     const bool two = (ch0 + 1) < M;
     simt::mbar_wait(&sm->bar, parity);
     parity ^= 1u;
-    pfa_stage_p<13, NT, true>(sm->z, sm->stage[0], sm->stage[1], two);
+    // channel levels -> exact power-of-two scales (level_scale)
+    float sc0, sc1, inv0, inv1;
+    {
+      float m0 = 0.f, m1 = 0.f;
+      for (int j = tid; j < kFrame2048 / 4; j += NT) {
+        const float4 a = reinterpret_cast<const float4*>(sm->stage[0])[j];
+        m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+        if (two) {
+          const float4 b = reinterpret_cast<const float4*>(sm->stage[1])[j];
+          m1 = fmaxf(m1, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+        }
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        m0 = fmaxf(m0, simt::shfl_xor(m0, m));
+        m1 = fmaxf(m1, simt::shfl_xor(m1, m));
+      }
+      if (simt::lane() == 0) { sm->lvl[simt::warp()] = m0; sm->lvl[16 + simt::warp()] = m1; }
+      simt::sync_block();
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) { m0 = fmaxf(m0, sm->lvl[w]); m1 = fmaxf(m1, sm->lvl[16 + w]); }
+      level_scale(m0, sc0, inv0);
+      level_scale(m1, sc1, inv1);
+    }
+    pfa_stage_p<13, NT, true>(sm->z, sm->stage[0], sm->stage[1], two, f2_make(sc0, sc1));
     simt::sync_block();
     // the landing zone is free again: the frames of this block's NEXT unit travel while this one is transformed
     if (tid == 0 && unit + simt::nblocks() < n_units) request(unit + simt::nblocks());
-    pfa_stage_p<9, NT, false>(sm->z, nullptr, nullptr, two);
+    pfa_stage_p<9, NT, false>(sm->z, nullptr, nullptr, two, f2_make(0.f, 0.f));
     simt::sync_block();
-    pfa_stage_p<7, NT, false>(sm->z, nullptr, nullptr, two);
+    pfa_stage_p<7, NT, false>(sm->z, nullptr, nullptr, two, f2_make(0.f, 0.f));
     simt::sync_block();
-    pfa_stage_p<5, NT, false>(sm->z, nullptr, nullptr, two);
+    pfa_stage_p<5, NT, false>(sm->z, nullptr, nullptr, two, f2_make(0.f, 0.f));
     simt::sync_block();
     f2* o0 = reinterpret_cast<f2*>(spec + (frame * M + ch0) * kSpecSlots);
     f2* o1 = o0 + kSpecSlots;
@@ -213,11 +255,16 @@ PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil
       f2 s0 = f2_mul(f2_add(zl, zm), half);
       const f2 d = f2_mul(f2_sub(zl, zm), half);          // i * S2
       f2 s1 = f2_make(f2_hi(d), -f2_lo(d));               // S2 = -i * d
+      if (sc0 == 0.f) s0 = f2_make(0.f, 0.f);             // all-zero channel: exact zeros, not the partner's residue
+      if (sc1 == 0.f) s1 = f2_make(0.f, 0.f);
 #if PAL_PREWHITEN
       // slot (q, r) stands for bins e and n - e when r > 0; row r = 0 holds both members of a conjugate pair
       const float wgt = r ? 2.f : 1.f;
       s0 = whiten_bin(s0, wgt, h0);
       if (two) s1 = whiten_bin(s1, wgt, h1);
+#else
+      s0 = f2_mul(s0, f2_bcast(inv0));                    // back to the signal's own level (exact)
+      s1 = f2_mul(s1, f2_bcast(inv1));
 #endif
       o0[o] = s0;
       if (two) o1[o] = s1;
@@ -235,8 +282,9 @@ PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int w = 0; w < NT / 32; ++w) { a0 += sm->red[w]; a1 += sm->red[16 + w]; }
-      hq[frame * M + ch0] = a0 * (1.0f / float(kN4095));
-      if (two) hq[frame * M + ch0 + 1] = a1 * (1.0f / float(kN4095));
+      // h is wanted at the signal's own level: |S| = |S_scaled| / sc
+      hq[frame * M + ch0] = a0 * (1.0f / float(kN4095)) * sc0 * sc0;
+      if (two) hq[frame * M + ch0 + 1] = a1 * (1.0f / float(kN4095)) * sc1 * sc1;
     }
 #endif
   }

@@ -239,7 +239,7 @@ struct RenderRows {
 // single-precision trigonometry (SURVEY.md hard part 6).
 template <int NT, int J>
 PAL_DEV void transfer_body(const cpxf* X, int N, RenderRows rr, long long row0, long long n_rows, double fs, cpxf* G,
-                           char* smem_raw) {
+                           int* live /* [n_rows]: 0 = the row has no audible path, its output is exactly zero */, char* smem_raw) {
   const int kcap = rr.k_stride;
   float* s_gain = reinterpret_cast<float*>(smem_raw);         // [k1]
   cpxf* s_rot = reinterpret_cast<cpxf*>(s_gain + ((kcap + 3) & ~3));   // [k1] rotation by NT bins
@@ -256,6 +256,7 @@ PAL_DEV void transfer_body(const cpxf* X, int N, RenderRows rr, long long row0, 
     const double* gk = rr.gain + size_t(grow) * rr.k_stride;
     double gmx = 0.0;
     for (int k = 0; k < k1; ++k) gmx = gk[k] > gmx ? gk[k] : gmx;        // small k1, L1-resident
+    if (live && m0 == 0 && tid == 0) live[lrow] = (k1 > 0 && gmx > 0.0) ? 1 : 0;
     for (int k = tid; k < k1; k += NT) {
       const double delta = tk[k] * fs / (2.0 * N);
       s_delta[k] = delta;
@@ -314,33 +315,48 @@ PAL_DEV void transfer_body(const cpxf* X, int N, RenderRows rr, long long row0, 
 
 // ------------------------------------------------------------------ Bluestein loader / storer
 // inverse DFT of length 2N of the Hermitian extension of G[row][0..N]
-template <typename T> struct LoadHermitian {
+// Two rows per transform (pal_bluestein.cuh): the rendered channels are real, so rows 2t and 2t+1 of a chunk travel as
+// the real and imaginary part of ONE inverse transform, a[k] = (Ga[k] + i Gb[k]) conj(chirp[k]) with Ga, Gb the
+// Hermitian extensions of the half spectra.  The imaginary parts of the DC and Nyquist bins, which a real inverse
+// transform ignores (and `.real` of signal_processing.py:72 discards), are dropped explicitly: they would otherwise
+// leak into the partner row.
+template <typename T> struct LoadHermitian2 {
   BluePlan p;              // p.n == 2N
   const cpx<T>* chirp;
   const cpxf* G;           // [rows][N+1]
   int N;
+  long long n_rows;        // rows of this launch
+  PAL_DEV cpx<T> half(long long row, int k) const {
+    const cpxf g = (k <= N) ? G[row * (N + 1) + k] : G[row * (N + 1) + (p.n - k)];
+    const bool self_conj = (k == 0) || (k == N);
+    return cpx<T>{T(g.x), self_conj ? T(0) : ((k <= N) ? T(g.y) : T(-g.y))};
+  }
   PAL_DEV cpx<T> operator()(long long t, int k) const {
     if (k >= p.n) return cpx<T>{T(0), T(0)};
-    const cpxf g = (k <= N) ? G[t * (N + 1) + k] : G[t * (N + 1) + (p.n - k)];
-    const cpx<T> v{T(g.x), (k <= N) ? T(g.y) : T(-g.y)};
-    return cmulc(v, chirp[k]);      // inverse transform: conjugate chirp
+    const cpx<T> a = half(2 * t, k);
+    const cpx<T> b = (2 * t + 1 < n_rows) ? half(2 * t + 1, k) : cpx<T>{T(0), T(0)};
+    return cmulc(cpx<T>{a.x - b.y, a.y + b.x}, chirp[k]);      // inverse transform: conjugate chirp
   }
 };
-// y[t] = Re(conv[t] * conj(chirp[t])) / (2N) * fade[t], t < n_keep   (signal_processing.py:72-79)
-template <typename T> struct StoreRender {
+// y[j] = Re / Im (conv[j] * conj(chirp[j])) / (2N) * fade[j], j < n_keep   (signal_processing.py:72-79)
+template <typename T> struct StoreRender2 {
   BluePlan p;
   const cpx<T>* chirp;
   float* out;              // [all rows][n_keep]
   int N, n_keep, fade;
-  RenderRows rr;           // chunk-local transform t -> output row rr.global_row(row0 + t)
-  long long row0;
+  RenderRows rr;           // chunk-local row r -> output row rr.global_row(row0 + r)
+  long long row0, n_rows;
+  const int* live;         // [n_rows] from the transfer kernel: a silent row must come out as exact zeros, not as the
+                           // rounding residue of its partner row (normalize_signal would blow that up to full scale)
   PAL_DEV void operator()(long long t, int j, cpx<T> y) const {
     if (j >= n_keep) return;
     const cpx<T> w = chirp[j];
-    T v = fma_(y.x, w.x, y.y * w.y) / T(p.n);
-    if (j < fade) v *= (fade > 1) ? T(j) / T(fade - 1) : T(0);                      // np.linspace(0, 1, fade)
-    if (j >= N - fade) v *= (fade > 1) ? T(N - 1 - j) / T(fade - 1) : T(1);         // np.linspace(1, 0, fade)
-    out[rr.global_row(row0 + t) * n_keep + j] = float(v);
+    T f = T(1) / T(p.n);
+    if (j < fade) f *= (fade > 1) ? T(j) / T(fade - 1) : T(0);                      // np.linspace(0, 1, fade)
+    if (j >= N - fade) f *= (fade > 1) ? T(N - 1 - j) / T(fade - 1) : T(1);         // np.linspace(1, 0, fade)
+    out[rr.global_row(row0 + 2 * t) * n_keep + j] = live[2 * t] ? float(fma_(y.x, w.x, y.y * w.y) * f) : 0.f;
+    if (2 * t + 1 < n_rows)
+      out[rr.global_row(row0 + 2 * t + 1) * n_keep + j] = live[2 * t + 1] ? float(fma_(y.y, w.x, -(y.x * w.y)) * f) : 0.f;
   }
 };
 

@@ -24,9 +24,9 @@ __global__ void k_path_table(const double* src, const double* img_pos, const int
   path_table_body(src, img_pos, img_mat, n_img, mics, n_mics, mat_abs, mat_freq, air_mat, frequency, c_sound, tau, gain);
 }
 __global__ void __launch_bounds__(kGT) k_transfer(const cpxf* X, int N, RenderRows rr, long long row0, long long n_rows,
-                                                  double fs, cpxf* G) {
+                                                  double fs, cpxf* G, int* live) {
   extern __shared__ __align__(16) char smem[];
-  transfer_body<kGT, kXferJ>(X, N, rr, row0, n_rows, fs, G, smem);
+  transfer_body<kGT, kXferJ>(X, N, rr, row0, n_rows, fs, G, live, smem);
 }
 __global__ void __launch_bounds__(128) k_path_table_batched(const double* sources, const double* img_pos, const int* img_mat,
                                                             const int* img_count, long long n_scenes, int k_max,
@@ -54,11 +54,11 @@ inline int image_grid(long long n_scenes, int sms) { return (int)std::min<long l
 // tables(2N) + X[2N] + per row in flight: G[N+1] + one convolution buffer
 inline size_t render_row_bytes(int N) {
   GenericLayout<float> L(2 * N);
-  return al(sizeof(cpxf) * size_t(N + 1)) + al(sizeof(cpxf) * size_t(L.p.M));
+  return al(sizeof(cpxf) * size_t(N + 1)) + al(sizeof(cpxf) * size_t(L.p.M)) + sizeof(int);   // G row, convolution buffer, live flag
 }
 inline size_t render_fixed_bytes(int N) {
   GenericLayout<float> L(2 * N);
-  return L.tables + al(sizeof(cpxf) * size_t(2 * N)) + 1024;
+  return L.tables + al(sizeof(cpxf) * size_t(2 * N)) + 2048;
 }
 inline size_t render_min_bytes(int N, int /*n_mics*/) { return render_fixed_bytes(N) + render_row_bytes(N); }
 inline size_t render_full_bytes(int N, long long rows) {
@@ -80,19 +80,23 @@ inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows 
   cpxf* X = reinterpret_cast<cpxf*>(b);
   b += al(sizeof(cpxf) * size_t(2 * N));
   const size_t g_one = al(sizeof(cpxf) * size_t(N + 1)), conv_one = al(sizeof(cpxf) * size_t(p.M));
-  long long cap = std::max<long long>(1, std::min<long long>(n_rows, (long long)((ws_bytes - size_t(b - ws)) / (g_one + conv_one))));
+  // rows in flight (kept even: two rows share a convolution buffer, which this sizing over-provisions)
+  long long cap = std::max<long long>(1, std::min<long long>(n_rows, (long long)((ws_bytes - size_t(b - ws) - 512) / (g_one + conv_one + sizeof(int)))));
   cap = std::max<long long>(1, std::min<long long>(cap, conv_chunk_bytes() / (long long)conv_one));   // chunk stays in L2
+  if (cap > 1) cap &= ~1LL;
   cpxf* G = reinterpret_cast<cpxf*>(b);          // rows addressed densely: G[t * (N+1)]
   b += size_t(cap) * g_one;
   cpxf* conv = reinterpret_cast<cpxf*>(b);       // conv[t * M]
+  b += size_t(cap) * conv_one;
+  int* live = reinterpret_cast<int*>(b);         // live[row of the chunk]
   const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   const BlueTables<T> tb = bb.tb();
-  cudaFuncSetAttribute(k_colpass_fwd<T, LoadHermitian<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  cudaFuncSetAttribute(k_colpass_inv<T, StoreRender<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_fwd<T, LoadHermitian2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  cudaFuncSetAttribute(k_colpass_inv<T, StoreRender2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   // X = fft(base zero-padded, 2N)                                      (signal_processing.py:69)
   k_colpass_fwd<T, LoadSignal<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(
-      p, tb, LoadSignal<T>{p, bb.chirp, base, n_base, n_base, n_base, nullptr}, 1, nullptr, conv);
+      p, tb, LoadSignal<T>{p, bb.chirp, base, n_base}, 1, nullptr, conv);
   k_rowpass<T, true, false><<<std::min(row_units<T>(p), 16 * sms), kGT, rs, s>>>(p, tb, 1, nullptr, conv);
   k_colpass_inv<T, StoreSpectrum<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(p, tb, StoreSpectrum<T>{p, bb.chirp, X}, 1, nullptr, conv);
   count_launch(3);
@@ -104,12 +108,14 @@ inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows 
   for (long long r0 = 0; r0 < n_rows; r0 += cap) {
     const long long nt = std::min<long long>(cap, n_rows - r0);
     // G = X * H                                                        (main.py:104-118)
-    k_transfer<<<(unsigned)std::min<long long>(nt * xtiles, 32LL * sms), kGT, ts, s>>>(X, N, rr, r0, nt, fs, G);
-    k_colpass_fwd<T, LoadHermitian<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * sms), kGT, cs, s>>>(
-        p, tb, LoadHermitian<T>{p, bb.chirp, G, N}, nt, nullptr, conv);
-    k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * sms), kGT, rs, s>>>(p, tb, nt, nullptr, conv);
-    k_colpass_inv<T, StoreRender<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * sms), kGT, cs, s>>>(
-        p, tb, StoreRender<T>{p, bb.chirp, out, N, n_keep, fade, rr, r0}, nt, nullptr, conv);
+    k_transfer<<<(unsigned)std::min<long long>(nt * xtiles, 32LL * sms), kGT, ts, s>>>(X, N, rr, r0, nt, fs, G, live);
+    // two rows per inverse transform (LoadHermitian2)
+    const long long ntr = (nt + 1) / 2;
+    k_colpass_fwd<T, LoadHermitian2<T>><<<(unsigned)std::min<long long>(ntr * tiles, 16LL * sms), kGT, cs, s>>>(
+        p, tb, LoadHermitian2<T>{p, bb.chirp, G, N, nt}, ntr, nullptr, conv);
+    k_rowpass<T, true, true><<<(unsigned)std::min<long long>(ntr * row_units<T>(p), 16LL * sms), kGT, rs, s>>>(p, tb, ntr, nullptr, conv);
+    k_colpass_inv<T, StoreRender2<T>><<<(unsigned)std::min<long long>(ntr * tiles, 16LL * sms), kGT, cs, s>>>(
+        p, tb, StoreRender2<T>{p, bb.chirp, out, N, n_keep, fade, rr, r0, nt, live}, ntr, nullptr, conv);
     count_launch(4);
   }
   return cudaGetLastError();

@@ -99,23 +99,24 @@ static void emu_generic_impl(const float* sig, long long B, int Mics, int ld, in
   const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2) * (std::min(p.M1, TRW) + 1);
   simt::launch(2, NT, cs, [&](char* sm) { colpass_fwd_body<T, NT, TC>(p, tb, LoadBhat<T>{p, chirp.data()}, 1, bhat.data(), sm); });
   simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, false, false>(p, tb, 1, bhat.data(), sm); });
-  const long long rows = B * Mics, items = B * P;
-  std::vector<cpx<T>> conv(size_t(std::max(rows, items)) * p.M), spec(size_t(rows) * n);
+  const int CP = (Mics + 1) / 2;
+  const long long rows = B * CP, items = B * P, itr = (items + 1) / 2;    // packed: two real sequences per transform
+  std::vector<cpx<T>> conv(size_t(std::max(rows, itr)) * p.M), spec(size_t(rows) * n);
   std::vector<T> corr(size_t(items) * n);
+  std::vector<float> scales(size_t(B) * Mics * 2);
+  simt::launch(2, NT, 64, [&](char* sm) { row_scale_body<NT>(sig, B * Mics, ld, n1, n2, scales.data(), sm); });
   simt::launch(3, NT, cs, [&](char* sm) {
-    colpass_fwd_body<T, NT, TC>(p, tb, LoadSignal<T>{p, chirp.data(), sig, ld, n1, n2, nullptr}, rows, conv.data(), sm);
+    colpass_fwd_body<T, NT, TC>(p, tb, LoadSignal2<T>{p, chirp.data(), sig, ld, Mics, CP, n1, n2, nullptr, 0, scales.data()}, rows, conv.data(), sm);
   });
   simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, false>(p, tb, rows, conv.data(), sm); });
   simt::launch(3, NT, cs, [&](char* sm) {
     colpass_inv_body<T, NT, TC>(p, tb, StoreSpectrum<T>{p, chirp.data(), spec.data()}, rows, conv.data(), sm);
   });
+  const LoadPhat2<T> lp{p, chirp.data(), spec.data(), pairs, Mics, CP, P, 0, items, false, scales.data(), 0, nullptr, 0};
+  simt::launch(3, NT, cs, [&](char* sm) { colpass_fwd_body<T, NT, TC>(p, tb, lp, itr, conv.data(), sm); });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, true>(p, tb, itr, conv.data(), sm); });
   simt::launch(3, NT, cs, [&](char* sm) {
-    colpass_fwd_body<T, NT, TC>(p, tb, LoadPhat<T>{p, chirp.data(), spec.data(), pairs, Mics, P, 0, false}, items,
-                                conv.data(), sm);
-  });
-  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, true>(p, tb, items, conv.data(), sm); });
-  simt::launch(3, NT, cs, [&](char* sm) {
-    colpass_inv_body<T, NT, TC>(p, tb, StoreCorr<T>{p, chirp.data(), corr.data()}, items, conv.data(), sm);
+    colpass_inv_body<T, NT, TC>(p, tb, StoreCorr2<T>{p, chirp.data(), corr.data(), items, lp}, itr, conv.data(), sm);
   });
   const int grid = 2;
   std::vector<unsigned char> pk(size_t(grid) * ((n + 15) / 16 * 16));
@@ -180,8 +181,9 @@ extern "C" void emu_render_scene(const float* base, int n_base, int N, const dou
   simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, false, false>(p, tb, 1, bhat.data(), sm); });
   std::vector<cpx<T>> conv(size_t(n_mics) * p.M), X(p.n);
   std::vector<cpxf> G(size_t(n_mics) * (N + 1));
+  std::vector<int> live(n_mics);
   simt::launch(3, NT, cs, [&](char* sm) {
-    colpass_fwd_body<T, NT, TC>(p, tb, LoadSignal<T>{p, chirp.data(), base, n_base, n_base, n_base, nullptr}, 1, conv.data(), sm);
+    colpass_fwd_body<T, NT, TC>(p, tb, LoadSignal<T>{p, chirp.data(), base, n_base}, 1, conv.data(), sm);
   });
   simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, false>(p, tb, 1, conv.data(), sm); });
   simt::launch(3, NT, cs, [&](char* sm) {
@@ -189,14 +191,14 @@ extern "C" void emu_render_scene(const float* base, int n_base, int N, const dou
   });
   const size_t ts = 4 * ((k1 + 3) & ~3) + 16 * size_t(k1) + 16;
   const RenderRows rr{tau, gain, nullptr, nullptr, k1, n_mics};
-  simt::launch(3, NT, ts, [&](char* sm) { transfer_body<NT, J>(X.data(), N, rr, 0, n_mics, fs, G.data(), sm); });
+  simt::launch(3, NT, ts, [&](char* sm) { transfer_body<NT, J>(X.data(), N, rr, 0, n_mics, fs, G.data(), live.data(), sm); });
   simt::launch(3, NT, cs, [&](char* sm) {
-    colpass_fwd_body<T, NT, TC>(p, tb, LoadHermitian<T>{p, chirp.data(), G.data(), N}, n_mics, conv.data(), sm);
+    colpass_fwd_body<T, NT, TC>(p, tb, LoadHermitian2<T>{p, chirp.data(), G.data(), N, n_mics}, (n_mics + 1) / 2, conv.data(), sm);
   });
-  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, true>(p, tb, n_mics, conv.data(), sm); });
+  simt::launch(3, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, true, true>(p, tb, (n_mics + 1) / 2, conv.data(), sm); });
   const int fade = int(0.01 * N);
   simt::launch(3, NT, cs, [&](char* sm) {
-    colpass_inv_body<T, NT, TC>(p, tb, StoreRender<T>{p, chirp.data(), out, N, n_keep, fade, rr, 0}, n_mics, conv.data(), sm);
+    colpass_inv_body<T, NT, TC>(p, tb, StoreRender2<T>{p, chirp.data(), out, N, n_keep, fade, rr, 0, n_mics, live.data()}, (n_mics + 1) / 2, conv.data(), sm);
   });
   simt::launch(2, NT, 64, [&](char* sm) { normalise_compress_body<NT>(out, n_mics, n_keep, 0.8f, 1e-8f, true, sm); });
 }

@@ -271,3 +271,60 @@ def test_sync_align_emulation_unequal_lengths_and_edges():
     same = [src[:256].copy() for _ in range(3)]
     out2, d2 = _sync_via_emulation(same, 16000.0)
     assert d2["ref"] == 0 and np.array_equal(out2, np.array(O.synchronize_signals_improved(same, 16000.0)))
+
+
+@pytest.mark.parametrize("use_double", [False, True])
+def test_generic_path_packs_two_real_sequences_per_transform(use_double):
+    """Two channels share a forward transform and two pair-correlations share an inverse one (odd channel count,
+    odd item count, several frames): every row must still be the reference's row, with no leakage between the
+    two correlation rows of a packed transform."""
+    rng = np.random.default_rng(77)
+    b, m, n = 3, 3, 180
+    sig = np.zeros((b, m, n), np.float32)
+    for f in range(b):
+        src = rng.standard_normal(n + 30)
+        for c in range(m):
+            d = int(rng.integers(0, 25))
+            sig[f, c] = (1.0 + c) * src[d:d + n] + 0.2 * rng.standard_normal(n)      # very different channel levels
+    pairs = E.pairs_of(m)
+    fs, med = 8000.0, 0.004
+    wh = O.window_half_width(n, n, fs, med)
+    k, cnt, pk, gm, fl, corr = E.generic_gcc_phat(sig, n, n, pairs, wh, O.peak_distance(fs), use_double=use_double)
+    for f in range(b):
+        for p, (i, j) in enumerate(pairs):
+            want_td, c, _ = O.get_time_delays_phat(sig[f, i].astype(np.float64), sig[f, j].astype(np.float64), fs,
+                                                   max_expected_delay=med)
+            assert np.abs(corr[f, p] - c).max() <= (2e-6 if use_double else 1e-4) * np.abs(c).max()
+            assert abs(gm[f, p] - c.max()) <= 1e-4 * c.max()
+            if use_double:
+                assert O.tdoa_from_index(int(k[f, p, 0]), n, fs) == want_td[0]
+
+
+def test_dead_and_weak_channels_next_to_a_loud_one():
+    """Two channels share one complex transform.  A dead (all-zero) microphone next to a live one must give the
+    reference's all-zero correlation (k = 0, max = 0), not the whitened rounding residue of its partner; a channel
+    60 dB below its partner must keep the float32 accuracy it has on its own (exact power-of-two pre-scaling)."""
+    rng = np.random.default_rng(3)
+    src = rng.standard_normal(2100)
+    fr = np.zeros((1, 4, 2048), np.float32)
+    fr[0, 0] = src[7:2055]
+    fr[0, 2] = 1e-3 * (src[:2048] + 0.3 * rng.standard_normal(2048))       # weak partner of the dead channel 3 ...
+    fr[0, 1] = 0.0                                                         # ... and a dead partner of the loud channel 0
+    fr[0, 3] = 1e-3 * src[20:2068]
+    sp = E.fwd4095(fr)
+    assert not np.asarray(sp[0, 1]).any() and sp.hq[0, 1] == 0
+    pairs = E.pairs_of(4)
+    k, pk, gm, fl, corr = E.pair_fast(sp, pairs, 800, 16, want_corr=True)
+    for p, (i, j) in enumerate(pairs):
+        c = O.phat_correlation(fr[0, i].astype(np.float64), fr[0, j].astype(np.float64))
+        assert np.abs(corr[0, p] - c).max() < 5e-7, (i, j)
+        if 1 in (i, j):
+            assert k[0, p] == 0 and gm[0, p] == 0 and fl[0, p] & 16
+    # the same through the arbitrary-length (Bluestein) path
+    sig = np.ascontiguousarray(fr[:, :, :300])
+    kg, cnt, pkg, gmg, flg, cg = E.generic_gcc_phat(sig, 300, 300, pairs, 40, 16)
+    for p, (i, j) in enumerate(pairs):
+        c = O.phat_correlation(sig[0, i].astype(np.float64), sig[0, j].astype(np.float64))
+        assert np.abs(cg[0, p] - c).max() <= 1e-4 * max(np.abs(c).max(), 1e-30) + (0 if c.any() else 0)
+        if 1 in (i, j):
+            assert not cg[0, p].any() and kg[0, p, 0] == 0

@@ -195,3 +195,35 @@ def test_host_streaming_entry_point_matches_device_path(pal):
         assert np.array_equal(r["gmax"], ref.gmax.cpu().numpy())
         assert r["tdoa"].dtype == np.float64 and np.array_equal(r["tdoa"], ref.tdoa_seconds())
         assert r["h2d_bytes"] == fr.numel() * 4
+
+
+@pytest.mark.parametrize("n", [2048, 1500])
+def test_dead_weak_and_quiet_channels(pal, n):
+    """Edge cases of sharing one complex transform between two real channels (both the fused n = 4095 kernels and the
+    Bluestein path do): a dead microphone next to a live one gives the reference's all-zero row (k = 0, max = 0), a
+    channel 60 dB below its partner keeps its accuracy, and frames so quiet that the absolute 1e-10 of utils.py:117
+    matters are still answered exactly (the whitened fast path hands them to the float64 kernel)."""
+    rng = np.random.default_rng(3)
+    src = rng.standard_normal(n + 100)
+    fr = np.zeros((3, 4, n), np.float32)
+    fr[0, 0] = src[7:7 + n]
+    fr[0, 2] = 1e-3 * (src[:n] + 0.3 * rng.standard_normal(n))
+    fr[0, 3] = 1e-3 * src[20:20 + n]                      # channel 1 stays dead
+    for c in range(4):                                    # a quiet frame (-90 dBFS) and an ordinary one
+        fr[1, c] = 3e-5 * (src[3 * c:3 * c + n] + 0.2 * rng.standard_normal(n))
+        fr[2, c] = src[5 * c:5 * c + n] + 0.2 * rng.standard_normal(n)
+    res = pal.gcc_phat_tdoa_batched(torch.from_numpy(fr).cuda(), 16000.0, max_expected_delay=0.05, return_corr=True)
+    td = res.tdoa_seconds()[..., 0]
+    corr, gm, k = res.corr.cpu().numpy(), res.gmax.cpu().numpy(), res.k_idx.cpu().numpy()[..., 0]
+    pairs = pal.all_pairs(4)
+    for f in range(3):
+        for p, (i, j) in enumerate(pairs):
+            want_td, c, _ = O.get_time_delays_phat(fr[f, i].astype(np.float64), fr[f, j].astype(np.float64), 16000.0,
+                                                   max_expected_delay=0.05)
+            assert td[f, p] == want_td[0], (f, i, j)
+            if f == 0 and 1 in (i, j):
+                assert k[f, p] == 0 and gm[f, p] == 0 and not corr[f, p].any()
+            else:
+                assert abs(gm[f, p] - c.max()) <= CORR_RTOL * c.max()
+                if f != 1:     # (a quiet row's fp32 correlation VALUES deviate by the documented bound; its lag and max are float64)
+                    assert np.abs(corr[f, p] - c).max() <= CORR_RTOL * np.abs(c).max()
