@@ -255,7 +255,7 @@ def run_gpu_arm(args):
     refined_frac = float(((flags & 8) != 0).float().mean().item())
 
     # ---- end-to-end through the public host-buffer API ------------------------------------
-    e2e = None
+    e2e = e2e_pcm16 = None
     if not args.no_e2e:
         host = torch.empty((frames_n, MICS, NS), dtype=torch.float32, pin_memory=True)
         host.copy_(frames)
@@ -277,6 +277,31 @@ def run_gpu_arm(args):
         e2e = {"value": world * frames_n * PAIRS / e_sec, "unit": UNIT, "h2d_bytes_per_step": r["h2d_bytes"],
                "d2h_bytes_per_step": r["d2h_bytes"], "ms_per_step": e_sec * 1e3, "steps": e_steps}
         del host
+        # The same call fed with 16-bit PCM host buffers (what capture hardware / WAV files deliver): half the
+        # PCIe bytes, converted to float32 x/32768 on the device.  Informational; `e2e` above is the float32 contract.
+        q = torch.clamp(torch.round(frames * (32767.0 / float(frames.abs().max()))), -32768, 32767).to(torch.int16)
+        host16 = torch.empty((frames_n, MICS, NS), dtype=torch.int16, pin_memory=True)
+        host16.copy_(q)
+        fq = pal.gcc_phat.pcm16_to_f32(q)
+        del q
+        want = pal.gcc_phat_tdoa_batched(fq, FS, MED, pairs_dev=pairs_dev).k_idx.cpu().numpy()
+        del fq
+        r16 = pal.gcc_phat.gcc_phat_tdoa_from_host(host16, FS, MED, chunk_frames=args.e2e_chunk, out_host=out_host)   # warm-up
+        assert np.array_equal(r16["k_idx"], want)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(e_steps):
+            r16 = pal.gcc_phat.gcc_phat_tdoa_from_host(host16, FS, MED, chunk_frames=args.e2e_chunk, out_host=out_host)
+        barrier()
+        p_sec = (time.perf_counter() - w0) / e_steps
+        if world > 1:
+            tt = torch.tensor([p_sec], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            p_sec = float(tt.item())
+        e2e_pcm16 = {"value": world * frames_n * PAIRS / p_sec, "unit": UNIT, "h2d_bytes_per_step": r16["h2d_bytes"],
+                     "d2h_bytes_per_step": r16["d2h_bytes"], "ms_per_step": p_sec * 1e3, "steps": e_steps,
+                     "input": "int16 PCM host frames (the synthetic frames quantised to 16 bits), float32 on the device"}
+        del host16
 
     if rank != 0:
         if world > 1:
@@ -318,6 +343,7 @@ def run_gpu_arm(args):
                    "refined_row_fraction": refined_frac},
         "clocks": clocks,
         "e2e": e2e,
+        "e2e_pcm16": e2e_pcm16,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic,

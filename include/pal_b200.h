@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PAL_ABI_VERSION 5
+#define PAL_ABI_VERSION 6
 
 /* error codes */
 #define PAL_OK 0
@@ -101,6 +101,12 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
                       int32_t* k_idx_dev, int32_t* k_count_dev, float* peak_dev, float* gmax_dev,
                       uint32_t* flags_dev, float* corr_opt_dev, void* ws_dev, size_t ws_bytes,
                       void* stream);
+
+/* 16-bit PCM samples (what capture hardware and WAV files deliver) to float32: out[i] = in[i] * scale.  With
+ * scale = 1/32768 this is the float conversion soundfile applies in utils.load_audio_file (utils.py:469), exact in
+ * float32.  Lets a caller ship int16 frames over PCIe (half the bytes of float32) and feed pal_gcc_phat_tdoa from
+ * out_dev.  in_dev / out_dev: `count` elements, in_dev 2-byte and out_dev 4-byte aligned. */
+int pal_pcm16_to_f32(const int16_t* in_dev, int64_t count, float scale, float* out_dev, void* stream);
 
 /* time_lags[k] of utils.py:141-142 for every selected peak: out[i] = (double)(k_idx[i] - (n_second - 1)) / fs
  * with an IEEE round-to-nearest float64 division, i.e. bit-identical to numpy's int64 / float64;

@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PAL_B200_LIB") or os.path.join(_PKG, "libpal_b200.so")   # env override: tuning experiments only
 
-PAL_ABI_VERSION = 5
+PAL_ABI_VERSION = 6
 
 # per-row flag bits (include/pal_b200.h)
 FLAG_NEAR_TIE = 1
@@ -82,6 +82,8 @@ def lib():
     L.pal_filtfilt.restype = C.c_int
     L.pal_filtfilt.argtypes = [VP, I64, I32, I32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), I32, I32,
                                VP, VP, C.c_size_t, VP]
+    L.pal_pcm16_to_f32.restype = C.c_int
+    L.pal_pcm16_to_f32.argtypes = [VP, I64, F32, VP, VP]
     L.pal_sync_align_workspace.restype = C.c_int
     L.pal_sync_align_workspace.argtypes = [I64, I32, I32, SZP, SZP]
     L.pal_sync_align.restype = C.c_int

@@ -438,6 +438,18 @@ template <typename T> struct StoreRaw {           // the chirp spectrum itself (
   PAL_DEV void operator()(long long t, int j, cpx<T> y) const { out[t * M + j] = y; }
 };
 
+// The butterflies' twiddles (L/2 complex numbers) are staged in shared memory once per block: a radix-4 step
+// reads three of them per butterfly, and from global memory each read is a long-scoreboard stall.
+template <typename T, int NT> PAL_DEV const cpx<T>* stage_twiddles(const cpx<T>* tw, int count, T* smem_after_tile) {
+  cpx<T>* s = reinterpret_cast<cpx<T>*>(smem_after_tile);
+  for (int i = simt::tid(); i < count; i += NT) s[i] = tw[i];
+  simt::sync_block();
+  return s;
+}
+PAL_HD size_t fft_tile_smem(size_t elem_bytes, int L, int lanes) {       // re + im tile, then the L/2 staged twiddles
+  return 2 * elem_bytes * size_t(L) * size_t(lanes) + 2 * elem_bytes * size_t(L / 2 > 0 ? L / 2 : 1);
+}
+
 // ---- pass 1: columns forward -------------------------------------------------------------------
 // work unit = (transform t, tile of TC adjacent columns j2).  buf[t][r][j2] <- twiddled column FFT
 template <typename T, int NT, int TC, class Loader>
@@ -447,6 +459,7 @@ PAL_DEV void colpass_fwd_body(BluePlan p, BlueTables<T> tb, Loader load, long lo
   const int tiles = p.M2 / tc;
   T* re = reinterpret_cast<T*>(smem);
   T* im = re + p.M1 * tc;
+  const cpx<T>* tw1 = stage_twiddles<T, NT>(tb.tw1, p.M1 / 2, im + p.M1 * tc);
   for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks()) {
     const long long t = u / tiles;
     const int j20 = int(u % tiles) * tc;
@@ -457,7 +470,7 @@ PAL_DEV void colpass_fwd_body(BluePlan p, BlueTables<T> tb, Loader load, long lo
       im[e] = a.y;
     }
     simt::sync_block();
-    fft_tile<T, NT>(re, im, p.lg1, tc, tc, 1, tb.tw1, false);
+    fft_tile<T, NT>(re, im, p.lg1, tc, tc, 1, tw1, false);
     cpx<T>* out = buf + t * p.M;
     for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
       const int r = e >> lgt, c = e & (tc - 1);
@@ -482,6 +495,7 @@ PAL_DEV void rowpass_body(BluePlan p, BlueTables<T> tb, long long n_tr, cpx<T>* 
   const int ld = tr + 1;
   T* re = reinterpret_cast<T*>(smem);
   T* im = re + p.M2 * ld;
+  const cpx<T>* tw2 = stage_twiddles<T, NT>(tb.tw2, p.M2 / 2, im + p.M2 * ld);
   for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks()) {
     const long long t = u / tiles;
     const int r0 = int(u % tiles) * tr;
@@ -493,7 +507,7 @@ PAL_DEV void rowpass_body(BluePlan p, BlueTables<T> tb, long long n_tr, cpx<T>* 
       im[e * ld + c] = v.y;
     }
     simt::sync_block();
-    fft_tile<T, NT>(re, im, p.lg2, tr, ld, 1, tb.tw2, false);
+    fft_tile<T, NT>(re, im, p.lg2, tr, ld, 1, tw2, false);
     if (CONV) {
       const cpx<T>* bh = tb.bhat + (long long)r0 * p.M2;
       for (int x = simt::tid(); x < tr * p.M2; x += NT) {
@@ -505,7 +519,7 @@ PAL_DEV void rowpass_body(BluePlan p, BlueTables<T> tb, long long n_tr, cpx<T>* 
         im[e * ld + c] = v.y;
       }
       simt::sync_block();
-      fft_tile<T, NT>(re, im, p.lg2, tr, ld, 1, tb.tw2, true);
+      fft_tile<T, NT>(re, im, p.lg2, tr, ld, 1, tw2, true);
       for (int x = simt::tid(); x < tr * p.M2; x += NT) {
         const int c = x >> p.lg2, e = x & (p.M2 - 1);
         const unsigned k1 = bitrev(unsigned(r0 + c), p.lg1);
@@ -531,6 +545,7 @@ PAL_DEV void colpass_inv_body(BluePlan p, BlueTables<T> tb, Storer store, long l
   const int tiles = p.M2 / tc;
   T* re = reinterpret_cast<T*>(smem);
   T* im = re + p.M1 * tc;
+  const cpx<T>* tw1 = stage_twiddles<T, NT>(tb.tw1, p.M1 / 2, im + p.M1 * tc);
   const T inv_m = T(1) / T(p.M);
   for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks()) {
     const long long t = u / tiles;
@@ -543,7 +558,7 @@ PAL_DEV void colpass_inv_body(BluePlan p, BlueTables<T> tb, Storer store, long l
       im[e] = v.y;
     }
     simt::sync_block();
-    fft_tile<T, NT>(re, im, p.lg1, tc, tc, 1, tb.tw1, true);
+    fft_tile<T, NT>(re, im, p.lg1, tc, tc, 1, tw1, true);
     for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
       const int j1 = e >> lgt, c = e & (tc - 1);
       store(t, j1 * p.M2 + j20 + c, cpx<T>{re[e] * inv_m, im[e] * inv_m});

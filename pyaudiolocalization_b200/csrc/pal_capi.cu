@@ -133,6 +133,36 @@ __global__ void k_tdoa_seconds(const int* __restrict__ k_idx, long long n, int c
   }
 }
 
+// 8 samples per thread: one 16-byte load, two 16-byte stores
+__global__ void __launch_bounds__(256) k_pcm16_to_f32(const short* __restrict__ in, long long count, float scale,
+                                                      float* __restrict__ out, int head) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gsz = (long long)gridDim.x * blockDim.x;
+  // `head` samples bring `in` to 16-byte alignment (and `out` to 32-byte alignment relative to its own base)
+  for (long long i = gid; i < head && i < count; i += gsz) out[i] = float(in[i]) * scale;
+  const long long body = (count - head) > 0 ? (count - head) / 8 : 0;
+  const int4* in8 = reinterpret_cast<const int4*>(in + head);
+  for (long long v = gid; v < body; v += gsz) {
+    const int4 q = in8[v];
+    float o[8];
+    const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[2 * k] = float(short(w[k] & 0xffff)) * scale;
+      o[2 * k + 1] = float(short(w[k] >> 16)) * scale;
+    }
+    float* dst = out + head + 8 * v;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[k] = o[k];
+    }
+  }
+  for (long long i = head + 8 * body + gid; i < count; i += gsz) out[i] = float(in[i]) * scale;
+}
+
 constexpr int kFiltThreads = 128;
 template <typename TIO>
 __global__ void __launch_bounds__(kFiltThreads) k_filtfilt(const TIO* __restrict__ x, long long n_rows, int n, FiltParams fp,
@@ -365,6 +395,22 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
     }
     PAL_CUDA(cudaGetLastError());
   }
+  return PAL_OK;
+}
+
+int pal_pcm16_to_f32(const int16_t* in_dev, int64_t count, float scale, float* out_dev, void* stream_) {
+  if (count < 0 || (count > 0 && (!in_dev || !out_dev))) return fail(PAL_ERR_INVALID, "pal_pcm16_to_f32: bad argument");
+  if ((reinterpret_cast<uintptr_t>(in_dev) & 1u) || (reinterpret_cast<uintptr_t>(out_dev) & 3u))
+    return fail(PAL_ERR_INVALID, "pal_pcm16_to_f32: misaligned pointer");
+  if (count == 0) return PAL_OK;
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  const int head = int(((16u - (reinterpret_cast<uintptr_t>(in_dev) & 15u)) & 15u) / 2u);
+  const unsigned grid = (unsigned)std::min<long long>((count / 8 + 255) / 256 + 1, 16LL * di.sms);
+  k_pcm16_to_f32<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(reinterpret_cast<const short*>(in_dev), count, scale,
+                                                                       out_dev, head);
+  ++g_launches;
+  PAL_CUDA(cudaGetLastError());
   return PAL_OK;
 }
 

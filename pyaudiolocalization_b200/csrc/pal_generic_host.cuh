@@ -119,12 +119,12 @@ template <typename T> struct BlueBuffers {
 
 template <typename T> inline size_t row_smem(const BluePlan& p) {
   const int tr = std::min(p.M1, ColTile<T>::TR);
-  return 2 * sizeof(T) * size_t(p.M2) * (tr + 1);
+  return fft_tile_smem(sizeof(T), p.M2, tr + 1);
 }
 template <typename T> inline int row_units(const BluePlan& p) { return p.M1 / std::min(p.M1, ColTile<T>::TR); }
 template <typename T> inline size_t col_smem(const BluePlan& p) {
   const int tc = std::min(p.M2, ColTile<T>::TC);
-  return 2 * sizeof(T) * size_t(p.M1) * tc;
+  return fft_tile_smem(sizeof(T), p.M1, tc);
 }
 
 // carve the tables out of `base`, fill them, and build the chirp spectrum

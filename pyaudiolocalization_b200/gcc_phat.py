@@ -156,6 +156,22 @@ def tdoa_seconds_device(k_idx: torch.Tensor, n_second: int, fs: float, out: Opti
     return out
 
 
+PCM16_SCALE = 1.0 / 32768.0     # soundfile's int16 -> float conversion (utils.py:469), exact in float32
+
+
+def pcm16_to_f32(x: torch.Tensor, scale: float = PCM16_SCALE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int16 CUDA tensor -> float32 (x * scale) on the current stream (pal_pcm16_to_f32)."""
+    if not (x.is_cuda and x.dtype == torch.int16 and x.is_contiguous()):
+        raise TypeError("x must be a contiguous int16 CUDA tensor")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().pal_pcm16_to_f32(x.data_ptr(), x.numel(), float(scale), out.data_ptr(),
+                                         torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "pal_pcm16_to_f32")
+    return out
+
+
 def alloc_host_outputs(b: int, p: int, num_peaks: int = 1) -> dict:
     """Pinned host buffers for gcc_phat_tdoa_from_host(out_host=...).  Pinning memory is slow (tens of
     milliseconds per 100 MB), so a caller that processes batch after batch allocates them once."""
@@ -170,9 +186,17 @@ def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_d
     makes the copies asynchronous).  Three streams form a pipeline over chunks of frames: host->device
     copy of chunk c+1, kernels of chunk c, device->host copy of the results of chunk c-1 (lag
     indices, max(corr) and the float64 TDOA seconds, all derived on the device).  Returns numpy
-    arrays backed by pinned memory."""
+    arrays backed by pinned memory.
+
+    frames_host may also be int16 (16-bit PCM as capture hardware / WAV files deliver it): the samples cross
+    PCIe as int16 -- half the bytes -- and are converted on the device to float32 x / 32768 (`pcm_scale`), which
+    is exactly the float signal the reference computes on after soundfile's conversion."""
     if frames_host.is_cuda:
         raise TypeError("frames_host must live in host memory")
+    pcm = frames_host.dtype == torch.int16
+    pcm_scale = float(kw.pop("pcm_scale", PCM16_SCALE))
+    if not pcm and frames_host.dtype != torch.float32:
+        raise TypeError("frames_host must be float32 or int16")
     if kw.get("return_corr"):
         raise ValueError("return_corr is not supported by the streaming host entry point")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -185,7 +209,8 @@ def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_d
     chunk = max(1, min(int(chunk_frames), b))
     full, _ = workspace_bytes(chunk, m, n, p)
     ws = torch.empty(full + 256, dtype=torch.uint8, device=dev)
-    bufs = [torch.empty((chunk, m, n), dtype=torch.float32, device=dev) for _ in range(2)]
+    bufs = [torch.empty((chunk, m, n), dtype=frames_host.dtype, device=dev) for _ in range(2)]
+    f32buf = torch.empty((chunk, m, n), dtype=torch.float32, device=dev) if pcm else None
     res = TdoaBatch(torch.empty((b, p, num_peaks), dtype=torch.int32, device=dev),
                     torch.empty((b, p), dtype=torch.int32, device=dev),
                     torch.empty((b, p), dtype=torch.float32, device=dev),
@@ -215,9 +240,15 @@ def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_d
             comp_s.wait_event(copied[sl])
             view = TdoaBatch(res.k_idx[f0:f0 + nb], res.k_count[f0:f0 + nb], res.peak[f0:f0 + nb],
                              res.gmax[f0:f0 + nb], res.flags[f0:f0 + nb], None, n, float(fs))
-            gcc_phat_tdoa_batched(bufs[sl][:nb], fs, max_expected_delay, workspace=ws, out=view,
-                                  pairs_dev=pairs_dev, **kw)
-            consumed[sl].record(comp_s)
+            if pcm:
+                pcm16_to_f32(bufs[sl][:nb], pcm_scale, out=f32buf[:nb])
+                consumed[sl].record(comp_s)          # the int16 landing buffer is free as soon as it is converted
+                gcc_phat_tdoa_batched(f32buf[:nb], fs, max_expected_delay, workspace=ws, out=view,
+                                      pairs_dev=pairs_dev, **kw)
+            else:
+                gcc_phat_tdoa_batched(bufs[sl][:nb], fs, max_expected_delay, workspace=ws, out=view,
+                                      pairs_dev=pairs_dev, **kw)
+                consumed[sl].record(comp_s)
             tdoa_seconds_device(res.k_idx[f0:f0 + nb], n, fs, out=td_dev[f0:f0 + nb])
             done = torch.cuda.Event()
             done.record(comp_s)
@@ -230,5 +261,5 @@ def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_d
     cur.wait_stream(comp_s)
     cur.wait_stream(copy_s)
     return {"k_idx": k_host.numpy(), "tdoa": td_host.numpy(), "gmax": g_host.numpy(),
-            "h2d_bytes": int(frames_host.numel() * 4),
+            "h2d_bytes": int(frames_host.numel() * frames_host.element_size()),
             "d2h_bytes": int(k_host.numel() * 4 + g_host.numel() * 4 + td_host.numel() * 8)}

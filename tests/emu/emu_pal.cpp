@@ -96,7 +96,7 @@ static void emu_generic_impl(const float* sig, long long B, int Mics, int ld, in
   BlueTables<T> tb{chirp.data(), tw1.data(), tw2.data(), twM.data(), bhat.data()};
   const int tc = std::min(p.M2, TC);
   constexpr int TRW = 4;
-  const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2) * (std::min(p.M1, TRW) + 1);
+  const size_t cs = fft_tile_smem(sizeof(T), p.M1, tc), rs = fft_tile_smem(sizeof(T), p.M2, std::min(p.M1, TRW) + 1);
   simt::launch(2, NT, cs, [&](char* sm) { colpass_fwd_body<T, NT, TC>(p, tb, LoadBhat<T>{p, chirp.data()}, 1, bhat.data(), sm); });
   simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, false, false>(p, tb, 1, bhat.data(), sm); });
   const int CP = (Mics + 1) / 2;
@@ -176,7 +176,7 @@ extern "C" void emu_render_scene(const float* base, int n_base, int N, const dou
   BlueTables<T> tb{chirp.data(), tw1.data(), tw2.data(), twM.data(), bhat.data()};
   const int tc = std::min(p.M2, TC);
   constexpr int TRW = 4;
-  const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2) * (std::min(p.M1, TRW) + 1);
+  const size_t cs = fft_tile_smem(sizeof(T), p.M1, tc), rs = fft_tile_smem(sizeof(T), p.M2, std::min(p.M1, TRW) + 1);
   simt::launch(2, NT, cs, [&](char* sm) { colpass_fwd_body<T, NT, TC>(p, tb, LoadBhat<T>{p, chirp.data()}, 1, bhat.data(), sm); });
   simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, false, false>(p, tb, 1, bhat.data(), sm); });
   std::vector<cpx<T>> conv(size_t(n_mics) * p.M), X(p.n);
@@ -246,7 +246,7 @@ extern "C" void emu_sync_align(const double* sig, long long S, int Mics, int ld,
   simt::launch(2, NT, 16, [&](char*) { blue_init_tables_body<T>(p, chirp.data(), tw1.data(), tw2.data(), twM.data()); });
   BlueTables<T> tb{chirp.data(), tw1.data(), tw2.data(), twM.data(), bhat.data()};
   const int tc = std::min(p.M2, TC);
-  const size_t cs = 2 * sizeof(T) * size_t(p.M1) * tc, rs = 2 * sizeof(T) * size_t(p.M2) * (std::min(p.M1, TRW) + 1);
+  const size_t cs = fft_tile_smem(sizeof(T), p.M1, tc), rs = fft_tile_smem(sizeof(T), p.M2, std::min(p.M1, TRW) + 1);
   simt::launch(2, NT, cs, [&](char* sm) { colpass_fwd_body<T, NT, TC>(p, tb, LoadBhat<T>{p, chirp.data()}, 1, bhat.data(), sm); });
   simt::launch(2, NT, rs, [&](char* sm) { rowpass_body<T, NT, TRW, false, false>(p, tb, 1, bhat.data(), sm); });
   simt::launch(2, NT, sizeof(double) * Mics, [&](char* sm) {

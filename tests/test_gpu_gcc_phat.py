@@ -227,3 +227,30 @@ def test_dead_weak_and_quiet_channels(pal, n):
                 assert abs(gm[f, p] - c.max()) <= CORR_RTOL * c.max()
                 if f != 1:     # (a quiet row's fp32 correlation VALUES deviate by the documented bound; its lag and max are float64)
                     assert np.abs(corr[f, p] - c).max() <= CORR_RTOL * np.abs(c).max()
+
+
+def test_pcm16_host_frames(pal):
+    """int16 PCM host buffers: pal_pcm16_to_f32 is exact (x / 32768, any alignment), and the streaming host entry
+    point fed with int16 gives the reference's TDOAs for the float signal soundfile would have produced."""
+    from pyaudiolocalization_b200 import gcc_phat as G
+    rng = np.random.default_rng(21)
+    raw = rng.integers(-32768, 32768, size=100003, dtype=np.int16)
+    dev = torch.from_numpy(raw).cuda()
+    for off, cnt in ((0, 100003), (1, 99999), (3, 17), (5, 4096), (7, 0)):
+        got = G.pcm16_to_f32(dev[off:off + cnt].contiguous() if off == 0 else dev[off:off + cnt]).cpu().numpy()
+        assert np.array_equal(got, raw[off:off + cnt].astype(np.float32) / np.float32(32768.0))
+    src = rng.standard_normal(2200)
+    fr = np.stack([np.stack([src[3 * c + f:3 * c + f + 2048] + 0.2 * rng.standard_normal(2048) for c in range(4)])
+                   for f in range(5)])
+    pcm = np.clip(np.round(fr * 6000.0), -32768, 32767).astype(np.int16)
+    res = G.gcc_phat_tdoa_from_host(torch.from_numpy(pcm).pin_memory(), 16000.0, 0.05, chunk_frames=2)
+    assert res["h2d_bytes"] == pcm.size * 2
+    x = pcm.astype(np.float64) / 32768.0
+    r = 0
+    for f in range(5):
+        for i in range(4):
+            for j in range(i + 1, 4):
+                want_td, c, _ = O.get_time_delays_phat(x[f, i], x[f, j], 16000.0, max_expected_delay=0.05)
+                assert res["tdoa"][f, r % 6, 0] == want_td[0]
+                assert abs(res["gmax"][f, r % 6] - c.max()) <= CORR_RTOL * c.max()
+                r += 1
