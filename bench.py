@@ -286,12 +286,12 @@ def run_gpu_arm(args):
         del q
         want = pal.gcc_phat_tdoa_batched(fq, FS, MED, pairs_dev=pairs_dev).k_idx.cpu().numpy()
         del fq
-        r16 = pal.gcc_phat.gcc_phat_tdoa_from_host(host16, FS, MED, chunk_frames=args.e2e_chunk, out_host=out_host)   # warm-up
+        r16 = pal.gcc_phat.gcc_phat_tdoa_from_host(host16, FS, MED, chunk_frames=args.e2e_pcm_chunk, out_host=out_host)   # warm-up
         assert np.array_equal(r16["k_idx"], want)
         barrier()
         w0 = time.perf_counter()
         for _ in range(e_steps):
-            r16 = pal.gcc_phat.gcc_phat_tdoa_from_host(host16, FS, MED, chunk_frames=args.e2e_chunk, out_host=out_host)
+            r16 = pal.gcc_phat.gcc_phat_tdoa_from_host(host16, FS, MED, chunk_frames=args.e2e_pcm_chunk, out_host=out_host)
         barrier()
         p_sec = (time.perf_counter() - w0) / e_steps
         if world > 1:
@@ -315,7 +315,7 @@ def run_gpu_arm(args):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     traffic, traffic_src = None, None
     try:   # DRAM bytes of the pair kernel from the committed ncu --set full capture, scaled to this launch size
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1d_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1e_traffic.json")))
         traffic = float(tj["dram_bytes_per_frame"]) * frames_n
         traffic_src = tj["source"]
     except (OSError, KeyError, ValueError):
@@ -349,7 +349,7 @@ def run_gpu_arm(args):
                      "frac": achieved / peak_gbs, "traffic": traffic,
                      "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
                      "traffic_source": traffic_src,
-                     "kernel": "k_pair4095_fast (fused cross-spectrum + PHAT + inverse DFT-4095 + peak pick)",
+                     "kernel": "k_pair4095_tmem (fused cross-spectrum of the whitened spectra + inverse DFT-4095 + peak pick)",
                      "kernel_ms": kernel_ms[1], "forward_ms": kernel_ms[0], "refine_ms": kernel_ms[2],
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME,
@@ -377,6 +377,8 @@ def main():
     ap.add_argument("--frames", type=int, default=16384, help="frames per GPU per step (cfg3: 16384)")
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of the CPU reference arm")
     ap.add_argument("--e2e-chunk", type=int, default=256)
+    ap.add_argument("--e2e-pcm-chunk", type=int, default=1024,
+                    help="frames per pipeline chunk of the int16 host path (compute-bound: fewer, larger launches)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic only: skip the NCCL all-gather (invalid as a result)")

@@ -286,8 +286,13 @@ template <typename T> struct LoadSignal2 {
   const int* row_list;
   long long t_off;
   const float* scales;     // [all rows][2] from row_scale_body
-  PAL_DEV cpx<T> operator()(long long t, int j) const {
-    if (j >= p.n) return cpx<T>{T(0), T(0)};
+  // everything that depends on the transform only is resolved once per work unit (begin), not once per sample
+  struct Ctx {
+    const float *xa, *xb;
+    int la, lb;
+    T sa, sb;
+  };
+  PAL_DEV Ctx begin(long long t) const {
     const long long g = t_off + t;
     long long ra, rb;
     if (row_list) {
@@ -299,8 +304,19 @@ template <typename T> struct LoadSignal2 {
       ra = f * Mics + 2 * c;
       rb = (2 * c + 1 < Mics) ? ra + 1 : -1;
     }
-    const T x = (j < ((ra & 1) ? len_odd : len_even)) ? T(sig[ra * ld + j] * scales[2 * ra]) : T(0);
-    const T y = (rb >= 0 && j < ((rb & 1) ? len_odd : len_even)) ? T(sig[rb * ld + j] * scales[2 * rb]) : T(0);
+    Ctx x;
+    x.xa = sig + ra * ld;
+    x.la = (ra & 1) ? len_odd : len_even;
+    x.sa = T(scales[2 * ra]);
+    x.xb = rb >= 0 ? sig + rb * ld : sig;
+    x.lb = rb >= 0 ? ((rb & 1) ? len_odd : len_even) : 0;
+    x.sb = rb >= 0 ? T(scales[2 * rb]) : T(0);
+    return x;
+  }
+  PAL_DEV cpx<T> operator()(const Ctx& c, int j) const {
+    if (j >= p.n) return cpx<T>{T(0), T(0)};
+    const T x = (j < c.la) ? T(c.xa[j] * float(c.sa)) : T(0);
+    const T y = (j < c.lb) ? T(c.xb[j] * float(c.sb)) : T(0);
     const cpx<T> w = chirp[j];
     return cpx<T>{fma_(x, w.x, -(y * w.y)), fma_(x, w.y, y * w.x)};
   }
@@ -346,51 +362,62 @@ template <typename T> struct LoadPhat2 {
   long long frame_base;    // frame-major: global index of resident frame 0
   const int* row_list;     // list mode: global channel rows of every flagged item ...
   long long item_base;     // ... and the list position of resident item 0
-  // an item with an all-zero channel: R == 0, the reference's correlation row is exactly zero
-  PAL_DEV bool dead(long long it) const {
-    long long gi, gj;
-    if (rows2) {
-      gi = row_list[2 * (item_base + it)];
-      gj = row_list[2 * (item_base + it) + 1];
-    } else {
-      const long long f = it / P;
-      const int pr = int(it - f * P);
-      gi = (frame_base + f) * Mics + pairs[2 * pr];
-      gj = (frame_base + f) * Mics + pairs[2 * pr + 1];
-    }
-    return scales[2 * gi] == 0.f || scales[2 * gj] == 0.f;
-  }
-  PAL_DEV cpx<T> one(long long it, int k) const {
+  // one item: where its two packed spectra live, which half of each it is, and the levels of its two channels
+  struct Item {
     const cpx<T>*zi, *zj;
-    bool oi, oj;
+    bool oi, oj, present, dead;
+    T ui, uj;
+  };
+  PAL_DEV Item item(long long it) const {
+    Item m;
+    m.present = it < n_items;
+    if (!m.present) {
+      m.zi = m.zj = spec;
+      m.oi = m.oj = false;
+      m.dead = true;
+      m.ui = m.uj = T(0);
+      return m;
+    }
     long long gi, gj;
     if (rows2) {
-      zi = zj = spec + it * p.n;
-      oi = false;
-      oj = true;
+      m.zi = m.zj = spec + it * p.n;
+      m.oi = false;
+      m.oj = true;
       gi = row_list[2 * (item_base + it)];
       gj = row_list[2 * (item_base + it) + 1];
     } else {
       const long long f = it / P;
       const int pr = int(it - f * P);
       const int mi = pairs[2 * pr], mj = pairs[2 * pr + 1];
-      zi = spec + (f * CP + (mi >> 1)) * p.n;
-      zj = spec + (f * CP + (mj >> 1)) * p.n;
-      oi = mi & 1;
-      oj = mj & 1;
+      m.zi = spec + (f * CP + (mi >> 1)) * p.n;
+      m.zj = spec + (f * CP + (mj >> 1)) * p.n;
+      m.oi = mi & 1;
+      m.oj = mj & 1;
       gi = (frame_base + f) * Mics + mi;
       gj = (frame_base + f) * Mics + mj;
     }
-    cpx<T> a = unpack_two_real<T>(zi, p.n, k, oi), b = unpack_two_real<T>(zj, p.n, k, oj);
-    const T ua = T(scales[2 * gi + 1]), ub = T(scales[2 * gj + 1]);     // back to the signal's own level (exact)
-    a.x *= ua; a.y *= ua; b.x *= ub; b.y *= ub;
+    m.ui = T(scales[2 * gi + 1]);      // back to the signal's own level (exact power of two)
+    m.uj = T(scales[2 * gj + 1]);
+    // an item with an all-zero channel: R == 0, the reference's correlation row is exactly zero
+    m.dead = scales[2 * gi] == 0.f || scales[2 * gj] == 0.f;
+    return m;
+  }
+  struct Ctx {
+    Item a, b;
+  };
+  PAL_DEV Ctx begin(long long t) const {
+    const long long ia = t_off + 2 * t;
+    return Ctx{item(ia), item(ia + 1)};
+  }
+  PAL_DEV cpx<T> one(const Item& m, int k) const {
+    cpx<T> a = unpack_two_real<T>(m.zi, p.n, k, m.oi), b = unpack_two_real<T>(m.zj, p.n, k, m.oj);
+    a.x *= m.ui; a.y *= m.ui; b.x *= m.uj; b.y *= m.uj;
     return phat_cross<T>(a, b, T(1) / T(p.n));
   }
-  PAL_DEV cpx<T> operator()(long long t, int k) const {
+  PAL_DEV cpx<T> operator()(const Ctx& c, int k) const {
     if (k >= p.n) return cpx<T>{T(0), T(0)};
-    const long long ia = t_off + 2 * t;
-    const cpx<T> ra = one(ia, k);
-    const cpx<T> rb = (ia + 1 < n_items) ? one(ia + 1, k) : cpx<T>{T(0), T(0)};
+    const cpx<T> ra = one(c.a, k);
+    const cpx<T> rb = c.b.present ? one(c.b, k) : cpx<T>{T(0), T(0)};
     return cmulc(cpx<T>{ra.x - rb.y, ra.y + rb.x}, chirp[k]);
   }
 };
@@ -423,12 +450,24 @@ template <typename T> struct StoreCorr2 {
   long long n_rows;        // corr rows of this launch (the last transform may own a single row)
   LoadPhat2<T> src;        // what was transformed: a dead item's row is written as exact zeros, not as the rounding
                            // residue of the item it shared the transform with
-  PAL_DEV void operator()(long long t, int k, cpx<T> y) const {
+  struct Ctx {
+    T *ra, *rb;            // rb == nullptr: no second row
+    bool dead_a, dead_b;
+  };
+  PAL_DEV Ctx begin(long long t) const {
+    const long long ia = src.t_off + 2 * t;
+    Ctx c;
+    c.ra = corr + (2 * t) * p.n;
+    c.rb = (2 * t + 1 < n_rows) ? c.ra + p.n : nullptr;
+    c.dead_a = src.item(ia).dead;
+    c.dead_b = src.item(ia + 1).dead;
+    return c;
+  }
+  PAL_DEV void operator()(const Ctx& c, int k, cpx<T> y) const {
     if (k < p.n) {
       const cpx<T> w = chirp[k];
-      const long long ia = src.t_off + 2 * t;
-      corr[(2 * t) * p.n + k] = src.dead(ia) ? T(0) : fma_(y.x, w.x, y.y * w.y);
-      if (2 * t + 1 < n_rows) corr[(2 * t + 1) * p.n + k] = src.dead(ia + 1) ? T(0) : fma_(y.y, w.x, -(y.x * w.y));
+      c.ra[k] = c.dead_a ? T(0) : fma_(y.x, w.x, y.y * w.y);
+      if (c.rb) c.rb[k] = c.dead_b ? T(0) : fma_(y.y, w.x, -(y.x * w.y));
     }
   }
 };
@@ -450,6 +489,11 @@ PAL_HD size_t fft_tile_smem(size_t elem_bytes, int L, int lanes) {       // re +
   return 2 * elem_bytes * size_t(L) * size_t(lanes) + 2 * elem_bytes * size_t(L / 2 > 0 ? L / 2 : 1);
 }
 
+// Loaders / storers that need per-transform set-up expose `Ctx begin(t)` and are then called with the context;
+// the plain ones are called with the transform index itself.
+template <class F> PAL_DEV auto unit_begin(const F& f, long long t, int) -> decltype(f.begin(t)) { return f.begin(t); }
+template <class F> PAL_DEV long long unit_begin(const F&, long long t, long) { return t; }
+
 // ---- pass 1: columns forward -------------------------------------------------------------------
 // work unit = (transform t, tile of TC adjacent columns j2).  buf[t][r][j2] <- twiddled column FFT
 template <typename T, int NT, int TC, class Loader>
@@ -463,9 +507,10 @@ PAL_DEV void colpass_fwd_body(BluePlan p, BlueTables<T> tb, Loader load, long lo
   for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks()) {
     const long long t = u / tiles;
     const int j20 = int(u % tiles) * tc;
+    const auto ctx = unit_begin(load, t, 0);
     for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
       const int j1 = e >> lgt, c = e & (tc - 1);
-      const cpx<T> a = load(t, j1 * p.M2 + j20 + c);
+      const cpx<T> a = load(ctx, j1 * p.M2 + j20 + c);
       re[e] = a.x;
       im[e] = a.y;
     }
@@ -476,8 +521,8 @@ PAL_DEV void colpass_fwd_body(BluePlan p, BlueTables<T> tb, Loader load, long lo
       const int r = e >> lgt, c = e & (tc - 1);
       const unsigned k1 = bitrev(unsigned(r), p.lg1);
       const int j2 = j20 + c;
-      const cpx<T> w = tb.twM[((long long)k1 * j2) & (p.M - 1)];
-      out[(long long)r * p.M2 + j2] = cmul(cpx<T>{re[e], im[e]}, w);
+      const cpx<T> w = tb.twM[(k1 * unsigned(j2)) & unsigned(p.M - 1)];     // k1 < M1, j2 < M2 <= 1024: 32-bit product
+      out[r * p.M2 + j2] = cmul(cpx<T>{re[e], im[e]}, w);
     }
     simt::sync_block();
   }
@@ -523,7 +568,7 @@ PAL_DEV void rowpass_body(BluePlan p, BlueTables<T> tb, long long n_tr, cpx<T>* 
       for (int x = simt::tid(); x < tr * p.M2; x += NT) {
         const int c = x >> p.lg2, e = x & (p.M2 - 1);
         const unsigned k1 = bitrev(unsigned(r0 + c), p.lg1);
-        const cpx<T> w = tb.twM[((long long)k1 * e) & (p.M - 1)];
+        const cpx<T> w = tb.twM[(k1 * unsigned(e)) & unsigned(p.M - 1)];
         rows[x] = cmulc(cpx<T>{re[e * ld + c], im[e * ld + c]}, w);
       }
     } else {
@@ -551,9 +596,10 @@ PAL_DEV void colpass_inv_body(BluePlan p, BlueTables<T> tb, Storer store, long l
     const long long t = u / tiles;
     const int j20 = int(u % tiles) * tc;
     const cpx<T>* in = buf + t * p.M;
+    const auto ctx = unit_begin(store, t, 0);
     for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
       const int r = e >> lgt, c = e & (tc - 1);
-      const cpx<T> v = in[(long long)r * p.M2 + j20 + c];
+      const cpx<T> v = in[r * p.M2 + j20 + c];
       re[e] = v.x;
       im[e] = v.y;
     }
@@ -561,7 +607,7 @@ PAL_DEV void colpass_inv_body(BluePlan p, BlueTables<T> tb, Storer store, long l
     fft_tile<T, NT>(re, im, p.lg1, tc, tc, 1, tw1, true);
     for (int e = simt::tid(); e < p.M1 * tc; e += NT) {
       const int j1 = e >> lgt, c = e & (tc - 1);
-      store(t, j1 * p.M2 + j20 + c, cpx<T>{re[e] * inv_m, im[e] * inv_m});
+      store(ctx, j1 * p.M2 + j20 + c, cpx<T>{re[e] * inv_m, im[e] * inv_m});
     }
     simt::sync_block();
   }

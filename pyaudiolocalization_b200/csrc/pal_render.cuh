@@ -326,15 +326,21 @@ template <typename T> struct LoadHermitian2 {
   const cpxf* G;           // [rows][N+1]
   int N;
   long long n_rows;        // rows of this launch
-  PAL_DEV cpx<T> half(long long row, int k) const {
-    const cpxf g = (k <= N) ? G[row * (N + 1) + k] : G[row * (N + 1) + (p.n - k)];
+  struct Ctx {
+    const cpxf *ga, *gb;   // gb == nullptr: no second row
+  };
+  PAL_DEV Ctx begin(long long t) const {
+    return Ctx{G + (2 * t) * (N + 1), (2 * t + 1 < n_rows) ? G + (2 * t + 1) * (N + 1) : nullptr};
+  }
+  PAL_DEV cpx<T> half(const cpxf* g_row, int k) const {
+    const cpxf g = (k <= N) ? g_row[k] : g_row[p.n - k];
     const bool self_conj = (k == 0) || (k == N);
     return cpx<T>{T(g.x), self_conj ? T(0) : ((k <= N) ? T(g.y) : T(-g.y))};
   }
-  PAL_DEV cpx<T> operator()(long long t, int k) const {
+  PAL_DEV cpx<T> operator()(const Ctx& c, int k) const {
     if (k >= p.n) return cpx<T>{T(0), T(0)};
-    const cpx<T> a = half(2 * t, k);
-    const cpx<T> b = (2 * t + 1 < n_rows) ? half(2 * t + 1, k) : cpx<T>{T(0), T(0)};
+    const cpx<T> a = half(c.ga, k);
+    const cpx<T> b = c.gb ? half(c.gb, k) : cpx<T>{T(0), T(0)};
     return cmulc(cpx<T>{a.x - b.y, a.y + b.x}, chirp[k]);      // inverse transform: conjugate chirp
   }
 };
@@ -348,15 +354,27 @@ template <typename T> struct StoreRender2 {
   long long row0, n_rows;
   const int* live;         // [n_rows] from the transfer kernel: a silent row must come out as exact zeros, not as the
                            // rounding residue of its partner row (normalize_signal would blow that up to full scale)
-  PAL_DEV void operator()(long long t, int j, cpx<T> y) const {
+  struct Ctx {
+    float *oa, *ob;        // ob == nullptr: no second row
+    bool live_a, live_b;
+  };
+  PAL_DEV Ctx begin(long long t) const {
+    Ctx c;
+    c.oa = out + rr.global_row(row0 + 2 * t) * n_keep;
+    c.live_a = live[2 * t] != 0;
+    const bool has_b = 2 * t + 1 < n_rows;
+    c.ob = has_b ? out + rr.global_row(row0 + 2 * t + 1) * n_keep : nullptr;
+    c.live_b = has_b && live[2 * t + 1] != 0;
+    return c;
+  }
+  PAL_DEV void operator()(const Ctx& c, int j, cpx<T> y) const {
     if (j >= n_keep) return;
     const cpx<T> w = chirp[j];
     T f = T(1) / T(p.n);
     if (j < fade) f *= (fade > 1) ? T(j) / T(fade - 1) : T(0);                      // np.linspace(0, 1, fade)
     if (j >= N - fade) f *= (fade > 1) ? T(N - 1 - j) / T(fade - 1) : T(1);         // np.linspace(1, 0, fade)
-    out[rr.global_row(row0 + 2 * t) * n_keep + j] = live[2 * t] ? float(fma_(y.x, w.x, y.y * w.y) * f) : 0.f;
-    if (2 * t + 1 < n_rows)
-      out[rr.global_row(row0 + 2 * t + 1) * n_keep + j] = live[2 * t + 1] ? float(fma_(y.y, w.x, -(y.x * w.y)) * f) : 0.f;
+    c.oa[j] = c.live_a ? float(fma_(y.x, w.x, y.y * w.y) * f) : 0.f;
+    if (c.ob) c.ob[j] = c.live_b ? float(fma_(y.y, w.x, -(y.x * w.y)) * f) : 0.f;
   }
 };
 
