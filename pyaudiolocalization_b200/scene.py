@@ -21,6 +21,17 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+_POOLS: Dict[Any, list] = {}
+
+
+def _stream_pool(dev, n):
+    """Side streams for launching independent buckets concurrently (created once per device)."""
+    pool = _POOLS.setdefault((dev.type, dev.index), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(dev))
+    return pool[:n]
+
+
 def _ws(nbytes, dev):
     t = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
     p = (t.data_ptr() + 255) // 256 * 256
@@ -151,7 +162,7 @@ def render_scene(base_signal, source_pos, img_pos: torch.Tensor, img_mat: torch.
 def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: torch.Tensor, img_count: torch.Tensor,
                           mic_positions, fs: float, c: float, duration: float, freq: float, table: MaterialTable,
                           trim_to_duration: bool = True, normalise: bool = True,
-                          max_workspace_bytes: int = 4 << 30) -> torch.Tensor:
+                          max_workspace_bytes: int = 4 << 30, max_streams: int = 16) -> torch.Tensor:
     """main.py:94-122 for MANY scenes that share fs / duration / base signal: sources [S, 3],
     img_pos [S, K, 3], img_mat [S, K], img_count [S] (output of image_sources_batched),
     mic_positions [M, 3] or [S, M, 3].  Returns [S, M, n_keep] float32 on the device.
@@ -198,16 +209,37 @@ def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: 
     order = np.argsort(totals, kind="stable")
     uniq, starts = np.unique(totals[order], return_index=True)
     idx_dev = torch.as_tensor(order.astype(np.int64)).to(dev)
-    need, small = C.c_size_t(0), C.c_size_t(0)
-    _lib.check(L.pal_render_scenes_workspace(int(uniq.max()), int(s_n) * m, C.byref(need), C.byref(small)),
-               "pal_render_scenes_workspace")
-    ws, wp, wl = _ws(max(small.value, min(need.value, int(max_workspace_bytes))), dev)
     bounds = list(starts) + [len(order)]
+    # Scenes that share N form a bucket = one pal_render_scenes call (about ten dependent launches).  With random
+    # rooms almost every N is different and a bucket holds a handful of scenes, so the buckets are issued
+    # round-robin on a pool of streams (the library is stateless and stream-ordered): the small grids of
+    # different buckets overlap instead of queueing behind each other.  Each stream owns a workspace slice.
+    rows_max = int(np.max(np.diff(bounds))) * m
+    need, small = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(L.pal_render_scenes_workspace(int(uniq.max()), rows_max, C.byref(need), C.byref(small)),
+               "pal_render_scenes_workspace")
+    n_streams = max(1, min(int(max_streams), len(uniq), int(max_workspace_bytes) // max(int(small.value), 1)))
+    per_stream = max(small.value, min(need.value, int(max_workspace_bytes) // n_streams))
+    cur = torch.cuda.current_stream(dev)
+    pool = [cur] if n_streams == 1 else _stream_pool(dev, n_streams)
+    slices = [_ws(per_stream, dev) for _ in range(n_streams)]
+    if n_streams > 1:
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        for st in pool:
+            st.wait_event(ready)
     for bi, total in enumerate(uniq):
         lo, hi = int(bounds[bi]), int(bounds[bi + 1])
+        k = bi % n_streams
         _lib.check(L.pal_render_scenes(base.data_ptr(), n_base, int(total), tau.data_ptr(), gain.data_ptr(), pcount.data_ptr(),
                                        k_stride, idx_dev.data_ptr() + 8 * lo, hi - lo, m, float(fs), n_keep, out.data_ptr(),
-                                       wp, wl, _stream(dev)), "pal_render_scenes")
+                                       slices[k][1], slices[k][2], pool[k].cuda_stream), "pal_render_scenes")
+    if n_streams > 1:
+        for st in pool:
+            cur.wait_stream(st)
+    ws = slices[0][0]
+    for sl in slices[1:]:
+        sl[0].record_stream(cur)
     if normalise:
         _lib.check(L.pal_normalise_compress(out.data_ptr(), s_n * m, n_keep, 0.8, 1e-8, 1, _stream(dev)),
                    "pal_normalise_compress")
