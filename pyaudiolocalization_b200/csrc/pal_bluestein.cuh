@@ -624,7 +624,7 @@ struct RowPickSmem {
 // window within eps of the winner, or a winner within eps of the threshold in force.
 template <typename T, int NT>
 PAL_DEV unsigned tie_audit(const T* c, int n, int c0, int win_half, int dist, int k_best, T h_best, T eps,
-                           unsigned pick_flags, PickScratch* ps) {
+                           unsigned pick_flags, T s_abs /* sum |c| of the row, from peakpick_row */, PickScratch* ps) {
   int lo = 0, hi = n - 1;
   if (!(pick_flags & PAL_FLAG_FALLBACK_ARGMAX) && win_half >= 0) {
     lo = c0 - win_half - dist;
@@ -633,14 +633,9 @@ PAL_DEV unsigned tie_audit(const T* c, int n, int c0, int win_half, int dist, in
     hi = hi > n - 1 ? n - 1 : hi;
   }
   int cnt = 0;
-  T s_abs = T(0);
-  for (int k = simt::tid(); k < n; k += NT) {
-    const T v = c[k];
-    s_abs += abs_(v);
-    if (k >= lo && k <= hi && k != k_best && v >= h_best - eps) ++cnt;
-  }
+  for (int k = lo + simt::tid(); k <= hi; k += NT)       // only the (extended) window is read again
+    if (k != k_best && c[k] >= h_best - eps) ++cnt;
   cnt = block_sum<int, NT>(cnt, ps->isum);
-  s_abs = block_sum<T, NT>(s_abs, reinterpret_cast<T*>(ps->dsum));
   unsigned fl = 0;
   if (cnt > 0 && s_abs != T(0)) fl |= PAL_FLAG_NEAR_TIE;
   if (!(pick_flags & PAL_FLAG_FALLBACK_ARGMAX) && h_best < s_abs / T(n) + eps) fl |= PAL_FLAG_NEAR_TIE;
@@ -667,7 +662,7 @@ PAL_DEV void pick_rows_body(const T* corr, int n, int c0, long long n_rows, cons
     pk = *op;
     const int k0 = sm->out_k[0];
     unsigned fl = pr.flags | extra_flag;
-    if (eps > 0.f) fl |= tie_audit<T, NT>(c, n, c0, win_half, dist, k0, pk, T(eps), pr.flags, &sm->ps);
+    if (eps > 0.f) fl |= tie_audit<T, NT>(c, n, c0, win_half, dist, k0, pk, T(eps), pr.flags, T(pr.sum_abs), &sm->ps);
     if (simt::tid() == 0) {
       for (int t = 0; t < num_peaks; ++t) k_idx[item * num_peaks + t] = (t < pr.count) ? sm->out_k[t] : -1;
       if (k_count) k_count[item] = pr.count;

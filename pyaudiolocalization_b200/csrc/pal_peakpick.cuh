@@ -121,6 +121,7 @@ template <typename T, int NT> PAL_DEV T select_abs(const T* c, int n, int rank, 
 struct PickResult {
   int count;        // number of indices written to out_k (<= num_peaks)
   unsigned flags;
+  double sum_abs;   // sum |c| over the row (pass A), for callers that audit the decision
 };
 
 struct PickScratch {  // lives in shared memory
@@ -222,7 +223,7 @@ PAL_DEV PickResult peakpick_row(const T* c, int n, int c0, int win_half, int dis
   }
   if (gpk_i < 0 || (have_thr && gpk < thr && gpk < mean_abs)) {          // utils.py:153-160
     if (tid == 0) { out_k[0] = gi; *out_peak = gm; }
-    PickResult r{1, flags | PAL_FLAG_FALLBACK_ARGMAX};
+    PickResult r{1, flags | PAL_FLAG_FALLBACK_ARGMAX, double(s_abs)};
     return r;
   }
   if (have_thr) {
@@ -332,7 +333,7 @@ PAL_DEV PickResult peakpick_row(const T* c, int n, int c0, int win_half, int dis
     count = 1;
     flags |= PAL_FLAG_FALLBACK_ARGMAX;
   }
-  PickResult r{count, flags};
+  PickResult r{count, flags, double(s_abs)};
   return r;
 }
 
