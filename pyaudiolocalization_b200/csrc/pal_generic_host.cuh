@@ -19,24 +19,31 @@ constexpr int kGT = 256;  // threads per block of every generic kernel
 template <typename T> struct ColTile { static constexpr int TC = 16; static constexpr int TR = 16; };
 template <> struct ColTile<double> { static constexpr int TC = 8; static constexpr int TR = 8; };
 
+#ifndef PAL_GEN_MINBLOCKS
+#define PAL_GEN_MINBLOCKS 5
+#endif
+// resident blocks per SM the float32 FFT passes are compiled for (register cap); float64 is left to the compiler
+template <typename T> struct MinBlocks { static constexpr int V = PAL_GEN_MINBLOCKS; };
+template <> struct MinBlocks<double> { static constexpr int V = 1; };
+
 template <typename T> __global__ void __launch_bounds__(kGT) k_blue_init(BluePlan p, cpx<T>* chirp, cpx<T>* tw1,
                                                                        cpx<T>* tw2, cpx<T>* twM) {
   blue_init_tables_body<T>(p, chirp, tw1, tw2, twM);
 }
 template <typename T, class Loader>
-__global__ void __launch_bounds__(kGT) k_colpass_fwd(BluePlan p, BlueTables<T> tb, Loader ld, long long n_tr,
+__global__ void __launch_bounds__(kGT, MinBlocks<T>::V) k_colpass_fwd(BluePlan p, BlueTables<T> tb, Loader ld, long long n_tr,
                                                      const int* n_tr_dev, cpx<T>* buf) {
   extern __shared__ __align__(128) char smem[];
   colpass_fwd_body<T, kGT, ColTile<T>::TC, Loader>(p, tb, ld, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
 }
 template <typename T, bool CONV, bool CONJ>
-__global__ void __launch_bounds__(kGT) k_rowpass(BluePlan p, BlueTables<T> tb, long long n_tr, const int* n_tr_dev,
+__global__ void __launch_bounds__(kGT, MinBlocks<T>::V) k_rowpass(BluePlan p, BlueTables<T> tb, long long n_tr, const int* n_tr_dev,
                                                  cpx<T>* buf) {
   extern __shared__ __align__(128) char smem[];
   rowpass_body<T, kGT, ColTile<T>::TR, CONV, CONJ>(p, tb, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
 }
 template <typename T, class Storer>
-__global__ void __launch_bounds__(kGT) k_colpass_inv(BluePlan p, BlueTables<T> tb, Storer st, long long n_tr,
+__global__ void __launch_bounds__(kGT, MinBlocks<T>::V) k_colpass_inv(BluePlan p, BlueTables<T> tb, Storer st, long long n_tr,
                                                      const int* n_tr_dev, const cpx<T>* buf) {
   extern __shared__ __align__(128) char smem[];
   colpass_inv_body<T, kGT, ColTile<T>::TC, Storer>(p, tb, st, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
