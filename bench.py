@@ -325,7 +325,7 @@ def run_gpu_arm(args):
     achieved = ALG_BYTES_PER_FRAME * frames_n / (kernel_ms[1] * 1e-3) / 1e9
     cores = os.cpu_count() or 1
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # the CPU baseline is reported at N = 1 only
         nfr = 48 * cores      # about 10-20 s of work on the box's cores
         rate, sec, per = cpu_reference_rate(nfr, MICS, cores)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
