@@ -254,3 +254,23 @@ def test_pcm16_host_frames(pal):
                 assert res["tdoa"][f, r % 6, 0] == want_td[0]
                 assert abs(res["gmax"][f, r % 6] - c.max()) <= CORR_RTOL * c.max()
                 r += 1
+
+
+def test_cfg3_parity_subset_every_pair(pal):
+    """SURVEY.md section 8d parity subset at the benchmark shape: every one of the 496 pairs of the first 8 frames of the
+    cfg3 workload (3968 rows, the generator and seed bench.py uses) against the reference algorithm: TDOA bit-exact,
+    max(corr) within 1e-4."""
+    from pyaudiolocalization_b200 import synth
+    fr = synth.cfg3_frames(8, mics=32, seed=3000)
+    res = pal.gcc_phat_tdoa_batched(fr, 16000.0, max_expected_delay=0.05)
+    td = res.tdoa_seconds()[..., 0]
+    gm = res.gmax.cpu().numpy()
+    frh = fr.cpu().numpy().astype(np.float64)
+    pairs = pal.all_pairs(32)
+    bad = 0
+    for f in range(8):
+        for p, (i, j) in enumerate(pairs):
+            want_td, c, _ = O.get_time_delays_phat(frh[f, i], frh[f, j], 16000.0, max_expected_delay=0.05)
+            bad += int(td[f, p] != want_td[0])
+            assert abs(gm[f, p] - c.max()) <= CORR_RTOL * c.max()
+    assert bad == 0
