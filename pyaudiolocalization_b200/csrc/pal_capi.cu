@@ -50,7 +50,10 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
   } while (0)
 
-constexpr int kFwdThreads = 256;
+#ifndef PAL_FWD_THREADS
+#define PAL_FWD_THREADS 256
+#endif
+constexpr int kFwdThreads = PAL_FWD_THREADS;
 #ifndef PAL_FAST_WARPS
 #define PAL_FAST_WARPS 8
 #endif
@@ -327,6 +330,10 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_exact<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exd_smem));
   PAL_CUDA(cudaFuncSetAttribute(k_fwd4095, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
 
+  int fwd_resident = 4;
+  PAL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd_resident, k_fwd4095, kFwdThreads, fwd_smem));
+  if (fwd_resident < 1) fwd_resident = 1;
+
   if (prm->num_peaks != 1) {
     // num_peaks > 1: every row goes through the exact float64 kernel, straight from the raw
     // frames (not the hot path: main.py:204 always asks for one peak)
@@ -348,7 +355,7 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
     const float* sig = sig_dev + f0 * M * kFrame2048;
     {
       const long long units = (long long)nb * ((M + 1) / 2);
-      const int gf = (int)std::min<long long>(units, (long long)di.sms * 4);   // 48 KB of shared memory per CTA: 4 CTAs per SM
+      const int gf = (int)std::min<long long>(units, (long long)di.sms * fwd_resident);   // persistent blocks: as many as fit
       {
         ProfScope ps(1, stream);
         k_fwd4095<<<gf, kFwdThreads, fwd_smem, stream>>>(sig, M, units, spec, hq);
