@@ -134,17 +134,22 @@ template <typename T> PAL_DEV void bfly_dit(T& ur, T& ui, T& vr, T& vi, cpx<T> w
   ur = ur + tr; ui = ui + ti;
 }
 
-// Two radix-2 stages are fused into one radix-4 step held in registers (half the block barriers and
-// half the shared-memory traffic); an odd log2 length ends (forward) or starts (inverse) with a
-// single radix-2 stage.
+// Consecutive radix-2 stages are fused into one step held in registers: three at a time (radix-8: a third of the
+// block barriers, shared-memory round trips and index arithmetic of plain radix-2), then two (radix-4) or one for
+// what is left.  Fusing never changes the ORDER of the stages (halves L/2 .. 1 forward, 1 .. L/2 inverse), so the
+// bit-reversed hand-over between the forward and the inverse transform is the same for every grouping.
+#ifndef PAL_FFT_MAX_FUSE
+#define PAL_FFT_MAX_FUSE 3
+#endif
 template <typename T, int NT>
 PAL_DEV void fft_tile(T* re, T* im, int lg, int TC /* power of two */, int sl, int sc, const cpx<T>* tw, bool inverse) {
   const int L = 1 << lg;
   const int lgc = ilog2(TC);
   int st = 0;
   while (st < lg) {
-    const bool pair = (lg - st) >= 2 && !(inverse && (lg & 1) && st == 0);
-    if (!pair) {
+    const int rem = lg - st;
+    const int fuse = rem >= 3 && PAL_FFT_MAX_FUSE >= 3 ? 3 : (rem >= 2 ? 2 : 1);
+    if (fuse == 1) {
       const int hl = inverse ? st : (lg - 1 - st);     // log2(half)
       const int half = 1 << hl;
       const int tws = lg - 1 - hl;                     // twiddle stride = L / (2*half)
@@ -160,8 +165,7 @@ PAL_DEV void fft_tile(T* re, T* im, int lg, int TC /* power of two */, int sl, i
         if (!inverse) bfly_dif(ur, ui, vr, vi, w); else bfly_dit(ur, ui, vr, vi, w);
         re[ap] = ur; im[ap] = ui; re[aq] = vr; im[aq] = vi;
       }
-      st += 1;
-    } else {
+    } else if (fuse == 2) {
       // forward: stages with half = H then H/2 (H = 1 << hl); inverse: half = h then 2h (h = 1 << hl)
       const int nq = (L >> 2) * TC;
       if (!inverse) {
@@ -201,8 +205,51 @@ PAL_DEV void fft_tile(T* re, T* im, int lg, int TC /* power of two */, int sl, i
           re[a0] = x0r; im[a0] = x0i; re[a1] = x1r; im[a1] = x1i; re[a2] = x2r; im[a2] = x2i; re[a3] = x3r; im[a3] = x3i;
         }
       }
-      st += 2;
+    } else {
+      // radix-8: eight elements e apart (e = the smallest of the three halves); element k sits at p + k e
+      const int n8 = (L >> 3) * TC;
+      const int hl = inverse ? st : (lg - 3 - st);     // log2(e)
+      const int e = 1 << hl;
+      const int tws = lg - 1 - hl;                     // twiddle stride of the stage with half = e
+      for (int t = simt::tid(); t < n8; t += NT) {
+        const int c = t & (TC - 1);
+        const int b = t >> lgc;
+        const int i = b & (e - 1);
+        const int p = ((b >> hl) << (hl + 3)) + i;
+        const int a0 = p * sl + c * sc, da = e * sl;
+        T xr[8], xi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { xr[k] = re[a0 + k * da]; xi[k] = im[a0 + k * da]; }
+        if (!inverse) {
+          // halves 4e, 2e, e: position of a butterfly's first element inside its half selects the twiddle
+#pragma unroll
+          for (int k = 0; k < 4; ++k) bfly_dif(xr[k], xi[k], xr[k + 4], xi[k + 4], tw[(i + k * e) << (tws - 2)]);
+          const cpx<T> wb0 = tw[i << (tws - 1)], wb1 = tw[(i + e) << (tws - 1)];
+          bfly_dif(xr[0], xi[0], xr[2], xi[2], wb0);
+          bfly_dif(xr[1], xi[1], xr[3], xi[3], wb1);
+          bfly_dif(xr[4], xi[4], xr[6], xi[6], wb0);
+          bfly_dif(xr[5], xi[5], xr[7], xi[7], wb1);
+          const cpx<T> wc = tw[i << tws];
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) bfly_dif(xr[k], xi[k], xr[k + 1], xi[k + 1], wc);
+        } else {
+          // halves e, 2e, 4e
+          const cpx<T> wa = tw[i << tws];
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) bfly_dit(xr[k], xi[k], xr[k + 1], xi[k + 1], wa);
+          const cpx<T> wb0 = tw[i << (tws - 1)], wb1 = tw[(i + e) << (tws - 1)];
+          bfly_dit(xr[0], xi[0], xr[2], xi[2], wb0);
+          bfly_dit(xr[1], xi[1], xr[3], xi[3], wb1);
+          bfly_dit(xr[4], xi[4], xr[6], xi[6], wb0);
+          bfly_dit(xr[5], xi[5], xr[7], xi[7], wb1);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) bfly_dit(xr[k], xi[k], xr[k + 4], xi[k + 4], tw[(i + k * e) << (tws - 2)]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { re[a0 + k * da] = xr[k]; im[a0 + k * da] = xi[k]; }
+      }
     }
+    st += fuse;
     simt::sync_block();
   }
 }

@@ -20,7 +20,7 @@ template <typename T> struct ColTile { static constexpr int TC = 16; static cons
 template <> struct ColTile<double> { static constexpr int TC = 8; static constexpr int TR = 8; };
 
 #ifndef PAL_GEN_MINBLOCKS
-#define PAL_GEN_MINBLOCKS 5
+#define PAL_GEN_MINBLOCKS 4
 #endif
 // resident blocks per SM the float32 FFT passes are compiled for (register cap); float64 is left to the compiler
 template <typename T> struct MinBlocks { static constexpr int V = PAL_GEN_MINBLOCKS; };
