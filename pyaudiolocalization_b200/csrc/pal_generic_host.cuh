@@ -161,7 +161,10 @@ template <typename T> cudaError_t setup_plan(const BluePlan& p, char*& base, Blu
   return cudaGetLastError();
 }
 
-inline int pick_grid(int sms) { return std::max(1, std::min(4 * sms, 1024)); }   // 60 registers x 256 threads: four blocks per SM
+#ifndef PAL_PICK_BLOCKS
+#define PAL_PICK_BLOCKS 4
+#endif
+inline int pick_grid(int sms) { return std::max(1, std::min(PAL_PICK_BLOCKS * sms, 1024)); }   // 60 registers x 256 threads: four blocks per SM
 inline size_t pkmap_bytes(int n, int sms) { return al(size_t((n + 15) / 16 * 16) * pick_grid(sms)); }
 
 // smallest / comfortable workspace of one sweep in precision T

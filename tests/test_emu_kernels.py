@@ -169,7 +169,8 @@ def test_path_table_batched_matches_per_scene():
         assert len(imgs) == k
 
 
-@pytest.mark.parametrize("n1,n2,use_double", [(300, 300, False), (257, 190, False), (140, 333, True), (64, 64, True)])
+@pytest.mark.parametrize("n1,n2,use_double", [(300, 300, False), (257, 190, False), (140, 333, True), (64, 64, True),
+                                              (9000, 8200, False), (8300, 9000, True)])     # 256-point tiles: radix-8 steps
 def test_generic_bluestein_path_vs_oracle(n1, n2, use_double):
     """Arbitrary-length GCC-PHAT (Bluestein over tiled two-pass FFTs) against the reference algorithm:
     float64 sweep bit-exact on the chosen lag, float32 sweep within 1e-4 on the correlation."""
