@@ -669,25 +669,35 @@ struct RowPickSmem {
   double out_gmax, out_peak;
 };
 
-// near-tie audit of an fp32 decision (SURVEY.md hard part 3): any other sample of the extended
-// window within eps of the winner, or a winner within eps of the threshold in force.
+// near-tie audit of an fp32 decision (SURVEY.md hard part 3).  For num_peaks == 1 the exact answer can differ from
+// the float32 one only if (a) another sample INSIDE the window comes within eps of the winner (a different peak may
+// be the tallest, or the tallest may have been wrongly killed / spared by a neighbour), (b) a sample within `dist`
+// of the winner -- inside the window or not -- comes within eps of it or exceeds it (the distance rule of
+// find_peaks may kill the winner, directly or through a chain that starts there), or (c) the winner is within eps
+// of the threshold in force.  Samples outside the window and farther than `dist` from the winner cannot matter:
+// they are never candidates and can only kill peaks that are lower than the winner.
 template <typename T, int NT>
 PAL_DEV unsigned tie_audit(const T* c, int n, int c0, int win_half, int dist, int k_best, T h_best, T eps,
                            unsigned pick_flags, T s_abs /* sum |c| of the row, from peakpick_row */, PickScratch* ps) {
   int lo = 0, hi = n - 1;
-  if (!(pick_flags & PAL_FLAG_FALLBACK_ARGMAX) && win_half >= 0) {
-    lo = c0 - win_half - dist;
-    hi = c0 + win_half + dist;
+  const bool windowed = !(pick_flags & PAL_FLAG_FALLBACK_ARGMAX) && win_half >= 0;
+  if (windowed) {
+    lo = c0 - win_half;
+    hi = c0 + win_half;
     lo = lo < 0 ? 0 : lo;
     hi = hi > n - 1 ? n - 1 : hi;
   }
   int cnt = 0;
-  for (int k = lo + simt::tid(); k <= hi; k += NT)       // only the (extended) window is read again
+  for (int k = lo + simt::tid(); k <= hi; k += NT)       // (a); the whole row when there is no window
     if (k != k_best && c[k] >= h_best - eps) ++cnt;
+  if (windowed) {                                         // (b): the neighbourhood of the winner that (a) did not cover
+    for (int k = k_best - dist + simt::tid(); k <= k_best + dist; k += NT)
+      if (k >= 0 && k < n && (k < lo || k > hi) && c[k] >= h_best - eps) ++cnt;
+  }
   cnt = block_sum<int, NT>(cnt, ps->isum);
   unsigned fl = 0;
   if (cnt > 0 && s_abs != T(0)) fl |= PAL_FLAG_NEAR_TIE;
-  if (!(pick_flags & PAL_FLAG_FALLBACK_ARGMAX) && h_best < s_abs / T(n) + eps) fl |= PAL_FLAG_NEAR_TIE;
+  if (!(pick_flags & PAL_FLAG_FALLBACK_ARGMAX) && h_best < s_abs / T(n) + eps) fl |= PAL_FLAG_NEAR_TIE;    // (c)
   return fl;
 }
 

@@ -217,7 +217,10 @@ int generic_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, 
                          PickParams{prm->win_half, prm->peak_dist, prm->thr_method, prm->thr_mult, prm->num_peaks},
                          prm->refine ? prm->tie_eps : 0.f, k_idx_dev, k_count_dev, peak_dev, gmax_dev, flags_dev,
                          corr_opt_dev, stream, di.sms, scales};
-  cudaError_t e = palhost::run_generic<float>(c, region, region_bytes, nullptr, 0, nullptr, 0u, 0u);
+  // num_peaks > 1 is not the hot path (main.py:204 always asks for one peak): the audit only covers the first peak,
+  // so every row is handed to the float64 sweep, as on the n = 4095 path
+  const unsigned all_rows = (prm->refine && prm->num_peaks != 1) ? PAL_FLAG_NEAR_TIE : 0u;
+  cudaError_t e = palhost::run_generic<float>(c, region, region_bytes, nullptr, 0, nullptr, all_rows, 0u);
   if (e != cudaSuccess) return cuda_fail(e, "generic float sweep");
   if (!prm->refine) return PAL_OK;
   PAL_CUDA(cudaMemsetAsync(count, 0, sizeof(int), stream));
