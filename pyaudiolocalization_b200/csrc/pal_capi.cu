@@ -106,7 +106,7 @@ bool use_tmem_kernel() {
 }
 
 template <typename T, bool FROM_SPECTRA>
-__global__ void __launch_bounds__(kExactThreads, 1)
+__global__ void __launch_bounds__(kExactThreads, 3)
     k_pair4095_exact(const float* __restrict__ sig, const cpxf* __restrict__ spec, const int* __restrict__ pairs,
                      int M, int P, long long n_items, const int* __restrict__ item_list,
                      const int* __restrict__ item_count, PickParams pp, int* k_idx, int* k_count, float* peak,
@@ -333,15 +333,17 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_exact<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exd_smem));
   PAL_CUDA(cudaFuncSetAttribute(k_fwd4095, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
 
-  int fwd_resident = 4;
+  int fwd_resident = 4, exact_resident = 1;
   PAL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd_resident, k_fwd4095, kFwdThreads, fwd_smem));
+  PAL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&exact_resident, k_pair4095_exact<double, false>, kExactThreads, exd_smem));
   if (fwd_resident < 1) fwd_resident = 1;
+  if (exact_resident < 1) exact_resident = 1;
 
   if (prm->num_peaks != 1) {
     // num_peaks > 1: every row goes through the exact float64 kernel, straight from the raw
     // frames (not the hot path: main.py:204 always asks for one peak)
     const long long n_items = (long long)B * P;
-    const int ge = (int)std::min<long long>(n_items, (long long)di.sms);
+    const int ge = (int)std::min<long long>(n_items, (long long)di.sms * exact_resident);
     k_pair4095_exact<double, false><<<ge, kExactThreads, exd_smem, stream>>>(
         sig_dev, nullptr, pairs_dev, M, P, n_items, nullptr, nullptr, pp, k_idx_dev, k_count_dev, peak_dev,
         gmax_dev, flags_dev, PAL_FLAG_REFINED, 0u, corr_opt_dev);
@@ -398,7 +400,7 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
     if (prm->refine) {
       // float64 re-evaluation of the flagged rows, straight from the raw frames (global item ids)
       ProfScope ps(3, stream);
-      k_pair4095_exact<double, false><<<di.sms, kExactThreads, exd_smem, stream>>>(
+      k_pair4095_exact<double, false><<<di.sms * exact_resident, kExactThreads, exd_smem, stream>>>(
           sig_dev, nullptr, pairs_dev, M, P, (long long)B * P, list, count, pp, k_idx_dev, nullptr, peak_dev,
           gmax_dev, flags_dev, PAL_FLAG_REFINED, kRefineMask, nullptr);
       ++g_launches;

@@ -291,11 +291,12 @@ PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil
 }
 
 // ---------------------------------------------------------------- exact pair kernel (block per pair)
+// One complex array, transformed in place twice: channels -> spectra (forward), cross spectrum written over the
+// spectra pair by pair (bins e and n-e), cross spectrum -> correlation (inverse).  64 KB in float64, so three
+// blocks share an SM.
 template <typename T> struct ExactSmem {
   T a_re[4096];
   T a_im[4096];
-  T b_re[4096];
-  T b_im[4096];
   unsigned char pkmap[4096];
   PickScratch ps;
   int out_k[16];
@@ -328,6 +329,10 @@ PAL_DEV void pair4095_exact_body(const float* sig, const cpxf* spec, const int* 
     const long long frame = item / P;
     const int p = int(item % P);
     const int mi = pairs[2 * p], mj = pairs[2 * p + 1];
+    // The in-place prime-factor transform leaves bin e at location loc(e) = G e mod n.  Feeding an array in THAT
+    // order to the transform again returns its result in natural order (DFT of x[G^-1 m] is X[G k], and G k is
+    // exactly where the transform puts output k), so the cross spectrum is written where the spectra already are
+    // and the correlation row comes out at a_re[k] -- no permutation pass, no second array.
     if (FROM_SPECTRA) {
       const cpxf* si = spec + (frame * M + mi) * kSpecSlots;
       const cpxf* sj = spec + (frame * M + mj) * kSpecSlots;
@@ -337,9 +342,10 @@ PAL_DEV void pair4095_exact_body(const float* sig, const cpxf* spec, const int* 
         const cpxf a = si[o], b = sj[o];
         T rr, ri;
         phat_bin<T>(T(a.x), T(a.y), T(b.x), T(b.y), inv_n, rr, ri);
-        sm->b_re[e] = rr;
-        sm->b_im[e] = ri;
-        if (e != 0) { sm->b_re[kN4095 - e] = rr; sm->b_im[kN4095 - e] = -ri; }
+        const int L = Pfa4095::loc(e);
+        sm->a_re[L] = rr;
+        sm->a_im[L] = ri;
+        if (e != 0) { sm->a_re[kN4095 - L] = rr; sm->a_im[kN4095 - L] = -ri; }      // loc(n - e) = n - loc(e)
       }
     } else {
       const float* xi = sig + (frame * M + mi) * kFrame2048;
@@ -350,24 +356,26 @@ PAL_DEV void pair4095_exact_body(const float* sig, const cpxf* spec, const int* 
       }
       simt::sync_block();
       pfa4095_inplace<-1, T, NT>(sm->a_re, sm->a_im);
-      for (int e = tid; e < kN4095; e += NT) {
+      // R[e] and R[n-e] = conj(R[e]) both come from Z[e] and Z[n-e] (at L and n - L): each thread owns such
+      // pairs and overwrites them
+      for (int e = tid; e <= kN4095 / 2; e += NT) {
         const int L = Pfa4095::loc(e);
         const int L2 = (L == 0) ? 0 : kN4095 - L;
         T s1r, s1i, s2r, s2i;
         split_two_real<T>(sm->a_re[L], sm->a_im[L], sm->a_re[L2], sm->a_im[L2], s1r, s1i, s2r, s2i);
         T rr, ri;
         phat_bin<T>(s1r, s1i, s2r, s2i, inv_n, rr, ri);
-        sm->b_re[e] = rr;
-        sm->b_im[e] = ri;
+        sm->a_re[L] = rr;
+        sm->a_im[L] = ri;
+        if (L2 != L) { sm->a_re[L2] = rr; sm->a_im[L2] = -ri; }
       }
     }
     simt::sync_block();
-    pfa4095_inplace<+1, T, NT>(sm->b_re, sm->b_im);
-    for (int k = tid; k < kN4095; k += NT) sm->a_re[k] = sm->b_re[Pfa4095::loc(k)];
-    simt::sync_block();
+    pfa4095_inplace<+1, T, NT>(sm->a_re, sm->a_im);
+    T* const crow = sm->a_re;
     if (corr_out)
-      for (int k = tid; k < kN4095; k += NT) corr_out[item * kN4095 + k] = float(sm->a_re[k]);
-    PickResult pr = peakpick_row<T, NT>(sm->a_re, kN4095, kFrame2048 - 1, pp.win_half, pp.dist, pp.method,
+      for (int k = tid; k < kN4095; k += NT) corr_out[item * kN4095 + k] = float(crow[k]);
+    PickResult pr = peakpick_row<T, NT>(crow, kN4095, kFrame2048 - 1, pp.win_half, pp.dist, pp.method,
                                         T(pp.mult), pp.num_peaks, sm->pkmap, &sm->ps, sm->out_k,
                                         &sm->out_gmax, &sm->out_peak);
     simt::sync_block();
