@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PAL_ABI_VERSION 6
+#define PAL_ABI_VERSION 7
 
 /* error codes */
 #define PAL_OK 0
@@ -174,6 +174,21 @@ int pal_render_scenes(const float* base_dev, int32_t n_base, int32_t N, const do
                       const int32_t* path_count_dev, int32_t k_stride, const int64_t* scene_index_dev,
                       int64_t n_bucket_scenes, int32_t n_mics, double fs, int32_t n_keep, float* out_dev, void* ws_dev,
                       size_t ws_bytes, void* stream);
+
+/* Plans.  Everything pal_render_scenes derives from (N, base signal) alone -- chirp and twiddle tables, the chirp
+ * spectrum, the spectrum of the zero-padded base signal (signal_processing.py:69) -- can be built once per N with
+ * pal_render_plan into caller-owned memory (pal_render_plan_bytes; scratch_dev: pal_render_plan_scratch_bytes, free
+ * again when the call's work has run) and reused by pal_render_scenes_planned for every later bucket of that N and
+ * that base signal.  With random rooms almost every scene has its own N, and the plan is about half of the GPU work of
+ * a small bucket.  Results are bit-identical to pal_render_scenes.  ws_dev of the planned call: pal_render_rows_workspace. */
+int pal_render_plan_bytes(int32_t N, size_t* plan_bytes, size_t* scratch_bytes);
+int pal_render_plan(const float* base_dev, int32_t n_base, int32_t N, void* plan_dev, size_t plan_bytes, void* scratch_dev,
+                    size_t scratch_bytes, void* stream);
+int pal_render_rows_workspace(int32_t N, int64_t n_rows, size_t* bytes, size_t* min_bytes);
+int pal_render_scenes_planned(const void* plan_dev, size_t plan_bytes, int32_t n_base, int32_t N, const double* tau_dev,
+                              const double* gain_dev, const int32_t* path_count_dev, int32_t k_stride,
+                              const int64_t* scene_index_dev, int64_t n_bucket_scenes, int32_t n_mics, double fs,
+                              int32_t n_keep, float* out_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
 /* In place on n_rows rows of n float32: mode 0 = normalize_signal (signal_processing.py:82-86),
  * mode 1 = dynamic_range_compression(threshold, epsilon) (signal_processing.py:88-94). */

@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PAL_B200_LIB") or os.path.join(_PKG, "libpal_b200.so")   # env override: tuning experiments only
 
-PAL_ABI_VERSION = 6
+PAL_ABI_VERSION = 7
 
 # per-row flag bits (include/pal_b200.h)
 FLAG_NEAR_TIE = 1
@@ -69,6 +69,14 @@ def lib():
     L.pal_render_scenes_workspace.argtypes = [I32, I64, SZP, SZP]
     L.pal_render_scenes.restype = C.c_int
     L.pal_render_scenes.argtypes = [VP, I32, I32, VP, VP, VP, I32, VP, I64, I32, F64, I32, VP, VP, C.c_size_t, VP]
+    L.pal_render_plan_bytes.restype = C.c_int
+    L.pal_render_plan_bytes.argtypes = [I32, SZP, SZP]
+    L.pal_render_plan.restype = C.c_int
+    L.pal_render_plan.argtypes = [VP, I32, I32, VP, C.c_size_t, VP, C.c_size_t, VP]
+    L.pal_render_rows_workspace.restype = C.c_int
+    L.pal_render_rows_workspace.argtypes = [I32, I64, SZP, SZP]
+    L.pal_render_scenes_planned.restype = C.c_int
+    L.pal_render_scenes_planned.argtypes = [VP, C.c_size_t, I32, I32, VP, VP, VP, I32, VP, I64, I32, F64, I32, VP, VP, C.c_size_t, VP]
     L.pal_path_table.restype = C.c_int
     L.pal_path_table.argtypes = [VP, VP, VP, I32, VP, I32, VP, VP, I32, F64, F64, VP, VP, VP]
     L.pal_render_workspace.restype = C.c_int

@@ -565,6 +565,60 @@ int pal_render_scenes(const float* base_dev, int32_t n_base, int32_t N, const do
   return PAL_OK;
 }
 
+int pal_render_plan_bytes(int32_t N, size_t* plan_bytes, size_t* scratch_bytes) {
+  if (N < 100 || N > (1 << 27) || !plan_bytes) return fail(PAL_ERR_INVALID, "pal_render_plan_bytes: bad argument");
+  *plan_bytes = palhost::render_plan_bytes(N);
+  if (scratch_bytes) *scratch_bytes = palhost::render_plan_scratch_bytes(N);
+  return PAL_OK;
+}
+
+int pal_render_plan(const float* base_dev, int32_t n_base, int32_t N, void* plan_dev, size_t plan_bytes, void* scratch_dev,
+                    size_t scratch_bytes, void* stream_) {
+  if (!base_dev || !plan_dev || !scratch_dev) return fail(PAL_ERR_INVALID, "pal_render_plan: NULL device pointer");
+  if (n_base < 1 || N < n_base || int(0.01 * N) < 1) return fail(PAL_ERR_INVALID, "pal_render_plan: need 1 <= n_base <= N, N >= 100");
+  if ((reinterpret_cast<uintptr_t>(plan_dev) | reinterpret_cast<uintptr_t>(scratch_dev)) & 255u)
+    return fail(PAL_ERR_INVALID, "pal_render_plan: plan_dev and scratch_dev must be 256-byte aligned");
+  if (plan_bytes < palhost::render_plan_bytes(N) || scratch_bytes < palhost::render_plan_scratch_bytes(N))
+    return fail(PAL_ERR_WORKSPACE, "pal_render_plan: plan or scratch memory too small");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  cudaError_t e = palhost::build_render_plan(base_dev, n_base, N, static_cast<char*>(plan_dev), static_cast<cpxf*>(scratch_dev),
+                                             static_cast<cudaStream_t>(stream_), di.sms);
+  if (e != cudaSuccess) return cuda_fail(e, "pal_render_plan");
+  return PAL_OK;
+}
+
+int pal_render_rows_workspace(int32_t N, int64_t n_rows, size_t* bytes, size_t* min_bytes) {
+  if (N < 1 || n_rows < 1 || !bytes) return fail(PAL_ERR_INVALID, "pal_render_rows_workspace: bad argument");
+  *bytes = size_t(std::min<long long>(n_rows, 4096)) * palhost::render_row_bytes(N) + 1024;
+  if (min_bytes) *min_bytes = palhost::render_rows_min_bytes(N);
+  return PAL_OK;
+}
+
+int pal_render_scenes_planned(const void* plan_dev, size_t plan_bytes, int32_t n_base, int32_t N, const double* tau_dev,
+                              const double* gain_dev, const int32_t* path_count_dev, int32_t k_stride,
+                              const int64_t* scene_index_dev, int64_t n_bucket_scenes, int32_t n_mics, double fs,
+                              int32_t n_keep, float* out_dev, void* ws_dev, size_t ws_bytes, void* stream_) {
+  if (!plan_dev || !tau_dev || !gain_dev || !path_count_dev || !out_dev || !ws_dev)
+    return fail(PAL_ERR_INVALID, "pal_render_scenes_planned: NULL device pointer");
+  if (n_base < 1 || N < n_base || n_mics < 1 || k_stride < 1 || n_keep < 1 || n_keep > N || n_bucket_scenes < 0)
+    return fail(PAL_ERR_INVALID, "pal_render_scenes_planned: need 1 <= n_base <= N, 1 <= n_keep <= N, n_mics, k_stride >= 1");
+  if (int(0.01 * N) < 1) return fail(PAL_ERR_INVALID, "pal_render_scenes_planned: N < 100 (empty fade window, signal_processing.py:74-79)");
+  if ((reinterpret_cast<uintptr_t>(ws_dev) | reinterpret_cast<uintptr_t>(plan_dev)) & 255u)
+    return fail(PAL_ERR_INVALID, "pal_render_scenes_planned: plan_dev and ws_dev must be 256-byte aligned");
+  if (plan_bytes < palhost::render_plan_bytes(N)) return fail(PAL_ERR_WORKSPACE, "pal_render_scenes_planned: plan memory too small for N");
+  if (n_bucket_scenes == 0) return PAL_OK;
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (ws_bytes < palhost::render_rows_min_bytes(N)) return fail(PAL_ERR_WORKSPACE, "pal_render_scenes_planned: workspace too small");
+  const RenderRows rr{tau_dev, gain_dev, path_count_dev, reinterpret_cast<const long long*>(scene_index_dev), k_stride, n_mics};
+  const palhost::RenderPlan rp = palhost::carve_render_plan(N, static_cast<char*>(const_cast<void*>(plan_dev)));
+  cudaError_t e = palhost::render_rows_planned(rp, N, rr, n_bucket_scenes * n_mics, fs, n_keep, out_dev, static_cast<char*>(ws_dev),
+                                               ws_bytes, static_cast<cudaStream_t>(stream_), di.sms);
+  if (e != cudaSuccess) return cuda_fail(e, "pal_render_scenes_planned");
+  return PAL_OK;
+}
+
 int pal_normalise_compress(float* rows_dev, int64_t n_rows, int32_t n, float threshold, float epsilon, int32_t mode,
                            void* stream_) {
   if (n_rows < 0 || n < 1 || (n_rows > 0 && !rows_dev) || (mode != 0 && mode != 1))

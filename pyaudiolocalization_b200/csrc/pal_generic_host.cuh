@@ -134,31 +134,44 @@ template <typename T> inline size_t col_smem(const BluePlan& p) {
   return fft_tile_smem(sizeof(T), p.M1, tc);
 }
 
-// carve the tables out of `base`, fill them, and build the chirp spectrum
-template <typename T> cudaError_t setup_plan(const BluePlan& p, char*& base, BlueBuffers<T>& bb, cudaStream_t s, int sms) {
+// carve the tables of a plan out of `base` (no launches)
+template <typename T> void carve_plan(const BluePlan& p, char*& base, BlueBuffers<T>& bb) {
   bb.chirp = reinterpret_cast<cpx<T>*>(base); base += al(sizeof(cpx<T>) * size_t(p.n));
   bb.tw1 = reinterpret_cast<cpx<T>*>(base);   base += al(sizeof(cpx<T>) * (p.M1 / 2 + 1));
   bb.tw2 = reinterpret_cast<cpx<T>*>(base);   base += al(sizeof(cpx<T>) * (p.M2 / 2 + 1));
   bb.twM = reinterpret_cast<cpx<T>*>(base);   base += al(sizeof(cpx<T>) * size_t(p.M));
   bb.bhat = reinterpret_cast<cpx<T>*>(base);  base += al(sizeof(cpx<T>) * size_t(p.M));
+}
+// fill them and build the chirp spectrum
+template <typename T> cudaError_t fill_plan(const BluePlan& p, const BlueBuffers<T>& bb, cudaStream_t s, int sms) {
   k_blue_init<T><<<std::min(4 * sms, (p.M + kGT - 1) / kGT), kGT, 0, s>>>(p, bb.chirp, bb.tw1, bb.tw2, bb.twM);
   const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadBhat<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
+  k_colpass_fwd<T, LoadBhat<T>><<<std::min(tiles, 8 * sms), kGT, cs, s>>>(p, bb.tb(), LoadBhat<T>{p, bb.chirp}, 1, nullptr,
+                                                                          bb.bhat);
+  cudaFuncSetAttribute(k_rowpass<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
+  k_rowpass<T, false, false><<<std::min(row_units<T>(p), 8 * sms), kGT, rs, s>>>(p, bb.tb(), 1, nullptr, bb.bhat);
+  count_launch(3);
+  return cudaGetLastError();
+}
+// opt every transform kernel of precision T into the shared memory this plan needs
+template <typename T> void plan_kernel_attributes(const BluePlan& p) {
+  const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignal<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignal2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadPhat2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_inv<T, StoreCorr2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_inv<T, StoreSpectrum<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_inv<T, StoreCorr<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
-  k_colpass_fwd<T, LoadBhat<T>><<<std::min(tiles, 8 * sms), kGT, cs, s>>>(p, bb.tb(), LoadBhat<T>{p, bb.chirp}, 1, nullptr,
-                                                                          bb.bhat);
-  cudaFuncSetAttribute(k_rowpass<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
   cudaFuncSetAttribute(k_rowpass<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
   cudaFuncSetAttribute(k_rowpass<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
-  k_rowpass<T, false, false><<<std::min(row_units<T>(p), 8 * sms), kGT, rs, s>>>(p, bb.tb(), 1, nullptr, bb.bhat);
-  count_launch(3);
-  return cudaGetLastError();
+}
+// carve + fill (the one-shot form every non-cached caller uses)
+template <typename T> cudaError_t setup_plan(const BluePlan& p, char*& base, BlueBuffers<T>& bb, cudaStream_t s, int sms) {
+  carve_plan<T>(p, base, bb);
+  plan_kernel_attributes<T>(p);
+  return fill_plan<T>(p, bb, s, sms);
 }
 
 #ifndef PAL_PICK_BLOCKS

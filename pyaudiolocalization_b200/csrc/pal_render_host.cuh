@@ -56,32 +56,73 @@ inline size_t render_row_bytes(int N) {
   GenericLayout<float> L(2 * N);
   return al(sizeof(cpxf) * size_t(N + 1)) + al(sizeof(cpxf) * size_t(L.p.M)) + sizeof(int);   // G row, convolution buffer, live flag
 }
-inline size_t render_fixed_bytes(int N) {
-  GenericLayout<float> L(2 * N);
-  return L.tables + al(sizeof(cpxf) * size_t(2 * N)) + 2048;
-}
+inline size_t render_plan_bytes(int N);
+inline size_t render_fixed_bytes(int N) { return render_plan_bytes(N) + 2048; }
 inline size_t render_min_bytes(int N, int /*n_mics*/) { return render_fixed_bytes(N) + render_row_bytes(N); }
 inline size_t render_full_bytes(int N, long long rows) {
   return render_fixed_bytes(N) + size_t(std::min<long long>(rows, 4096)) * render_row_bytes(N);
 }
 
-// Render `n_rows` rows (bucket-local order, see RenderRows) of transform length 2N into `out`
-// (row r of the batch at out + r * n_keep).  No normalisation here.
-inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows rr, long long n_rows, double fs, int n_keep,
-                               float* out, char* ws, size_t ws_bytes, cudaStream_t s, int sms) {
+// ---- plan of one transform length: everything the renderer derives from (N, base signal) alone -----------------
+// [chirp | twiddles | chirp spectrum | X = fft(base zero-padded, 2N)].  With random rooms nearly every scene of a
+// batch has its own N, and building these tables is about half of the GPU work of a small bucket: a caller that
+// renders batch after batch keeps the plans (pal_render_plan) and pays for each N once.
+inline size_t render_plan_bytes(int N) {
+  GenericLayout<float> L(2 * N);
+  return L.tables + al(sizeof(cpxf) * size_t(2 * N)) + 256;
+}
+inline size_t render_plan_scratch_bytes(int N) {
+  GenericLayout<float> L(2 * N);
+  return al(sizeof(cpxf) * size_t(L.p.M));
+}
+struct RenderPlan {
+  BluePlan p;
+  BlueBuffers<float> bb;
+  cpxf* X;
+};
+inline RenderPlan carve_render_plan(int N, char* mem) {
+  RenderPlan rp;
+  rp.p = GenericLayout<float>(2 * N).p;
+  char* b = mem;
+  carve_plan<float>(rp.p, b, rp.bb);
+  rp.X = reinterpret_cast<cpxf*>(b);
+  return rp;
+}
+// fill the plan at `mem`; `conv` is scratch for one convolution (M complex)
+inline cudaError_t build_render_plan(const float* base, int n_base, int N, char* mem, cpxf* conv, cudaStream_t s, int sms) {
   using T = float;
-  if (ws_bytes < render_min_bytes(N, 1)) return cudaErrorMemoryAllocation;
-  GenericLayout<T> L(2 * N);
-  const BluePlan p = L.p;
-  char* b = ws;
-  BlueBuffers<T> bb;
-  cudaError_t e = setup_plan<T>(p, b, bb, s, sms);
+  const RenderPlan rp = carve_render_plan(N, mem);
+  const BluePlan& p = rp.p;
+  plan_kernel_attributes<T>(p);
+  cudaError_t e = fill_plan<T>(p, rp.bb, s, sms);
   if (e != cudaSuccess) return e;
-  cpxf* X = reinterpret_cast<cpxf*>(b);
-  b += al(sizeof(cpxf) * size_t(2 * N));
+  const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
+  const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
+  const BlueTables<T> tb = rp.bb.tb();
+  // X = fft(base zero-padded, 2N)                                      (signal_processing.py:69)
+  k_colpass_fwd<T, LoadSignal<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(
+      p, tb, LoadSignal<T>{p, rp.bb.chirp, base, n_base}, 1, nullptr, conv);
+  k_rowpass<T, true, false><<<std::min(row_units<T>(p), 16 * sms), kGT, rs, s>>>(p, tb, 1, nullptr, conv);
+  k_colpass_inv<T, StoreSpectrum<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(p, tb, StoreSpectrum<T>{p, rp.bb.chirp, rp.X}, 1,
+                                                                                nullptr, conv);
+  count_launch(3);
+  return cudaGetLastError();
+}
+
+// workspace of the row loop alone (plan held elsewhere): per row in flight G[N+1], a convolution buffer, a live flag
+inline size_t render_rows_min_bytes(int N) { return render_row_bytes(N) + 1024; }
+
+// Render `n_rows` rows (bucket-local order, see RenderRows) of transform length 2N into `out`
+// (row r of the batch at out + r * n_keep) with a ready plan.  No normalisation here.
+inline cudaError_t render_rows_planned(const RenderPlan& rp, int N, RenderRows rr, long long n_rows, double fs, int n_keep,
+                                       float* out, char* ws, size_t ws_bytes, cudaStream_t s, int sms) {
+  using T = float;
+  if (ws_bytes < render_rows_min_bytes(N)) return cudaErrorMemoryAllocation;
+  const BluePlan& p = rp.p;
+  char* b = ws;
   const size_t g_one = al(sizeof(cpxf) * size_t(N + 1)), conv_one = al(sizeof(cpxf) * size_t(p.M));
   // rows in flight (kept even: two rows share a convolution buffer, which this sizing over-provisions)
-  long long cap = std::max<long long>(1, std::min<long long>(n_rows, (long long)((ws_bytes - size_t(b - ws) - 512) / (g_one + conv_one + sizeof(int)))));
+  long long cap = std::max<long long>(1, std::min<long long>(n_rows, (long long)((ws_bytes - 512) / (g_one + conv_one + sizeof(int)))));
   cap = std::max<long long>(1, std::min<long long>(cap, conv_chunk_bytes() / (long long)conv_one));   // chunk stays in L2
   if (cap > 1) cap &= ~1LL;
   cpxf* G = reinterpret_cast<cpxf*>(b);          // rows addressed densely: G[t * (N+1)]
@@ -91,15 +132,10 @@ inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows 
   int* live = reinterpret_cast<int*>(b);         // live[row of the chunk]
   const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
-  const BlueTables<T> tb = bb.tb();
+  const BlueTables<T> tb = rp.bb.tb();
+  plan_kernel_attributes<T>(p);
   cudaFuncSetAttribute(k_colpass_fwd<T, LoadHermitian2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_inv<T, StoreRender2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  // X = fft(base zero-padded, 2N)                                      (signal_processing.py:69)
-  k_colpass_fwd<T, LoadSignal<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(
-      p, tb, LoadSignal<T>{p, bb.chirp, base, n_base}, 1, nullptr, conv);
-  k_rowpass<T, true, false><<<std::min(row_units<T>(p), 16 * sms), kGT, rs, s>>>(p, tb, 1, nullptr, conv);
-  k_colpass_inv<T, StoreSpectrum<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(p, tb, StoreSpectrum<T>{p, bb.chirp, X}, 1, nullptr, conv);
-  count_launch(3);
   const int xtiles = (N + 1 + kGT * kXferJ - 1) / (kGT * kXferJ);
   const int kcap = rr.k_stride;
   const size_t ts = 4 * size_t((kcap + 3) & ~3) + 16 * size_t(kcap) + 16;
@@ -108,17 +144,30 @@ inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows 
   for (long long r0 = 0; r0 < n_rows; r0 += cap) {
     const long long nt = std::min<long long>(cap, n_rows - r0);
     // G = X * H                                                        (main.py:104-118)
-    k_transfer<<<(unsigned)std::min<long long>(nt * xtiles, 32LL * sms), kGT, ts, s>>>(X, N, rr, r0, nt, fs, G, live);
+    k_transfer<<<(unsigned)std::min<long long>(nt * xtiles, 32LL * sms), kGT, ts, s>>>(rp.X, N, rr, r0, nt, fs, G, live);
     // two rows per inverse transform (LoadHermitian2)
     const long long ntr = (nt + 1) / 2;
     k_colpass_fwd<T, LoadHermitian2<T>><<<(unsigned)std::min<long long>(ntr * tiles, 16LL * sms), kGT, cs, s>>>(
-        p, tb, LoadHermitian2<T>{p, bb.chirp, G, N, nt}, ntr, nullptr, conv);
+        p, tb, LoadHermitian2<T>{p, rp.bb.chirp, G, N, nt}, ntr, nullptr, conv);
     k_rowpass<T, true, true><<<(unsigned)std::min<long long>(ntr * row_units<T>(p), 16LL * sms), kGT, rs, s>>>(p, tb, ntr, nullptr, conv);
     k_colpass_inv<T, StoreRender2<T>><<<(unsigned)std::min<long long>(ntr * tiles, 16LL * sms), kGT, cs, s>>>(
-        p, tb, StoreRender2<T>{p, bb.chirp, out, N, n_keep, fade, rr, r0, nt, live}, ntr, nullptr, conv);
+        p, tb, StoreRender2<T>{p, rp.bb.chirp, out, N, n_keep, fade, rr, r0, nt, live}, ntr, nullptr, conv);
     count_launch(4);
   }
   return cudaGetLastError();
+}
+
+// one-shot form: the plan is built at the head of the workspace, the row loop uses the rest
+inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows rr, long long n_rows, double fs, int n_keep,
+                               float* out, char* ws, size_t ws_bytes, cudaStream_t s, int sms) {
+  if (ws_bytes < render_min_bytes(N, 1)) return cudaErrorMemoryAllocation;
+  const size_t plan = (render_plan_bytes(N) + 255) / 256 * 256;
+  char* rest = ws + plan;
+  // the head of the row loop's workspace (at least one G row + one convolution buffer) doubles as the scratch of
+  // the plan build: the build is stream-ordered before the first kernel that writes there
+  cudaError_t e = build_render_plan(base, n_base, N, ws, reinterpret_cast<cpxf*>(rest), s, sms);
+  if (e != cudaSuccess) return e;
+  return render_rows_planned(carve_render_plan(N, ws), N, rr, n_rows, fs, n_keep, out, rest, ws_bytes - plan, s, sms);
 }
 
 inline cudaError_t normalise_rows(float* out, long long n_rows, int n_keep, cudaStream_t s, int sms) {

@@ -45,7 +45,8 @@ config = {
 
 def simulate_signals_device(source_pos, mic_positions, fs, c, duration=1.0, signal_type='sine', freq=1000,
                             reflective_planes=None, material_properties=None, max_reflections=2,
-                            absorption_threshold=0.01, trim_to_duration=True, base_signal=None) -> torch.Tensor:
+                            absorption_threshold=0.01, trim_to_duration=True, base_signal=None,
+                            plan_cache=None) -> torch.Tensor:
     """Same computation as simulate_signals_with_multipath, result left on the device as a
     [M, n] float32 tensor.  `base_signal` optionally replaces generate_signal (e.g. a seeded
     noise burst)."""
@@ -71,12 +72,15 @@ def simulate_signals_device(source_pos, mic_positions, fs, c, duration=1.0, sign
 
 def simulate_scenes_batched(source_positions, mic_positions, fs, c, duration=1.0, signal_type='sine', freq=1000,
                             reflective_planes=None, material_properties=None, max_reflections=2,
-                            absorption_threshold=0.01, trim_to_duration=True, base_signal=None) -> torch.Tensor:
+                            absorption_threshold=0.01, trim_to_duration=True, base_signal=None,
+                            plan_cache=None) -> torch.Tensor:
     """simulate_signals_with_multipath (main.py:66-124) for MANY source positions / scenes in one go:
     source_positions [S, 3]; mic_positions [M, 3] (shared array) or [S, M, 3]; reflective_planes one
     list (shared room) or a list of S lists (one room per scene, same plane count and materials).
     Returns a [S, M, n] float32 tensor on the device.  Image sources, path tables, transfer
-    functions, inverse transforms and the normalise / compress epilogue all run batched."""
+    functions, inverse transforms and the normalise / compress epilogue all run batched.  A sweep that calls
+    this batch after batch passes one `scene.RenderPlanCache()` (and a device-resident `base_signal`) so that the
+    per-length tables of the renderer are built once."""
     base = generate_signal(signal_type, fs, duration, freq) if base_signal is None else base_signal
     mats = material_properties
     planes = list(reflective_planes or [])
@@ -96,7 +100,7 @@ def simulate_scenes_batched(source_positions, mic_positions, fs, c, duration=1.0
         mat = torch.zeros((len(srcs), 1), dtype=torch.int32, device=dev)
         cnt = torch.zeros((len(srcs),), dtype=torch.int32, device=dev)
     return _s.render_scenes_batched(base, srcs, pos, mat, cnt, mic_positions, fs, c, duration, freq, table,
-                                    trim_to_duration=trim_to_duration)
+                                    trim_to_duration=trim_to_duration, plan_cache=plan_cache)
 
 
 def simulate_signals_with_multipath(source_pos, mic_positions, fs, c, duration=1.0, signal_type='sine', freq=1000,

@@ -32,6 +32,57 @@ def _stream_pool(dev, n):
     return pool[:n]
 
 
+class RenderPlanCache:
+    """Per-length plans of the renderer (pal_render_plan) kept on the device between calls.
+
+    Everything the renderer derives from (N, base signal) alone -- chirp / twiddle tables, the chirp spectrum and the
+    spectrum of the zero-padded base signal -- is about half of the GPU work of a small bucket, and with random rooms
+    almost every scene has its own N.  A caller that renders batch after batch with the same base signal (a sweep)
+    passes one cache to every call; each N is then planned once.  Plans are evicted oldest-first beyond `max_bytes`.
+    Results are bit-identical with and without a cache."""
+
+    def __init__(self, max_bytes: int = 2 << 30):
+        self.max_bytes = int(max_bytes)
+        self.bytes = 0
+        self.plans: Dict[int, torch.Tensor] = {}
+        self.key = None
+        self.hits = 0
+        self.misses = 0
+
+    def _reset_for(self, base: torch.Tensor, n_base: int, dev):
+        key = (base.data_ptr(), int(n_base), str(dev), int(base._version))
+        if key != self.key:
+            self.plans.clear()
+            self.bytes = 0
+            self.key = key
+            self._base = base          # keeps the signal (and therefore the key's data_ptr) alive
+
+    def get(self, base: torch.Tensor, n_base: int, total: int, dev, stream) -> Tuple[torch.Tensor, int, int]:
+        """(tensor, aligned pointer, bytes) of the plan of transform length `total`, built on `stream` when missing."""
+        self._reset_for(base, n_base, dev)
+        t = self.plans.get(total)
+        L = _lib.lib()
+        need, scratch = C.c_size_t(0), C.c_size_t(0)
+        _lib.check(L.pal_render_plan_bytes(int(total), C.byref(need), C.byref(scratch)), "pal_render_plan_bytes")
+        if t is None:
+            self.misses += 1
+            while self.plans and self.bytes + need.value > self.max_bytes:
+                old = next(iter(self.plans))
+                self.bytes -= self.plans.pop(old).numel()
+            t = torch.empty(need.value + 256, dtype=torch.uint8, device=dev)
+            sc, sp, sl = _ws(scratch.value, dev)
+            tp = (t.data_ptr() + 255) // 256 * 256
+            _lib.check(L.pal_render_plan(base.data_ptr(), int(n_base), int(total), tp, need.value, sp, sl, stream.cuda_stream),
+                       "pal_render_plan")
+            sc.record_stream(stream)
+            t.record_stream(stream)
+            self.plans[total] = t
+            self.bytes += t.numel()
+        else:
+            self.hits += 1
+        return t, (t.data_ptr() + 255) // 256 * 256, need.value
+
+
 def _ws(nbytes, dev):
     t = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
     p = (t.data_ptr() + 255) // 256 * 256
@@ -162,14 +213,16 @@ def render_scene(base_signal, source_pos, img_pos: torch.Tensor, img_mat: torch.
 def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: torch.Tensor, img_count: torch.Tensor,
                           mic_positions, fs: float, c: float, duration: float, freq: float, table: MaterialTable,
                           trim_to_duration: bool = True, normalise: bool = True,
-                          max_workspace_bytes: int = 4 << 30, max_streams: int = 16) -> torch.Tensor:
+                          max_workspace_bytes: int = 4 << 30, max_streams: int = 16,
+                          plan_cache: Optional[RenderPlanCache] = None) -> torch.Tensor:
     """main.py:94-122 for MANY scenes that share fs / duration / base signal: sources [S, 3],
     img_pos [S, K, 3], img_mat [S, K], img_count [S] (output of image_sources_batched),
     mic_positions [M, 3] or [S, M, 3].  Returns [S, M, n_keep] float32 on the device.
 
     The transform length N = int((duration + max delay) * fs) (main.py:102) differs from scene to
     scene; delays are computed for all scenes in one launch, N is formed on the host in float64
-    exactly like the reference (one small read-back), and scenes that share N are rendered together."""
+    exactly like the reference (one small read-back), and scenes that share N are rendered together.
+    `plan_cache` (RenderPlanCache) keeps the per-N tables between calls that share the base signal."""
     dev = _dev()
     L = _lib.lib()
     if 'air' not in table.index:
@@ -216,8 +269,12 @@ def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: 
     # different buckets overlap instead of queueing behind each other.  Each stream owns a workspace slice.
     rows_max = int(np.max(np.diff(bounds))) * m
     need, small = C.c_size_t(0), C.c_size_t(0)
-    _lib.check(L.pal_render_scenes_workspace(int(uniq.max()), rows_max, C.byref(need), C.byref(small)),
-               "pal_render_scenes_workspace")
+    if plan_cache is None:
+        _lib.check(L.pal_render_scenes_workspace(int(uniq.max()), rows_max, C.byref(need), C.byref(small)),
+                   "pal_render_scenes_workspace")
+    else:
+        _lib.check(L.pal_render_rows_workspace(int(uniq.max()), rows_max, C.byref(need), C.byref(small)),
+                   "pal_render_rows_workspace")
     n_streams = max(1, min(int(max_streams), len(uniq), int(max_workspace_bytes) // max(int(small.value), 1)))
     per_stream = max(small.value, min(need.value, int(max_workspace_bytes) // n_streams))
     cur = torch.cuda.current_stream(dev)
@@ -231,9 +288,19 @@ def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: 
     for bi, total in enumerate(uniq):
         lo, hi = int(bounds[bi]), int(bounds[bi + 1])
         k = bi % n_streams
-        _lib.check(L.pal_render_scenes(base.data_ptr(), n_base, int(total), tau.data_ptr(), gain.data_ptr(), pcount.data_ptr(),
-                                       k_stride, idx_dev.data_ptr() + 8 * lo, hi - lo, m, float(fs), n_keep, out.data_ptr(),
-                                       slices[k][1], slices[k][2], pool[k].cuda_stream), "pal_render_scenes")
+        if plan_cache is None:
+            _lib.check(L.pal_render_scenes(base.data_ptr(), n_base, int(total), tau.data_ptr(), gain.data_ptr(), pcount.data_ptr(),
+                                           k_stride, idx_dev.data_ptr() + 8 * lo, hi - lo, m, float(fs), n_keep, out.data_ptr(),
+                                           slices[k][1], slices[k][2], pool[k].cuda_stream), "pal_render_scenes")
+        else:
+            # the plan is built (first use) on the bucket's own stream; later buckets of any stream see it through
+            # the end-of-call join below
+            pt, pp, pb = plan_cache.get(base, n_base, int(total), dev, pool[k])
+            _lib.check(L.pal_render_scenes_planned(pp, pb, n_base, int(total), tau.data_ptr(), gain.data_ptr(), pcount.data_ptr(),
+                                                   k_stride, idx_dev.data_ptr() + 8 * lo, hi - lo, m, float(fs), n_keep,
+                                                   out.data_ptr(), slices[k][1], slices[k][2], pool[k].cuda_stream),
+                       "pal_render_scenes_planned")
+            pt.record_stream(pool[k])
     if n_streams > 1:
         for st in pool:
             cur.wait_stream(st)

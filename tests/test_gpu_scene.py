@@ -257,3 +257,30 @@ def test_synchronize_signals_vs_reference_golden(pal, sync_golden):
     for i in range(s):
         w = np.array(O.synchronize_signals_improved([r.astype(np.float64) for r in frames[i]], fs))
         assert np.array_equal(out[i, :, :w.shape[1]], w.astype(np.float32)) and not out[i, :, w.shape[1]:].any()
+
+
+def test_render_plan_cache_bit_identical(pal):
+    """pal_render_plan / pal_render_scenes_planned: the per-length tables of the renderer kept between calls
+    (scene.RenderPlanCache) must not change a single bit of the rendered batch, on the first (all plans built) and on a
+    second call with other scenes (plans mostly reused)."""
+    from pyaudiolocalization_b200 import main as M, scene
+    from pyaudiolocalization_b200.signal_processing import generate_signal
+    rng = np.random.default_rng(8)
+    base = torch.as_tensor(generate_signal("chirp", 16000, 0.25, 500).astype(np.float32)).cuda()
+    cache = scene.RenderPlanCache()
+
+    def batch(n):
+        dims = rng.uniform([3, 3, 2.5], [4.0, 3.5, 3.0], size=(n, 3))        # small rooms: transform lengths repeat
+        rooms = [shoebox(*d) for d in dims]
+        mics = 0.3 + rng.uniform(size=(n, 4, 3)) * (dims[:, None, :] - 0.6)
+        srcs = 0.3 + rng.uniform(size=(n, 3)) * (dims - 0.6)
+        return srcs, mics, rooms
+
+    for rep in range(2):
+        srcs, mics, rooms = batch(48)
+        a = M.simulate_scenes_batched(srcs, mics, 16000, 343.62, 0.25, "chirp", 500, rooms, CUSTOM_MATERIALS, 2, 0.01,
+                                      base_signal=base)
+        b = M.simulate_scenes_batched(srcs, mics, 16000, 343.62, 0.25, "chirp", 500, rooms, CUSTOM_MATERIALS, 2, 0.01,
+                                      base_signal=base, plan_cache=cache)
+        assert torch.equal(a, b)
+    assert cache.hits > 0 and cache.misses == len(cache.plans)

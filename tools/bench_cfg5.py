@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--no-plan-cache", action="store_true", help="rebuild the renderer's per-length tables for every bucket")
     args = ap.parse_args()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -51,20 +52,32 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     s_n = args.scenes_per_gpu
-    rng = np.random.default_rng(5000 + rank)
-    dims = rng.uniform([3, 3, 2.5], [10, 8, 4], size=(s_n, 3))
-    mics = 0.3 + rng.uniform(size=(s_n, MICS, 3)) * (dims[:, None, :] - 0.6)
-    srcs = 0.3 + rng.uniform(size=(s_n, 3)) * (dims - 0.6)
-    rooms = [shoebox(*d) for d in dims]
+    from pyaudiolocalization_b200 import scene
+    from pyaudiolocalization_b200.signal_processing import generate_signal
+
+    def scene_set(seed):
+        rng = np.random.default_rng(seed)
+        dims = rng.uniform([3, 3, 2.5], [10, 8, 4], size=(s_n, 3))
+        mics = 0.3 + rng.uniform(size=(s_n, MICS, 3)) * (dims[:, None, :] - 0.6)
+        srcs = 0.3 + rng.uniform(size=(s_n, 3)) * (dims - 0.6)
+        return srcs, mics, [shoebox(*d) for d in dims]
+
+    # a DIFFERENT random scene set for every step (as in a real sweep), generated before the timed region
+    sets = [scene_set(5000 + rank + 1000 * i) for i in range(args.warmup + args.steps)]
+    base = torch.as_tensor(generate_signal("chirp", FS, DUR, FREQ).astype(np.float32)).to(dev)
+    cache = None if args.no_plan_cache else scene.RenderPlanCache()
     P = MICS * (MICS - 1) // 2
     k_all = torch.empty((s_n, P, 1), dtype=torch.int32, device=dev)
     gathered = torch.empty((world, s_n, P, 1), dtype=torch.int32, device=dev) if world > 1 else None
+    step_no = [0]
 
     def step():
+        srcs, mics, rooms = sets[step_no[0] % len(sets)]
+        step_no[0] += 1
         for c0 in range(0, s_n, args.chunk):
             c1 = min(c0 + args.chunk, s_n)
             sig = pmain.simulate_scenes_batched(srcs[c0:c1], mics[c0:c1], FS, 343.62, DUR, "chirp", FREQ, rooms[c0:c1], MATS,
-                                                ORDER, 0.01)
+                                                ORDER, 0.01, base_signal=base, plan_cache=cache)
             res = pal.gcc_phat_tdoa_batched(sig, float(FS), MED)
             k_all[c0:c1] = res.k_idx
         if world > 1:
@@ -100,6 +113,9 @@ def main():
                 "config": {"workload": "cfg5: random shoebox scenes, 8 mics, 0.25 s @ 16 kHz chirp 500 Hz, max_reflections=3, "
                                        "rendered then GCC-PHAT TDOA (28 pairs, n = 7999), max_expected_delay=0.05 s",
                            "scenes_per_gpu": s_n, "chunk_scenes": args.chunk,
+                           "scene_sets": "a different random set per step, generated before the timed region",
+                           "render_plan_cache": None if cache is None else
+                           {"hits": cache.hits, "misses": cache.misses, "plans": len(cache.plans), "bytes": cache.bytes},
                            "parallelism": f"scenes sharded over {world} GPU(s); one NCCL all-gather of lag indices per step"},
                 "gpu_launches": int(launches), "sample_tdoa_s": [float(x) for x in td[0, :4, 0]]}
         out_stream.write(json.dumps(line) + "\n")
