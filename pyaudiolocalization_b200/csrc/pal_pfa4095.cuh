@@ -244,10 +244,15 @@ PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil
     f2* o0 = reinterpret_cast<f2*>(spec + (frame * M + ch0) * kSpecSlots);
     f2* o1 = o0 + kSpecSlots;
     float h0 = 0.f, h1 = 0.f;
-    for (int o = tid; o < kSpecSlots; o += NT) {
-      const int q = o >> 5, r = o & 31;
-      const int e = Idx4095::elem(r, q);
-      const int L = Pfa4095::loc(e);
+    // slot o = (q, r) holds bin e(r, q), which the transform left at location loc(e) = G e mod n; both maps are
+    // linear mod n, so the location is (A r + B q) mod n, and a step of NT slots (q += NT / 32, same r) is one
+    // add-and-wrap
+    static_assert(NT % 32 == 0, "a block step must keep r");
+    constexpr int kLocR = (Pfa4095::G * Idx4095::UR) % kN4095, kLocQ = (Pfa4095::G * Idx4095::UQ) % kN4095;
+    constexpr int kLocStep = (kLocQ * (NT / 32)) % kN4095;
+    int L = (kLocR * (tid & 31) + kLocQ * (tid >> 5)) % kN4095;
+    for (int o = tid; o < kSpecSlots; o += NT, L = (L + kLocStep >= kN4095) ? L + kLocStep - kN4095 : L + kLocStep) {
+      const int r = o & 31;
       const int L2 = (L == 0) ? 0 : kN4095 - L;
       // Z = DFT(x1 + i x2): S1[e] = (Z[e] + conj(Z[n-e])) / 2, S2[e] = (Z[e] - conj(Z[n-e])) / (2i)
       const f2 zl = sm->z[L], zm = f2_conj(sm->z[L2]);
