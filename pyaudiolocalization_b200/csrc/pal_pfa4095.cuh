@@ -684,9 +684,13 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const float* hq, const int* pa
   const f2* sj;
   f2 pa[kPrefetchBins], pb[kPrefetchBins];
   float wb, wb_next = 0.f;     // whiten_bound of the current / next pair
+  long long frame_it = item / P;          // (frame, pair) of the item in flight: add-and-carry per step, no division
+  int pair_it = int(item - frame_it * P);
+  const long long stride_f = stride / P;
+  const int stride_p = int(stride - stride_f * P);
   {
-    const long long frame = item / P;
-    const int p = int(item % P);
+    const long long frame = frame_it;
+    const int p = pair_it;
     si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
     sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
     wb = whiten_bound(hq, frame * M + pairs[2 * p], frame * M + pairs[2 * p + 1]);
@@ -813,8 +817,11 @@ PAL_DEV void pair4095_fast_body(const cpxf* spec, const float* hq, const int* pa
     const long long next = item + stride;
     const bool has_next = next < n_items;
     if (has_next) {
-      const long long frame = next / P;
-      const int p = int(next % P);
+      pair_it += stride_p;
+      frame_it += stride_f;
+      if (pair_it >= P) { pair_it -= P; ++frame_it; }
+      const long long frame = frame_it;
+      const int p = pair_it;
       si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
       sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
       wb_next = whiten_bound(hq, frame * M + pairs[2 * p], frame * M + pairs[2 * p + 1]);
@@ -907,8 +914,14 @@ PAL_DEV void pair4095_tmem_body(const cpxf* spec, const float* hq, const int* pa
     const f2* sj;
     f2 ra[kLA][5], rb[kLA][5];
     float wb, wb_next = 0.f;     // whiten_bound of the current / next pair
+    // (frame, pair) of the item in flight, advanced by the constant stride with an add-and-carry instead of a
+    // 64-bit division per pair
+    long long frame_it = item / P;
+    int pair_it = int(item - frame_it * P);
+    const long long stride_f = stride / P;
+    const int stride_p = int(stride - stride_f * P);
     {
-      const long long frame = item / P;
+      const long long frame = frame_it;
       si = reinterpret_cast<const f2*>(spec + (frame * M + mi0) * kSpecSlots) + lane;
       sj = reinterpret_cast<const f2*>(spec + (frame * M + mj0) * kSpecSlots) + lane;
       wb = whiten_bound(hq, frame * M + mi0, frame * M + mj0);
@@ -1066,8 +1079,11 @@ PAL_DEV void pair4095_tmem_body(const cpxf* spec, const float* hq, const int* pa
       const long long next = item + stride;
       const bool has_next = next < n_items;
       if (has_next) {
-        const long long frame = next / P;
-        const int p = int(next % P);
+        pair_it += stride_p;
+        frame_it += stride_f;
+        if (pair_it >= P) { pair_it -= P; ++frame_it; }
+        const long long frame = frame_it;
+        const int p = pair_it;
         si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
         sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
         wb_next = whiten_bound(hq, frame * M + pairs[2 * p], frame * M + pairs[2 * p + 1]);
