@@ -70,7 +70,7 @@ unsigned long long pal_launch_count(void);
  * `stop_event` right after every launch of the named stage on the stream of that launch, so a
  * caller can time ONE kernel inside the pipeline with CUDA events.  Both are cudaEvent_t
  * created by the caller (timing enabled).  stage: 0 = off, 1 = forward transforms,
- * 2 = fused pair kernel (cross-spectrum + PHAT + inverse DFT + peak pick), 3 = float64
+ * 2 = fused pair kernel (cross-spectrum of the whitened spectra + inverse DFT + peak pick), 3 = float64
  * re-evaluation of flagged rows.  Process-global; not for concurrent use. */
 int pal_profile_hook(int32_t stage, void* start_event, void* stop_event);
 
@@ -95,6 +95,10 @@ int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, s
  * n_samples == 2048 (n = 4095 = 5*7*9*13) takes the fused prime-factor kernels and never
  * synchronises; any other length takes the Bluestein path, which synchronises `stream` once
  * when refine != 0 (to learn how many rows were flagged).
+ * Exactness: the float32 kernels flag every row whose decision is closer than tie_eps to an alternative (and, on
+ * the fused path, every row of a frame so quiet -- below about -69 dBFS -- that the absolute 1e-10 of utils.py:117
+ * is not negligible); with refine != 0 flagged rows are re-evaluated in float64 from the raw samples, so that lag
+ * indices equal the reference's.  num_peaks > 1 is evaluated in float64 throughout.
  */
 int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples,
                       const int32_t* pairs_dev, int32_t P, const pal_tdoa_params* prm,
