@@ -36,11 +36,11 @@ __global__ void __launch_bounds__(kGT, MinBlocks<T>::V) k_colpass_fwd(BluePlan p
   extern __shared__ __align__(128) char smem[];
   colpass_fwd_body<T, kGT, ColTile<T>::TC, Loader>(p, tb, ld, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
 }
-template <typename T, bool CONV, bool CONJ>
+template <typename T, bool CONV, bool CONJ, int TRV = ColTile<T>::TR>
 __global__ void __launch_bounds__(kGT, MinBlocks<T>::V) k_rowpass(BluePlan p, BlueTables<T> tb, long long n_tr, const int* n_tr_dev,
                                                  cpx<T>* buf) {
   extern __shared__ __align__(128) char smem[];
-  rowpass_body<T, kGT, ColTile<T>::TR, CONV, CONJ>(p, tb, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
+  rowpass_body<T, kGT, TRV, CONV, CONJ>(p, tb, n_tr_dev ? (long long)*n_tr_dev * n_tr : n_tr, buf, smem);
 }
 template <typename T, class Storer>
 __global__ void __launch_bounds__(kGT, MinBlocks<T>::V) k_colpass_inv(BluePlan p, BlueTables<T> tb, Storer st, long long n_tr,
@@ -134,6 +134,31 @@ template <typename T> inline size_t col_smem(const BluePlan& p) {
   return fft_tile_smem(sizeof(T), p.M1, tc);
 }
 
+// Row pass of `nt` transforms.  Short rows (M2 <= 128, float32) use tiles of 32 interleaved rows instead of 16: a
+// warp then covers 32 different rows at one position, which is free of shared-memory bank conflicts (16-row tiles
+// put two butterflies of a warp on overlapping banks), and the tile is still only 34 KB.
+#ifndef PAL_WIDE_ROWS
+#define PAL_WIDE_ROWS 1
+#endif
+constexpr int kWideRows = 32;
+template <typename T> inline bool wide_rows(const BluePlan& p) {
+  return PAL_WIDE_ROWS && sizeof(T) == 4 && p.M2 <= 128 && p.M1 >= kWideRows;
+}
+template <typename T, bool CONV, bool CONJ>
+inline void launch_rowpass(const BluePlan& p, const BlueTables<T>& tb, long long nt, cpx<T>* buf, cudaStream_t s, long long max_blocks) {
+  if (wide_rows<T>(p)) {
+    const size_t sm = fft_tile_smem(sizeof(T), p.M2, kWideRows + 1);
+    auto kern = k_rowpass<T, CONV, CONJ, kWideRows>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    kern<<<(unsigned)std::min<long long>(nt * (p.M1 / kWideRows), max_blocks), kGT, sm, s>>>(p, tb, nt, nullptr, buf);
+  } else {
+    const size_t sm = row_smem<T>(p);
+    auto kern = k_rowpass<T, CONV, CONJ>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    kern<<<(unsigned)std::min<long long>(nt * row_units<T>(p), max_blocks), kGT, sm, s>>>(p, tb, nt, nullptr, buf);
+  }
+}
+
 // carve the tables of a plan out of `base` (no launches)
 template <typename T> void carve_plan(const BluePlan& p, char*& base, BlueBuffers<T>& bb) {
   bb.chirp = reinterpret_cast<cpx<T>*>(base); base += al(sizeof(cpx<T>) * size_t(p.n));
@@ -150,8 +175,7 @@ template <typename T> cudaError_t fill_plan(const BluePlan& p, const BlueBuffers
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   k_colpass_fwd<T, LoadBhat<T>><<<std::min(tiles, 8 * sms), kGT, cs, s>>>(p, bb.tb(), LoadBhat<T>{p, bb.chirp}, 1, nullptr,
                                                                           bb.bhat);
-  cudaFuncSetAttribute(k_rowpass<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
-  k_rowpass<T, false, false><<<std::min(row_units<T>(p), 8 * sms), kGT, rs, s>>>(p, bb.tb(), 1, nullptr, bb.bhat);
+  launch_rowpass<T, false, false>(p, bb.tb(), 1, bb.bhat, s, 8LL * sms);
   count_launch(3);
   return cudaGetLastError();
 }
@@ -164,8 +188,6 @@ template <typename T> void plan_kernel_attributes(const BluePlan& p) {
   cudaFuncSetAttribute(k_colpass_inv<T, StoreCorr2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_inv<T, StoreSpectrum<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
   cudaFuncSetAttribute(k_colpass_inv<T, StoreCorr<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  cudaFuncSetAttribute(k_rowpass<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
-  cudaFuncSetAttribute(k_rowpass<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
 }
 // carve + fill (the one-shot form every non-cached caller uses)
 template <typename T> cudaError_t setup_plan(const BluePlan& p, char*& base, BlueBuffers<T>& bb, cudaStream_t s, int sms) {
@@ -247,7 +269,7 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
       LoadSignal2<T> ld{p, bb.chirp, c.sig, c.ld, c.Mics, CP, c.n1, c.n2, row_list, g0 + r0, c.scales};
       k_colpass_fwd<T, LoadSignal2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, ld, nt, nullptr, conv);
-      k_rowpass<T, true, false><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * c.sms), kGT, rs, c.stream>>>(p, tb, nt, nullptr, conv);
+      launch_rowpass<T, true, false>(p, tb, nt, conv, c.stream, 16LL * c.sms);
       StoreSpectrum<T> st{p, bb.chirp, spec_out + r0 * n};
       k_colpass_inv<T, StoreSpectrum<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, st, nt, nullptr, conv);
@@ -263,7 +285,7 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
       LoadPhat2<T> ld{p, bb.chirp, spec_in, c.pairs, c.Mics, CP, c.P, i0, nitems, ilist != nullptr, c.scales, frame0, rows_scratch, list0};
       k_colpass_fwd<T, LoadPhat2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, ld, nt, nullptr, conv);
-      k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * c.sms), kGT, rs, c.stream>>>(p, tb, nt, nullptr, conv);
+        launch_rowpass<T, true, true>(p, tb, nt, conv, c.stream, 16LL * c.sms);
       StoreCorr2<T> st{p, bb.chirp, corr, ni, ld};
       k_colpass_inv<T, StoreCorr2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, st, nt, nullptr, conv);
@@ -378,8 +400,7 @@ template <typename T> cudaError_t run_sync_align(const SyncCall& c, char* ws, si
       LoadSignalF64<T> ld{p, bb.chirp, c.sig, c.ld, c.ld, c.lens, s0 * c.Mics + r0};
       k_colpass_fwd<T, LoadSignalF64<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, ld, nt, nullptr, conv);
-      k_rowpass<T, true, false><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * c.sms), kGT, rs, c.stream>>>(
-          p, tb, nt, nullptr, conv);
+      launch_rowpass<T, true, false>(p, tb, nt, conv, c.stream, 16LL * c.sms);
       StoreSpectrum<T> st{p, bb.chirp, spec + r0 * n};
       k_colpass_inv<T, StoreSpectrum<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, st, nt, nullptr, conv);
@@ -390,8 +411,7 @@ template <typename T> cudaError_t run_sync_align(const SyncCall& c, char* ws, si
       LoadCross<T> ld{p, bb.chirp, spec, c.ref_idx, s0, c.Mics, i0};
       k_colpass_fwd<T, LoadCross<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, ld, nt, nullptr, conv);
-      k_rowpass<T, true, true><<<(unsigned)std::min<long long>(nt * row_units<T>(p), 16LL * c.sms), kGT, rs, c.stream>>>(
-          p, tb, nt, nullptr, conv);
+      launch_rowpass<T, true, true>(p, tb, nt, conv, c.stream, 16LL * c.sms);
       StoreCorr<T> st{p, bb.chirp, corr};
       k_colpass_inv<T, StoreCorr<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, st, nt, nullptr, conv);

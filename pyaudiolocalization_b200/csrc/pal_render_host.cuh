@@ -102,7 +102,7 @@ inline cudaError_t build_render_plan(const float* base, int n_base, int N, char*
   // X = fft(base zero-padded, 2N)                                      (signal_processing.py:69)
   k_colpass_fwd<T, LoadSignal<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(
       p, tb, LoadSignal<T>{p, rp.bb.chirp, base, n_base}, 1, nullptr, conv);
-  k_rowpass<T, true, false><<<std::min(row_units<T>(p), 16 * sms), kGT, rs, s>>>(p, tb, 1, nullptr, conv);
+  launch_rowpass<T, true, false>(p, tb, 1, conv, s, 16LL * sms);
   k_colpass_inv<T, StoreSpectrum<T>><<<std::min(tiles, 16 * sms), kGT, cs, s>>>(p, tb, StoreSpectrum<T>{p, rp.bb.chirp, rp.X}, 1,
                                                                                 nullptr, conv);
   count_launch(3);
@@ -149,7 +149,7 @@ inline cudaError_t render_rows_planned(const RenderPlan& rp, int N, RenderRows r
     const long long ntr = (nt + 1) / 2;
     k_colpass_fwd<T, LoadHermitian2<T>><<<(unsigned)std::min<long long>(ntr * tiles, 16LL * sms), kGT, cs, s>>>(
         p, tb, LoadHermitian2<T>{p, rp.bb.chirp, G, N, nt}, ntr, nullptr, conv);
-    k_rowpass<T, true, true><<<(unsigned)std::min<long long>(ntr * row_units<T>(p), 16LL * sms), kGT, rs, s>>>(p, tb, ntr, nullptr, conv);
+    launch_rowpass<T, true, true>(p, tb, ntr, conv, s, 16LL * sms);
     k_colpass_inv<T, StoreRender2<T>><<<(unsigned)std::min<long long>(ntr * tiles, 16LL * sms), kGT, cs, s>>>(
         p, tb, StoreRender2<T>{p, rp.bb.chirp, out, N, n_keep, fade, rr, r0, nt, live}, ntr, nullptr, conv);
     count_launch(4);
