@@ -117,30 +117,53 @@ def image_sources_batched(sources, planes: Sequence[Dict[str, Any]], max_order: 
     mics = torch.as_tensor(np.ascontiguousarray(mics_np)).to(dev)
     n_mics = mics_np.shape[-2]
     table = MaterialTable(material_properties, dev)
-    planes = list(planes or [])
-    # planes: one list shared by all scenes, or (per-scene geometry) a list of B such lists that
-    # agree in the number of planes and in their materials
-    per_scene_planes = bool(planes) and isinstance(planes[0], (list, tuple))
-    plane_sets = planes if per_scene_planes else [planes]
-    if per_scene_planes and len(plane_sets) != b:
-        raise ValueError("per-scene planes: need one plane list per source")
-    n_pl = len(plane_sets[0])
-    pl = np.zeros((len(plane_sets), max(n_pl, 1), 4), np.float64)
-    pm = np.zeros(max(n_pl, 1), np.int32)
-    for si_, pls in enumerate(plane_sets):
-        if len(pls) != n_pl:
-            raise ValueError("per-scene planes: every scene needs the same number of planes")
-        for i, p in enumerate(pls):
-            a, bb, c, d = [float(v) for v in p['plane']]
-            if a * a + bb * bb + c * c == 0:
-                raise ValueError("Ungültige Ebene: a^2 + b^2 + c^2 ist 0.")
-            mat = p.get('material', 'air')
+    # planes: one list of {'plane', 'material'} dicts shared by all scenes, or (per-scene geometry) a list of B such
+    # lists that agree in the number of planes and in their materials, or -- the form a sweep should use, because
+    # walking B lists of dicts in Python costs more than rendering the scenes -- a pair
+    # (coefficients ndarray [B, n_planes, 4], material names [n_planes])
+    array_form = (isinstance(planes, (tuple, list)) and len(planes) == 2 and isinstance(planes[0], np.ndarray)
+                  and planes[0].ndim == 3)
+    if array_form:
+        pl = np.ascontiguousarray(planes[0], dtype=np.float64)
+        names = list(planes[1])
+        if pl.shape[0] != b or pl.shape[2] != 4 or pl.shape[1] != len(names):
+            raise ValueError("planes array form: need coefficients [B, n_planes, 4] and n_planes material names")
+        if (np.einsum('spk,spk->sp', pl[:, :, :3], pl[:, :, :3]) == 0).any():
+            raise ValueError("Ungültige Ebene: a^2 + b^2 + c^2 ist 0.")
+        for mat in names:
             if mat not in table.index:
                 raise ValueError(f"Material '{mat}' ist nicht definiert. Bitte zum Dictionary hinzufügen.")
-            if si_ and table.index[mat] != pm[i]:
-                raise ValueError("per-scene planes: plane materials must agree between scenes")
-            pl[si_, i] = (a, bb, c, d)
-            pm[i] = table.index[mat]
+        pm = np.array([table.index[mat] for mat in names], np.int32)
+        n_pl = len(names)
+        per_scene_planes = True
+        plane_sets = [[None] * n_pl]
+        if n_pl == 0:
+            pl = np.zeros((1, 1, 4), np.float64)
+            pm = np.zeros(1, np.int32)
+            per_scene_planes = False
+    else:
+        planes = list(planes or [])
+        per_scene_planes = bool(planes) and isinstance(planes[0], (list, tuple))
+        plane_sets = planes if per_scene_planes else [planes]
+        if per_scene_planes and len(plane_sets) != b:
+            raise ValueError("per-scene planes: need one plane list per source")
+        n_pl = len(plane_sets[0])
+        pl = np.zeros((len(plane_sets), max(n_pl, 1), 4), np.float64)
+        pm = np.zeros(max(n_pl, 1), np.int32)
+        for si_, pls in enumerate(plane_sets):
+            if len(pls) != n_pl:
+                raise ValueError("per-scene planes: every scene needs the same number of planes")
+            for i, p in enumerate(pls):
+                a, bb, c, d = [float(v) for v in p['plane']]
+                if a * a + bb * bb + c * c == 0:
+                    raise ValueError("Ungültige Ebene: a^2 + b^2 + c^2 ist 0.")
+                mat = p.get('material', 'air')
+                if mat not in table.index:
+                    raise ValueError(f"Material '{mat}' ist nicht definiert. Bitte zum Dictionary hinzufügen.")
+                if si_ and table.index[mat] != pm[i]:
+                    raise ValueError("per-scene planes: plane materials must agree between scenes")
+                pl[si_, i] = (a, bb, c, d)
+                pm[i] = table.index[mat]
     planes = plane_sets[0]
     planes_dev = torch.as_tensor(pl).to(dev)
     pm_dev = torch.as_tensor(pm).to(dev)

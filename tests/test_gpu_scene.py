@@ -284,3 +284,21 @@ def test_render_plan_cache_bit_identical(pal):
                                       base_signal=base, plan_cache=cache)
         assert torch.equal(a, b)
     assert cache.hits > 0 and cache.misses == len(cache.plans)
+
+
+def test_planes_array_form_equals_list_form(pal):
+    """Per-scene rooms given as (coefficients [S, P, 4], material names) -- the form a sweep uses, because walking S
+    lists of dicts costs more host time than rendering -- must give exactly the image sources of the list-of-dicts form."""
+    from pyaudiolocalization_b200 import scene
+    rng = np.random.default_rng(4)
+    dims = rng.uniform([3, 3, 2.5], [10, 8, 4], size=(24, 3))
+    rooms = [shoebox(*d) for d in dims]
+    mics = 0.3 + rng.uniform(size=(24, 4, 3)) * (dims[:, None, :] - 0.6)
+    srcs = 0.3 + rng.uniform(size=(24, 3)) * (dims - 0.6)
+    arr = np.array([[p["plane"] for p in r] for r in rooms], dtype=np.float64)
+    names = [p["material"] for p in rooms[0]]
+    a = scene.image_sources_batched(srcs, rooms, 3, 500.0, CUSTOM_MATERIALS, mics, 0.01)
+    b = scene.image_sources_batched(srcs, (arr, names), 3, 500.0, CUSTOM_MATERIALS, mics, 0.01)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    with pytest.raises(ValueError):
+        scene.image_sources_batched(srcs, (arr[:, :, :3], names), 3, 500.0, CUSTOM_MATERIALS, mics, 0.01)

@@ -25,6 +25,7 @@ from pyaudiolocalization_b200 import main as pmain, shard  # noqa: E402
 MATS = {"air": {"absorption": 0.01, "freq": 1e-6}, "wood": {"absorption": 0.05, "freq": 1e-5},
         "metal": {"absorption": 0.1, "freq": 2e-5}, "glass": {"absorption": 0.07, "freq": 1.5e-5}}
 FS, DUR, FREQ, MICS, ORDER, MED = 16000, 0.25, 500, 8, 3, 0.05
+ROOM_MATERIALS = ["wood", "metal", "glass", "wood", "wood", "metal"]      # planes x=0, x=lx, y=0, y=ly, z=0, z=lz
 
 
 def shoebox(lx, ly, lz):
@@ -60,7 +61,11 @@ def main():
         dims = rng.uniform([3, 3, 2.5], [10, 8, 4], size=(s_n, 3))
         mics = 0.3 + rng.uniform(size=(s_n, MICS, 3)) * (dims[:, None, :] - 0.6)
         srcs = 0.3 + rng.uniform(size=(s_n, 3)) * (dims - 0.6)
-        return srcs, mics, [shoebox(*d) for d in dims]
+        # rooms in the array form of scene.image_sources_batched: coefficients [S, 6, 4] + the six material names
+        pl = np.zeros((s_n, 6, 4))
+        pl[:, 0, 0] = pl[:, 1, 0] = pl[:, 2, 1] = pl[:, 3, 1] = pl[:, 4, 2] = pl[:, 5, 2] = 1.0
+        pl[:, 1, 3], pl[:, 3, 3], pl[:, 5, 3] = -dims[:, 0], -dims[:, 1], -dims[:, 2]
+        return srcs, mics, pl
 
     # a DIFFERENT random scene set for every step (as in a real sweep), generated before the timed region
     sets = [scene_set(5000 + rank + 1000 * i) for i in range(args.warmup + args.steps)]
@@ -76,8 +81,9 @@ def main():
         step_no[0] += 1
         for c0 in range(0, s_n, args.chunk):
             c1 = min(c0 + args.chunk, s_n)
-            sig = pmain.simulate_scenes_batched(srcs[c0:c1], mics[c0:c1], FS, 343.62, DUR, "chirp", FREQ, rooms[c0:c1], MATS,
-                                                ORDER, 0.01, base_signal=base, plan_cache=cache)
+            sig = pmain.simulate_scenes_batched(srcs[c0:c1], mics[c0:c1], FS, 343.62, DUR, "chirp", FREQ,
+                                                (rooms[c0:c1], ROOM_MATERIALS), MATS, ORDER, 0.01, base_signal=base,
+                                                plan_cache=cache)
             res = pal.gcc_phat_tdoa_batched(sig, float(FS), MED)
             k_all[c0:c1] = res.k_idx
         if world > 1:
