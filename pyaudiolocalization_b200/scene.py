@@ -102,6 +102,48 @@ class MaterialTable:
         self.freq = torch.tensor([float(mats[n]['freq']) for n in self.names], dtype=torch.float64, device=dev)
 
 
+def parse_planes(planes, n_scenes: int, material_index: Dict[str, int]):
+    """Host-side decoding of the reflective planes of a batch (no GPU involved).
+
+    planes: one list of {'plane': [a, b, c, d], 'material': name} dicts shared by all scenes (the reference's form,
+    main.py:66-79), or a list of `n_scenes` such lists (one room per scene; same plane count and materials), or --
+    the form a sweep should use, because walking tens of thousands of lists of dicts in Python costs more than
+    rendering the scenes -- a pair (coefficients ndarray [n_scenes, n_planes, 4], material names [n_planes]).
+    Returns (coefficients [S or 1, max(n_planes, 1), 4] float64, material ids [max(n_planes, 1)] int32, n_planes,
+    per_scene).  Errors are the reference's: zero normal (utils.py:36-37), unknown material (utils.py:93-94)."""
+    array_form = (isinstance(planes, (tuple, list)) and len(planes) == 2 and isinstance(planes[0], np.ndarray)
+                  and planes[0].ndim == 3)
+    if array_form:
+        pl = np.ascontiguousarray(planes[0], dtype=np.float64)
+        names = [list(planes[1])]
+        if pl.shape[0] != n_scenes or pl.shape[2] != 4 or pl.shape[1] != len(names[0]):
+            raise ValueError("planes array form: need coefficients [B, n_planes, 4] and n_planes material names")
+        per_scene = True
+    else:
+        planes = list(planes or [])
+        per_scene = bool(planes) and isinstance(planes[0], (list, tuple))
+        plane_sets = planes if per_scene else [planes]
+        if per_scene and len(plane_sets) != n_scenes:
+            raise ValueError("per-scene planes: need one plane list per source")
+        n0 = len(plane_sets[0])
+        if any(len(pls) != n0 for pls in plane_sets):
+            raise ValueError("per-scene planes: every scene needs the same number of planes")
+        pl = np.array([[p['plane'] for p in pls] for pls in plane_sets], dtype=np.float64).reshape(len(plane_sets), n0, 4)
+        names = [[p.get('material', 'air') for p in pls] for pls in plane_sets]
+        if any(nm != names[0] for nm in names[1:]):
+            raise ValueError("per-scene planes: plane materials must agree between scenes")
+    n_pl = pl.shape[1]
+    if n_pl and (np.einsum('spk,spk->sp', pl[:, :, :3], pl[:, :, :3]) == 0).any():
+        raise ValueError("Ungültige Ebene: a^2 + b^2 + c^2 ist 0.")
+    for mat in names[0]:
+        if mat not in material_index:
+            raise ValueError(f"Material '{mat}' ist nicht definiert. Bitte zum Dictionary hinzufügen.")
+    pm = np.array([material_index[mat] for mat in names[0]], np.int32)
+    if n_pl == 0:
+        return np.zeros((1, 1, 4), np.float64), np.zeros(1, np.int32), 0, False
+    return pl, pm, n_pl, per_scene
+
+
 def image_sources_batched(sources, planes: Sequence[Dict[str, Any]], max_order: int, frequency: float,
                           material_properties: Dict[str, Any], mic_positions, absorption_threshold: float = 0.01,
                           round_decimals: int = 6, k_max: Optional[int] = None
@@ -117,54 +159,8 @@ def image_sources_batched(sources, planes: Sequence[Dict[str, Any]], max_order: 
     mics = torch.as_tensor(np.ascontiguousarray(mics_np)).to(dev)
     n_mics = mics_np.shape[-2]
     table = MaterialTable(material_properties, dev)
-    # planes: one list of {'plane', 'material'} dicts shared by all scenes, or (per-scene geometry) a list of B such
-    # lists that agree in the number of planes and in their materials, or -- the form a sweep should use, because
-    # walking B lists of dicts in Python costs more than rendering the scenes -- a pair
-    # (coefficients ndarray [B, n_planes, 4], material names [n_planes])
-    array_form = (isinstance(planes, (tuple, list)) and len(planes) == 2 and isinstance(planes[0], np.ndarray)
-                  and planes[0].ndim == 3)
-    if array_form:
-        pl = np.ascontiguousarray(planes[0], dtype=np.float64)
-        names = list(planes[1])
-        if pl.shape[0] != b or pl.shape[2] != 4 or pl.shape[1] != len(names):
-            raise ValueError("planes array form: need coefficients [B, n_planes, 4] and n_planes material names")
-        if (np.einsum('spk,spk->sp', pl[:, :, :3], pl[:, :, :3]) == 0).any():
-            raise ValueError("Ungültige Ebene: a^2 + b^2 + c^2 ist 0.")
-        for mat in names:
-            if mat not in table.index:
-                raise ValueError(f"Material '{mat}' ist nicht definiert. Bitte zum Dictionary hinzufügen.")
-        pm = np.array([table.index[mat] for mat in names], np.int32)
-        n_pl = len(names)
-        per_scene_planes = True
-        plane_sets = [[None] * n_pl]
-        if n_pl == 0:
-            pl = np.zeros((1, 1, 4), np.float64)
-            pm = np.zeros(1, np.int32)
-            per_scene_planes = False
-    else:
-        planes = list(planes or [])
-        per_scene_planes = bool(planes) and isinstance(planes[0], (list, tuple))
-        plane_sets = planes if per_scene_planes else [planes]
-        if per_scene_planes and len(plane_sets) != b:
-            raise ValueError("per-scene planes: need one plane list per source")
-        n_pl = len(plane_sets[0])
-        pl = np.zeros((len(plane_sets), max(n_pl, 1), 4), np.float64)
-        pm = np.zeros(max(n_pl, 1), np.int32)
-        for si_, pls in enumerate(plane_sets):
-            if len(pls) != n_pl:
-                raise ValueError("per-scene planes: every scene needs the same number of planes")
-            for i, p in enumerate(pls):
-                a, bb, c, d = [float(v) for v in p['plane']]
-                if a * a + bb * bb + c * c == 0:
-                    raise ValueError("Ungültige Ebene: a^2 + b^2 + c^2 ist 0.")
-                mat = p.get('material', 'air')
-                if mat not in table.index:
-                    raise ValueError(f"Material '{mat}' ist nicht definiert. Bitte zum Dictionary hinzufügen.")
-                if si_ and table.index[mat] != pm[i]:
-                    raise ValueError("per-scene planes: plane materials must agree between scenes")
-                pl[si_, i] = (a, bb, c, d)
-                pm[i] = table.index[mat]
-    planes = plane_sets[0]
+    pl, pm, n_pl, per_scene_planes = parse_planes(planes, b, table.index)
+    planes = [None] * n_pl
     planes_dev = torch.as_tensor(pl).to(dev)
     pm_dev = torch.as_tensor(pm).to(dev)
     if k_max is None:

@@ -86,3 +86,33 @@ def test_gather_rows_without_process_group():
     assert shard.gather_rows(x, 4) is x
     with pytest.raises(ValueError):
         shard.gather_rows(x, 5)
+
+
+def test_parse_planes_host_logic():
+    """scene.parse_planes (pure host code): the reference's list-of-dicts form, per-scene lists and the array form
+    decode to the same coefficients / material ids; the reference's errors are kept."""
+    import numpy as np
+    import pytest
+    from pyaudiolocalization_b200.scene import parse_planes
+    idx = {"air": 0, "wood": 1, "metal": 2}
+    one = [{"plane": [1, 0, 0, -5], "material": "wood"}, {"plane": [0, 1, 0, -4], "material": "metal"},
+           {"plane": [0, 0, 2, -3]}]
+    pl, pm, n, per = parse_planes(one, 7, idx)
+    assert pl.shape == (1, 3, 4) and list(pm) == [1, 2, 0] and n == 3 and not per
+    rooms = [[{"plane": [1, 0, 0, -float(s + 1)], "material": "wood"}, {"plane": [0, 1, 0, -2.0], "material": "metal"}]
+             for s in range(5)]
+    pl2, pm2, n2, per2 = parse_planes(rooms, 5, idx)
+    assert pl2.shape == (5, 2, 4) and per2 and list(pm2) == [1, 2] and pl2[3, 0, 3] == -4.0
+    pl3, pm3, n3, per3 = parse_planes((pl2.copy(), ["wood", "metal"]), 5, idx)
+    assert np.array_equal(pl3, pl2) and np.array_equal(pm3, pm2) and n3 == 2 and per3
+    assert parse_planes([], 3, idx)[2] == 0 and parse_planes(None, 3, idx)[2] == 0
+    with pytest.raises(ValueError, match="a\\^2"):
+        parse_planes([{"plane": [0, 0, 0, 1], "material": "wood"}], 1, idx)
+    with pytest.raises(ValueError, match="nicht definiert"):
+        parse_planes([{"plane": [1, 0, 0, 1], "material": "glass"}], 1, idx)
+    with pytest.raises(ValueError):
+        parse_planes(rooms, 4, idx)                                   # one room per source
+    with pytest.raises(ValueError):
+        parse_planes(rooms[:4] + [[rooms[4][0], {"plane": [0, 1, 0, -2.0], "material": "wood"}]], 5, idx)   # materials differ
+    with pytest.raises(ValueError):
+        parse_planes((pl2[:, :, :3], ["wood", "metal"]), 5, idx)
