@@ -26,6 +26,15 @@ inline double ddiv(double a, double b) { volatile double r = a / b; return r; }
 inline long long round_key(double x, double scale) { return (long long)std::nearbyint(dmul(x, scale)); }
 #endif
 
+// np.linalg.norm of a 3-vector (utils.py:44-48) is sqrt(x.dot(x)); the BLAS dot of three elements evaluates
+// fma(z, z, fma(y, y, x*x)) (checked against numpy on 20000 random vectors, tests/test_oracle.py), so the distance
+// is formed with exactly these roundings -- a prune decision at a 1-ulp tie then falls the same way.
+#if PAL_GPU
+PAL_DEV double norm3(double x, double y, double z) { return __dsqrt_rn(__fma_rn(z, z, __fma_rn(y, y, __dmul_rn(x, x)))); }
+#else
+inline double norm3(double x, double y, double z) { return std::sqrt(std::fma(z, z, std::fma(y, y, dmul(x, x)))); }
+#endif
+
 struct ImgParams {
   int n_planes, n_mics, max_order, k_max;
   double frequency, threshold, round_scale;
@@ -35,6 +44,35 @@ struct ImgParams {
 PAL_DEV double attenuation(double d, double absorption, double freq_factor, double frequency) {
   d = d < 0.1 ? 0.1 : d;
   return (1.0 / d) * exp(-freq_factor * frequency * d) * exp(-absorption * d);
+}
+
+// numpy's add.reduce over a contiguous float64 array (what np.mean of a list does): fewer than 8 values are summed
+// left to right; up to 128 values go through eight interleaved accumulators combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) with the tail added one by one; longer arrays are split in halves (the first
+// a multiple of 8) and the two partial sums added.  f(q) yields value q.
+template <class F> PAL_DEV double numpy_pairwise_sum(F& f, int lo, int n) {
+  if (n < 8) {
+    double r = 0.0;
+    for (int i = 0; i < n; ++i) r = dadd(r, f(lo + i));
+    return r;
+  }
+  if (n <= 128) {
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = f(lo + j);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = dadd(r[j], f(lo + i + j));
+    }
+    double res = dadd(dadd(dadd(r[0], r[1]), dadd(r[2], r[3])), dadd(dadd(r[4], r[5]), dadd(r[6], r[7])));
+    for (; i < n; ++i) res = dadd(res, f(lo + i));
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  const double a = numpy_pairwise_sum(f, lo, n2);
+  return dadd(a, numpy_pairwise_sum(f, lo + n2, n - n2));
 }
 
 // One block per scene (grid-stride).  Scratch per BLOCK: cand_pos[cmax][3] f64, cand_key[cmax][3] i64,
@@ -82,14 +120,15 @@ PAL_DEV void image_sources_body(ImgParams ip, const double* sources, long long n
         cand_key[c * 3 + 1] = round_key(y, ip.round_scale);
         cand_key[c * 3 + 2] = round_key(z, ip.round_scale);
         const int m = plane_mat[pl];
-        double sum = 0.0, mn = 1e300;
-        for (int q = 0; q < ip.n_mics; ++q) {
-          const double dx = x - mic[q * 3], dy = y - mic[q * 3 + 1], dz = z - mic[q * 3 + 2];
-          const double att = attenuation(sqrt(dx * dx + dy * dy + dz * dz), mat_abs[m], mat_freq[m], ip.frequency);
-          sum += att;
+        double mn = 1e300;
+        auto att_of = [&](int q) {
+          const double att = attenuation(norm3(dadd(x, -mic[q * 3]), dadd(y, -mic[q * 3 + 1]), dadd(z, -mic[q * 3 + 2])),
+                                         mat_abs[m], mat_freq[m], ip.frequency);
           mn = att < mn ? att : mn;
-        }
-        cand_ok[c] = (sum / ip.n_mics > ip.threshold && mn > ip.threshold / 2) ? 1 : 0;
+          return att;
+        };
+        const double sum = numpy_pairwise_sum(att_of, 0, ip.n_mics);        // np.mean(attenuations), utils.py:99
+        cand_ok[c] = (ddiv(sum, double(ip.n_mics)) > ip.threshold && mn > ip.threshold / 2) ? 1 : 0;
       }
       simt::sync_block();
       // 2. a passing candidate is new iff its key is neither among the seen keys (source + accepted
@@ -165,7 +204,7 @@ PAL_DEV void path_table_body(const double* src, const double* img_pos, const int
   const double* p = (k == 0) ? src : img_pos + size_t(k - 1) * 3;
   const int mat = (k == 0) ? air_mat : img_mat[k - 1];
   const double dx = p[0] - mics[m * 3], dy = p[1] - mics[m * 3 + 1], dz = p[2] - mics[m * 3 + 2];
-  const double d = sqrt(dx * dx + dy * dy + dz * dz);
+  const double d = norm3(dx, dy, dz);
   tau[i] = d / c_sound;
   gain[i] = attenuation(d, mat_abs[mat], mat_freq[mat], frequency);
 }
@@ -191,7 +230,7 @@ PAL_DEV void path_table_batched_body(const double* sources, const double* img_po
       const double* p = (k == 0) ? src : img_pos + (size_t(s) * k_max + (k - 1)) * 3;
       const int mat = (k == 0) ? air_mat : img_mat[size_t(s) * k_max + (k - 1)];
       const double dx = p[0] - mic[m * 3], dy = p[1] - mic[m * 3 + 1], dz = p[2] - mic[m * 3 + 2];
-      const double d = sqrt(dx * dx + dy * dy + dz * dz);
+      const double d = norm3(dx, dy, dz);
       const double t = d / c_sound;
       const size_t o = (size_t(s) * n_mics + m) * k_stride + k;
       tau[o] = t;

@@ -40,6 +40,35 @@ def window_half_width(n1: int, n2: int, fs: float, max_expected_delay: Optional[
     return m
 
 
+def pairs_to_device(pairs, m: int, dev) -> torch.Tensor:
+    """Validated [P, 2] int32 device copy of a pair list (0 <= index < m), marked as checked."""
+    pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+    if pr.size and (pr.min() < 0 or pr.max() >= m):
+        raise ValueError("pair index out of range")
+    t = torch.from_numpy(pr).to(dev)
+    t._pal_checked = (int(pr.max()) + 1 if pr.size else 0, t._version)
+    return t
+
+
+def check_pairs_dev(pairs_dev: torch.Tensor, m: int) -> None:
+    """A caller-supplied device pair list is range-checked once per tensor object and version (one min/max
+    read-back), not once per call: an out-of-range microphone index would be an out-of-bounds read in the kernels."""
+    if not (pairs_dev.is_cuda and pairs_dev.dtype == torch.int32 and pairs_dev.dim() == 2 and pairs_dev.shape[1] == 2
+            and pairs_dev.is_contiguous()):
+        raise ValueError("pairs_dev must be a contiguous [P, 2] int32 CUDA tensor")
+    seen = getattr(pairs_dev, "_pal_checked", None)
+    if seen is None or seen[1] != pairs_dev._version:
+        hi = -1
+        if pairs_dev.numel():
+            lo, hi = int(pairs_dev.min().item()), int(pairs_dev.max().item())
+            if lo < 0:
+                raise ValueError("pair index out of range")
+        seen = (hi + 1, pairs_dev._version)
+        pairs_dev._pal_checked = seen
+    if seen[0] > m:
+        raise ValueError("pair index out of range")
+
+
 def all_pairs(m: int) -> np.ndarray:
     """(i, j) for i < j in the order of main.py:202-203."""
     return np.array([(i, j) for i in range(m) for j in range(i + 1, m)], dtype=np.int32).reshape(-1, 2)
@@ -100,10 +129,9 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
     b, m, n = frames.shape
     dev = frames.device
     if pairs_dev is None:
-        pr = all_pairs(m) if pairs is None else np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
-        if pr.size and (pr.min() < 0 or pr.max() >= m):
-            raise ValueError("pair index out of range")
-        pairs_dev = torch.from_numpy(pr).to(dev)
+        pairs_dev = pairs_to_device(all_pairs(m) if pairs is None else pairs, m, dev)
+    else:
+        check_pairs_dev(pairs_dev, m)
     p = pairs_dev.shape[0]
     n1, n2 = (n, n) if lengths is None else (int(lengths[0]), int(lengths[1]))
     if not (1 <= n1 <= n and 1 <= n2 <= n):
@@ -205,7 +233,7 @@ def gcc_phat_tdoa_from_host(frames_host: torch.Tensor, fs: float, max_expected_d
     pr = all_pairs(m) if kw.get("pairs") is None else np.asarray(kw.pop("pairs"), dtype=np.int32).reshape(-1, 2)
     kw.pop("pairs", None)
     p = len(pr)
-    pairs_dev = torch.from_numpy(np.ascontiguousarray(pr)).to(dev)
+    pairs_dev = pairs_to_device(pr, m, dev)
     chunk = max(1, min(int(chunk_frames), b))
     full, _ = workspace_bytes(chunk, m, n, p)
     ws = torch.empty(full + 256, dtype=torch.uint8, device=dev)

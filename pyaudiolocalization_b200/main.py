@@ -169,7 +169,13 @@ def localize_sound_source(config, calibration_data=None, audio_files=None, use_s
 
     signals = _sync.synchronize_signals_improved(signals, fs)      # utils.py:407-457 on the GPU (sync.py)
     logging.info("Signale synchronisiert.")
-    filtered = [H.noise_reduction(sig, fs, method=filter_method) for sig in signals]
+    if filter_method == 'butterworth' and len({len(sig) for sig in signals}) == 1:
+        # all channels through pal_filtfilt in ONE call (float64, bit-identical to scipy's filtfilt per channel)
+        from .filters import noise_reduction_batched
+        x = torch.as_tensor(np.ascontiguousarray(np.stack([np.asarray(sig, dtype=np.float64) for sig in signals]))).to(_s._dev())
+        filtered = list(noise_reduction_batched(x, fs).cpu().numpy())
+    else:
+        filtered = [H.noise_reduction(sig, fs, method=filter_method) for sig in signals]
     for i in range(len(filtered)):
         logging.info(f"Signal {i+1} gefiltert mit '{filter_method}' Noise Reduction.")
 

@@ -89,6 +89,15 @@ def _ws(nbytes, dev):
     return t, p, t.numel() - (p - t.data_ptr())
 
 
+def _check_mics(mics_np: np.ndarray, n_scenes: int) -> None:
+    """mic_positions is [M, 3] (shared) or [S, M, 3] (one array per scene); anything else would make the kernels read
+    past the allocation (they step through it with a stride of 3*M per scene)."""
+    if mics_np.ndim not in (2, 3) or mics_np.shape[-1] != 3 or mics_np.shape[-2] < 1:
+        raise ValueError("mic_positions must have shape [M, 3] or [S, M, 3]")
+    if mics_np.ndim == 3 and mics_np.shape[0] != n_scenes:
+        raise ValueError(f"per-scene mic_positions: got {mics_np.shape[0]} arrays for {n_scenes} scenes")
+
+
 class MaterialTable:
     """material_properties dict (materials.py:2-16) as index-addressed device arrays."""
 
@@ -156,6 +165,7 @@ def image_sources_batched(sources, planes: Sequence[Dict[str, Any]], max_order: 
     b = src.shape[0]
     mics_np = np.asarray(mic_positions, dtype=np.float64)
     per_scene = mics_np.ndim == 3
+    _check_mics(mics_np, b)
     mics = torch.as_tensor(np.ascontiguousarray(mics_np)).to(dev)
     n_mics = mics_np.shape[-2]
     table = MaterialTable(material_properties, dev)
@@ -250,8 +260,17 @@ def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: 
     s_n = src.shape[0]
     mics_np = np.asarray(mic_positions, dtype=np.float64)
     per_scene = mics_np.ndim == 3
+    _check_mics(mics_np, s_n)
     mics = torch.as_tensor(np.ascontiguousarray(mics_np)).to(dev)
     m = mics_np.shape[-2]
+    for t, shape, dt, what in ((img_pos, (s_n, None, 3), torch.float64, "img_pos [S, K, 3] float64"),
+                               (img_mat, (s_n, None), torch.int32, "img_mat [S, K] int32"),
+                               (img_count, (s_n,), torch.int32, "img_count [S] int32")):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dt and t.is_contiguous() and t.dim() == len(shape)
+                and all(w is None or int(g) == w for g, w in zip(t.shape, shape))):
+            raise ValueError(f"render_scenes_batched: need a contiguous CUDA tensor {what} with S = {s_n} scenes")
+    if img_mat.shape[1] != img_pos.shape[1]:
+        raise ValueError("render_scenes_batched: img_pos and img_mat disagree on K")
     k_max = int(img_pos.shape[1])
     if (img_count < 0).any().item():
         raise RuntimeError("image_sources_batched overflowed k_max for some scene; call it again with a larger k_max")

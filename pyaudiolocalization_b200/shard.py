@@ -62,3 +62,65 @@ def tdoa_seconds_from_indices(k_idx, n_samples: int, fs: float) -> np.ndarray:
     td = (k - (n_samples - 1)) / float(fs)
     td[k < 0] = np.nan
     return td
+
+
+class ShardedTdoa:
+    """The per-rank driver of a sharded GCC-PHAT sweep: this rank's frames go through `gcc_phat_tdoa_batched`
+    and the integer lag indices of all ranks are all-gathered once per step.
+
+    Results are double-buffered: the all-gather of step i is asynchronous (NCCL's own stream) and overlaps the
+    kernels of step i+1, so a rank never idles inside a step waiting for a slower peer; `drain()` waits for every
+    outstanding gather.  With one rank (or no process group) there is no collective at all.
+    `gathered(step)` is the [world, B_local, P, num_peaks] int32 tensor of a finished step."""
+
+    def __init__(self, frames_per_rank: int, mics: int, n_samples: int, fs: float, max_expected_delay: Optional[float] = None,
+                 pairs=None, device=None, group=None, gather: bool = True, **kw):
+        from . import gcc_phat as g
+        self.g = g
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.fs, self.med, self.kw = float(fs), max_expected_delay, kw
+        self.b, self.m, self.n = int(frames_per_rank), int(mics), int(n_samples)
+        self.pairs_dev = g.pairs_to_device(g.all_pairs(mics) if pairs is None else pairs, mics, self.dev)
+        self.p = int(self.pairs_dev.shape[0])
+        full, _ = g.workspace_bytes(self.b, self.m, self.n, self.p)
+        self.ws = torch.empty(full + 256, dtype=torch.uint8, device=self.dev)
+        self.do_gather = bool(gather) and self.world > 1
+        nbuf = 2 if self.do_gather else 1
+        self.outs = [self._new_out() for _ in range(nbuf)]
+        self.bufs = [torch.empty((self.world, self.b, self.p, 1), dtype=torch.int32, device=self.dev) for _ in range(nbuf)] \
+            if self.do_gather else None
+        self.works = [None] * nbuf
+        self.steps = 0
+
+    def _new_out(self):
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.dev)      # noqa: E731
+        return self.g.TdoaBatch(e((self.b, self.p, 1), torch.int32), e((self.b, self.p), torch.int32),
+                                e((self.b, self.p), torch.float32), e((self.b, self.p), torch.float32),
+                                e((self.b, self.p), torch.int32), None, self.n, self.fs)
+
+    def step(self, frames_local: torch.Tensor):
+        """Enqueue one step; returns this rank's TdoaBatch (valid once the stream has run)."""
+        s = self.steps % len(self.outs)
+        self.steps += 1
+        if self.works[s] is not None:
+            self.works[s].wait()
+            self.works[s] = None
+        out = self.g.gcc_phat_tdoa_batched(frames_local, self.fs, self.med, workspace=self.ws, out=self.outs[s],
+                                           pairs_dev=self.pairs_dev, **self.kw)
+        if self.do_gather:
+            self.works[s] = dist.all_gather_into_tensor(self.bufs[s], out.k_idx, group=self.group, async_op=True)
+        return out
+
+    def drain(self):
+        for s, w in enumerate(self.works):
+            if w is not None:
+                w.wait()
+                self.works[s] = None
+
+    def last(self):
+        """(gathered lag indices or None, local TdoaBatch) of the most recent step, after drain()."""
+        s = (self.steps - 1) % len(self.outs)
+        return (self.bufs[s] if self.do_gather else None), self.outs[s]

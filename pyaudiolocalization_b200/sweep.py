@@ -1,0 +1,118 @@
+"""Scene sweep: many random scenes rendered by stage 1 (main.py:66-124) and fed to stage 2
+(utils.py:121-181, looped over all pairs as main.py:202-228), scenes sharded over the ranks of one box and the
+per-scene integer lag vectors all-gathered once per step (BASELINE.json configs[4]).
+
+The reference has no batch driver (one `localize_sound_source` call is one scene); this module is the batch loop a
+user of the drop-in writes around `simulate_scenes_batched` + `gcc_phat_tdoa_batched`, kept in the package so that
+bench.py, the tools and the tests time and check the same code.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import gcc_phat as _g
+from . import scene as _scene
+
+# The materials of BASELINE cfg4 / cfg5: the stock table of materials.py prunes every
+# reflection at audio-rate `freq` (headline fact 5), so sweeps that want reflections bring their own.
+SWEEP_MATERIALS = {"air": {"absorption": 0.01, "freq": 1e-6}, "wood": {"absorption": 0.05, "freq": 1e-5},
+                   "metal": {"absorption": 0.1, "freq": 2e-5}, "glass": {"absorption": 0.07, "freq": 1.5e-5}}
+ROOM_MATERIALS = ["wood", "metal", "glass", "wood", "wood", "metal"]      # planes x=0, x=lx, y=0, y=ly, z=0, z=lz
+
+
+@dataclass
+class SweepConfig:
+    """cfg5 of BASELINE.json: 8 mics, 0.25 s @ 16 kHz chirp (500 Hz -> 2.5 kHz), max_reflections = 3."""
+    fs: int = 16000
+    duration: float = 0.25
+    freq: float = 500.0
+    mics: int = 8
+    max_reflections: int = 3
+    max_expected_delay: float = 0.05
+    absorption_threshold: float = 0.01
+    c: float = 343.62
+    signal_type: str = "chirp"
+
+    @property
+    def pairs(self) -> int:
+        return self.mics * (self.mics - 1) // 2
+
+    @property
+    def samples(self) -> int:
+        return int(self.duration * self.fs)
+
+
+def random_shoebox_scenes(n: int, mics: int, seed: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(sources [n, 3], mics [n, M, 3], plane coefficients [n, 6, 4]) of n random shoebox rooms with dimensions
+    U([3, 3, 2.5], [10, 8, 4]) m, microphones and source uniform inside with a 0.3 m wall margin."""
+    rng = np.random.default_rng(seed)
+    dims = rng.uniform([3, 3, 2.5], [10, 8, 4], size=(n, 3))
+    mic = 0.3 + rng.uniform(size=(n, mics, 3)) * (dims[:, None, :] - 0.6)
+    src = 0.3 + rng.uniform(size=(n, 3)) * (dims - 0.6)
+    pl = np.zeros((n, 6, 4))
+    pl[:, 0, 0] = pl[:, 1, 0] = pl[:, 2, 1] = pl[:, 3, 1] = pl[:, 4, 2] = pl[:, 5, 2] = 1.0
+    pl[:, 1, 3], pl[:, 3, 3], pl[:, 5, 3] = -dims[:, 0], -dims[:, 1], -dims[:, 2]
+    return src, mic, pl
+
+
+def planes_as_dicts(coeff: np.ndarray):
+    """One scene's [6, 4] coefficients in the reference's list-of-dicts form (main.py:66-79)."""
+    return [{"plane": [float(v) for v in coeff[i]], "material": ROOM_MATERIALS[i]} for i in range(coeff.shape[0])]
+
+
+class SceneSweep:
+    """Per-rank driver: `step(sources, mics, planes)` renders this rank's scenes chunk by chunk, runs the batched
+    GCC-PHAT / TDOA pick on the rendered channels and all-gathers the lag indices of all ranks."""
+
+    def __init__(self, cfg: SweepConfig, scenes_per_rank: int, chunk: int = 16384, device=None, group=None,
+                 gather: bool = True, keep_signals: int = 0, materials=None):
+        from .signal_processing import generate_signal
+        self.cfg = cfg
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n = int(scenes_per_rank)
+        self.chunk = max(1, min(int(chunk), self.n))
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.do_gather = bool(gather) and self.world > 1
+        self.mats = dict(SWEEP_MATERIALS if materials is None else materials)
+        self.base = torch.as_tensor(generate_signal(cfg.signal_type, cfg.fs, cfg.duration, cfg.freq).astype(np.float32)).to(self.dev)
+        self.cache = _scene.RenderPlanCache()
+        self.k_all = torch.empty((self.n, cfg.pairs, 1), dtype=torch.int32, device=self.dev)
+        self.flags = torch.empty((self.n, cfg.pairs), dtype=torch.int32, device=self.dev)
+        self.gathered = torch.empty((self.world, self.n, cfg.pairs, 1), dtype=torch.int32, device=self.dev) if self.do_gather else None
+        self.keep = int(keep_signals)
+        self.signals: Optional[torch.Tensor] = None       # the first `keep_signals` rendered scenes of the last step
+        self.render_ms = self.gcc_ms = 0.0
+        self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self.timed = False
+
+    def step(self, sources: np.ndarray, mics: np.ndarray, planes: np.ndarray):
+        from . import main as pmain
+        cfg = self.cfg
+        for c0 in range(0, self.n, self.chunk):
+            c1 = min(c0 + self.chunk, self.n)
+            if self.timed:
+                self._ev[0].record()
+            sig = pmain.simulate_scenes_batched(sources[c0:c1], mics[c0:c1], cfg.fs, cfg.c, cfg.duration, cfg.signal_type,
+                                                cfg.freq, (planes[c0:c1], ROOM_MATERIALS), self.mats, cfg.max_reflections,
+                                                cfg.absorption_threshold, base_signal=self.base, plan_cache=self.cache)
+            if self.timed:
+                self._ev[1].record()
+            res = _g.gcc_phat_tdoa_batched(sig, float(cfg.fs), cfg.max_expected_delay)
+            self.k_all[c0:c1] = res.k_idx
+            self.flags[c0:c1] = res.flags
+            if self.timed:
+                self._ev[2].record()
+                torch.cuda.synchronize()
+                self.render_ms += self._ev[0].elapsed_time(self._ev[1])
+                self.gcc_ms += self._ev[1].elapsed_time(self._ev[2])
+            if c0 == 0 and self.keep:
+                self.signals = sig[:self.keep].clone()
+        if self.do_gather:
+            dist.all_gather_into_tensor(self.gathered, self.k_all, group=self.group)
+        return self.k_all

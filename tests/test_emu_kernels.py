@@ -329,3 +329,58 @@ def test_dead_and_weak_channels_next_to_a_loud_one():
         assert np.abs(cg[0, p] - c).max() <= 1e-4 * max(np.abs(c).max(), 1e-30) + (0 if c.any() else 0)
         if 1 in (i, j):
             assert not cg[0, p].any() and kg[0, p, 0] == 0
+
+
+def test_image_sources_cfg4_shape_64_mics_order_6():
+    """BASELINE cfg4 geometry: shoebox 6 x 5 x 3 m, 64 microphones, max_reflections = 6 -> 376 images (SURVEY.md 8c
+    golden (3)); positions, discovery order and materials bit-identical to the oracle.  64 attenuations per candidate
+    go through numpy's pairwise np.mean (eight interleaved accumulators), which the kernel reproduces."""
+    from oracle import pal_oracle as O
+    from tests.golden.make_golden import CUSTOM_MATERIALS, shoebox
+    mics = np.random.default_rng(0).uniform([1, 1, 0.5], [5, 4, 2.5], size=(64, 3))
+    srcs = np.random.default_rng(1).uniform([0.5, 0.5, 0.3], [5.5, 4.5, 2.7], size=(2, 3))
+    names = list(CUSTOM_MATERIALS)
+    planes = shoebox(6, 5, 3)
+    for thr, expect in ((0.01, None), (-1.0, 376)):      # cfg4's threshold (prunes some), and no pruning at all
+        pos, mat, cnt = E.image_sources(srcs, [p["plane"] for p in planes], [names.index(p["material"]) for p in planes],
+                                        [CUSTOM_MATERIALS[n]["absorption"] for n in names],
+                                        [CUSTOM_MATERIALS[n]["freq"] for n in names], mics, 6, 1000.0, thr, 400)
+        for s in range(2):
+            imgs = O.generate_image_sources_iterative(srcs[s], planes, 6, 1000.0, CUSTOM_MATERIALS, mics, thr)
+            k = len(imgs)
+            assert cnt[s] == k and (expect is None or k == expect) and k > 200
+            assert np.array_equal(pos[s, :k], np.array([im["source"] for im in imgs]))
+            assert [names[i] for i in mat[s, :k]] == [im["material"] for im in imgs]
+
+
+def test_numpy_norm_and_mean_rounding_order():
+    """The two numpy facts the image-source kernel relies on for its prune test (pal_render.cuh: norm3,
+    numpy_pairwise_sum): np.linalg.norm of a 3-vector is sqrt(fma(z, z, fma(y, y, x*x))), and np.mean of 8..128 values
+    sums eight interleaved accumulators.  A numpy / BLAS build that rounds differently shows up here, not as a
+    silent 1-ulp prune difference."""
+    from fractions import Fraction as F
+    rng = np.random.default_rng(5)
+
+    def fma(a, b, c):
+        return float(F(float(a)) * F(float(b)) + F(float(c)))
+    for _ in range(400):
+        d = rng.uniform(-10, 10, 3)
+        assert float(np.linalg.norm(d)) == float(np.sqrt(fma(d[2], d[2], fma(d[1], d[1], d[0] * d[0]))))
+    for n in (5, 8, 13, 64):
+        for _ in range(50):
+            x = rng.uniform(0, 1, n)
+            if n < 8:
+                want = 0.0
+                for t in x:
+                    want += t
+            else:
+                r = list(x[:8])
+                i = 8
+                while i < n - n % 8:
+                    for j in range(8):
+                        r[j] += x[i + j]
+                    i += 8
+                want = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+                for t in x[i:]:
+                    want += t
+            assert float(np.mean(list(x))) == want / n
