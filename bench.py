@@ -575,10 +575,15 @@ def main():
     ap.add_argument("--no-scenes", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic only: skip the NCCL all-gather (invalid as a result)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_gpu_arm(args)
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_gpu_arm(args)
+    finally:
+        if _POOL is not None:
+            _POOL[0].terminate()
+            _POOL[0].join()
 
 
 if __name__ == "__main__":
