@@ -389,8 +389,16 @@ template <typename T> struct LoadSignal {
 template <typename T> PAL_DEV cpx<T> phat_cross(cpx<T> a, cpx<T> b, T inv_n) {
   const T xr = fma_(a.x, b.x, a.y * b.y);
   const T xi = fma_(a.y, b.x, -(a.x * b.y));
-  const T mag = sqrt_(fma_(xr, xr, xi * xi));
-  const T sc = inv_n / (mag + T(1e-10));
+  const T m2 = fma_(xr, xr, xi * xi);
+#if PAL_GPU
+  // float32: above |R| = 1e-2 the absolute 1e-10 of the reference is far below half an ulp of |R| (6e-10), so
+  // |R| + 1e-10 == |R| and the weight is one reciprocal square root (MUFU.RSQ, < 2 ulp) instead of sqrt + divide
+  if (sizeof(T) == 4 && m2 > T(1e-4)) {
+    const T sc = inv_n * T(rsqrtf(float(m2)));
+    return cpx<T>{xr * sc, xi * sc};
+  }
+#endif
+  const T sc = inv_n / (sqrt_(m2) + T(1e-10));
   return cpx<T>{xr * sc, xi * sc};
 }
 

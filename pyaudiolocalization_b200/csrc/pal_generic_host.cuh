@@ -6,8 +6,11 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <type_traits>
 
 #include "pal_bluestein.cuh"
+#include "pal_fft2.cuh"
+#include "pal_winpick.cuh"
 #include "pal_sync.cuh"
 
 namespace palhost {
@@ -58,6 +61,11 @@ __global__ void __launch_bounds__(kGT) k_pick_rows(const T* corr, int n, int c0,
   pick_rows_body<T, kGT>(corr, n, c0, n_rows_dev ? (long long)*n_rows_dev : n_rows, item_list, win_half, dist, method,
                          mult, num_peaks, eps, pkmap_ws, k_idx, k_count, peak, gmax, flags, extra_flag, keep_mask, corr_out, smem);
 }
+__global__ void __launch_bounds__(kGT) k_win_pick(const float* win, const float* pmax, int tiles, long long n_rows, WinGeom g,
+                                                  long long item0, int* k_idx, int* k_count, float* peak, float* gmax,
+                                                  unsigned* flags, unsigned extra_flag) {
+  win_pick_rows_body<kGT>(win, pmax, tiles, n_rows, g, item0, k_idx, k_count, peak, gmax, flags, extra_flag);
+}
 __global__ void __launch_bounds__(kGT) k_row_scales(const float* sig, long long n_rows, long long ld, int len_even, int len_odd,
                                                     float* scales) {
   __shared__ float sh[kGT / 32];
@@ -89,8 +97,9 @@ template <typename T> struct GenericLayout {
   size_t per_tr;      // conv buffer + two corr rows, per (packed) transform in flight
   size_t per_row;     // one packed spectrum row (two channels)
   GenericLayout(int n) : p(make_blue_plan(n)) {
+    // (+ 8 KB: the second-generation float32 engine keeps full-circle stage twiddles, 512 entries at most per axis)
     tables = al(sizeof(cpx<T>) * size_t(p.n)) + al(sizeof(cpx<T>) * (p.M1 / 2 + 1)) +
-             al(sizeof(cpx<T>) * (p.M2 / 2 + 1)) + 2 * al(sizeof(cpx<T>) * size_t(p.M));
+             al(sizeof(cpx<T>) * (p.M2 / 2 + 1)) + 2 * al(sizeof(cpx<T>) * size_t(p.M)) + 8192;
     per_tr = al(sizeof(cpx<T>) * size_t(p.M)) + 2 * al(sizeof(T) * size_t(p.n));   // a packed inverse yields two rows
     per_row = al(sizeof(cpx<T>) * size_t(p.n));
   }
@@ -116,7 +125,22 @@ struct GenericCall {
 };
 
 inline void count_launch(int k = 1) {
-  if (g_launch_counter) g_launch_counter->fetch_add(k);
+  if (g_launch_counter) g_launch_counter->fetch_add((unsigned long long)(long long)k);
+}
+inline bool use_fast_pick() {      // PAL_FAST_PICK=0: full find_peaks emulation on every float32 row (A/B measurements)
+  static const bool on = [] {
+    const char* e = std::getenv("PAL_FAST_PICK");
+    return e ? (e[0] != '0') : true;
+  }();
+  return on;
+}
+// PAL_FFT2=0 keeps every float32 sweep on the first-generation (power-of-two, run-time-sized) engine: A/B measurements
+inline bool use_fft2() {
+  static const bool on = [] {
+    const char* e = std::getenv("PAL_FFT2");
+    return e ? (e[0] != '0') : true;
+  }();
+  return on;
 }
 
 template <typename T> struct BlueBuffers {
@@ -196,6 +220,104 @@ template <typename T> cudaError_t setup_plan(const BluePlan& p, char*& base, Blu
   return fill_plan<T>(p, bb, s, sms);
 }
 
+// ---------------------------------------------------------------- second-generation float32 engine (pal_fft2.cuh)
+namespace f2h {
+using namespace pal::fft2;
+constexpr int kNT2 = 256;
+#ifndef PAL_FFT2_MINBLOCKS
+#define PAL_FFT2_MINBLOCKS 4
+#endif
+
+template <class P, class Loader>
+__global__ void __launch_bounds__(kNT2, PAL_FFT2_MINBLOCKS) k2_colpass_fwd(Tables tb, Loader ld, long long n_tr, cpxf* buf) {
+  extern __shared__ __align__(128) char smem[];
+  colpass_fwd_body<P, kNT2, Loader>(tb, ld, n_tr, buf, smem);
+}
+template <class P, int MODE>
+__global__ void __launch_bounds__(kNT2, PAL_FFT2_MINBLOCKS) k2_rowpass(Tables tb, long long n_tr, cpxf* buf, cpxf* bhat_out) {
+  extern __shared__ __align__(128) char smem[];
+  rowpass_body<P, kNT2, MODE>(tb, n_tr, buf, bhat_out, smem);
+}
+template <class P, class Storer>
+__global__ void __launch_bounds__(kNT2, PAL_FFT2_MINBLOCKS) k2_colpass_inv(Tables tb, Storer st, long long n_tr, const cpxf* buf) {
+  extern __shared__ __align__(128) char smem[];
+  colpass_inv_body<P, kNT2, Storer>(tb, st, n_tr, buf, smem);
+}
+__global__ void __launch_bounds__(256) k2_init_tables(int n, int M1, int M2, cpxf* chirp, cpxf* tw1, cpxf* tw2, cpxf* twf) {
+  init_tables_body(n, M1, M2, chirp, tw1, tw2, twf);
+}
+
+// Resident blocks per SM of a kernel at its (compile-time) shared-memory size; the opt-in above 48 KB and the
+// occupancy query run once per kernel and device, not once per call (and never shrink an attribute another caller set).
+// (the kernel is a template ARGUMENT: kernels of equal signature share one function-pointer type, and a cache keyed
+// by that type would be shared between them)
+template <auto kern> inline int resident_blocks(size_t smem) {
+  static std::atomic<int> cache[32];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 31;
+  int v = cache[dev].load(std::memory_order_acquire);
+  if (v > 0) return v;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kNT2, smem) != cudaSuccess || occ < 1) occ = 1;
+  cache[dev].store(occ, std::memory_order_release);
+  return occ;
+}
+template <auto kern> inline unsigned grid_for(size_t smem, long long units, int sms) {
+  return (unsigned)std::max<long long>(1, std::min<long long>(units, (long long)sms * resident_blocks<kern>(smem)));
+}
+
+struct Buffers {
+  int plan = -1;
+  BluePlan p{};          // n and the convolution length (what the loaders / storers look at)
+  cpxf *chirp = nullptr, *tw1 = nullptr, *tw2 = nullptr, *twf = nullptr, *bhat = nullptr;
+  Tables tb() const { return Tables{chirp, tw1, tw2, twf, bhat}; }
+};
+inline size_t table_bytes(int n, int plan) {
+  const PlanDims d = plan_dims(plan);
+  return al(sizeof(cpxf) * size_t(n)) + al(sizeof(cpxf) * d.M1) + al(sizeof(cpxf) * d.M2) + 2 * al(sizeof(cpxf) * size_t(d.M1) * d.M2);
+}
+inline void carve(int n, int plan, char*& base, Buffers& b) {
+  const PlanDims d = plan_dims(plan);
+  const size_t M = size_t(d.M1) * d.M2;
+  b.plan = plan;
+  b.p = BluePlan{n, int(M), d.M1, d.M2, 0, 0};
+  b.chirp = reinterpret_cast<cpxf*>(base); base += al(sizeof(cpxf) * size_t(n));
+  b.tw1 = reinterpret_cast<cpxf*>(base);   base += al(sizeof(cpxf) * d.M1);
+  b.tw2 = reinterpret_cast<cpxf*>(base);   base += al(sizeof(cpxf) * d.M2);
+  b.twf = reinterpret_cast<cpxf*>(base);   base += al(sizeof(cpxf) * M);
+  b.bhat = reinterpret_cast<cpxf*>(base);  base += al(sizeof(cpxf) * M);
+}
+// chirp, twiddles and the chirp spectrum; `scratch` holds one convolution (M complex)
+inline cudaError_t fill(const Buffers& b, cpxf* scratch, cudaStream_t s, int sms) {
+  const PlanDims d = plan_dims(b.plan);
+  k2_init_tables<<<std::min(4 * sms, (b.p.M + 255) / 256), 256, 0, s>>>(b.p.n, d.M1, d.M2, b.chirp, b.tw1, b.tw2, b.twf);
+  with_plan(b.plan, [&](auto pl) {
+    using P = decltype(pl);
+    k2_colpass_fwd<P, LoadBhat<float>><<<grid_for<k2_colpass_fwd<P, LoadBhat<float>>>(P::col_smem, P::M2 / P::TC, sms), kNT2, P::col_smem, s>>>(
+        b.tb(), LoadBhat<float>{b.p, b.chirp}, 1, scratch);
+    k2_rowpass<P, 2><<<grid_for<k2_rowpass<P, 2>>(P::row_smem, P::M1 / P::TR, sms), kNT2, P::row_smem, s>>>(b.tb(), 1, scratch, b.bhat);
+  });
+  count_launch(3);
+  return cudaGetLastError();
+}
+// one batch of `nt` convolutions: loader -> (x chirp spectrum, conjugated when CONJ) -> storer
+template <bool CONJ, class Loader, class Storer>
+inline void conv(const Buffers& b, const Loader& ld, const Storer& st, long long nt, cpxf* buf, cudaStream_t s, int sms) {
+  with_plan(b.plan, [&](auto pl) {
+    using P = decltype(pl);
+    k2_colpass_fwd<P, Loader><<<grid_for<k2_colpass_fwd<P, Loader>>(P::col_smem, nt * (P::M2 / P::TC), sms), kNT2, P::col_smem, s>>>(
+        b.tb(), ld, nt, buf);
+    k2_rowpass<P, CONJ ? 1 : 0><<<grid_for<k2_rowpass<P, CONJ ? 1 : 0>>(P::row_smem, nt * (P::M1 / P::TR), sms), kNT2, P::row_smem, s>>>(
+        b.tb(), nt, buf, nullptr);
+    k2_colpass_inv<P, Storer><<<grid_for<k2_colpass_inv<P, Storer>>(P::col_smem, nt * (P::M2 / P::TC), sms), kNT2, P::col_smem, s>>>(
+        b.tb(), st, nt, buf);
+  });
+  count_launch(3);
+}
+}  // namespace f2h
+
 #ifndef PAL_PICK_BLOCKS
 #define PAL_PICK_BLOCKS 4
 #endif
@@ -228,8 +350,18 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   if (ws_bytes < generic_min_bytes<T>(n, list ? 2 : c.Mics, c.sms)) return cudaErrorMemoryAllocation;
   char* base = ws;
   BlueBuffers<T> bb;
-  cudaError_t e = setup_plan<T>(p, base, bb, c.stream, c.sms);
-  if (e != cudaSuccess) return e;
+  // float32 sweeps run on the second-generation engine whenever one of its plans holds 2n - 1 points
+  f2h::Buffers b2;
+  const int plan2 = (std::is_same<T, float>::value && use_fft2()) ? fft2::choose_plan(n) : -1;
+  cudaError_t e = cudaSuccess;
+  if (plan2 >= 0) {
+    f2h::carve(n, plan2, base, b2);
+    bb.chirp = reinterpret_cast<cpx<T>*>(b2.chirp);
+    base = ws + L.tables;        // same budget as the first-generation tables (never smaller)
+  } else {
+    e = setup_plan<T>(p, base, bb, c.stream, c.sms);
+    if (e != cudaSuccess) return e;
+  }
   const int grid_pick = pick_grid(c.sms);
   unsigned char* pkmap = reinterpret_cast<unsigned char*>(base);
   base += pkmap_bytes(n, c.sms);
@@ -256,6 +388,18 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   const BlueTables<T> tb = bb.tb();
   const int c0 = c.n2 - 1;
+  const BluePlan pl = plan2 >= 0 ? b2.p : p;        // what loaders / storers see: n and the convolution length
+  if (plan2 >= 0) {
+    if constexpr (std::is_same<T, float>::value) {
+      e = f2h::fill(b2, reinterpret_cast<cpxf*>(conv), c.stream, c.sms);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  // reduced pick (pal_winpick.cuh): one peak, no correlation rows wanted, near-tie audit on, first sweep only
+  const WinGeom wg = make_win_geom(n, c0, c.pp.win_half, c.pp.dist, c.eps);
+  const int win_tiles = plan2 >= 0 ? fft2::plan_dims(plan2).M2 / (fft2::plan_dims(plan2).M1 <= 192 ? 32 : 16) : 0;
+  const bool fast_pick = plan2 >= 0 && !list && c.pp.num_peaks == 1 && !c.corr_out && c.eps > 0.f && use_fast_pick() &&
+                         size_t(wg.wstride + win_tiles) * sizeof(float) <= al(sizeof(T) * size_t(n));
   if (!list) {
     k_row_scales<<<(unsigned)std::min<long long>(c.B * c.Mics, 16LL * c.sms), kGT, 0, c.stream>>>(c.sig, c.B * c.Mics, c.ld, c.n1,
                                                                                                 c.n2, c.scales);
@@ -266,7 +410,13 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   auto forward = [&](long long g0, long long ntr, const int* row_list, cpx<T>* spec_out) {
     for (long long r0 = 0; r0 < ntr; r0 += tr_cap) {
       const long long nt = std::min(tr_cap, ntr - r0);
-      LoadSignal2<T> ld{p, bb.chirp, c.sig, c.ld, c.Mics, CP, c.n1, c.n2, row_list, g0 + r0, c.scales};
+      LoadSignal2<T> ld{pl, bb.chirp, c.sig, c.ld, c.Mics, CP, c.n1, c.n2, row_list, g0 + r0, c.scales};
+      if constexpr (std::is_same<T, float>::value) {
+        if (plan2 >= 0) {
+          f2h::conv<false>(b2, ld, StoreSpectrum<T>{pl, bb.chirp, spec_out + r0 * n}, nt, reinterpret_cast<cpxf*>(conv), c.stream, c.sms);
+          continue;
+        }
+      }
       k_colpass_fwd<T, LoadSignal2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
           p, tb, ld, nt, nullptr, conv);
       launch_rowpass<T, true, false>(p, tb, nt, conv, c.stream, 16LL * c.sms);
@@ -282,13 +432,35 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
     for (long long i0 = 0; i0 < nitems; i0 += 2 * tr_cap) {
       const long long ni = std::min(2 * tr_cap, nitems - i0);
       const long long nt = (ni + 1) / 2;
-      LoadPhat2<T> ld{p, bb.chirp, spec_in, c.pairs, c.Mics, CP, c.P, i0, nitems, ilist != nullptr, c.scales, frame0, rows_scratch, list0};
-      k_colpass_fwd<T, LoadPhat2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
-          p, tb, ld, nt, nullptr, conv);
+      LoadPhat2<T> ld{pl, bb.chirp, spec_in, c.pairs, c.Mics, CP, c.P, i0, nitems, ilist != nullptr, c.scales, frame0, rows_scratch, list0};
+      StoreCorr2<T> st{pl, bb.chirp, corr, ni, ld};
+      bool done2 = false;
+      if constexpr (std::is_same<T, float>::value) {
+        if (fast_pick) {
+          // only the window (+ margin) and per-tile row maxima leave the inverse column pass; one warp per row picks
+          float* win = reinterpret_cast<float*>(corr);
+          float* pmax = win + size_t(2 * tr_cap) * wg.wstride;
+          StoreWin2 sw{pl, b2.chirp, win, pmax, ni, ld, wg, win_tiles};
+          f2h::conv<true>(b2, ld, sw, nt, reinterpret_cast<cpxf*>(conv), c.stream, c.sms);
+          const long long o = out0 + i0;
+          k_win_pick<<<(unsigned)std::min<long long>((ni + kGT / 32 - 1) / (kGT / 32), 8LL * c.sms), kGT, 0, c.stream>>>(
+              win, pmax, win_tiles, ni, wg, o, c.k_idx, c.k_count, c.peak, c.gmax, c.flags, extra_flag);
+          count_launch(1);
+          continue;
+        }
+        if (plan2 >= 0) {
+          f2h::conv<true>(b2, ld, st, nt, reinterpret_cast<cpxf*>(conv), c.stream, c.sms);
+          count_launch(-2);      // (the four launches of this chunk are counted below)
+          done2 = true;
+        }
+      }
+      if (!done2) {
+        k_colpass_fwd<T, LoadPhat2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+            p, tb, ld, nt, nullptr, conv);
         launch_rowpass<T, true, true>(p, tb, nt, conv, c.stream, 16LL * c.sms);
-      StoreCorr2<T> st{p, bb.chirp, corr, ni, ld};
-      k_colpass_inv<T, StoreCorr2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
-          p, tb, st, nt, nullptr, conv);
+        k_colpass_inv<T, StoreCorr2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+            p, tb, st, nt, nullptr, conv);
+      }
       const long long o = ilist ? 0 : out0 + i0;
       k_pick_rows<T><<<(unsigned)std::min<long long>(ni, grid_pick), kGT, sizeof(RowPickSmem), c.stream>>>(
           corr, n, c0, ni, nullptr, ilist ? ilist + i0 : nullptr, c.pp.win_half, c.pp.dist, c.pp.method, c.pp.mult,

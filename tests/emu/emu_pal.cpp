@@ -138,6 +138,76 @@ extern "C" void emu_generic_gcc_phat(int use_double, const float* sig, long long
                             k_count, peak, gmax, flags, corr_out);
 }
 
+// ---------------------------------------------------------------- second-generation float32 convolution engine
+#include "pal_fft2.cuh"
+#include "pal_winpick.cuh"
+
+// the arbitrary-length GCC-PHAT path on the compile-time-planned engine (pal_fft2.cuh), plan `plan_id`
+// (fft2::plan_dims; its M must be >= 2n - 1); same loaders / storers / pick kernel as emu_generic_impl<float>
+extern "C" int emu_fft2_gcc_phat(int plan_id_and_mode, const float* sig, long long B, int Mics, int ld, int n1, int n2,
+                                 const int* pairs, int P, int win_half, int dist, int method, float mult,
+                                 int num_peaks, float eps, int* k_idx, int* k_count, float* peak, float* gmax,
+                                 unsigned* flags, float* corr_out) {
+  using T = float;
+  constexpr int NT = 64;
+  const int n = n1 + n2 - 1;
+  // plan_id_and_mode: plan index (or -1: the product's choice); + 100: reduced pick (StoreWin2 + win_pick_rows_body)
+  const bool fast = plan_id_and_mode >= 50;
+  int plan_id = fast ? plan_id_and_mode - 100 : plan_id_and_mode;
+  if (plan_id < 0) plan_id = fft2::choose_plan(n);
+  if (plan_id < 0 || plan_id >= fft2::kNumPlans) return -1;
+  const fft2::PlanDims pd = fft2::plan_dims(plan_id);
+  const long long M = (long long)pd.M1 * pd.M2;
+  if (M < 2LL * n - 1) return -2;
+  BluePlan p{n, int(M), pd.M1, pd.M2, 0, 0};
+  std::vector<cpxf> chirp(n), tw1(pd.M1), tw2(pd.M2), twf(M), bhat(M), scratch(M);
+  simt::launch(2, NT, 16, [&](char*) { fft2::init_tables_body(n, pd.M1, pd.M2, chirp.data(), tw1.data(), tw2.data(), twf.data()); });
+  fft2::Tables tb{chirp.data(), tw1.data(), tw2.data(), twf.data(), bhat.data()};
+  const int CP = (Mics + 1) / 2;
+  const long long rows = B * CP, items = B * P, itr = (items + 1) / 2;
+  std::vector<cpxf> conv(size_t(std::max(rows, itr)) * M), spec(size_t(rows) * n);
+  std::vector<T> corr(size_t(items) * n);
+  std::vector<float> scales(size_t(B) * Mics * 2);
+  simt::launch(2, NT, 64, [&](char* sm) { row_scale_body<NT>(sig, B * Mics, ld, n1, n2, scales.data(), sm); });
+  const LoadSignal2<T> ls{p, chirp.data(), sig, ld, Mics, CP, n1, n2, nullptr, 0, scales.data()};
+  const LoadPhat2<T> lp{p, chirp.data(), spec.data(), pairs, Mics, CP, P, 0, items, false, scales.data(), 0, nullptr, 0};
+  fft2::with_plan(plan_id, [&](auto pl) {
+    using PL = decltype(pl);
+    simt::launch(2, NT, PL::col_smem, [&](char* sm) { fft2::colpass_fwd_body<PL, NT>(tb, LoadBhat<T>{p, chirp.data()}, 1, scratch.data(), sm); });
+    simt::launch(2, NT, PL::row_smem, [&](char* sm) { fft2::rowpass_body<PL, NT, 2>(tb, 1, scratch.data(), bhat.data(), sm); });
+    simt::launch(3, NT, PL::col_smem, [&](char* sm) { fft2::colpass_fwd_body<PL, NT>(tb, ls, rows, conv.data(), sm); });
+    simt::launch(3, NT, PL::row_smem, [&](char* sm) { fft2::rowpass_body<PL, NT, 0>(tb, rows, conv.data(), nullptr, sm); });
+    simt::launch(3, NT, PL::col_smem, [&](char* sm) {
+      fft2::colpass_inv_body<PL, NT>(tb, StoreSpectrum<T>{p, chirp.data(), spec.data()}, rows, conv.data(), sm);
+    });
+    simt::launch(3, NT, PL::col_smem, [&](char* sm) { fft2::colpass_fwd_body<PL, NT>(tb, lp, itr, conv.data(), sm); });
+    simt::launch(3, NT, PL::row_smem, [&](char* sm) { fft2::rowpass_body<PL, NT, 1>(tb, itr, conv.data(), nullptr, sm); });
+    if (fast) {
+      const WinGeom wg = make_win_geom(n, n2 - 1, win_half, dist, eps);
+      const int tiles = PL::M2 / PL::TC;
+      std::vector<float> win(size_t(2 * itr) * wg.wstride, -7.f), pmax(size_t(2 * itr) * tiles, -7.f);
+      simt::launch(3, NT, PL::col_smem, [&](char* sm) {
+        fft2::colpass_inv_body<PL, NT>(tb, StoreWin2{p, chirp.data(), win.data(), pmax.data(), items, lp, wg, tiles}, itr, conv.data(), sm);
+      });
+      simt::launch(2, NT, 16, [&](char*) {
+        win_pick_rows_body<NT>(win.data(), pmax.data(), tiles, items, wg, 0, k_idx, k_count, peak, gmax, flags, 0u);
+      });
+      return;
+    }
+    simt::launch(3, NT, PL::col_smem, [&](char* sm) {
+      fft2::colpass_inv_body<PL, NT>(tb, StoreCorr2<T>{p, chirp.data(), corr.data(), items, lp}, itr, conv.data(), sm);
+    });
+  });
+  if (fast) return plan_id;
+  const int grid = 2;
+  std::vector<unsigned char> pk(size_t(grid) * ((n + 15) / 16 * 16));
+  simt::launch(grid, NT, sizeof(RowPickSmem), [&](char* sm) {
+    pick_rows_body<T, NT>(corr.data(), n, n2 - 1, items, nullptr, win_half, dist, method, mult, num_peaks, eps,
+                          pk.data(), k_idx, k_count, peak, gmax, flags, 0u, 0u, corr_out, sm);
+  });
+  return plan_id;
+}
+
 // ---------------------------------------------------------------- stage 1: image sources + renderer
 #include "pal_render.cuh"
 

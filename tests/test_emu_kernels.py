@@ -384,3 +384,72 @@ def test_numpy_norm_and_mean_rounding_order():
                 for t in x[i:]:
                     want += t
             assert float(np.mean(list(x))) == want / n
+
+
+@pytest.mark.parametrize("plan,n1,n2", [(0, 700, 650), (1, 1500, 1500), (2, 4000, 4000), (3, 5000, 6100), (4, 8000, 8000),
+                                        (5, 9000, 8200), (6, 1200, 1300), (7, 44100, 44100), (8, 3000, 2500)])
+def test_fft2_engine_every_plan_vs_oracle(plan, n1, n2):
+    """Second-generation float32 convolution engine (pal_fft2.cuh: compile-time plans M1 x M2 incl. 3 * 2^k lengths,
+    radix-3/8/16 register steps, fused row pass) through the whole GCC-PHAT path against the reference algorithm, one
+    case per plan: correlation within 1e-4 of max|corr| (float32) and the reference's lag.  Plan 7 (384 x 512 = 196608)
+    at n = 88199 is BASELINE cfg2's transform."""
+    rng = np.random.default_rng(n1 + plan)
+    x = rng.standard_normal(max(n1, n2) + 40)
+    ld = max(n1, n2)
+    sig = np.zeros((1, 2, ld), np.float32)
+    sig[0, 0, :n1] = x[7:7 + n1] + 0.1 * rng.standard_normal(n1)
+    sig[0, 1, :n2] = x[:n2] + 0.1 * rng.standard_normal(n2)
+    fs, med = 8000.0, 0.01
+    want_td, want_corr, _ = O.get_time_delays_phat(sig[0, 0, :n1].astype(np.float64), sig[0, 1, :n2].astype(np.float64), fs,
+                                                   max_expected_delay=med)
+    k, _, _, _, _, corr, used = E.fft2_gcc_phat(sig, n1, n2, np.array([[0, 1]], np.int32), O.window_half_width(n1, n2, fs, med),
+                                                 O.peak_distance(fs), plan_id=plan)
+    assert used == plan
+    assert np.abs(corr[0, 0] - want_corr).max() <= 1e-4 * np.abs(want_corr).max()
+    assert O.tdoa_from_index(int(k[0, 0, 0]), n2, fs) == want_td[0]
+
+
+def test_fft2_packs_channels_and_pairs_like_the_first_engine():
+    """4 channels / 6 pairs of 2 frames (two real sequences per complex transform in both directions, a dead channel in
+    one frame): the second-generation engine must agree with the first-generation float32 sweep to float32 rounding and
+    pick the same lags."""
+    rng = np.random.default_rng(12)
+    n = 1600
+    src = rng.standard_normal((2, n + 32))
+    sig = np.stack([np.stack([src[f, 8 * c:8 * c + n] + 0.2 * rng.standard_normal(n) for c in range(4)]) for f in range(2)]).astype(np.float32)
+    sig[1, 2] = 0.0
+    pairs = E.pairs_of(4)
+    a = E.generic_gcc_phat(sig, n, n, pairs, 80, 8)
+    b = E.fft2_gcc_phat(sig, n, n, pairs, 80, 8)
+    assert np.array_equal(a[0], b[0])
+    assert np.abs(a[5] - b[5]).max() <= 2e-6
+    assert not b[5][1, [1, 3, 5]].any()          # pairs with the dead channel: exact zeros
+
+
+@pytest.mark.parametrize("med", [0.02, 0.003, None])
+def test_reduced_window_pick_vs_oracle(med):
+    """pal_winpick.cuh: the inverse column pass keeps only the window (+ `distance` margin) and per-tile row maxima; a
+    warp picks the window maximum and flags everything a float64 look could change.  Every UNFLAGGED row must already
+    be the reference's answer, max(corr) must match on every row, and few rows may be flagged."""
+    rng = np.random.default_rng(31)
+    b, m, n, fs = 12, 4, 1400, 16000.0
+    src = rng.standard_normal((b, n + 64))
+    d = rng.integers(0, 40, size=(b, m))
+    sig = np.stack([np.stack([src[f, 40 - d[f, c]:40 - d[f, c] + n] for c in range(m)]) for f in range(b)])
+    sig = (sig + 0.3 * rng.standard_normal(sig.shape)).astype(np.float32)
+    sig[3, 1] = 0.0                                                   # a dead channel: rows of exact zeros
+    pairs = E.pairs_of(m)
+    wh = O.window_half_width(n, n, fs, med)
+    k, cnt, pk, gm, fl, _, _ = E.fft2_gcc_phat(sig, n, n, pairs, wh, O.peak_distance(fs), eps=1e-6, fast=True)
+    flagged = (fl & 1) != 0
+    for f in range(b):
+        for p, (i, j) in enumerate(pairs):
+            td, corr, _ = O.get_time_delays_phat(sig[f, i].astype(np.float64), sig[f, j].astype(np.float64), fs, max_expected_delay=med)
+            assert abs(gm[f, p] - corr.max()) <= 1e-4 * max(abs(corr.max()), 1e-30)
+            if not flagged[f, p]:
+                assert O.tdoa_from_index(int(k[f, p, 0]), n, fs) == td[0], (f, p)
+                assert abs(pk[f, p] - corr[k[f, p, 0]]) <= 1e-4 * abs(corr).max()
+    assert flagged[3, [0, 3, 4]].all()                                # zero rows: the reference's argmax fallback decides
+    # (a 97-sample window holds only noise-level samples -- the reference's window is centred on IFFT index n2-1, not
+    # on lag 0 -- and its maximum is not always clear of the mean|c| bound: those rows go to the float64 sweep)
+    assert flagged.mean() < (0.35 if med == 0.003 else 0.12)
