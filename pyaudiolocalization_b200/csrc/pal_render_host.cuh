@@ -76,15 +76,25 @@ inline size_t render_plan_scratch_bytes(int N) {
   return al(sizeof(cpxf) * size_t(L.p.M));
 }
 struct RenderPlan {
-  BluePlan p;
+  BluePlan p;              // first-generation engine (power-of-two convolution length)
   BlueBuffers<float> bb;
+  f2h::Buffers b2;         // second-generation engine (pal_fft2.cuh) when one of its plans holds 4N - 1 points
   cpxf* X;
+  BluePlan seen() const { return b2.plan >= 0 ? b2.p : p; }       // what loaders / storers look at
 };
 inline RenderPlan carve_render_plan(int N, char* mem) {
   RenderPlan rp;
-  rp.p = GenericLayout<float>(2 * N).p;
+  const GenericLayout<float> L(2 * N);
+  rp.p = L.p;
   char* b = mem;
-  carve_plan<float>(rp.p, b, rp.bb);
+  const int plan2 = use_fft2() ? fft2::choose_plan(2 * N) : -1;
+  if (plan2 >= 0) {
+    f2h::carve(2 * N, plan2, b, rp.b2);
+    rp.bb.chirp = rp.b2.chirp;
+    b = mem + L.tables;          // same budget as the first-generation tables (never smaller)
+  } else {
+    carve_plan<float>(rp.p, b, rp.bb);
+  }
   rp.X = reinterpret_cast<cpxf*>(b);
   return rp;
 }
@@ -92,6 +102,14 @@ inline RenderPlan carve_render_plan(int N, char* mem) {
 inline cudaError_t build_render_plan(const float* base, int n_base, int N, char* mem, cpxf* conv, cudaStream_t s, int sms) {
   using T = float;
   const RenderPlan rp = carve_render_plan(N, mem);
+  if (rp.b2.plan >= 0) {
+    cudaError_t e2 = f2h::fill(rp.b2, conv, s, sms);
+    if (e2 != cudaSuccess) return e2;
+    const BluePlan pl = rp.seen();
+    // X = fft(base zero-padded, 2N)                                    (signal_processing.py:69)
+    f2h::conv<false>(rp.b2, LoadSignal<T>{pl, rp.b2.chirp, base, n_base}, StoreSpectrum<T>{pl, rp.b2.chirp, rp.X}, 1, conv, s, sms);
+    return cudaGetLastError();
+  }
   const BluePlan& p = rp.p;
   plan_kernel_attributes<T>(p);
   cudaError_t e = fill_plan<T>(p, rp.bb, s, sms);
@@ -133,9 +151,11 @@ inline cudaError_t render_rows_planned(const RenderPlan& rp, int N, RenderRows r
   const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   const BlueTables<T> tb = rp.bb.tb();
-  plan_kernel_attributes<T>(p);
-  cudaFuncSetAttribute(k_colpass_fwd<T, LoadHermitian2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  cudaFuncSetAttribute(k_colpass_inv<T, StoreRender2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  if (rp.b2.plan < 0) {
+    plan_kernel_attributes<T>(p);
+    cudaFuncSetAttribute(k_colpass_fwd<T, LoadHermitian2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+    cudaFuncSetAttribute(k_colpass_inv<T, StoreRender2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  }
   const int xtiles = (N + 1 + kGT * kXferJ - 1) / (kGT * kXferJ);
   const int kcap = rr.k_stride;
   const size_t ts = 4 * size_t((kcap + 3) & ~3) + 16 * size_t(kcap) + 16;
@@ -147,6 +167,13 @@ inline cudaError_t render_rows_planned(const RenderPlan& rp, int N, RenderRows r
     k_transfer<<<(unsigned)std::min<long long>(nt * xtiles, 32LL * sms), kGT, ts, s>>>(rp.X, N, rr, r0, nt, fs, G, live);
     // two rows per inverse transform (LoadHermitian2)
     const long long ntr = (nt + 1) / 2;
+    if (rp.b2.plan >= 0) {
+      const BluePlan pl = rp.seen();
+      f2h::conv<true>(rp.b2, LoadHermitian2<T>{pl, rp.b2.chirp, G, N, nt},
+                      StoreRender2<T>{pl, rp.b2.chirp, out, N, n_keep, fade, rr, r0, nt, live}, ntr, conv, s, sms);
+      count_launch(1);
+      continue;
+    }
     k_colpass_fwd<T, LoadHermitian2<T>><<<(unsigned)std::min<long long>(ntr * tiles, 16LL * sms), kGT, cs, s>>>(
         p, tb, LoadHermitian2<T>{p, rp.bb.chirp, G, N, nt}, ntr, nullptr, conv);
     launch_rowpass<T, true, true>(p, tb, ntr, conv, s, 16LL * sms);
