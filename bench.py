@@ -265,7 +265,7 @@ def run_scenes(args, world, rank, dev, dist, torch, peak_gbs):
     cfg = sweep.SweepConfig()
     s_n = args.scenes
     n_par = min(args.scene_parity, s_n)
-    sw = sweep.SceneSweep(cfg, s_n, chunk=args.scene_chunk, device=dev, keep_signals=n_par)
+    sw = sweep.SceneSweep(cfg, s_n, chunk=args.scene_chunk, device=dev, keep_signals=n_par, solve=not args.no_scene_solve)
     steps, warm = max(1, min(args.steps, 3)), 1
     sets = [sweep.random_shoebox_scenes(s_n, cfg.mics, 5000 + rank + 1000 * i) for i in range(warm + steps)]
 
@@ -333,7 +333,9 @@ def run_scenes(args, world, rank, dev, dist, torch, peak_gbs):
             "pair_corr_per_s": world * s_n * p / (ms * 1e-3),
             "workload": "cfg5: random shoebox rooms, 8 mics, 0.25 s @ 16 kHz chirp 500 Hz, max_reflections=3, rendered then "
                         "GCC-PHAT TDOA (28 pairs, n = 7999), max_expected_delay=0.05 s; a different scene set per step",
-            "split_ms": {"render": sw.render_ms, "gcc_phat": sw.gcc_ms,
+            "ends_in": "source positions (batched bounded least squares on the device, pal_solve_positions) + gathered lag vectors"
+                       if sw.solve else "gathered lag vectors",
+            "split_ms": {"render": sw.render_ms, "gcc_phat": sw.gcc_ms, "position_solve": sw.solve_ms,
                          "note": "one extra step with events around each stage (synchronising per chunk)"},
             "gcc_scenes_per_s_per_gpu": s_n / gcc_s if gcc_s > 0 else None,
             "render_scenes_per_s_per_gpu": s_n / (sw.render_ms * 1e-3) if sw.render_ms > 0 else None,
@@ -366,7 +368,8 @@ def run_gpu_arm(args):
     strong = args.scaling == "strong"
     frames_n = max(1, args.frames // world) if strong else args.frames
     frames = synth.cfg3_frames(frames_n, MICS, seed=3000 + rank, device=dev)
-    drv = shard.ShardedTdoa(frames_n, MICS, NS, FS, MED, device=dev, gather=not args.no_gather)
+    drv = shard.ShardedTdoa(frames_n, MICS, NS, FS, MED, device=dev, gather=not args.no_gather,
+                            reserve_sms=None if args.reserve_sms < 0 else args.reserve_sms)
 
     def step():
         drv.step(frames)
@@ -415,6 +418,7 @@ def run_gpu_arm(args):
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+    drv_reserved = drv.reserved
     gathered, out = drv.last()
     if gathered is not None:   # sharded + gathered lags of the last step: this rank's slice must be its own result
         assert torch.equal(gathered[rank], out.k_idx)
@@ -481,6 +485,7 @@ def run_gpu_arm(args):
     scenes = None
     if not args.no_scenes:
         del frames, drv
+        _lib.reserve_sms(0)
         torch.cuda.empty_cache()
         scenes = run_scenes(args, world, rank, dev, dist, torch, peak_gbs)
 
@@ -514,7 +519,7 @@ def run_gpu_arm(args):
                    "l2": "inputs (4.3 GB/GPU at 16384 frames) exceed L2; no flush needed",
                    "parallelism": f"frames sharded over {world} GPU(s); one NCCL all-gather of lag indices per step"
                    if world > 1 else "1 GPU", "frames_per_s": value / PAIRS,
-                   "refined_row_fraction": refined_frac, "gather": not args.no_gather},
+                   "refined_row_fraction": refined_frac, "gather": not args.no_gather, "reserved_sms": drv_reserved},
         "clocks": clocks,
         "e2e": e2e,
         "e2e_pcm16": e2e_pcm16,
@@ -569,10 +574,12 @@ def main():
     ap.add_argument("--scenes", type=int, default=32768, help="cfg5 scenes per GPU per step of the scenes/s block")
     ap.add_argument("--scene-chunk", type=int, default=16384)
     ap.add_argument("--scene-parity", type=int, default=16, help="cfg5 scenes per rank checked against the reference")
+    ap.add_argument("--no-scene-solve", action="store_true", help="scenes block: stop at the gathered lag vectors")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-scenes", action="store_true")
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left to the concurrent all-gather (default: 2 when N > 1)")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic only: skip the NCCL all-gather (invalid as a result)")
     args = ap.parse_args()
     try:

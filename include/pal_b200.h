@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PAL_ABI_VERSION 7
+#define PAL_ABI_VERSION 8
 
 /* error codes */
 #define PAL_OK 0
@@ -234,6 +234,33 @@ int pal_sync_align(const double* sig_dev, int64_t n_scenes, int32_t n_ch, int32_
  * (NULL = ld_in), zero elsewhere; rows of float64 (io_f32 == 0) or float32 (io_f32 == 1). */
 int pal_pad_rows(const void* in_dev, int64_t n_rows, int64_t ld_in, const int32_t* lens_dev, const int32_t* pad_left_dev,
                  void* out_dev, int64_t ld_out, int32_t io_f32, void* stream);
+
+/* The kernels of this library size their (persistent) grids by the number of SMs, one resident block -- or as many as
+ * fit -- per SM.  A collective that must run WHILE they run (the all-gather of the previous step's lag indices, SURVEY.md
+ * section 8e) then finds no SM to start on until a whole kernel has drained, which turns every step boundary into a
+ * cross-rank synchronisation point.  pal_reserve_sms(n) makes every later call size its grids for (SM count - n) SMs;
+ * 0 (the default) gives the kernels the whole device.  Process-wide; no reference counterpart (the reference is
+ * single-process). */
+int pal_reserve_sms(int32_t n_sms);
+
+/* ---- batched position solve of a scene sweep ---------------------------------------
+ * Replaces, for MANY scenes at once, what main.py:246-274 does per scene on the host: the bounded least-squares fit of
+ * the source position to the pair TDOAs with the residuals of utils.py:384-405,
+ *     r_p = ((|x - m_j| - |x - m_i|) - c * td_p) * w_p,
+ * inside the box of utils.py:364-382 (dynamic_bounds_extended: microphone extent +- (buffer + max(percentile75(c |td|), 1))),
+ * which is formed on the device when lo_dev / hi_dev are NULL.  One warp per scene, float64, Levenberg-Marquardt with the
+ * step clipped to the box; x0_dev NULL starts at the array centroid (clipped like main.py:250-252).
+ *   mics_dev [S or 1][n_mics][3] (mic_stride = 0: one array shared by all scenes, else 3 * n_mics), pairs_dev [P][2],
+ *   tdoa_dev [S][P] seconds (pal_tdoa_seconds of the lag indices), weights_dev [P] or NULL (utils.py:484-497),
+ *   out_pos_dev [S][3], out_cost_dev [S] or NULL (0.5 sum r^2, scipy's `cost`), out_iter_dev [S] or NULL (iterations;
+ *   negative: stopped by max_iter).  xtol / ftol / gtol have scipy.optimize.least_squares' meaning.
+ * `localize_sound_source` keeps the reference's host solver (clustering starts, scipy trf, Differential Evolution). */
+int pal_solve_positions_workspace(int32_t n_pairs, size_t* bytes);
+int pal_solve_positions(const double* mics_dev, int64_t mic_stride, int32_t n_mics, const int32_t* pairs_dev, int32_t n_pairs,
+                        const double* tdoa_dev, const double* weights_dev, const double* x0_dev, const double* lo_dev,
+                        const double* hi_dev, int64_t n_scenes, double c_sound, double buffer, int32_t max_iter, double xtol,
+                        double ftol, double gtol, double* out_pos_dev, double* out_cost_dev, int32_t* out_iter_dev, void* ws_dev,
+                        size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PAL_B200_LIB") or os.path.join(_PKG, "libpal_b200.so")   # env override: tuning experiments only
 
-PAL_ABI_VERSION = 7
+PAL_ABI_VERSION = 8
 
 # per-row flag bits (include/pal_b200.h)
 FLAG_NEAR_TIE = 1
@@ -98,6 +98,13 @@ def lib():
     L.pal_sync_align.argtypes = [VP, I64, I32, I32, VP, VP, VP, VP, VP, VP, VP, C.c_size_t, VP]
     L.pal_pad_rows.restype = C.c_int
     L.pal_pad_rows.argtypes = [VP, I64, I64, VP, VP, VP, I64, I32, VP]
+    L.pal_reserve_sms.restype = C.c_int
+    L.pal_reserve_sms.argtypes = [I32]
+    L.pal_solve_positions_workspace.restype = C.c_int
+    L.pal_solve_positions_workspace.argtypes = [I32, SZP]
+    L.pal_solve_positions.restype = C.c_int
+    L.pal_solve_positions.argtypes = [VP, I64, I32, VP, I32, VP, VP, VP, VP, VP, I64, F64, F64, I32, F64, F64, F64, VP, VP, VP, VP,
+                                      C.c_size_t, VP]
     if L.pal_abi_version() != PAL_ABI_VERSION:
         raise PalError(f"libpal_b200.so ABI {L.pal_abi_version()} != expected {PAL_ABI_VERSION}; rebuild")
     _lib = L
@@ -110,6 +117,11 @@ def check(rc: int, what: str):
         if rc == -1:
             raise ValueError(f"{what}: {msg}")
         raise PalError(f"{what} failed ({rc}): {msg}")
+
+
+def reserve_sms(n: int) -> None:
+    """Leave `n` SMs out of the persistent grids of every later call (pal_reserve_sms), e.g. for a concurrent collective."""
+    check(lib().pal_reserve_sms(int(n)), "pal_reserve_sms")
 
 
 def launch_count() -> int:

@@ -12,6 +12,7 @@
 #include "pal_generic_host.cuh"
 #include "pal_render_host.cuh"
 #include "pal_filter.cuh"
+#include "pal_solver.cuh"
 
 using namespace pal;
 
@@ -174,13 +175,27 @@ __global__ void __launch_bounds__(kFiltThreads) k_filtfilt(const TIO* __restrict
   filtfilt_body<TIO, kFiltThreads>(x, n_rows, n, fp, work, y, smem);
 }
 
+constexpr int kSolveThreads = 128;
+__global__ void __launch_bounds__(kSolveThreads) k_solve_positions(SolveParams sp, const double* mics, long long mic_stride,
+                                                                  const int* pairs, const double* tdoa, const double* weights,
+                                                                  const double* x0, const double* lo, const double* hi,
+                                                                  long long n_scenes, double* scratch, double* out_pos,
+                                                                  double* out_cost, int* out_iter) {
+  solve_positions_body<kSolveThreads>(sp, mics, mic_stride, pairs, tdoa, weights, x0, lo, hi, n_scenes, scratch, out_pos, out_cost,
+                                      out_iter);
+}
+inline int solve_grid(int sms) { return 8 * sms; }
+
 struct DevInfo {
   int sms = 0;
   int dev = -1;
 };
+std::atomic<int> g_reserved_sms{0};      // pal_reserve_sms: SMs the persistent grids leave to other work (a collective)
 int device_info(DevInfo& d) {
   PAL_CUDA(cudaGetDevice(&d.dev));
   PAL_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.dev));
+  const int keep = g_reserved_sms.load(std::memory_order_relaxed);
+  if (keep > 0 && d.sms > 2 * keep) d.sms -= keep;
   return PAL_OK;
 }
 
@@ -249,6 +264,11 @@ extern "C" {
 int pal_abi_version(void) { return PAL_ABI_VERSION; }
 const char* pal_last_error(void) { return g_err.c_str(); }
 unsigned long long pal_launch_count(void) { return g_launches.load(); }
+int pal_reserve_sms(int32_t n_sms) {
+  if (n_sms < 0 || n_sms > 64) return fail(PAL_ERR_INVALID, "pal_reserve_sms: need 0 <= n_sms <= 64");
+  g_reserved_sms.store(n_sms);
+  return PAL_OK;
+}
 int pal_profile_hook(int32_t stage, void* start_event, void* stop_event) {
   if (stage < 0 || stage > 3) return fail(PAL_ERR_INVALID, "pal_profile_hook: stage must be 0..3");
   g_prof_stage = stage;
@@ -719,6 +739,41 @@ int pal_pad_rows(const void* in_dev, int64_t n_rows, int64_t ld_in, const int32_
   else
     palhost::k_pad_rows<double><<<grid, 256, 0, st>>>(static_cast<const double*>(in_dev), n_rows, ld_in, (int)ld_in, lens_dev,
                                                       pad_left_dev, static_cast<double*>(out_dev), ld_out);
+  ++g_launches;
+  PAL_CUDA(cudaGetLastError());
+  return PAL_OK;
+}
+
+int pal_solve_positions_workspace(int32_t n_pairs, size_t* bytes) {
+  if (n_pairs < 1 || !bytes) return fail(PAL_ERR_INVALID, "pal_solve_positions_workspace: bad argument");
+  int sms = 148;
+  DevInfo di;
+  if (device_info(di) == PAL_OK && di.sms > 0) sms = di.sms;
+  *bytes = size_t(solve_grid(sms)) * (kSolveThreads / 32) * size_t(n_pairs) * sizeof(double) + 256;
+  return PAL_OK;
+}
+
+int pal_solve_positions(const double* mics_dev, int64_t mic_stride, int32_t n_mics, const int32_t* pairs_dev, int32_t n_pairs,
+                        const double* tdoa_dev, const double* weights_dev, const double* x0_dev, const double* lo_dev,
+                        const double* hi_dev, int64_t n_scenes, double c_sound, double buffer, int32_t max_iter, double xtol,
+                        double ftol, double gtol, double* out_pos_dev, double* out_cost_dev, int32_t* out_iter_dev, void* ws_dev,
+                        size_t ws_bytes, void* stream_) {
+  if (n_scenes < 0 || n_mics < 2 || n_pairs < 1 || max_iter < 1 || !(c_sound > 0.0) || mic_stride < 0)
+    return fail(PAL_ERR_INVALID, "pal_solve_positions: need n_scenes >= 0, n_mics >= 2, n_pairs >= 1, max_iter >= 1, c_sound > 0");
+  if ((lo_dev == nullptr) != (hi_dev == nullptr)) return fail(PAL_ERR_INVALID, "pal_solve_positions: lo_dev and hi_dev go together");
+  if (n_scenes == 0) return PAL_OK;
+  if (!mics_dev || !pairs_dev || !tdoa_dev || !out_pos_dev || !ws_dev) return fail(PAL_ERR_INVALID, "pal_solve_positions: NULL device pointer");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  size_t need = 0;
+  pal_solve_positions_workspace(n_pairs, &need);
+  if (ws_bytes < need - 256) return fail(PAL_ERR_WORKSPACE, "pal_solve_positions: workspace too small");
+  const SolveParams sp{n_mics, n_pairs, max_iter, c_sound, buffer, xtol, ftol, gtol};
+  const int wpb = kSolveThreads / 32;
+  const unsigned grid = (unsigned)std::min<long long>((n_scenes + wpb - 1) / wpb, solve_grid(di.sms));
+  k_solve_positions<<<grid, kSolveThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      sp, mics_dev, mic_stride, pairs_dev, tdoa_dev, weights_dev, x0_dev, lo_dev, hi_dev, n_scenes, static_cast<double*>(ws_dev),
+      out_pos_dev, out_cost_dev, out_iter_dev);
   ++g_launches;
   PAL_CUDA(cudaGetLastError());
   return PAL_OK;

@@ -70,7 +70,7 @@ class SceneSweep:
     GCC-PHAT / TDOA pick on the rendered channels and all-gathers the lag indices of all ranks."""
 
     def __init__(self, cfg: SweepConfig, scenes_per_rank: int, chunk: int = 16384, device=None, group=None,
-                 gather: bool = True, keep_signals: int = 0, materials=None):
+                 gather: bool = True, keep_signals: int = 0, materials=None, solve: bool = False):
         from .signal_processing import generate_signal
         self.cfg = cfg
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -87,8 +87,12 @@ class SceneSweep:
         self.gathered = torch.empty((self.world, self.n, cfg.pairs, 1), dtype=torch.int32, device=self.dev) if self.do_gather else None
         self.keep = int(keep_signals)
         self.signals: Optional[torch.Tensor] = None       # the first `keep_signals` rendered scenes of the last step
-        self.render_ms = self.gcc_ms = 0.0
-        self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        # solve=True: the sweep ends in source positions (pal_solve_positions: the reference's residuals and box, one
+        # warp per scene) instead of TDOA vectors; the lag indices are gathered either way
+        self.solve = bool(solve)
+        self.positions = torch.empty((self.n, 3), dtype=torch.float64, device=self.dev) if self.solve else None
+        self.render_ms = self.gcc_ms = self.solve_ms = 0.0
+        self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         self.timed = False
 
     def step(self, sources: np.ndarray, mics: np.ndarray, planes: np.ndarray):
@@ -108,9 +112,18 @@ class SceneSweep:
             self.flags[c0:c1] = res.flags
             if self.timed:
                 self._ev[2].record()
+            if self.solve:
+                from . import solver
+                td = _g.tdoa_seconds_device(res.k_idx[..., 0].contiguous(), cfg.samples, float(cfg.fs))
+                pos, _, _ = solver.solve_positions_batched(mics[c0:c1], _g.all_pairs(cfg.mics), td, cfg.c, max_iter=60,
+                                                           xtol=1e-8, ftol=1e-8, gtol=1e-8)
+                self.positions[c0:c1] = pos
+            if self.timed:
+                self._ev[3].record()
                 torch.cuda.synchronize()
                 self.render_ms += self._ev[0].elapsed_time(self._ev[1])
                 self.gcc_ms += self._ev[1].elapsed_time(self._ev[2])
+                self.solve_ms += self._ev[2].elapsed_time(self._ev[3])
             if c0 == 0 and self.keep:
                 self.signals = sig[:self.keep].clone()
         if self.do_gather:

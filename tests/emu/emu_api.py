@@ -227,3 +227,20 @@ def pad_rows_f64(x, pad, ld_out, lens=None):
     lib().emu_pad_rows_f64(_pd(x), C.c_longlong(rows), C.c_longlong(ld), _p(ln, C.c_int), _p(pad, C.c_int), _pd(out),
                            C.c_longlong(ld_out))
     return out
+
+
+def solve_positions(mics, pairs, tdoa, c, weights=None, x0=None, lo=None, hi=None, buffer=5.0, max_iter=100, tol=1e-12):
+    mics = np.ascontiguousarray(mics, np.float64)
+    pairs = np.ascontiguousarray(pairs, np.int32)
+    tdoa = np.ascontiguousarray(tdoa, np.float64)
+    s_n, p_n = tdoa.shape
+    m = mics.shape[-2]
+    opt = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)      # noqa: E731
+    weights, x0, lo, hi = opt(weights), opt(x0), opt(lo), opt(hi)
+    pos = np.zeros((s_n, 3))
+    cost = np.zeros(s_n)
+    it = np.zeros(s_n, np.int32)
+    lib().emu_solve_positions(_pd(mics), C.c_longlong(3 * m if mics.ndim == 3 else 0), m, _p(pairs, C.c_int), p_n, _pd(tdoa),
+                              _pd(weights), _pd(x0), _pd(lo), _pd(hi), C.c_longlong(s_n), C.c_double(c), C.c_double(buffer),
+                              max_iter, C.c_double(tol), C.c_double(tol), C.c_double(tol), _pd(pos), _pd(cost), _p(it, C.c_int))
+    return pos, cost, it

@@ -348,3 +348,18 @@ extern "C" void emu_pad_rows_f64(const double* in, long long n_rows, long long l
                                  double* out, long long ld_out) {
   simt::launch(3, 64, 16, [&](char*) { pad_rows_body<double>(in, n_rows, ld_in, int(ld_in), lens, pad, out, ld_out); });
 }
+
+// ---------------------------------------------------------------- batched position solve (pal_solver.cuh)
+#include "pal_solver.cuh"
+extern "C" void emu_solve_positions(const double* mics, long long mic_stride, int n_mics, const int* pairs, int n_pairs,
+                                    const double* tdoa, const double* weights, const double* x0, const double* lo, const double* hi,
+                                    long long n_scenes, double c, double buffer, int max_iter, double xtol, double ftol, double gtol,
+                                    double* out_pos, double* out_cost, int* out_iter) {
+  constexpr int NT = 64;
+  const int grid = 2;
+  std::vector<double> scratch(size_t(grid) * (NT / 32) * n_pairs);
+  const SolveParams sp{n_mics, n_pairs, max_iter, c, buffer, xtol, ftol, gtol};
+  simt::launch(grid, NT, 16, [&](char*) {
+    solve_positions_body<NT>(sp, mics, mic_stride, pairs, tdoa, weights, x0, lo, hi, n_scenes, scratch.data(), out_pos, out_cost, out_iter);
+  });
+}

@@ -20,7 +20,7 @@ def test_library_exports_declared_symbols():
             "pal_profile_hook", "pal_launch_count"} <= set(names)
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.pal_abi_version() == 7
+    assert lib.pal_abi_version() == 8
 
 
 def test_argument_errors_without_gpu():

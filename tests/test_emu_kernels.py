@@ -453,3 +453,63 @@ def test_reduced_window_pick_vs_oracle(med):
     # (a 97-sample window holds only noise-level samples -- the reference's window is centred on IFFT index n2-1, not
     # on lag 0 -- and its maximum is not always clear of the mean|c| bound: those rows go to the float64 sweep)
     assert flagged.mean() < (0.35 if med == 0.003 else 0.12)
+
+
+def test_batched_position_solve_vs_scipy():
+    """pal_solver.cuh on the host emulation: the reference's residuals (utils.py:384-405) and dynamic box
+    (utils.py:364-382) solved per scene by one warp; positions within 1e-6 m of scipy's bounded trf run to tight
+    tolerances from the same start."""
+    from scipy.optimize import least_squares
+    rng = np.random.default_rng(17)
+    s_n, m, c = 12, 6, 343.62
+    dims = rng.uniform([3, 3, 2.5], [10, 8, 4], size=(s_n, 3))
+    mics = 0.3 + rng.uniform(size=(s_n, m, 3)) * (dims[:, None, :] - 0.6)
+    src = 0.3 + rng.uniform(size=(s_n, 3)) * (dims - 0.6)
+    pairs = E.pairs_of(m)
+    d = np.linalg.norm(src[:, None, :] - mics, axis=2)
+    td = (d[:, pairs[:, 1]] - d[:, pairs[:, 0]]) / c + 2e-6 * rng.standard_normal((s_n, len(pairs)))
+    w = rng.uniform(0.5, 1.5, size=len(pairs))
+    pos, cost, it = E.solve_positions(mics, pairs, td, c, weights=w)
+
+    def eq(x, mc, t):
+        dd = np.linalg.norm(x[None, :] - mc, axis=1)
+        return ((dd[pairs[:, 1]] - dd[pairs[:, 0]]) - c * t) * w
+    same = 0
+    for s in range(s_n):
+        margin = 5.0 + max(np.percentile(c * np.abs(td[s]), 75), 1.0)
+        lo, hi = mics[s].min(axis=0) - margin, mics[s].max(axis=0) + margin
+        ref = least_squares(eq, np.clip(mics[s].mean(axis=0), lo, hi), args=(mics[s], td[s]), bounds=(lo, hi), method="trf",
+                            ftol=1e-14, xtol=1e-14, gtol=1e-14, max_nfev=2000)
+        assert it[s] > 0
+        if abs(ref.cost - cost[s]) <= 1e-9 * ref.cost + 1e-18:
+            same += 1
+            assert np.abs(ref.x - pos[s]).max() <= 1e-6, (s, ref.x, pos[s])
+        else:
+            assert cost[s] <= ref.cost * (1 + 1e-9)
+    assert same >= s_n - 2
+
+
+def test_batched_position_solve_on_an_active_bound():
+    """Sources above the box's ceiling: the minimiser lies on the bound; the active-set step must reach the constrained
+    minimum scipy's trf finds (cost equal to 1e-9), not the clipped unconstrained step."""
+    from scipy.optimize import least_squares
+    rng = np.random.default_rng(3)
+    mics = rng.uniform([0, 0, 0], [4, 3, 2], size=(6, 3))
+    pairs = E.pairs_of(6)
+    srcs = rng.uniform([0.5, 0.5, 0.3], [3.5, 2.5, 1.7], size=(5, 3))
+    c = 343.0
+    d = np.linalg.norm(srcs[:, None, :] - mics[None], axis=2)
+    td = (d[:, pairs[:, 1]] - d[:, pairs[:, 0]]) / c
+    lo, hi = np.tile([0.0, 0.0, 0.0], (5, 1)), np.tile([4.0, 3.0, 1.0], (5, 1))
+    x0 = np.tile([2.0, 1.5, 0.5], (5, 1))
+    pos, cost, it = E.solve_positions(mics, pairs, td, c, x0=x0, lo=lo, hi=hi)
+
+    def eq(x, t):
+        dd = np.linalg.norm(x[None, :] - mics, axis=1)
+        return (dd[pairs[:, 1]] - dd[pairs[:, 0]]) - c * t
+    assert (pos >= lo - 1e-12).all() and (pos <= hi + 1e-12).all()
+    for s in range(5):
+        ref = least_squares(eq, x0[s], args=(td[s],), bounds=(lo[s], hi[s]), method="trf", ftol=1e-14, xtol=1e-14, gtol=1e-14)
+        assert cost[s] <= ref.cost + 1e-9, (s, cost[s], ref.cost)
+        if srcs[s, 2] <= 1.0:
+            assert np.abs(pos[s] - srcs[s]).max() < 1e-6
