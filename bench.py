@@ -579,7 +579,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-scenes", action="store_true")
-    ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left to the concurrent all-gather (default: 2 when N > 1)")
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left out of the persistent grids for the concurrent all-gather (default 0, see shard.ShardedTdoa)")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic only: skip the NCCL all-gather (invalid as a result)")
     args = ap.parse_args()
     try:

@@ -235,6 +235,20 @@ int pal_sync_align(const double* sig_dev, int64_t n_scenes, int32_t n_ch, int32_
 int pal_pad_rows(const void* in_dev, int64_t n_rows, int64_t ld_in, const int32_t* lens_dev, const int32_t* pad_left_dev,
                  void* out_dev, int64_t ld_out, int32_t io_f32, void* stream);
 
+/* FLOAT64 INGEST.  pal_gcc_phat_tdoa takes float32 rows: a caller that holds float64 signals (the reference computes
+ * in float64 throughout: utils.py:113-118; main.py:191 hands the float64 output of filtfilt to the pair loop) would
+ * have to round them first, and a float64 re-evaluation that starts from rounded samples cannot restore the reference's
+ * decision at a near tie -- nor its VALUES for band-limited signals, whose stop-band bins lie below the float32
+ * quantisation noise and get unit weight from PHAT.  This entry point reads float64 rows [B][M][n_samples] and runs the
+ * float64 kernels (complete find_peaks emulation, utils.py:140-181) on EVERY (frame, pair): same outputs and workspace
+ * as pal_gcc_phat_tdoa, every row carries PAL_FLAG_REFINED, prm->tie_eps / prm->refine are ignored.  It is the path of
+ * the drop-in single-call functions (utils.get_time_delays_phat, utils.phat_correlation, localize_sound_source); the
+ * batched float32 entry point is the throughput path and states its contract above: lags are the reference's for
+ * float32-representable inputs. */
+int pal_gcc_phat_tdoa_f64(const double* sig_dev, int64_t B, int32_t M, int32_t n_samples, const int32_t* pairs_dev, int32_t P,
+                          const pal_tdoa_params* prm, int32_t* k_idx_dev, int32_t* k_count_dev, float* peak_dev, float* gmax_dev,
+                          uint32_t* flags_dev, float* corr_opt_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* The kernels of this library size their (persistent) grids by the number of SMs, one resident block -- or as many as
  * fit -- per SM.  A collective that must run WHILE they run (the all-gather of the previous step's lag indices, SURVEY.md
  * section 8e) then finds no SM to start on until a whole kernel has drained, which turns every step boundary into a

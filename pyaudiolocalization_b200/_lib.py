@@ -55,6 +55,8 @@ def lib():
     L.pal_gcc_phat_tdoa.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                     C.POINTER(TdoaParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pal_gcc_phat_tdoa_f64.restype = C.c_int
+    L.pal_gcc_phat_tdoa_f64.argtypes = L.pal_gcc_phat_tdoa.argtypes
     L.pal_tdoa_seconds.restype = C.c_int
     L.pal_tdoa_seconds.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
     VP, I32, I64, F64, F32, SZP = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_float, C.POINTER(C.c_size_t)

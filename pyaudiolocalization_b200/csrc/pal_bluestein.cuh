@@ -290,14 +290,19 @@ template <typename T> PAL_DEV cpx<T> unpack_two_real(const cpx<T>* z, int n, int
 // it is packed, by an exact power of two (no rounding): scales[row] = {2^-e, 2^e}, max|x| 2^-e in [0.5, 1); an
 // all-zero row gets {0, 0}, which makes its spectrum exactly zero as in the reference (R = 0, corr = 0) instead of
 // the partner's residue.  The loaders undo the scale where absolute levels matter (the 1e-10 of utils.py:117).
-template <int NT> PAL_DEV void row_scale_body(const float* sig, long long n_rows, long long ld, int len_even, int len_odd,
-                                              float* scales /* [n_rows][2] */, char* smem) {
+template <int NT, typename TS = float>
+PAL_DEV void row_scale_body(const TS* sig, long long n_rows, long long ld, int len_even, int len_odd,
+                            float* scales /* [n_rows][2] */, char* smem) {
   float* sh = reinterpret_cast<float*>(smem);
   for (long long row = simt::bid(); row < n_rows; row += simt::nblocks()) {
     const int len = (row & 1) ? len_odd : len_even;
-    const float* x = sig + row * ld;
+    const TS* x = sig + row * ld;
     float mx = 0.f;
-    for (int j = simt::tid(); j < len; j += NT) mx = max_(mx, abs_(x[j]));
+    for (int j = simt::tid(); j < len; j += NT) {
+      const float v = abs_(float(x[j]));
+      // a float64 sample below the float32 range must still count as "not silent" (its row is not all-zero)
+      mx = max_(mx, (v == 0.f && x[j] != TS(0)) ? 1.2e-38f : v);
+    }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) mx = max_(mx, simt::shfl_xor(mx, m));
     if (simt::lane() == 0) sh[simt::warp()] = mx;
@@ -325,10 +330,10 @@ template <int NT> PAL_DEV void row_scale_body(const float* sig, long long n_rows
 // frame-major: packed transform g = t_off + t <-> frame g / CP, channels 2c and 2c+1 (c = g % CP, CP = ceil(Mics/2));
 // list mode: transform g <-> channel rows row_list[2g], row_list[2g+1].  Rows have `ld` floats; even / odd rows
 // hold len_even / len_odd valid samples (n1, n2 of a single unequal pair), zero beyond.
-template <typename T> struct LoadSignal2 {
+template <typename T, typename TS = float> struct LoadSignal2 {
   BluePlan p;
   const cpx<T>* chirp;
-  const float* sig;
+  const TS* sig;           // float32 rows, or float64 rows for float64 callers (then T is double as well)
   long long ld;
   int Mics, CP;
   int len_even, len_odd;
@@ -337,7 +342,7 @@ template <typename T> struct LoadSignal2 {
   const float* scales;     // [all rows][2] from row_scale_body
   // everything that depends on the transform only is resolved once per work unit (begin), not once per sample
   struct Ctx {
-    const float *xa, *xb;
+    const TS *xa, *xb;
     int la, lb;
     T sa, sb;
   };
@@ -364,8 +369,9 @@ template <typename T> struct LoadSignal2 {
   }
   PAL_DEV cpx<T> operator()(const Ctx& c, int j) const {
     if (j >= p.n) return cpx<T>{T(0), T(0)};
-    const T x = (j < c.la) ? T(c.xa[j] * float(c.sa)) : T(0);
-    const T y = (j < c.lb) ? T(c.xb[j] * float(c.sb)) : T(0);
+    // the scale is an exact power of two: the product is exact in the sample type
+    const T x = (j < c.la) ? T(c.xa[j] * TS(c.sa)) : T(0);
+    const T y = (j < c.lb) ? T(c.xb[j] * TS(c.sb)) : T(0);
     const cpx<T> w = chirp[j];
     return cpx<T>{fma_(x, w.x, -(y * w.y)), fma_(x, w.y, y * w.x)};
   }

@@ -106,14 +106,14 @@ bool use_tmem_kernel() {
   return on;
 }
 
-template <typename T, bool FROM_SPECTRA>
+template <typename T, bool FROM_SPECTRA, typename TS = float>
 __global__ void __launch_bounds__(kExactThreads, 3)
-    k_pair4095_exact(const float* __restrict__ sig, const cpxf* __restrict__ spec, const int* __restrict__ pairs,
+    k_pair4095_exact(const TS* __restrict__ sig, const cpxf* __restrict__ spec, const int* __restrict__ pairs,
                      int M, int P, long long n_items, const int* __restrict__ item_list,
                      const int* __restrict__ item_count, PickParams pp, int* k_idx, int* k_count, float* peak,
                      float* gmax, unsigned* flags, unsigned extra_flag, unsigned keep_mask, float* corr_out) {
   extern __shared__ __align__(128) char smem[];
-  pair4095_exact_body<T, kExactThreads, FROM_SPECTRA>(sig, spec, pairs, M, P, n_items, item_list, item_count, pp,
+  pair4095_exact_body<T, kExactThreads, FROM_SPECTRA, TS>(sig, spec, pairs, M, P, n_items, item_list, item_count, pp,
                                                       k_idx, k_count, peak, gmax, flags, extra_flag, keep_mask,
                                                       corr_out, smem);
 }
@@ -208,7 +208,7 @@ constexpr unsigned kRefineMask = PAL_FLAG_NEAR_TIE | PAL_FLAG_CHAIN | PAL_FLAG_P
 int generic_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, int n1, int n2, const int32_t* pairs_dev,
                  int32_t P, const pal_tdoa_params* prm, int32_t* k_idx_dev, int32_t* k_count_dev, float* peak_dev,
                  float* gmax_dev, uint32_t* flags_dev, float* corr_opt_dev, void* ws_dev, size_t ws_bytes,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const double* sig64_dev = nullptr) {
   if (B * (int64_t)P > 0x3fffffffLL) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: B*P too large; split the batch");
   if (reinterpret_cast<uintptr_t>(ws_dev) & 255u) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: ws_dev must be 256-byte aligned");
   if (n1 + n2 - 1 < 3) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: signals too short (n1+n2-1 < 3)");
@@ -234,6 +234,15 @@ int generic_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, 
                          corr_opt_dev, stream, di.sms, scales};
   // num_peaks > 1 is not the hot path (main.py:204 always asks for one peak): the audit only covers the first peak,
   // so every row is handed to the float64 sweep, as on the n = 4095 path
+  if (sig64_dev) {
+    // float64 rows: ONE float64 sweep over every item, complete find_peaks emulation -- no float32 stage at all
+    c.sig64 = sig64_dev;
+    c.eps = 0.f;
+    cudaError_t e64 = palhost::run_generic<double>(c, region, region_bytes, nullptr, 0, nullptr, PAL_FLAG_REFINED, 0u);
+    if (e64 != cudaSuccess) return cuda_fail(e64, "generic float64 sweep");
+    PAL_CUDA(cudaGetLastError());
+    return PAL_OK;
+  }
   const unsigned all_rows = (prm->refine && prm->num_peaks != 1) ? PAL_FLAG_NEAR_TIE : 0u;
   cudaError_t e = palhost::run_generic<float>(c, region, region_bytes, nullptr, 0, nullptr, all_rows, 0u);
   if (e != cudaSuccess) return cuda_fail(e, "generic float sweep");
@@ -427,6 +436,42 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
     }
     PAL_CUDA(cudaGetLastError());
   }
+  return PAL_OK;
+}
+
+int pal_gcc_phat_tdoa_f64(const double* sig_dev, int64_t B, int32_t M, int32_t n_samples, const int32_t* pairs_dev, int32_t P,
+                          const pal_tdoa_params* prm, int32_t* k_idx_dev, int32_t* k_count_dev, float* peak_dev, float* gmax_dev,
+                          uint32_t* flags_dev, float* corr_opt_dev, void* ws_dev, size_t ws_bytes, void* stream_) {
+  if (!prm) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa_f64: prm is NULL");
+  if (B < 0 || M < 2 || P < 1) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa_f64: need B >= 0, M >= 2, P >= 1");
+  if (B == 0) return PAL_OK;
+  if (!sig_dev || !pairs_dev || !k_idx_dev || !peak_dev || !gmax_dev || !flags_dev || !ws_dev)
+    return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa_f64: NULL device pointer");
+  if (prm->peak_dist < 1) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa_f64: peak_dist must be >= 1 (scipy: `distance` must be greater or equal to 1)");
+  if (prm->num_peaks < 1 || prm->num_peaks > 16) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa_f64: num_peaks must be in 1..16");
+  const int n1 = prm->len_first > 0 ? prm->len_first : n_samples;
+  const int n2 = prm->len_second > 0 ? prm->len_second : n_samples;
+  if (n1 > n_samples || n2 > n_samples) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa_f64: len_first/len_second exceed n_samples");
+  if (n1 != n2 && M != 2) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa_f64: unequal lengths need M == 2");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_samples != kFrame2048 || n1 != kFrame2048 || n2 != kFrame2048)
+    return generic_tdoa(nullptr, B, M, n_samples, n1, n2, pairs_dev, P, prm, k_idx_dev, k_count_dev, peak_dev, gmax_dev, flags_dev,
+                        corr_opt_dev, ws_dev, ws_bytes, stream, sig_dev);
+  if (B * (int64_t)P > 0x7fffffffLL) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa_f64: B*P exceeds 2^31-1; split the batch");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  const PickParams pp{prm->win_half, prm->peak_dist, prm->thr_method, prm->thr_mult, prm->num_peaks};
+  const size_t exd_smem = sizeof(ExactSmem<double>);
+  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_exact<double, false, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exd_smem));
+  int resident = 1;
+  PAL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_pair4095_exact<double, false, double>, kExactThreads, exd_smem));
+  const long long n_items = (long long)B * P;
+  const int ge = (int)std::min<long long>(n_items, (long long)di.sms * std::max(resident, 1));
+  k_pair4095_exact<double, false, double><<<ge, kExactThreads, exd_smem, stream>>>(
+      sig_dev, nullptr, pairs_dev, M, P, n_items, nullptr, nullptr, pp, k_idx_dev, k_count_dev, peak_dev, gmax_dev, flags_dev,
+      PAL_FLAG_REFINED, 0u, corr_opt_dev);
+  ++g_launches;
+  PAL_CUDA(cudaGetLastError());
   return PAL_OK;
 }
 

@@ -66,10 +66,11 @@ __global__ void __launch_bounds__(kGT) k_win_pick(const float* win, const float*
                                                   unsigned* flags, unsigned extra_flag) {
   win_pick_rows_body<kGT>(win, pmax, tiles, n_rows, g, item0, k_idx, k_count, peak, gmax, flags, extra_flag);
 }
-__global__ void __launch_bounds__(kGT) k_row_scales(const float* sig, long long n_rows, long long ld, int len_even, int len_odd,
+template <typename TS>
+__global__ void __launch_bounds__(kGT) k_row_scales(const TS* sig, long long n_rows, long long ld, int len_even, int len_odd,
                                                     float* scales) {
   __shared__ float sh[kGT / 32];
-  row_scale_body<kGT>(sig, n_rows, ld, len_even, len_odd, scales, reinterpret_cast<char*>(sh));
+  row_scale_body<kGT, TS>(sig, n_rows, ld, len_even, len_odd, scales, reinterpret_cast<char*>(sh));
 }
 // flagged item -> its two channel rows (for the float64 re-evaluation)
 __global__ void k_rows_of_items(const int* item_list, const int* count, const int* pairs, int Mics, int P, int* rows) {
@@ -122,6 +123,7 @@ struct GenericCall {
   cudaStream_t stream;
   int sms;
   float* scales;     // [B * Mics][2] per-row power-of-two normalisation (filled by the first sweep, reused by the float64 one)
+  const double* sig64 = nullptr;   // float64 rows (pal_gcc_phat_tdoa_f64): the float64 sweep then reads these instead of `sig`
 };
 
 inline void count_launch(int k = 1) {
@@ -401,8 +403,12 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   const bool fast_pick = plan2 >= 0 && !list && c.pp.num_peaks == 1 && !c.corr_out && c.eps > 0.f && use_fast_pick() &&
                          size_t(wg.wstride + win_tiles) * sizeof(float) <= al(sizeof(T) * size_t(n));
   if (!list) {
-    k_row_scales<<<(unsigned)std::min<long long>(c.B * c.Mics, 16LL * c.sms), kGT, 0, c.stream>>>(c.sig, c.B * c.Mics, c.ld, c.n1,
-                                                                                                c.n2, c.scales);
+    if (c.sig64)
+      k_row_scales<double><<<(unsigned)std::min<long long>(c.B * c.Mics, 16LL * c.sms), kGT, 0, c.stream>>>(c.sig64, c.B * c.Mics, c.ld,
+                                                                                                          c.n1, c.n2, c.scales);
+    else
+      k_row_scales<float><<<(unsigned)std::min<long long>(c.B * c.Mics, 16LL * c.sms), kGT, 0, c.stream>>>(c.sig, c.B * c.Mics, c.ld, c.n1,
+                                                                                                         c.n2, c.scales);
     count_launch();
   }
 
@@ -410,6 +416,20 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   auto forward = [&](long long g0, long long ntr, const int* row_list, cpx<T>* spec_out) {
     for (long long r0 = 0; r0 < ntr; r0 += tr_cap) {
       const long long nt = std::min(tr_cap, ntr - r0);
+      if constexpr (std::is_same<T, double>::value) {
+        if (c.sig64) {       // float64 rows straight into the float64 transforms
+          LoadSignal2<T, double> ld64{pl, bb.chirp, c.sig64, c.ld, c.Mics, CP, c.n1, c.n2, row_list, g0 + r0, c.scales};
+          cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignal2<T, double>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+          k_colpass_fwd<T, LoadSignal2<T, double>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+              p, tb, ld64, nt, nullptr, conv);
+          launch_rowpass<T, true, false>(p, tb, nt, conv, c.stream, 16LL * c.sms);
+          StoreSpectrum<T> st64{p, bb.chirp, spec_out + r0 * n};
+          k_colpass_inv<T, StoreSpectrum<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+              p, tb, st64, nt, nullptr, conv);
+          count_launch(3);
+          continue;
+        }
+      }
       LoadSignal2<T> ld{pl, bb.chirp, c.sig, c.ld, c.Mics, CP, c.n1, c.n2, row_list, g0 + r0, c.scales};
       if constexpr (std::is_same<T, float>::value) {
         if (plan2 >= 0) {

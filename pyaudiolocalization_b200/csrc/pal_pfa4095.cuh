@@ -319,8 +319,9 @@ struct PickParams {
 // items: either all B*P (item_list == nullptr) or the compacted list of flagged items.
 // FROM_SPECTRA: read the fp32 spectra written by fwd4095; otherwise transform the two raw
 // frames here in precision T (the float64 refinement never sees an fp32-rounded spectrum).
-template <typename T, int NT, bool FROM_SPECTRA>
-PAL_DEV void pair4095_exact_body(const float* sig, const cpxf* spec, const int* pairs, int M, int P,
+// TS: sample type of `sig` (float: the batched float32 path; double: float64 callers, pal_gcc_phat_tdoa_f64)
+template <typename T, int NT, bool FROM_SPECTRA, typename TS = float>
+PAL_DEV void pair4095_exact_body(const TS* sig, const cpxf* spec, const int* pairs, int M, int P,
                                  long long n_items, const int* item_list, const int* item_count,
                                  PickParams pp, int* k_idx, int* k_count, float* peak, float* gmax,
                                  unsigned* flags, unsigned extra_flag, unsigned keep_mask, float* corr_out,
@@ -353,8 +354,8 @@ PAL_DEV void pair4095_exact_body(const float* sig, const cpxf* spec, const int* 
         if (e != 0) { sm->a_re[kN4095 - L] = rr; sm->a_im[kN4095 - L] = -ri; }      // loc(n - e) = n - loc(e)
       }
     } else {
-      const float* xi = sig + (frame * M + mi) * kFrame2048;
-      const float* xj = sig + (frame * M + mj) * kFrame2048;
+      const TS* xi = sig + (frame * M + mi) * kFrame2048;
+      const TS* xj = sig + (frame * M + mj) * kFrame2048;
       for (int k = tid; k < 4096; k += NT) {
         sm->a_re[k] = (k < kFrame2048) ? T(xi[k]) : T(0);
         sm->a_im[k] = (k < kFrame2048) ? T(xj[k]) : T(0);

@@ -113,7 +113,8 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
                           max_workspace_bytes: Optional[int] = None,
                           out: Optional["TdoaBatch"] = None, pairs_dev: Optional[torch.Tensor] = None,
                           lengths: Optional[tuple] = None) -> TdoaBatch:
-    """frames: [B, M, N] float32 CUDA tensor.  Same options as utils.get_time_delays_phat
+    """frames: [B, M, N] float32 CUDA tensor (float64: every row runs through the float64 kernels, the reference's own
+    arithmetic type -- the path of the drop-in single-call functions).  Same options as utils.get_time_delays_phat
     (utils.py:121-127), applied to every pair of every frame.  Everything stays on the device
     and on the current CUDA stream.  N == 2048 (n = 4095) takes the fused prime-factor kernels
     and never synchronises; other lengths take the Bluestein path.  `lengths=(n1, n2)` (M == 2
@@ -124,7 +125,10 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
     if frames.dim() != 3:
         raise ValueError("frames must have shape [B, M, N]")
     frames = frames.contiguous()
-    if frames.dtype != torch.float32:
+    # float64 frames take the float64 ingest (pal_gcc_phat_tdoa_f64): every row through the float64 kernels, the
+    # reference's arithmetic type; anything else is the float32 throughput path
+    f64 = frames.dtype == torch.float64
+    if not f64 and frames.dtype != torch.float32:
         frames = frames.float()
     b, m, n = frames.shape
     dev = frames.device
@@ -160,7 +164,8 @@ def gcc_phat_tdoa_batched(frames: torch.Tensor, fs: float, max_expected_delay: O
     ws_len = workspace.numel() - (ws_ptr - workspace.data_ptr())
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = _lib.lib().pal_gcc_phat_tdoa(frames.data_ptr(), b, m, n, pairs_dev.data_ptr(), p, C.byref(prm),
+        entry = _lib.lib().pal_gcc_phat_tdoa_f64 if f64 else _lib.lib().pal_gcc_phat_tdoa
+        rc = entry(frames.data_ptr(), b, m, n, pairs_dev.data_ptr(), p, C.byref(prm),
                                           k_idx.data_ptr(), k_count.data_ptr(), peak.data_ptr(), gmax.data_ptr(),
                                           flags.data_ptr(), corr.data_ptr() if corr is not None else None,
                                           ws_ptr, ws_len, stream)

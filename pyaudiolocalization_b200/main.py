@@ -182,7 +182,9 @@ def localize_sound_source(config, calibration_data=None, audio_files=None, use_s
     # ---- stage 2 on the GPU: every pair in one call (main.py:202-228) ------------------------
     m = len(filtered)
     n = len(filtered[0])
-    frames = torch.from_numpy(np.ascontiguousarray(np.stack(filtered).astype(np.float32))[None]).to(_s._dev())
+    # float64 rows -> float64 ingest (pal_gcc_phat_tdoa_f64): the filtered channels are band-limited, and PHAT gives the
+    # stop-band bins unit weight -- rounding them to float32 first would change the correlation, not just its last digits
+    frames = torch.from_numpy(np.ascontiguousarray(np.stack(filtered).astype(np.float64))[None]).to(_s._dev())
     res = _g.gcc_phat_tdoa_batched(frames, fs, max_expected_delay, num_peaks=1,
                                    return_corr=bool(analyze_correlation or visualize_correlation))
     td_all = res.tdoa_seconds()[0, :, 0]

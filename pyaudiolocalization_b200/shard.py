@@ -88,10 +88,11 @@ class ShardedTdoa:
         full, _ = g.workspace_bytes(self.b, self.m, self.n, self.p)
         self.ws = torch.empty(full + 256, dtype=torch.uint8, device=self.dev)
         self.do_gather = bool(gather) and self.world > 1
-        # The asynchronous all-gather of step i has to find an SM while the persistent kernels of step i+1 hold the
-        # device; otherwise it only runs once a kernel has drained and every step boundary becomes a cross-rank
-        # synchronisation point (measured: +2.3 ms per 48 ms step at 2 GPUs).  Two SMs are left to it by default.
-        self.reserved = (2 if self.do_gather else 0) if reserve_sms is None else int(reserve_sms)
+        # `reserve_sms` leaves SMs out of the persistent grids for the concurrent all-gather (pal_reserve_sms).  Measured
+        # on 2 x B200 (profiles/r2d_reserved_sms.md): 48.25 ms per step with 0 reserved SMs against 48.0 ms without any
+        # gather and 47.95 ms on one GPU; 2 reserved SMs cost 0.7 ms, 4 cost 1.5 ms, an NCCL_MAX_CTAS cap costs up to
+        # 5.6 ms.  The gather already hides behind the next step, so the default is 0.
+        self.reserved = 0 if reserve_sms is None else int(reserve_sms)
         _lib.reserve_sms(self.reserved)
         nbuf = 2 if self.do_gather else 1
         self.outs = [self._new_out() for _ in range(nbuf)]
