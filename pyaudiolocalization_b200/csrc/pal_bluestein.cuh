@@ -425,6 +425,8 @@ template <typename T> struct LoadPhat2 {
   long long frame_base;    // frame-major: global index of resident frame 0
   const int* row_list;     // list mode: global channel rows of every flagged item ...
   long long item_base;     // ... and the list position of resident item 0
+  const int* n_items_dev = nullptr;   // when set, the resident item count is read on the device (no host round trip)
+  PAL_DEV long long items() const { return n_items_dev ? (long long)*n_items_dev : n_items; }
   // one item: where its two packed spectra live, which half of each it is, and the levels of its two channels
   struct Item {
     const cpx<T>*zi, *zj;
@@ -433,7 +435,7 @@ template <typename T> struct LoadPhat2 {
   };
   PAL_DEV Item item(long long it) const {
     Item m;
-    m.present = it < n_items;
+    m.present = it < items();
     if (!m.present) {
       m.zi = m.zj = spec;
       m.oi = m.oj = false;
@@ -521,7 +523,7 @@ template <typename T> struct StoreCorr2 {
     const long long ia = src.t_off + 2 * t;
     Ctx c;
     c.ra = corr + (2 * t) * p.n;
-    c.rb = (2 * t + 1 < n_rows) ? c.ra + p.n : nullptr;
+    c.rb = (2 * t + 1 < (src.n_items_dev ? src.items() : n_rows)) ? c.ra + p.n : nullptr;
     c.dead_a = src.item(ia).dead;
     c.dead_b = src.item(ia + 1).dead;
     return c;

@@ -251,6 +251,26 @@ int generic_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, 
   const long long n_items = (long long)B * P;
   k_compact_flagged<<<(unsigned)((n_items + 255) / 256), 256, 0, stream>>>(flags_dev, n_items, 0, PAL_FLAG_NEAR_TIE, list, count);
   ++g_launches;
+  // float64 re-evaluation of the flagged rows.  The list length stays on the device: the sweep is issued in rounds
+  // sized for the worst case, and rounds beyond the real count find nothing to do (a few microseconds each).  Only
+  // when the workspace is so small that this would take more than kMaxDevRounds rounds is the count read back.
+  {
+    palhost::k_rows_of_items<<<(unsigned)((n_items + 255) / 256), 256, 0, stream>>>(list, count, pairs_dev, M, P, rows);
+    ++g_launches;
+    palhost::GenericCall cd = c;
+    cd.eps = 0.f;
+    cd.corr_out = nullptr;
+    int* dev_items = count + 1;
+    int* dev_packed = count + 1 + palhost::kMaxDevRounds;
+    e = palhost::run_generic<double>(cd, region, region_bytes, list, (int)n_items, rows, PAL_FLAG_REFINED, kRefineMask, count,
+                                     dev_items, dev_packed);
+    if (e == cudaSuccess) {
+      PAL_CUDA(cudaGetLastError());
+      return PAL_OK;
+    }
+    if (e != cudaErrorNotSupported) return cuda_fail(e, "generic float64 sweep");
+    (void)cudaGetLastError();
+  }
   int h_count = 0;
   PAL_CUDA(cudaMemcpyAsync(&h_count, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
   PAL_CUDA(cudaStreamSynchronize(stream));

@@ -72,6 +72,19 @@ __global__ void __launch_bounds__(kGT) k_row_scales(const TS* sig, long long n_r
   __shared__ float sh[kGT / 32];
   row_scale_body<kGT, TS>(sig, n_rows, ld, len_even, len_odd, scales, reinterpret_cast<char*>(sh));
 }
+// device-side chunking of a list whose length only the device knows: round k of `chunk` items holds
+// items[k] = clamp(count - k * chunk, 0, chunk) items = packed[k] = ceil(items[k] / 2) packed inverse transforms
+__global__ void k_chunk_counts(const int* count, int chunk, int rounds, int* items, int* packed) {
+  const int k = threadIdx.x;
+  if (k < rounds) {
+    long long left = (long long)*count - (long long)k * chunk;
+    left = left < 0 ? 0 : (left > chunk ? chunk : left);
+    items[k] = int(left);
+    packed[k] = int((left + 1) / 2);
+  }
+}
+constexpr int kMaxDevRounds = 30;    // rounds of the device-counted float64 sweep (two int arrays next to the counter)
+
 // flagged item -> its two channel rows (for the float64 re-evaluation)
 __global__ void k_rows_of_items(const int* item_list, const int* count, const int* pairs, int Mics, int P, int* rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,18 +183,21 @@ constexpr int kWideRows = 32;
 template <typename T> inline bool wide_rows(const BluePlan& p) {
   return PAL_WIDE_ROWS && sizeof(T) == 4 && p.M2 <= 128 && p.M1 >= kWideRows;
 }
+// `n_tr_dev` != nullptr: the transform count is read on the device (nt then only sizes the grid)
 template <typename T, bool CONV, bool CONJ>
-inline void launch_rowpass(const BluePlan& p, const BlueTables<T>& tb, long long nt, cpx<T>* buf, cudaStream_t s, long long max_blocks) {
+inline void launch_rowpass(const BluePlan& p, const BlueTables<T>& tb, long long nt, cpx<T>* buf, cudaStream_t s, long long max_blocks,
+                           const int* n_tr_dev = nullptr) {
+  const long long n_arg = n_tr_dev ? 1 : nt;
   if (wide_rows<T>(p)) {
     const size_t sm = fft_tile_smem(sizeof(T), p.M2, kWideRows + 1);
     auto kern = k_rowpass<T, CONV, CONJ, kWideRows>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    kern<<<(unsigned)std::min<long long>(nt * (p.M1 / kWideRows), max_blocks), kGT, sm, s>>>(p, tb, nt, nullptr, buf);
+    kern<<<(unsigned)std::min<long long>(nt * (p.M1 / kWideRows), max_blocks), kGT, sm, s>>>(p, tb, n_arg, n_tr_dev, buf);
   } else {
     const size_t sm = row_smem<T>(p);
     auto kern = k_rowpass<T, CONV, CONJ>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    kern<<<(unsigned)std::min<long long>(nt * row_units<T>(p), max_blocks), kGT, sm, s>>>(p, tb, nt, nullptr, buf);
+    kern<<<(unsigned)std::min<long long>(nt * row_units<T>(p), max_blocks), kGT, sm, s>>>(p, tb, n_arg, n_tr_dev, buf);
   }
 }
 
@@ -342,9 +358,14 @@ template <typename T> size_t generic_full_bytes(int n, long long B, int Mics, in
 // Two real sequences share every complex transform (pal_bluestein.cuh): the channels of a frame are
 // transformed in pairs (CP = ceil(Mics/2) packed spectrum rows per frame; in list mode the two channels of
 // an item form one row), and every inverse transform yields the correlation rows of two items.
+// `count_dev` (list mode only): the list length lives on the device.  n_list is then an upper bound, the sweep runs in
+// rounds whose sizes are derived on the device (k_chunk_counts -> dev_items / dev_packed, kMaxDevRounds ints each) and
+// every kernel reads its own count: no host round trip.  Returns cudaErrorNotSupported when the workspace would need
+// more than kMaxDevRounds rounds (the caller then reads the count back and uses the host-counted form).
 template <typename T>
 cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const int* list, int n_list, int* rows_scratch,
-                        unsigned extra_flag, unsigned keep_mask) {
+                        unsigned extra_flag, unsigned keep_mask, const int* count_dev = nullptr, int* dev_items = nullptr,
+                        int* dev_packed = nullptr) {
   const int n = c.n1 + c.n2 - 1;
   GenericLayout<T> L(n);
   const BluePlan p = L.p;
@@ -381,8 +402,16 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   T* corr = reinterpret_cast<T*>(base);
   base += 2 * tr_cap * al(sizeof(T) * size_t(n));
   rem = ws_bytes - size_t(base - ws);
-  const long long row_cap = (long long)(rem / L.per_row);
+  long long row_cap = (long long)(rem / L.per_row);
   if (row_cap < min_rows) return cudaErrorMemoryAllocation;
+  if (count_dev) {
+    // one round = one pass of every kernel: forward transforms (one per item) and inverse transforms share the chunk
+    const long long chunk = std::min(tr_cap, row_cap);
+    if ((n_list + chunk - 1) / chunk > kMaxDevRounds) return cudaErrorNotSupported;
+    tr_cap = row_cap = chunk;
+    k_chunk_counts<<<1, 32, 0, c.stream>>>(count_dev, int(chunk), int((n_list + chunk - 1) / chunk), dev_items, dev_packed);
+    count_launch();
+  }
   cpx<T>* spec = reinterpret_cast<cpx<T>*>(base);
   // note: conv rows / corr rows / spectrum rows are addressed densely (t * M, t * n), the al()
   // padding above only makes the regions start aligned
@@ -413,9 +442,21 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   }
 
   // packed forward transforms g0 .. g0+ntr-1 (global packed index; list mode: flagged-item index) -> spec_out rows 0..
+  int dev_round = 0;      // device-counted list mode: index of the round being issued
   auto forward = [&](long long g0, long long ntr, const int* row_list, cpx<T>* spec_out) {
     for (long long r0 = 0; r0 < ntr; r0 += tr_cap) {
       const long long nt = std::min(tr_cap, ntr - r0);
+      if (count_dev) {       // every kernel of the round reads its transform count on the device
+        LoadSignal2<T> ldd{pl, bb.chirp, c.sig, c.ld, c.Mics, CP, c.n1, c.n2, row_list, g0 + r0, c.scales};
+        k_colpass_fwd<T, LoadSignal2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+            p, tb, ldd, 1, dev_items + dev_round, conv);
+        launch_rowpass<T, true, false>(p, tb, nt, conv, c.stream, 16LL * c.sms, dev_items + dev_round);
+        StoreSpectrum<T> std_{p, bb.chirp, spec_out + r0 * n};
+        k_colpass_inv<T, StoreSpectrum<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+            p, tb, std_, 1, dev_items + dev_round, conv);
+        count_launch(3);
+        continue;
+      }
       if constexpr (std::is_same<T, double>::value) {
         if (c.sig64) {       // float64 rows straight into the float64 transforms
           LoadSignal2<T, double> ld64{pl, bb.chirp, c.sig64, c.ld, c.Mics, CP, c.n1, c.n2, row_list, g0 + r0, c.scales};
@@ -453,8 +494,21 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
       const long long ni = std::min(2 * tr_cap, nitems - i0);
       const long long nt = (ni + 1) / 2;
       LoadPhat2<T> ld{pl, bb.chirp, spec_in, c.pairs, c.Mics, CP, c.P, i0, nitems, ilist != nullptr, c.scales, frame0, rows_scratch, list0};
+      if (count_dev) ld.n_items_dev = dev_items + dev_round;
       StoreCorr2<T> st{pl, bb.chirp, corr, ni, ld};
       bool done2 = false;
+      if (count_dev) {
+        k_colpass_fwd<T, LoadPhat2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+            p, tb, ld, 1, dev_packed + dev_round, conv);
+        launch_rowpass<T, true, true>(p, tb, nt, conv, c.stream, 16LL * c.sms, dev_packed + dev_round);
+        k_colpass_inv<T, StoreCorr2<T>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
+            p, tb, st, 1, dev_packed + dev_round, conv);
+        k_pick_rows<T><<<(unsigned)std::min<long long>(ni, grid_pick), kGT, sizeof(RowPickSmem), c.stream>>>(
+            corr, n, c0, ni, dev_items + dev_round, ilist + i0, c.pp.win_half, c.pp.dist, c.pp.method, c.pp.mult, c.pp.num_peaks,
+            c.eps, pkmap, c.k_idx, c.k_count, c.peak, c.gmax, c.flags, extra_flag, keep_mask, nullptr);
+        count_launch(4);
+        continue;
+      }
       if constexpr (std::is_same<T, float>::value) {
         if (fast_pick) {
           // only the window (+ margin) and per-tile row maxima leave the inverse column pass; one warp per row picks
@@ -504,6 +558,7 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
       const long long ni = std::min<long long>(ichunk, n_list - i0);
       forward(i0, ni, rows_scratch, spec);
       inverse(ni, spec, 0, list + i0, 0, i0);
+      ++dev_round;
     }
   }
   return cudaGetLastError();

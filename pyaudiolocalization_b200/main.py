@@ -70,6 +70,37 @@ def simulate_signals_device(source_pos, mic_positions, fs, c, duration=1.0, sign
                            trim_to_duration=trim_to_duration)
 
 
+def prepare_scenes_batched(source_positions, mic_positions, fs, c, duration=1.0, signal_type='sine', freq=1000,
+                           reflective_planes=None, material_properties=None, max_reflections=2,
+                           absorption_threshold=0.01, trim_to_duration=True, base_signal=None):
+    """Geometry half of simulate_scenes_batched (image sources, path tables, transform lengths; ends with the
+    renderer's one read-back).  Returns a scene.RenderJob for `scene.execute_render`; everything is issued on the
+    current stream, so a sweep can prepare its next batch on a side stream while the GPU renders the current one."""
+    base = generate_signal(signal_type, fs, duration, freq) if base_signal is None else base_signal
+    mats = material_properties
+    planes = list(reflective_planes or [])
+    srcs = np.asarray(source_positions, dtype=np.float64).reshape(-1, 3)
+    dev = _s._dev()
+    if max_reflections >= 1 and planes:
+        k_max = None
+        while True:
+            pos, mat, cnt, table = _s.image_sources_batched(srcs, planes, max_reflections, freq, mats, mic_positions,
+                                                            absorption_threshold, 6, k_max)
+            try:
+                return _s.prepare_render(base, srcs, pos, mat, cnt, mic_positions, fs, c, duration, freq, table,
+                                         trim_to_duration=trim_to_duration)
+            except RuntimeError as e:          # image list overflow: retry with a larger k_max
+                if "overflowed k_max" not in str(e):
+                    raise
+                k_max = pos.shape[1] * 4
+    table = _s.MaterialTable(mats, dev)
+    pos = torch.zeros((len(srcs), 1, 3), dtype=torch.float64, device=dev)
+    mat = torch.zeros((len(srcs), 1), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((len(srcs),), dtype=torch.int32, device=dev)
+    return _s.prepare_render(base, srcs, pos, mat, cnt, mic_positions, fs, c, duration, freq, table,
+                             trim_to_duration=trim_to_duration)
+
+
 def simulate_scenes_batched(source_positions, mic_positions, fs, c, duration=1.0, signal_type='sine', freq=1000,
                             reflective_planes=None, material_properties=None, max_reflections=2,
                             absorption_threshold=0.01, trim_to_duration=True, base_signal=None,
@@ -81,26 +112,9 @@ def simulate_scenes_batched(source_positions, mic_positions, fs, c, duration=1.0
     functions, inverse transforms and the normalise / compress epilogue all run batched.  A sweep that calls
     this batch after batch passes one `scene.RenderPlanCache()` (and a device-resident `base_signal`) so that the
     per-length tables of the renderer are built once."""
-    base = generate_signal(signal_type, fs, duration, freq) if base_signal is None else base_signal
-    mats = material_properties
-    planes = list(reflective_planes or [])
-    srcs = np.asarray(source_positions, dtype=np.float64).reshape(-1, 3)
-    dev = _s._dev()
-    if max_reflections >= 1 and planes:
-        k_max = None
-        while True:
-            pos, mat, cnt, table = _s.image_sources_batched(srcs, planes, max_reflections, freq, mats, mic_positions,
-                                                            absorption_threshold, 6, k_max)
-            if not bool((cnt < 0).any().item()):
-                break
-            k_max = pos.shape[1] * 4
-    else:
-        table = _s.MaterialTable(mats, dev)
-        pos = torch.zeros((len(srcs), 1, 3), dtype=torch.float64, device=dev)
-        mat = torch.zeros((len(srcs), 1), dtype=torch.int32, device=dev)
-        cnt = torch.zeros((len(srcs),), dtype=torch.int32, device=dev)
-    return _s.render_scenes_batched(base, srcs, pos, mat, cnt, mic_positions, fs, c, duration, freq, table,
-                                    trim_to_duration=trim_to_duration, plan_cache=plan_cache)
+    job = prepare_scenes_batched(source_positions, mic_positions, fs, c, duration, signal_type, freq, reflective_planes,
+                                 material_properties, max_reflections, absorption_threshold, trim_to_duration, base_signal)
+    return _s.execute_render(job, plan_cache=plan_cache)
 
 
 def simulate_signals_with_multipath(source_pos, mic_positions, fs, c, duration=1.0, signal_type='sine', freq=1000,

@@ -239,19 +239,19 @@ def render_scene(base_signal, source_pos, img_pos: torch.Tensor, img_mat: torch.
     return out
 
 
-def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: torch.Tensor, img_count: torch.Tensor,
-                          mic_positions, fs: float, c: float, duration: float, freq: float, table: MaterialTable,
-                          trim_to_duration: bool = True, normalise: bool = True,
-                          max_workspace_bytes: int = 4 << 30, max_streams: int = 16,
-                          plan_cache: Optional[RenderPlanCache] = None) -> torch.Tensor:
-    """main.py:94-122 for MANY scenes that share fs / duration / base signal: sources [S, 3],
-    img_pos [S, K, 3], img_mat [S, K], img_count [S] (output of image_sources_batched),
-    mic_positions [M, 3] or [S, M, 3].  Returns [S, M, n_keep] float32 on the device.
+class RenderJob:
+    """Everything `execute_render` needs, produced by `prepare_render`: the per-path delay / gain tables on the device and
+    the host-side bucketing of the scenes by transform length.  Preparing ends with the one read-back the renderer cannot
+    avoid (N = int((duration + max delay) * fs) is formed in float64 on the host, main.py:102); executing only enqueues
+    work.  A sweep prepares batch c+1 on a side stream while the GPU is busy with batch c (sweep.SceneSweep)."""
+    __slots__ = ("base", "n_base", "src", "mics", "m", "tau", "gain", "pcount", "k_stride", "totals", "n_keep", "s_n", "fs",
+                 "order", "uniq", "bounds", "idx_dev", "dev", "done")
 
-    The transform length N = int((duration + max delay) * fs) (main.py:102) differs from scene to
-    scene; delays are computed for all scenes in one launch, N is formed on the host in float64
-    exactly like the reference (one small read-back), and scenes that share N are rendered together.
-    `plan_cache` (RenderPlanCache) keeps the per-N tables between calls that share the base signal."""
+
+def prepare_render(base_signal, sources, img_pos: torch.Tensor, img_mat: torch.Tensor, img_count: torch.Tensor, mic_positions,
+                   fs: float, c: float, duration: float, freq: float, table: MaterialTable,
+                   trim_to_duration: bool = True) -> RenderJob:
+    """Geometry half of render_scenes_batched: path tables for all scenes in one launch, transform lengths, buckets."""
     dev = _dev()
     L = _lib.lib()
     if 'air' not in table.index:
@@ -272,8 +272,6 @@ def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: 
     if img_mat.shape[1] != img_pos.shape[1]:
         raise ValueError("render_scenes_batched: img_pos and img_mat disagree on K")
     k_max = int(img_pos.shape[1])
-    if (img_count < 0).any().item():
-        raise RuntimeError("image_sources_batched overflowed k_max for some scene; call it again with a larger k_max")
     k_stride = k_max + 1
     tau = torch.empty((s_n, m, k_stride), dtype=torch.float64, device=dev)
     gain = torch.empty((s_n, m, k_stride), dtype=torch.float64, device=dev)
@@ -287,7 +285,11 @@ def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: 
     base = torch.as_tensor(np.ascontiguousarray(np.asarray(base_signal, dtype=np.float32))).to(dev) \
         if not isinstance(base_signal, torch.Tensor) else base_signal.to(dev, torch.float32).contiguous()
     n_base = base.numel()
-    totals = ((duration + max_tau.cpu().numpy()) * fs).astype(np.int64)          # main.py:102, float64 then int()
+    # ONE read-back: overflow marks of the image lists and the largest delay per scene
+    stats = torch.cat([max_tau, img_count.to(torch.float64)]).cpu().numpy()
+    if (stats[s_n:] < 0).any():
+        raise RuntimeError("image_sources_batched overflowed k_max for some scene; call it again with a larger k_max")
+    totals = ((duration + stats[:s_n]) * fs).astype(np.int64)          # main.py:102, float64 then int()
     if (totals < n_base).any():
         raise ValueError("negative dimensions are not allowed")
     if (np.floor(0.01 * totals) < 1).any():
@@ -295,16 +297,30 @@ def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: 
     n_dur = int(duration * fs)
     if not trim_to_duration and len(np.unique(totals)) > 1:
         raise ValueError("trim_to_duration=False gives rows of different length; render such scenes one by one")
-    n_keep = min(n_dur, int(totals.min())) if trim_to_duration else int(totals[0])
+    job = RenderJob()
+    job.base, job.n_base, job.src, job.mics, job.m = base, n_base, src, mics, m
+    job.tau, job.gain, job.pcount, job.k_stride, job.totals = tau, gain, pcount, k_stride, totals
+    job.n_keep = min(n_dur, int(totals.min())) if trim_to_duration else int(totals[0])
+    job.s_n, job.fs, job.dev = s_n, float(fs), dev
+    job.order = np.argsort(totals, kind="stable")
+    job.uniq, starts = np.unique(totals[job.order], return_index=True)
+    job.bounds = list(starts) + [len(job.order)]
+    job.idx_dev = torch.as_tensor(job.order.astype(np.int64)).to(dev)
+    return job
+
+
+def execute_render(job: RenderJob, normalise: bool = True, max_workspace_bytes: int = 4 << 30, max_streams: int = 16,
+                   plan_cache: Optional[RenderPlanCache] = None) -> torch.Tensor:
+    """Rendering half of render_scenes_batched: every bucket of scenes that share N is one pal_render_scenes(_planned)
+    call; only enqueues work on the current stream (and a pool of side streams joined at the end)."""
+    dev, L = job.dev, _lib.lib()
+    base, n_base, tau, gain, pcount, k_stride, m, fs = job.base, job.n_base, job.tau, job.gain, job.pcount, job.k_stride, job.m, job.fs
+    s_n, n_keep, uniq, bounds, idx_dev = job.s_n, job.n_keep, job.uniq, job.bounds, job.idx_dev
     out = torch.empty((s_n, m, n_keep), dtype=torch.float32, device=dev)
-    order = np.argsort(totals, kind="stable")
-    uniq, starts = np.unique(totals[order], return_index=True)
-    idx_dev = torch.as_tensor(order.astype(np.int64)).to(dev)
-    bounds = list(starts) + [len(order)]
-    # Scenes that share N form a bucket = one pal_render_scenes call (about ten dependent launches).  With random
-    # rooms almost every N is different and a bucket holds a handful of scenes, so the buckets are issued
-    # round-robin on a pool of streams (the library is stateless and stream-ordered): the small grids of
-    # different buckets overlap instead of queueing behind each other.  Each stream owns a workspace slice.
+    # Scenes that share N form a bucket = one pal_render_scenes call (a few dependent launches).  With random rooms
+    # almost every N is different and a bucket holds a handful of scenes, so the buckets are issued round-robin on a
+    # pool of streams (the library is stateless and stream-ordered): the small grids of different buckets overlap
+    # instead of queueing behind each other.  Each stream owns a workspace slice.
     rows_max = int(np.max(np.diff(bounds))) * m
     need, small = C.c_size_t(0), C.c_size_t(0)
     if plan_cache is None:
@@ -348,9 +364,28 @@ def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: 
     if normalise:
         _lib.check(L.pal_normalise_compress(out.data_ptr(), s_n * m, n_keep, 0.8, 1e-8, 1, _stream(dev)),
                    "pal_normalise_compress")
-    for t in (base, tau, gain, pcount, ws, mics, src, idx_dev):
+    for t in (base, tau, gain, pcount, ws, job.mics, job.src, idx_dev):
         t.record_stream(torch.cuda.current_stream(dev))
     return out
+
+
+def render_scenes_batched(base_signal, sources, img_pos: torch.Tensor, img_mat: torch.Tensor, img_count: torch.Tensor,
+                          mic_positions, fs: float, c: float, duration: float, freq: float, table: MaterialTable,
+                          trim_to_duration: bool = True, normalise: bool = True,
+                          max_workspace_bytes: int = 4 << 30, max_streams: int = 16,
+                          plan_cache: Optional[RenderPlanCache] = None) -> torch.Tensor:
+    """main.py:94-122 for MANY scenes that share fs / duration / base signal: sources [S, 3],
+    img_pos [S, K, 3], img_mat [S, K], img_count [S] (output of image_sources_batched),
+    mic_positions [M, 3] or [S, M, 3].  Returns [S, M, n_keep] float32 on the device.
+
+    The transform length N = int((duration + max delay) * fs) (main.py:102) differs from scene to
+    scene; delays are computed for all scenes in one launch, N is formed on the host in float64
+    exactly like the reference (one small read-back), and scenes that share N are rendered together.
+    `plan_cache` (RenderPlanCache) keeps the per-N tables between calls that share the base signal.
+    = execute_render(prepare_render(...))."""
+    job = prepare_render(base_signal, sources, img_pos, img_mat, img_count, mic_positions, fs, c, duration, freq, table,
+                         trim_to_duration)
+    return execute_render(job, normalise, max_workspace_bytes, max_streams, plan_cache)
 
 
 def normalise_compress(x: torch.Tensor, threshold: float = 0.8, epsilon: float = 1e-8, compress: bool = True):

@@ -94,17 +94,37 @@ class SceneSweep:
         self.render_ms = self.gcc_ms = self.solve_ms = 0.0
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         self.timed = False
+        self.geom_stream = torch.cuda.Stream(self.dev)
 
-    def step(self, sources: np.ndarray, mics: np.ndarray, planes: np.ndarray):
+    def _prepare(self, sources, mics, planes, c0, c1):
+        """Geometry of one chunk on the side stream (ends with the renderer's one read-back, which then waits for the
+        side stream only -- not for the rendering / GCC-PHAT work of the previous chunk on the main stream)."""
         from . import main as pmain
         cfg = self.cfg
-        for c0 in range(0, self.n, self.chunk):
-            c1 = min(c0 + self.chunk, self.n)
+        with torch.cuda.stream(self.geom_stream):
+            job = pmain.prepare_scenes_batched(sources[c0:c1], mics[c0:c1], cfg.fs, cfg.c, cfg.duration, cfg.signal_type, cfg.freq,
+                                               (planes[c0:c1], ROOM_MATERIALS), self.mats, cfg.max_reflections,
+                                               cfg.absorption_threshold, base_signal=self.base)
+            job.done = torch.cuda.Event()
+            job.done.record(self.geom_stream)
+        return job
+
+    def step(self, sources: np.ndarray, mics: np.ndarray, planes: np.ndarray):
+        """One sweep step, software-pipelined over chunks: while the GPU renders chunk c and runs its GCC-PHAT stage
+        (both only enqueued: neither call waits for the device), the host prepares chunk c+1 -- image sources, path
+        tables, transform lengths, bucketing -- on a side stream."""
+        cfg = self.cfg
+        cur = torch.cuda.current_stream(self.dev)
+        chunks = [(c0, min(c0 + self.chunk, self.n)) for c0 in range(0, self.n, self.chunk)]
+        self.geom_stream.wait_stream(cur)
+        job = self._prepare(sources, mics, planes, *chunks[0])
+        for ci, (c0, c1) in enumerate(chunks):
             if self.timed:
                 self._ev[0].record()
-            sig = pmain.simulate_scenes_batched(sources[c0:c1], mics[c0:c1], cfg.fs, cfg.c, cfg.duration, cfg.signal_type,
-                                                cfg.freq, (planes[c0:c1], ROOM_MATERIALS), self.mats, cfg.max_reflections,
-                                                cfg.absorption_threshold, base_signal=self.base, plan_cache=self.cache)
+            cur.wait_event(job.done)
+            sig = _scene.execute_render(job, plan_cache=self.cache)
+            for t in (job.tau, job.gain, job.pcount, job.src, job.mics, job.idx_dev):
+                t.record_stream(cur)            # allocated under the side stream, consumed on this one
             if self.timed:
                 self._ev[1].record()
             res = _g.gcc_phat_tdoa_batched(sig, float(cfg.fs), cfg.max_expected_delay)
@@ -118,14 +138,19 @@ class SceneSweep:
                 pos, _, _ = solver.solve_positions_batched(mics[c0:c1], _g.all_pairs(cfg.mics), td, cfg.c, max_iter=60,
                                                            xtol=1e-8, ftol=1e-8, gtol=1e-8)
                 self.positions[c0:c1] = pos
+            if self.keep and c0 < self.keep:
+                if self.signals is None or self.signals.shape[0] != self.keep or self.signals.shape[2] != sig.shape[2]:
+                    self.signals = torch.empty((self.keep,) + tuple(sig.shape[1:]), dtype=sig.dtype, device=self.dev)
+                hi = min(c1, self.keep)
+                self.signals[c0:hi] = sig[:hi - c0]
+            if ci + 1 < len(chunks):
+                job = self._prepare(sources, mics, planes, *chunks[ci + 1])       # overlaps the GPU work enqueued above
             if self.timed:
                 self._ev[3].record()
                 torch.cuda.synchronize()
                 self.render_ms += self._ev[0].elapsed_time(self._ev[1])
                 self.gcc_ms += self._ev[1].elapsed_time(self._ev[2])
                 self.solve_ms += self._ev[2].elapsed_time(self._ev[3])
-            if c0 == 0 and self.keep:
-                self.signals = sig[:self.keep].clone()
         if self.do_gather:
             dist.all_gather_into_tensor(self.gathered, self.k_all, group=self.group)
         return self.k_all

@@ -113,7 +113,7 @@ def test_cfg5_chain_render_then_gcc(pal):
     cfg = sweep.SweepConfig()
     n_sc = 16
     src, mic, pl = sweep.random_shoebox_scenes(n_sc, cfg.mics, 5000)
-    sw = sweep.SceneSweep(cfg, n_sc, keep_signals=n_sc)
+    sw = sweep.SceneSweep(cfg, n_sc, chunk=6, keep_signals=n_sc)       # three chunks: the software-pipelined path
     k = sw.step(src, mic, pl)
     torch.cuda.synchronize()
     sig = sw.signals.cpu().numpy()

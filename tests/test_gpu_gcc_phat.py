@@ -299,3 +299,61 @@ def test_generic_path_parity_sweep_and_flag_rate(pal):
             if td[f, p] != want[0]:
                 bad.append((f, p, td[f, p], want[0], int(flags[f, p])))
     assert not bad, bad[:5]
+
+
+def test_float64_ingest_band_limited_signals(pal):
+    """Genuine float64 inputs take the float64 ingest (pal_gcc_phat_tdoa_f64): band-passed channels at fs = 44.1 kHz
+    (order-5 Butterworth 300-3400 Hz + filtfilt, what main.py:191 hands to the pair loop).  Their stop-band bins sit far
+    below the float32 quantisation noise yet PHAT gives them unit weight, so the correlation of the float32-rounded
+    channels differs visibly from the reference's; through the float64 path lags are the reference's and the
+    correlation agrees to 1e-6 of its maximum -- for the generic length and for 2048-sample frames (n = 4095)."""
+    from scipy.signal import butter, filtfilt
+    from pyaudiolocalization_b200 import utils as U
+    rng = np.random.default_rng(44)
+    fs = 44100.0
+    b, a = butter(5, [300 / (0.5 * fs), 3400 / (0.5 * fs)], btype="band")
+    src = rng.standard_normal(6000)
+    x1 = filtfilt(b, a, src[40:40 + 5000] + 0.05 * rng.standard_normal(5000))
+    x2 = filtfilt(b, a, src[33:33 + 5000] + 0.05 * rng.standard_normal(5000))
+    assert x1.dtype == np.float64
+    for med in (None, 0.01):
+        want_td, want_corr, _ = O.get_time_delays_phat(x1, x2, fs, max_expected_delay=med)
+        td, corr, lags = U.get_time_delays_phat(x1, x2, fs, max_expected_delay=med)
+        assert td == want_td
+        assert np.abs(corr - want_corr).max() <= 1e-6 * np.abs(want_corr).max()
+    c32 = U.phat_correlation(x1.astype(np.float32), x2.astype(np.float32))           # the float32 throughput path
+    c64 = U.phat_correlation(x1, x2)
+    want = O.phat_correlation(x1, x2)
+    e32, e64 = np.abs(c32 - want).max() / np.abs(want).max(), np.abs(c64 - want).max() / np.abs(want).max()
+    print(f"band-limited channels: corr error float32 ingest {e32:.2e}, float64 ingest {e64:.2e} (relative to max|corr|)")
+    assert e64 <= 1e-6
+    # n = 4095: float64 frames [B, M, 2048]
+    fr = np.stack([np.stack([filtfilt(b, a, rng.standard_normal(2048)) for _ in range(3)]) for _ in range(2)])
+    res = pal.gcc_phat_tdoa_batched(torch.from_numpy(fr).cuda(), 16000.0, max_expected_delay=0.05, return_corr=True)
+    assert int(((res.flags & 8) == 0).sum().item()) == 0           # every row went through the float64 kernel
+    td = res.tdoa_seconds()[..., 0]
+    corr = res.corr.cpu().numpy()
+    pairs = pal.all_pairs(3)
+    for f in range(2):
+        for p, (i, j) in enumerate(pairs):
+            w_td, w_corr, _ = O.get_time_delays_phat(fr[f, i], fr[f, j], 16000.0, max_expected_delay=0.05)
+            assert td[f, p] == w_td[0]
+            assert np.abs(corr[f, p] - w_corr).max() <= 1e-6 * np.abs(w_corr).max()
+
+
+def test_generic_path_small_workspace_equals_full(pal):
+    """Arbitrary-length path with the smallest workspace the library accepts (many rounds; the device-counted float64
+    sweep gives way to the host-counted one) against the comfortable workspace: identical lags, peaks and flags."""
+    rng = np.random.default_rng(5)
+    b, m, n, fs, med = 48, 6, 1500, 16000.0, 0.01
+    src = rng.standard_normal((b, n + 64)).astype(np.float32)
+    d = rng.integers(0, 48, size=(b, m))
+    fr = np.stack([np.stack([src[f, 48 - d[f, c]:48 - d[f, c] + n] for c in range(m)]) for f in range(b)])
+    fr = torch.from_numpy((fr + 0.4 * rng.standard_normal(fr.shape)).astype(np.float32)).cuda()
+    full, small = pal.gcc_phat.workspace_bytes(b, m, n, m * (m - 1) // 2)
+    a = pal.gcc_phat_tdoa_batched(fr, fs, max_expected_delay=med)
+    c = pal.gcc_phat_tdoa_batched(fr, fs, max_expected_delay=med, max_workspace_bytes=small)
+    assert small < full
+    assert torch.equal(a.k_idx, c.k_idx) and torch.equal(a.flags, c.flags)
+    assert torch.allclose(a.peak, c.peak, rtol=0, atol=1e-6) and torch.allclose(a.gmax, c.gmax, rtol=0, atol=1e-6)
+    assert int(((a.flags & 8) != 0).sum().item()) > 0          # some rows did go through the float64 sweep
