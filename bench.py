@@ -266,7 +266,7 @@ def run_scenes(args, world, rank, dev, dist, torch, peak_gbs):
     s_n = args.scenes
     n_par = min(args.scene_parity, s_n)
     sw = sweep.SceneSweep(cfg, s_n, chunk=args.scene_chunk, device=dev, keep_signals=n_par, solve=not args.no_scene_solve)
-    steps, warm = max(1, min(args.steps, 3)), 1
+    steps, warm = max(1, min(args.steps, 3)), 3      # three warm-up steps: the renderer's per-length plan cache fills up
     sets = [sweep.random_shoebox_scenes(s_n, cfg.mics, 5000 + rank + 1000 * i) for i in range(warm + steps)]
 
     def barrier():

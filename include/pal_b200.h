@@ -235,6 +235,19 @@ int pal_sync_align(const double* sig_dev, int64_t n_scenes, int32_t n_ch, int32_
 int pal_pad_rows(const void* in_dev, int64_t n_rows, int64_t ld_in, const int32_t* lens_dev, const int32_t* pad_left_dev,
                  void* out_dev, int64_t ld_out, int32_t io_f32, void* stream);
 
+/* Many buckets per launch.  With one room per scene nearly every scene has its own transform length (main.py:102), and
+ * one pal_render_scenes_planned call per bucket leaves a sweep bound by launch overhead (thousands of 16-block grids).
+ * This entry point renders ALL buckets of a batch: bucket i holds the scenes scene_index_dev[first[i] .. first[i+1]) which
+ * share N_of_bucket[i] and whose plan (pal_render_plan) lives at plan_dev_of_bucket[i].  The three arrays are HOST arrays
+ * (n_buckets, n_buckets, n_buckets + 1 entries); everything else as in pal_render_scenes_planned.  Buckets that share a
+ * convolution plan are issued together, four launches per group, as many buckets per group as the workspace holds.
+ * PAL_ERR_UNSUPPORTED: some bucket has no compile-time convolution plan (4 N - 1 > 262144 or 2 N < 1025) or does not fit
+ * the workspace on its own -- render that batch bucket by bucket.  Output is identical to the per-bucket calls. */
+int pal_render_scenes_grouped(int32_t n_buckets, const void* const* plan_dev_of_bucket, const int32_t* N_of_bucket,
+                              const int64_t* first_scene_of_bucket, const double* tau_dev, const double* gain_dev,
+                              const int32_t* path_count_dev, int32_t k_stride, const int64_t* scene_index_dev, int32_t n_mics,
+                              double fs, int32_t n_keep, float* out_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* FLOAT64 INGEST.  pal_gcc_phat_tdoa takes float32 rows: a caller that holds float64 signals (the reference computes
  * in float64 throughout: utils.py:113-118; main.py:191 hands the float64 output of filtfilt to the pair loop) would
  * have to round them first, and a float64 re-evaluation that starts from rounded samples cannot restore the reference's

@@ -100,6 +100,8 @@ def lib():
     L.pal_sync_align.argtypes = [VP, I64, I32, I32, VP, VP, VP, VP, VP, VP, VP, C.c_size_t, VP]
     L.pal_pad_rows.restype = C.c_int
     L.pal_pad_rows.argtypes = [VP, I64, I64, VP, VP, VP, I64, I32, VP]
+    L.pal_render_scenes_grouped.restype = C.c_int
+    L.pal_render_scenes_grouped.argtypes = [I32, VP, VP, VP, VP, VP, VP, I32, VP, I32, F64, I32, VP, VP, C.c_size_t, VP]
     L.pal_reserve_sms.restype = C.c_int
     L.pal_reserve_sms.argtypes = [I32]
     L.pal_solve_positions_workspace.restype = C.c_int

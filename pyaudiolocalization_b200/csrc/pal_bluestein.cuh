@@ -87,6 +87,16 @@ template <typename T> PAL_DEV void sincospi_(double x, T& s, T& c) {
   c = T(cd);
 }
 
+// single-precision sin / cos of pi x for an argument already reduced to a few turns
+PAL_DEV void sincospif_(float x, float& s, float& c) {
+#if PAL_GPU
+  sincospif(x, &s, &c);
+#else
+  s = float(std::sin(3.14159265358979323846 * double(x)));
+  c = float(std::cos(3.14159265358979323846 * double(x)));
+#endif
+}
+
 // grid-stride fill of chirp / twiddle tables
 template <typename T>
 PAL_DEV void blue_init_tables_body(BluePlan p, cpx<T>* chirp, cpx<T>* tw1, cpx<T>* tw2, cpx<T>* twM) {

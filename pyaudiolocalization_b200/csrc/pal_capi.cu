@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "../../include/pal_b200.h"
 #include "pal_pfa4095.cuh"
@@ -201,6 +202,10 @@ int device_info(DevInfo& d) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// tail of the flagged-row list in the workspace: the device-side counter followed by the per-round counts of the
+// device-counted float64 sweep (2 x kMaxDevRounds ints)
+constexpr size_t kListTail = 1024;
+static_assert((1 + 2 * palhost::kMaxDevRounds) * sizeof(int) <= kListTail, "list tail too small");
 constexpr unsigned kRefineMask = PAL_FLAG_NEAR_TIE | PAL_FLAG_CHAIN | PAL_FLAG_PLATEAU;
 
 // arbitrary-length path (Bluestein): float32 sweep with a near-tie audit, then a float64 sweep
@@ -214,7 +219,7 @@ int generic_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, 
   if (n1 + n2 - 1 < 3) return fail(PAL_ERR_INVALID, "pal_gcc_phat_tdoa: signals too short (n1+n2-1 < 3)");
   DevInfo di;
   if (int rc = device_info(di)) return rc;
-  const size_t list_bytes = align_up(size_t(B) * P * sizeof(int), 256) + 256;
+  const size_t list_bytes = align_up(size_t(B) * P * sizeof(int), 256) + kListTail;
   const size_t rows_bytes = align_up(size_t(B) * P * 2 * sizeof(int), 256);
   const size_t scale_bytes = align_up(size_t(B) * M * 2 * sizeof(float), 256);
   const int n = n1 + n2 - 1;
@@ -223,7 +228,7 @@ int generic_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, 
     return fail(PAL_ERR_WORKSPACE, "pal_gcc_phat_tdoa: workspace too small");
   char* ws = static_cast<char*>(ws_dev);
   int* list = reinterpret_cast<int*>(ws);
-  int* count = reinterpret_cast<int*>(ws + list_bytes - 256);
+  int* count = reinterpret_cast<int*>(ws + list_bytes - kListTail);
   int* rows = reinterpret_cast<int*>(ws + list_bytes);
   float* scales = reinterpret_cast<float*>(ws + list_bytes + rows_bytes);
   char* region = ws + list_bytes + rows_bytes + scale_bytes;
@@ -308,7 +313,7 @@ int pal_profile_hook(int32_t stage, void* start_event, void* stop_event) {
 
 int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, size_t* bytes, size_t* min_bytes) {
   if (B < 0 || M < 2 || P < 1 || n_samples < 1 || !bytes) return fail(PAL_ERR_INVALID, "pal_gcc_phat_workspace: bad argument");
-  const size_t list = align_up(size_t(B) * P * sizeof(int), 256) + 256;
+  const size_t list = align_up(size_t(B) * P * sizeof(int), 256) + kListTail;
   if (n_samples == kFrame2048) {
     const size_t per_frame = align_up(size_t(M) * kSpecSlots * sizeof(cpxf), 256);
     const size_t hq_frame = size_t(M) * sizeof(float);     // whitening bound, one float per channel
@@ -357,12 +362,12 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
   if (int rc = device_info(di)) return rc;
 
   const size_t per_frame = align_up(size_t(M) * kSpecSlots * sizeof(cpxf), 256);
-  const size_t list_bytes = align_up(size_t(B) * P * sizeof(int), 256) + 256;
+  const size_t list_bytes = align_up(size_t(B) * P * sizeof(int), 256) + kListTail;
   const size_t hq_frame = size_t(M) * sizeof(float);
   if (ws_bytes < per_frame + hq_frame + list_bytes + 256) return fail(PAL_ERR_WORKSPACE, "pal_gcc_phat_tdoa: workspace too small");
   char* ws = static_cast<char*>(ws_dev);
   int* list = reinterpret_cast<int*>(ws);
-  int* count = reinterpret_cast<int*>(ws + list_bytes - 256);
+  int* count = reinterpret_cast<int*>(ws + list_bytes - kListTail);
   cpxf* spec = reinterpret_cast<cpxf*>(ws + list_bytes);
   const int64_t chunk = std::min<int64_t>(B, int64_t((ws_bytes - list_bytes - 256) / (per_frame + hq_frame)));
   float* hq = reinterpret_cast<float*>(ws + list_bytes + align_up(size_t(chunk) * per_frame, 256));   // [chunk][M]
@@ -701,6 +706,34 @@ int pal_render_scenes_planned(const void* plan_dev, size_t plan_bytes, int32_t n
   cudaError_t e = palhost::render_rows_planned(rp, N, rr, n_bucket_scenes * n_mics, fs, n_keep, out_dev, static_cast<char*>(ws_dev),
                                                ws_bytes, static_cast<cudaStream_t>(stream_), di.sms);
   if (e != cudaSuccess) return cuda_fail(e, "pal_render_scenes_planned");
+  return PAL_OK;
+}
+
+int pal_render_scenes_grouped(int32_t n_buckets, const void* const* plan_dev_of_bucket, const int32_t* N_of_bucket,
+                              const int64_t* first_scene_of_bucket, const double* tau_dev, const double* gain_dev,
+                              const int32_t* path_count_dev, int32_t k_stride, const int64_t* scene_index_dev, int32_t n_mics,
+                              double fs, int32_t n_keep, float* out_dev, void* ws_dev, size_t ws_bytes, void* stream_) {
+  if (n_buckets < 0 || n_mics < 1 || k_stride < 1 || n_keep < 1) return fail(PAL_ERR_INVALID, "pal_render_scenes_grouped: bad size argument");
+  if (n_buckets == 0) return PAL_OK;
+  if (!plan_dev_of_bucket || !N_of_bucket || !first_scene_of_bucket || !tau_dev || !gain_dev || !path_count_dev || !scene_index_dev ||
+      !out_dev || !ws_dev)
+    return fail(PAL_ERR_INVALID, "pal_render_scenes_grouped: NULL pointer");
+  if (reinterpret_cast<uintptr_t>(ws_dev) & 255u) return fail(PAL_ERR_INVALID, "pal_render_scenes_grouped: ws_dev must be 256-byte aligned");
+  DevInfo di;
+  if (int rc = device_info(di)) return rc;
+  std::vector<palhost::GroupedBucketIn> in(n_buckets);
+  for (int i = 0; i < n_buckets; ++i) {
+    const int N = N_of_bucket[i];
+    const long long cnt = first_scene_of_bucket[i + 1] - first_scene_of_bucket[i];
+    if (!plan_dev_of_bucket[i] || (reinterpret_cast<uintptr_t>(plan_dev_of_bucket[i]) & 255u) || N < 100 || n_keep > N || cnt < 1)
+      return fail(PAL_ERR_INVALID, "pal_render_scenes_grouped: bad bucket (NULL / misaligned plan, N < 100, n_keep > N or no scene)");
+    in[i] = palhost::GroupedBucketIn{static_cast<const char*>(plan_dev_of_bucket[i]), N, first_scene_of_bucket[i], cnt};
+  }
+  const RenderRows rr{tau_dev, gain_dev, path_count_dev, nullptr, k_stride, n_mics};
+  cudaError_t e = palhost::render_grouped(in.data(), n_buckets, rr, reinterpret_cast<const long long*>(scene_index_dev), fs, n_keep,
+                                          out_dev, static_cast<char*>(ws_dev), ws_bytes, static_cast<cudaStream_t>(stream_), di.sms);
+  if (e == cudaErrorNotSupported) return fail(PAL_ERR_UNSUPPORTED, "pal_render_scenes_grouped: a bucket has no compile-time plan or exceeds the workspace; use pal_render_scenes_planned per bucket");
+  if (e != cudaSuccess) return cuda_fail(e, "pal_render_scenes_grouped");
   return PAL_OK;
 }
 

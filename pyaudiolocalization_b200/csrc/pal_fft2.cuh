@@ -257,30 +257,34 @@ template <int NT> PAL_DEV const f2* stage_tw(const cpxf* g, int count, f2* s) {
 
 // ---------------------------------------------------------------------------------------------- pass 1: columns forward
 // work unit = (transform t, tile of TC adjacent columns).  buf[t][r][j2] <- twiddled column FFT (r = digit-reversed k1)
+// one work unit: transform t, column tile tile_i (ends with a block barrier: the tile is free again)
 template <class P, int NT, class Loader>
-PAL_DEV void colpass_fwd_body(Tables tb, Loader load, long long n_tr, cpxf* buf, char* smem) {
-  constexpr int L = P::M1, TC = P::TC, NS = Radices<L>::NS, tiles = P::M2 / TC;
-  f2* tile = reinterpret_cast<f2*>(smem);
-  const f2* tw = stage_tw<NT>(tb.tw1, L, tile + L * TC);
+PAL_DEV void colpass_fwd_unit(const Tables& tb, const Loader& load, long long t, int tile_i, cpxf* buf, f2* tile, const f2* tw) {
+  constexpr int L = P::M1, TC = P::TC, NS = Radices<L>::NS;
   auto rd = [&](int pos, int lane) { return tile[pos * TC + lane]; };
   auto wr = [&](int pos, int lane, f2 v) { tile[pos * TC + lane] = v; };
-  for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks()) {
-    const long long t = u / tiles;
-    const int j20 = int(u % tiles) * TC;
-    const auto ctx = unit_begin(load, t, 0);
-    radix_step<L, 0, false, TC, NT>(tw, [&](int pos, int lane) { return as_f2(load(ctx, pos * P::M2 + j20 + lane)); }, wr);
-    simt::sync_block();
-    if (NS == 3) {
-      radix_step<L, NS == 3 ? 1 : 0, false, TC, NT>(tw, rd, wr);
-      simt::sync_block();
-    }
-    cpxf* out = buf + t * P::M;
-    radix_step<L, NS - 1, false, TC, NT>(tw, rd, [&](int pos, int lane, f2 v) {
-      const int idx = pos * P::M2 + j20 + lane;
-      st_f2(out + idx, cmul(v, ld_f2(tb.twf + idx)));
-    });
+  const int j20 = tile_i * TC;
+  const auto ctx = unit_begin(load, t, 0);
+  radix_step<L, 0, false, TC, NT>(tw, [&](int pos, int lane) { return as_f2(load(ctx, pos * P::M2 + j20 + lane)); }, wr);
+  simt::sync_block();
+  if (NS == 3) {
+    radix_step<L, NS == 3 ? 1 : 0, false, TC, NT>(tw, rd, wr);
     simt::sync_block();
   }
+  cpxf* out = buf + t * P::M;
+  radix_step<L, NS - 1, false, TC, NT>(tw, rd, [&](int pos, int lane, f2 v) {
+    const int idx = pos * P::M2 + j20 + lane;
+    st_f2(out + idx, cmul(v, ld_f2(tb.twf + idx)));
+  });
+  simt::sync_block();
+}
+template <class P, int NT, class Loader>
+PAL_DEV void colpass_fwd_body(Tables tb, Loader load, long long n_tr, cpxf* buf, char* smem) {
+  constexpr int L = P::M1, TC = P::TC, tiles = P::M2 / TC;
+  f2* tile = reinterpret_cast<f2*>(smem);
+  const f2* tw = stage_tw<NT>(tb.tw1, L, tile + L * TC);
+  for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks())
+    colpass_fwd_unit<P, NT, Loader>(tb, load, u / tiles, int(u % tiles), buf, tile, tw);
 }
 
 // ---------------------------------------------------------------------------------------------- pass 2: rows
@@ -289,65 +293,67 @@ PAL_DEV void colpass_fwd_body(Tables tb, Loader load, long long n_tr, cpxf* buf,
 // the chirp spectrum, scaled by 1/M, in the register order of the fused middle step:
 //   bhat[((row_tile * (M2 / RL) + butterfly) * TR + lane) * RL + q]
 template <class P, int NT, int MODE>
-PAL_DEV void rowpass_body(Tables tb, long long n_tr, cpxf* buf, cpxf* bhat_out, char* smem) {
-  constexpr int L = P::M2, TR = P::TR, LD = P::LDR, NS = Radices<L>::NS, RL = P::RL, tiles = P::M1 / TR;
+PAL_DEV void rowpass_unit(const Tables& tb, long long t, int rt, cpxf* buf, cpxf* bhat_out, f2* tile, const f2* tw) {
+  constexpr int L = P::M2, TR = P::TR, LD = P::LDR, NS = Radices<L>::NS, RL = P::RL;
   constexpr int NB = L / RL, G = NT / TR;
-  f2* tile = reinterpret_cast<f2*>(smem);
-  const f2* tw = stage_tw<NT>(tb.tw2, L, tile + L * LD);
   auto rd = [&](int pos, int lane) { return tile[pos * LD + lane]; };
   auto wr = [&](int pos, int lane, f2 v) { tile[pos * LD + lane] = v; };
   const int lane = simt::tid() % TR, grp = simt::tid() / TR;
-  for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks()) {
-    const long long t = u / tiles;
-    const int rt = int(u % tiles);
-    cpxf* rows = buf + t * P::M + (long long)rt * TR * L;
-    for (int x = simt::tid(); x < TR * L; x += NT) tile[(x % L) * LD + x / L] = ld_f2(rows + x);       // transpose in
+  cpxf* rows = buf + t * P::M + (long long)rt * TR * L;
+  for (int x = simt::tid(); x < TR * L; x += NT) tile[(x % L) * LD + x / L] = ld_f2(rows + x);       // transpose in
+  simt::sync_block();
+  radix_step<L, 0, false, TR, NT>(tw, rd, wr);
+  simt::sync_block();
+  if (NS == 3) {
+    radix_step<L, NS == 3 ? 1 : 0, false, TR, NT>(tw, rd, wr);
     simt::sync_block();
-    radix_step<L, 0, false, TR, NT>(tw, rd, wr);
-    simt::sync_block();
-    if (NS == 3) {
-      radix_step<L, NS == 3 ? 1 : 0, false, TR, NT>(tw, rd, wr);
-      simt::sync_block();
-    }
-    // fused middle: last forward step (consecutive elements, no twiddle), x chirp spectrum, first inverse step
+  }
+  // fused middle: last forward step (consecutive elements, no twiddle), x chirp spectrum, first inverse step
 #pragma unroll
-    for (int it = 0; it < (NB + G - 1) / G; ++it) {
-      const int b = grp + it * G;
-      if (NB % G != 0 && b >= NB) break;
-      f2 x[RL];
+  for (int it = 0; it < (NB + G - 1) / G; ++it) {
+    const int b = grp + it * G;
+    if (NB % G != 0 && b >= NB) break;
+    f2 x[RL];
 #pragma unroll
-      for (int q = 0; q < RL; ++q) x[q] = tile[(b * RL + q) * LD + lane];
-      Dft<RL, false>::run(x);
-      const size_t bo = ((size_t(rt) * NB + b) * TR + lane) * RL;
-      if (MODE == 2) {
-        const f2 sc = f2_bcast(1.0f / float(P::M));
+    for (int q = 0; q < RL; ++q) x[q] = tile[(b * RL + q) * LD + lane];
+    Dft<RL, false>::run(x);
+    const size_t bo = ((size_t(rt) * NB + b) * TR + lane) * RL;
+    if (MODE == 2) {
+      const f2 sc = f2_bcast(1.0f / float(P::M));
 #pragma unroll
-        for (int q = 0; q < RL; ++q) st_f2(bhat_out + bo + q, f2_mul(x[q], sc));
-      } else {
-        const float4* bp = reinterpret_cast<const float4*>(tb.bhat + bo);
+      for (int q = 0; q < RL; ++q) st_f2(bhat_out + bo + q, f2_mul(x[q], sc));
+    } else {
+      const float4* bp = reinterpret_cast<const float4*>(tb.bhat + bo);
 #pragma unroll
-        for (int q = 0; q < RL; q += 2) {
-          const float4 w = bp[q / 2];
-          x[q] = cmul_t<MODE == 1>(x[q], f2_make(w.x, w.y));
-          x[q + 1] = cmul_t<MODE == 1>(x[q + 1], f2_make(w.z, w.w));
-        }
-        Dft<RL, true>::run(x);
-#pragma unroll
-        for (int q = 0; q < RL; ++q) tile[(b * RL + q) * LD + lane] = x[q];
+      for (int q = 0; q < RL; q += 2) {
+        const float4 w = bp[q / 2];
+        x[q] = cmul_t<MODE == 1>(x[q], f2_make(w.x, w.y));
+        x[q + 1] = cmul_t<MODE == 1>(x[q + 1], f2_make(w.z, w.w));
       }
-    }
-    simt::sync_block();
-    if (MODE != 2) {
-      if (NS == 3) {
-        radix_step<L, NS == 3 ? 1 : 0, true, TR, NT>(tw, rd, wr);
-        simt::sync_block();
-      }
-      radix_step<L, 0, true, TR, NT>(tw, rd, wr);
-      simt::sync_block();
-      for (int x = simt::tid(); x < TR * L; x += NT) st_f2(rows + x, tile[(x % L) * LD + x / L]);         // transpose out
-      simt::sync_block();
+      Dft<RL, true>::run(x);
+#pragma unroll
+      for (int q = 0; q < RL; ++q) tile[(b * RL + q) * LD + lane] = x[q];
     }
   }
+  simt::sync_block();
+  if (MODE != 2) {
+    if (NS == 3) {
+      radix_step<L, NS == 3 ? 1 : 0, true, TR, NT>(tw, rd, wr);
+      simt::sync_block();
+    }
+    radix_step<L, 0, true, TR, NT>(tw, rd, wr);
+    simt::sync_block();
+    for (int x = simt::tid(); x < TR * L; x += NT) st_f2(rows + x, tile[(x % L) * LD + x / L]);         // transpose out
+    simt::sync_block();
+  }
+}
+template <class P, int NT, int MODE>
+PAL_DEV void rowpass_body(Tables tb, long long n_tr, cpxf* buf, cpxf* bhat_out, char* smem) {
+  constexpr int L = P::M2, tiles = P::M1 / P::TR;
+  f2* tile = reinterpret_cast<f2*>(smem);
+  const f2* tw = stage_tw<NT>(tb.tw2, L, tile + L * P::LDR);
+  for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks())
+    rowpass_unit<P, NT, MODE>(tb, u / tiles, int(u % tiles), buf, bhat_out, tile, tw);
 }
 
 // a storer may reduce something over the whole work unit (e.g. the row maximum): finish(ctx, t, tile, scratch) is then
@@ -360,30 +366,33 @@ template <class S, class C> PAL_DEV void unit_end(const S&, C&, long long, int, 
 
 // ---------------------------------------------------------------------------------------------- pass 3: columns inverse
 template <class P, int NT, class Storer>
-PAL_DEV void colpass_inv_body(Tables tb, Storer store, long long n_tr, const cpxf* buf, char* smem) {
-  constexpr int L = P::M1, TC = P::TC, NS = Radices<L>::NS, tiles = P::M2 / TC;
-  f2* tile = reinterpret_cast<f2*>(smem);
-  const f2* tw = stage_tw<NT>(tb.tw1, L, tile + L * TC);
+PAL_DEV void colpass_inv_unit(const Tables& tb, const Storer& store, long long t, int tile_i, const cpxf* buf, f2* tile, const f2* tw) {
+  constexpr int L = P::M1, TC = P::TC, NS = Radices<L>::NS;
   auto rd = [&](int pos, int lane) { return tile[pos * TC + lane]; };
   auto wr = [&](int pos, int lane, f2 v) { tile[pos * TC + lane] = v; };
-  for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks()) {
-    const long long t = u / tiles;
-    const int j20 = int(u % tiles) * TC;
-    const cpxf* in = buf + t * P::M;
-    auto ctx = unit_begin(store, t, 0);
-    radix_step<L, NS - 1, true, TC, NT>(tw, [&](int pos, int lane) {
-      const int idx = pos * P::M2 + j20 + lane;
-      return cmulc(ld_f2(in + idx), ld_f2(tb.twf + idx));
-    }, wr);
+  const int j20 = tile_i * TC;
+  const cpxf* in = buf + t * P::M;
+  auto ctx = unit_begin(store, t, 0);
+  radix_step<L, NS - 1, true, TC, NT>(tw, [&](int pos, int lane) {
+    const int idx = pos * P::M2 + j20 + lane;
+    return cmulc(ld_f2(in + idx), ld_f2(tb.twf + idx));
+  }, wr);
+  simt::sync_block();
+  if (NS == 3) {
+    radix_step<L, NS == 3 ? 1 : 0, true, TC, NT>(tw, rd, wr);
     simt::sync_block();
-    if (NS == 3) {
-      radix_step<L, NS == 3 ? 1 : 0, true, TC, NT>(tw, rd, wr);
-      simt::sync_block();
-    }
-    radix_step<L, 0, true, TC, NT>(tw, rd, [&](int pos, int lane, f2 v) { store(ctx, pos * P::M2 + j20 + lane, as_cpx(v)); });
-    simt::sync_block();
-    unit_end(store, ctx, t, int(u % tiles), reinterpret_cast<float*>(tile), 0);
   }
+  radix_step<L, 0, true, TC, NT>(tw, rd, [&](int pos, int lane, f2 v) { store(ctx, pos * P::M2 + j20 + lane, as_cpx(v)); });
+  simt::sync_block();
+  unit_end(store, ctx, t, tile_i, reinterpret_cast<float*>(tile), 0);
+}
+template <class P, int NT, class Storer>
+PAL_DEV void colpass_inv_body(Tables tb, Storer store, long long n_tr, const cpxf* buf, char* smem) {
+  constexpr int L = P::M1, TC = P::TC, tiles = P::M2 / TC;
+  f2* tile = reinterpret_cast<f2*>(smem);
+  const f2* tw = stage_tw<NT>(tb.tw1, L, tile + L * TC);
+  for (long long u = simt::bid(); u < n_tr * tiles; u += simt::nblocks())
+    colpass_inv_unit<P, NT, Storer>(tb, store, u / tiles, int(u % tiles), buf, tile, tw);
 }
 
 // ---------------------------------------------------------------------------------------------- plan selection

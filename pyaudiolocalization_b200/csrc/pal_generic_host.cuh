@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kGT) k_row_scales(const TS* sig, long long n_r
 // device-side chunking of a list whose length only the device knows: round k of `chunk` items holds
 // items[k] = clamp(count - k * chunk, 0, chunk) items = packed[k] = ceil(items[k] / 2) packed inverse transforms
 __global__ void k_chunk_counts(const int* count, int chunk, int rounds, int* items, int* packed) {
-  const int k = threadIdx.x;
+  const int k = threadIdx.x;          // launched with >= kMaxDevRounds threads
   if (k < rounds) {
     long long left = (long long)*count - (long long)k * chunk;
     left = left < 0 ? 0 : (left > chunk ? chunk : left);
@@ -83,7 +83,7 @@ __global__ void k_chunk_counts(const int* count, int chunk, int rounds, int* ite
     packed[k] = int((left + 1) / 2);
   }
 }
-constexpr int kMaxDevRounds = 30;    // rounds of the device-counted float64 sweep (two int arrays next to the counter)
+constexpr int kMaxDevRounds = 96;    // rounds of the device-counted float64 sweep (two int arrays next to the counter)
 
 // flagged item -> its two channel rows (for the float64 re-evaluation)
 __global__ void k_rows_of_items(const int* item_list, const int* count, const int* pairs, int Mics, int P, int* rows) {
@@ -405,11 +405,18 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   long long row_cap = (long long)(rem / L.per_row);
   if (row_cap < min_rows) return cudaErrorMemoryAllocation;
   if (count_dev) {
-    // one round = one pass of every kernel: forward transforms (one per item) and inverse transforms share the chunk
-    const long long chunk = std::min(tr_cap, row_cap);
-    if ((n_list + chunk - 1) / chunk > kMaxDevRounds) return cudaErrorNotSupported;
+    // one round = one pass of every kernel: forward transforms (one per item) and inverse transforms share the chunk.
+    // The rounds must cover the worst case (every item flagged) although a fraction of a percent is the rule, so the
+    // chunk is made as large as the workspace allows: rounds that find nothing cost a few microseconds each.
+    const long long fit = (long long)((ws_bytes - size_t(reinterpret_cast<char*>(conv) - ws)) / (L.per_tr + L.per_row));
+    const long long chunk = std::max<long long>(1, std::min<long long>(fit, 32768));
+    const long long rounds = (n_list + chunk - 1) / chunk;
+    if (rounds > kMaxDevRounds) return cudaErrorNotSupported;
     tr_cap = row_cap = chunk;
-    k_chunk_counts<<<1, 32, 0, c.stream>>>(count_dev, int(chunk), int((n_list + chunk - 1) / chunk), dev_items, dev_packed);
+    base = reinterpret_cast<char*>(conv) + chunk * al(sizeof(cpx<T>) * size_t(p.M));
+    corr = reinterpret_cast<T*>(base);
+    base += 2 * chunk * al(sizeof(T) * size_t(n));
+    k_chunk_counts<<<1, 128, 0, c.stream>>>(count_dev, int(chunk), int(rounds), dev_items, dev_packed);
     count_launch();
   }
   cpx<T>* spec = reinterpret_cast<cpx<T>*>(base);

@@ -10,6 +10,7 @@
 //   normalise_compress_body       main.py:119-122, signal_processing.py:82-94
 #pragma once
 #include "pal_bluestein.cuh"
+#include "pal_fft2.cuh"
 
 namespace pal {
 
@@ -276,8 +277,9 @@ struct RenderRows {
 // One block per (mic, tile of NT*J bins); each thread owns bins m0 + t + NT*j and advances its
 // phasor by a per-path rotation of NT bins; phases are reduced mod 1 in float64 before any
 // single-precision trigonometry (SURVEY.md hard part 6).
+// one work unit: row `lrow` of the chunk (G / live are the chunk's buffers), bins m0 .. m0 + NT*J - 1
 template <int NT, int J>
-PAL_DEV void transfer_body(const cpxf* X, int N, RenderRows rr, long long row0, long long n_rows, double fs, cpxf* G,
+PAL_DEV void transfer_unit(const cpxf* X, int N, const RenderRows& rr, long long row0, long long lrow, int m0, double fs, cpxf* G,
                            int* live /* [n_rows]: 0 = the row has no audible path, its output is exactly zero */, char* smem_raw) {
   const int kcap = rr.k_stride;
   float* s_gain = reinterpret_cast<float*>(smem_raw);         // [k1]
@@ -285,12 +287,9 @@ PAL_DEV void transfer_body(const cpxf* X, int N, RenderRows rr, long long row0, 
   double* s_delta = reinterpret_cast<double*>(s_rot + kcap);   // [k1] turns per bin
   const int tid = simt::tid();
   const int nbins = N + 1;
-  const int tiles = (nbins + NT * J - 1) / (NT * J);
-  for (long long u = simt::bid(); u < n_rows * tiles; u += simt::nblocks()) {
-    const long long lrow = u / tiles;                       // row of this chunk
+  {
     const long long grow = rr.global_row(row0 + lrow);
     const int k1 = rr.paths(grow);
-    const int m0 = int(u % tiles) * NT * J;
     const double* tk = rr.tau + size_t(grow) * rr.k_stride;
     const double* gk = rr.gain + size_t(grow) * rr.k_stride;
     double gmx = 0.0;
@@ -311,21 +310,29 @@ PAL_DEV void transfer_body(const cpxf* X, int N, RenderRows rr, long long row0, 
 #pragma unroll
     for (int j = 0; j < J; ++j) { ar[j] = 0.f; ai[j] = 0.f; }
     const int mt = m0 + tid;
+    // bins this thread really owns (the last tile of a row is partly empty: its threads stop early instead of
+    // accumulating phasors nobody stores)
+    const int jn = mt < nbins ? ((nbins - mt + NT - 1) / NT < J ? (nbins - mt + NT - 1) / NT : J) : 0;
     for (int k = 0; k < k1; ++k) {
+      // seed phasor at bin mt: the phase is reduced mod 1 in float64 (m tau fs / 2N reaches thousands of turns,
+      // SURVEY.md hard part 6); the reduced turn fraction in [0, 1) is then exact to 6e-8 in float32, which is what
+      // the single-precision sincospi needs (3.7e-7 rad: far inside the 1e-5 rendering tolerance)
       double fr = s_delta[k] * double(mt);
       fr -= floor(fr);
       float sn, cs;
-      sincospi_<float>(2.0 * fr, sn, cs);
+      sincospif_(float(2.0 * fr), sn, cs);
       float zr = cs, zi = -sn;
       const float g = s_gain[k];
       const cpxf r = s_rot[k];
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        ar[j] = fmaf(g, zr, ar[j]);
-        ai[j] = fmaf(g, zi, ai[j]);
-        const float nr = fmaf(zr, r.x, -(zi * r.y));
-        zi = fmaf(zr, r.y, zi * r.x);
-        zr = nr;
+        if (j < jn) {
+          ar[j] = fmaf(g, zr, ar[j]);
+          ai[j] = fmaf(g, zi, ai[j]);
+          const float nr = fmaf(zr, r.x, -(zi * r.y));
+          zi = fmaf(zr, r.y, zi * r.x);
+          zr = nr;
+        }
       }
     }
 #pragma unroll
@@ -350,6 +357,13 @@ PAL_DEV void transfer_body(const cpxf* X, int N, RenderRows rr, long long row0, 
     }
     simt::sync_block();
   }
+}
+template <int NT, int J>
+PAL_DEV void transfer_body(const cpxf* X, int N, RenderRows rr, long long row0, long long n_rows, double fs, cpxf* G, int* live,
+                           char* smem_raw) {
+  const int tiles = (N + 1 + NT * J - 1) / (NT * J);
+  for (long long u = simt::bid(); u < n_rows * tiles; u += simt::nblocks())
+    transfer_unit<NT, J>(X, N, rr, row0, u / tiles, int(u % tiles) * NT * J, fs, G, live, smem_raw);
 }
 
 // ------------------------------------------------------------------ Bluestein loader / storer
@@ -416,6 +430,93 @@ template <typename T> struct StoreRender2 {
     if (c.ob) c.ob[j] = c.live_b ? float(fma_(y.y, w.x, -(y.x * w.y)) * f) : 0.f;
   }
 };
+
+// ------------------------------------------------------------------ many buckets per launch
+// With random rooms nearly every scene has its own transform length 2N (N = int((duration + max delay) fs),
+// main.py:102): a batch of 16384 scenes falls into ~1500 buckets of a dozen scenes, and one set of launches per
+// bucket (16-block grids, four launches each) leaves the renderer bound by launch overhead.  A GROUP is a list of
+// buckets that share the convolution plan (M1 x M2; only the chirp tables and the base spectrum differ with N): each
+// of the four kernels runs ONCE per group, a block looks its work unit up in the bucket table (prefix sums of units)
+// and builds the bucket's loader / storer on the fly.
+struct RenderBucket {
+  fft2::Tables tb;                // chirp (length 2N), stage twiddles, twf, chirp spectrum of THIS N
+  const cpxf* X;                  // fft(base zero-padded, 2N)                         (signal_processing.py:69)
+  const long long* scene_index;   // the bucket's scenes (indices into the batch)
+  cpxf* G;                        // [n_rows][N + 1]
+  cpxf* conv;                     // [ceil(n_rows / 2)][M]
+  int* live;                      // [n_rows]
+  long long n_rows;               // bucket scenes x microphones
+  long long xfer0, col0, row0;    // first work unit of the bucket in the transfer / column / row kernels
+  int N, fade;
+};
+template <int WHICH> PAL_DEV long long bucket_first(const RenderBucket& b) { return WHICH == 0 ? b.xfer0 : (WHICH == 1 ? b.col0 : b.row0); }
+// index of the bucket that owns unit u (the table ends with a sentinel bucket holding the unit totals)
+template <int WHICH> PAL_DEV int find_bucket(const RenderBucket* bk, int nb, long long u) {
+  int lo = 0, hi = nb - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (bucket_first<WHICH>(bk[mid]) <= u) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+struct RenderGroupArgs {
+  const RenderBucket* buckets;    // [n_buckets + 1] (last: sentinel with the unit totals)
+  int n_buckets;
+  RenderRows rr;                  // batch-wide path tables; scene_index is taken from the bucket
+  double fs;
+  float* out;                     // [all rows][n_keep]
+  int n_keep;
+};
+template <int NT, int J> PAL_DEV void transfer_group_body(RenderGroupArgs a, char* smem) {
+  const long long total = a.buckets[a.n_buckets].xfer0;
+  for (long long u = simt::bid(); u < total; u += simt::nblocks()) {
+    const RenderBucket& b = a.buckets[find_bucket<0>(a.buckets, a.n_buckets, u)];
+    const int tiles = (b.N + 1 + NT * J - 1) / (NT * J);
+    const long long lu = u - b.xfer0;
+    RenderRows rr = a.rr;
+    rr.scene_index = b.scene_index;
+    transfer_unit<NT, J>(b.X, b.N, rr, 0, lu / tiles, int(lu % tiles) * NT * J, a.fs, b.G, b.live, smem);
+  }
+}
+template <class P, int NT> PAL_DEV void render_group_colfwd_body(RenderGroupArgs a, char* smem) {
+  constexpr int tiles = P::M2 / P::TC;
+  f2* tile = reinterpret_cast<f2*>(smem);
+  const f2* tw = fft2::stage_tw<NT>(a.buckets[0].tb.tw1, P::M1, tile + P::M1 * P::TC);      // plan-wide: any bucket's copy
+  const long long total = a.buckets[a.n_buckets].col0;
+  for (long long u = simt::bid(); u < total; u += simt::nblocks()) {
+    const RenderBucket& b = a.buckets[find_bucket<1>(a.buckets, a.n_buckets, u)];
+    const long long lu = u - b.col0;
+    const BluePlan pl{2 * b.N, P::M, P::M1, P::M2, 0, 0};
+    const LoadHermitian2<float> ld{pl, b.tb.chirp, b.G, b.N, b.n_rows};
+    fft2::colpass_fwd_unit<P, NT>(b.tb, ld, lu / tiles, int(lu % tiles), b.conv, tile, tw);
+  }
+}
+template <class P, int NT> PAL_DEV void render_group_row_body(RenderGroupArgs a, char* smem) {
+  constexpr int tiles = P::M1 / P::TR;
+  f2* tile = reinterpret_cast<f2*>(smem);
+  const f2* tw = fft2::stage_tw<NT>(a.buckets[0].tb.tw2, P::M2, tile + P::M2 * P::LDR);
+  const long long total = a.buckets[a.n_buckets].row0;
+  for (long long u = simt::bid(); u < total; u += simt::nblocks()) {
+    const RenderBucket& b = a.buckets[find_bucket<2>(a.buckets, a.n_buckets, u)];
+    const long long lu = u - b.row0;
+    fft2::rowpass_unit<P, NT, 1>(b.tb, lu / tiles, int(lu % tiles), b.conv, nullptr, tile, tw);
+  }
+}
+template <class P, int NT> PAL_DEV void render_group_colinv_body(RenderGroupArgs a, char* smem) {
+  constexpr int tiles = P::M2 / P::TC;
+  f2* tile = reinterpret_cast<f2*>(smem);
+  const f2* tw = fft2::stage_tw<NT>(a.buckets[0].tb.tw1, P::M1, tile + P::M1 * P::TC);
+  const long long total = a.buckets[a.n_buckets].col0;
+  for (long long u = simt::bid(); u < total; u += simt::nblocks()) {
+    const RenderBucket& b = a.buckets[find_bucket<1>(a.buckets, a.n_buckets, u)];
+    const long long lu = u - b.col0;
+    const BluePlan pl{2 * b.N, P::M, P::M1, P::M2, 0, 0};
+    RenderRows rr = a.rr;
+    rr.scene_index = b.scene_index;
+    const StoreRender2<float> st{pl, b.tb.chirp, a.out, b.N, a.n_keep, b.fade, rr, 0, b.n_rows, b.live};
+    fft2::colpass_inv_unit<P, NT>(b.tb, st, lu / tiles, int(lu % tiles), b.conv, tile, tw);
+  }
+}
 
 // ------------------------------------------------------------------ normalise + log compressor
 // one block per row, in place: x / max|x| ; sign(x) * log1p(|x|/0.8 + 1e-8) / log1p(1.25 + 1e-8)

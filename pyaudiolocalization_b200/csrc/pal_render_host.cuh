@@ -4,6 +4,9 @@
 #include "pal_generic_host.cuh"
 #include "pal_render.cuh"
 
+#include <cstring>
+#include <vector>
+
 namespace palhost {
 
 constexpr int kImgThreads = 128;
@@ -195,6 +198,141 @@ inline cudaError_t render_rows(const float* base, int n_base, int N, RenderRows 
   cudaError_t e = build_render_plan(base, n_base, N, ws, reinterpret_cast<cpxf*>(rest), s, sms);
   if (e != cudaSuccess) return e;
   return render_rows_planned(carve_render_plan(N, ws), N, rr, n_rows, fs, n_keep, out, rest, ws_bytes - plan, s, sms);
+}
+
+// ---------------------------------------------------------------- grouped form: many buckets (transform lengths) per launch
+__global__ void __launch_bounds__(kGT) k_transfer_group(RenderGroupArgs a) {
+  extern __shared__ __align__(16) char smem[];
+  transfer_group_body<kGT, kXferJ>(a, smem);
+}
+template <class P> __global__ void __launch_bounds__(f2h::kNT2, PAL_FFT2_MINBLOCKS) k_render_group_colfwd(RenderGroupArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  render_group_colfwd_body<P, f2h::kNT2>(a, smem);
+}
+template <class P> __global__ void __launch_bounds__(f2h::kNT2, PAL_FFT2_MINBLOCKS) k_render_group_row(RenderGroupArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  render_group_row_body<P, f2h::kNT2>(a, smem);
+}
+template <class P> __global__ void __launch_bounds__(f2h::kNT2, PAL_FFT2_MINBLOCKS) k_render_group_colinv(RenderGroupArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  render_group_colinv_body<P, f2h::kNT2>(a, smem);
+}
+
+// pinned staging for the bucket tables (host -> device, asynchronous): a small ring per process, a slot is reused only
+// after the copy that read it has completed
+struct StagingRing {
+  static constexpr int kSlots = 64;
+  void* host[kSlots] = {};
+  size_t cap[kSlots] = {};
+  cudaEvent_t ev[kSlots] = {};
+  int next = 0;
+  void* acquire(size_t bytes, int& slot) {
+    slot = next;
+    next = (next + 1) % kSlots;
+    if (ev[slot]) cudaEventSynchronize(ev[slot]);
+    else cudaEventCreateWithFlags(&ev[slot], cudaEventDisableTiming);
+    if (cap[slot] < bytes) {
+      if (host[slot]) cudaFreeHost(host[slot]);
+      cap[slot] = std::max<size_t>(bytes, 1 << 18);
+      if (cudaHostAlloc(&host[slot], cap[slot], cudaHostAllocDefault) != cudaSuccess) { host[slot] = nullptr; cap[slot] = 0; }
+    }
+    return host[slot];
+  }
+};
+inline StagingRing& staging_ring() {
+  static thread_local StagingRing r;
+  return r;
+}
+
+struct GroupedBucketIn {
+  const char* plan;        // device memory of the bucket's render plan (pal_render_plan)
+  int N;
+  long long first, count;  // the bucket's scenes: scene_index[first .. first + count)
+};
+inline size_t grouped_bucket_bytes(int N, long long rows, int plan2) {
+  const fft2::PlanDims d = fft2::plan_dims(plan2);
+  return al(sizeof(cpxf) * size_t(rows) * (N + 1)) + al(sizeof(cpxf) * size_t((rows + 1) / 2) * d.M1 * d.M2) + al(sizeof(int) * size_t(rows));
+}
+// Render every bucket of `in` (all planned, all on the second-generation engine) into `out`; buckets that share a
+// convolution plan are issued together, as many per group as the workspace holds.  cudaErrorNotSupported: a bucket has no
+// second-generation plan or does not fit the workspace on its own (the caller renders that batch bucket by bucket).
+inline cudaError_t render_grouped(const GroupedBucketIn* in, int n_in, RenderRows rr_all, const long long* scene_index_dev, double fs,
+                                  int n_keep, float* out, char* ws, size_t ws_bytes, cudaStream_t s, int sms) {
+  if (!use_fft2()) return cudaErrorNotSupported;
+  const int kcap = rr_all.k_stride;
+  const size_t ts = 4 * size_t((kcap + 3) & ~3) + 16 * size_t(kcap) + 16;
+  if (ts > 48 * 1024) cudaFuncSetAttribute(k_transfer_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts);
+  std::vector<int> plan_of(n_in);
+  for (int i = 0; i < n_in; ++i) {
+    plan_of[i] = fft2::choose_plan(2 * in[i].N);
+    if (plan_of[i] < 0) return cudaErrorNotSupported;
+    if (grouped_bucket_bytes(in[i].N, in[i].count * rr_all.n_mics, plan_of[i]) + (1 << 16) > ws_bytes) return cudaErrorNotSupported;
+  }
+  std::vector<RenderBucket> tab;
+  int i0 = 0;
+  while (i0 < n_in) {
+    // group = maximal run i0 .. i1-1 of one plan that fits the workspace
+    const int plan2 = plan_of[i0];
+    const fft2::PlanDims d = fft2::plan_dims(plan2);
+    size_t used = 0;
+    int i1 = i0;
+    while (i1 < n_in && plan_of[i1] == plan2 && i1 - i0 < 8192) {
+      const size_t need = grouped_bucket_bytes(in[i1].N, in[i1].count * rr_all.n_mics, plan2);
+      const size_t table = al(sizeof(RenderBucket) * size_t(i1 - i0 + 2));
+      if (used + need + table + 4096 > ws_bytes) break;
+      used += need;
+      ++i1;
+    }
+    const int nb = i1 - i0;
+    char* base = ws;
+    RenderBucket* tab_dev = reinterpret_cast<RenderBucket*>(base);
+    base += al(sizeof(RenderBucket) * size_t(nb + 1));
+    tab.assign(nb + 1, RenderBucket{});
+    long long xfer = 0, col = 0, row = 0;
+    int tc = 16, tr = 16;
+    fft2::with_plan(plan2, [&](auto pl) { tc = decltype(pl)::TC; tr = decltype(pl)::TR; });
+    for (int k = 0; k < nb; ++k) {
+      const GroupedBucketIn& bi = in[i0 + k];
+      const RenderPlan rp = carve_render_plan(bi.N, const_cast<char*>(bi.plan));
+      RenderBucket& b = tab[k];
+      b.tb = rp.b2.tb();
+      b.X = rp.X;
+      b.scene_index = scene_index_dev + bi.first;
+      b.n_rows = bi.count * rr_all.n_mics;
+      b.N = bi.N;
+      b.fade = int(0.01 * bi.N);
+      b.G = reinterpret_cast<cpxf*>(base);    base += al(sizeof(cpxf) * size_t(b.n_rows) * (bi.N + 1));
+      b.conv = reinterpret_cast<cpxf*>(base); base += al(sizeof(cpxf) * size_t((b.n_rows + 1) / 2) * d.M1 * d.M2);
+      b.live = reinterpret_cast<int*>(base);  base += al(sizeof(int) * size_t(b.n_rows));
+      b.xfer0 = xfer; b.col0 = col; b.row0 = row;
+      const long long ntr = (b.n_rows + 1) / 2;
+      xfer += b.n_rows * ((bi.N + 1 + kGT * kXferJ - 1) / (kGT * kXferJ));
+      col += ntr * (d.M2 / tc);
+      row += ntr * (d.M1 / tr);
+    }
+    tab[nb].xfer0 = xfer; tab[nb].col0 = col; tab[nb].row0 = row;      // sentinel: unit totals
+    int slot = 0;
+    void* host = staging_ring().acquire(sizeof(RenderBucket) * size_t(nb + 1), slot);
+    if (!host) return cudaErrorMemoryAllocation;
+    std::memcpy(host, tab.data(), sizeof(RenderBucket) * size_t(nb + 1));
+    cudaError_t e = cudaMemcpyAsync(tab_dev, host, sizeof(RenderBucket) * size_t(nb + 1), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    cudaEventRecord(staging_ring().ev[slot], s);
+    RenderGroupArgs a{tab_dev, nb, rr_all, fs, out, n_keep};
+    a.rr.scene_index = nullptr;
+    k_transfer_group<<<(unsigned)std::min<long long>(xfer, 32LL * sms), kGT, ts, s>>>(a);
+    fft2::with_plan(plan2, [&](auto pl) {
+      using P = decltype(pl);
+      k_render_group_colfwd<P><<<f2h::grid_for<k_render_group_colfwd<P>>(P::col_smem, col, sms), f2h::kNT2, P::col_smem, s>>>(a);
+      k_render_group_row<P><<<f2h::grid_for<k_render_group_row<P>>(P::row_smem, row, sms), f2h::kNT2, P::row_smem, s>>>(a);
+      k_render_group_colinv<P><<<f2h::grid_for<k_render_group_colinv<P>>(P::col_smem, col, sms), f2h::kNT2, P::col_smem, s>>>(a);
+    });
+    count_launch(4);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    i0 = i1;
+  }
+  return cudaSuccess;
 }
 
 inline cudaError_t normalise_rows(float* out, long long n_rows, int n_keep, cudaStream_t s, int sms) {

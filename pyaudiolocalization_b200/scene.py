@@ -310,7 +310,7 @@ def prepare_render(base_signal, sources, img_pos: torch.Tensor, img_mat: torch.T
 
 
 def execute_render(job: RenderJob, normalise: bool = True, max_workspace_bytes: int = 4 << 30, max_streams: int = 16,
-                   plan_cache: Optional[RenderPlanCache] = None) -> torch.Tensor:
+                   plan_cache: Optional[RenderPlanCache] = None, grouped: bool = True, grouped_parts: int = 4) -> torch.Tensor:
     """Rendering half of render_scenes_batched: every bucket of scenes that share N is one pal_render_scenes(_planned)
     call; only enqueues work on the current stream (and a pool of side streams joined at the end)."""
     dev, L = job.dev, _lib.lib()
@@ -321,6 +321,62 @@ def execute_render(job: RenderJob, normalise: bool = True, max_workspace_bytes: 
     # almost every N is different and a bucket holds a handful of scenes, so the buckets are issued round-robin on a
     # pool of streams (the library is stateless and stream-ordered): the small grids of different buckets overlap
     # instead of queueing behind each other.  Each stream owns a workspace slice.
+    if plan_cache is not None and grouped and len(uniq) > 1:
+        # every bucket in ONE call (pal_render_scenes_grouped): plans first (cache misses are built here), then four
+        # launches per group of buckets instead of four per bucket
+        cur = torch.cuda.current_stream(dev)
+        # plans the cache does not hold yet are built round-robin on the stream pool (a dozen small launches each)
+        missing = [int(t) for t in uniq if int(t) not in plan_cache.plans]
+        if missing:
+            bpool = _stream_pool(dev, min(int(max_streams), len(missing)))
+            ev0 = torch.cuda.Event()
+            ev0.record(cur)
+            for st in bpool:
+                st.wait_event(ev0)
+            for i, t in enumerate(missing):
+                plan_cache.get(base, n_base, t, dev, bpool[i % len(bpool)])
+            for st in bpool:
+                cur.wait_stream(st)
+        plans = [plan_cache.get(base, n_base, int(total), dev, cur) for total in uniq]
+        n_arr = np.ascontiguousarray(uniq, dtype=np.int32)
+        first = np.ascontiguousarray(bounds, dtype=np.int64)
+        # The buckets go down in a few parts, each on its own stream: the transfer-function kernel of one part (FP32-bound)
+        # then overlaps the convolution passes of another (shared-memory / bandwidth-bound).
+        rows_cum = first * m
+        n_parts = max(1, min(int(grouped_parts), len(uniq)))
+        cuts = [int(np.searchsorted(rows_cum, rows_cum[-1] * k / n_parts)) for k in range(n_parts + 1)]
+        cuts[0], cuts[-1] = 0, len(uniq)
+        cuts = sorted(set(cuts))
+        pool = _stream_pool(dev, len(cuts) - 1) if len(cuts) > 2 else [cur]
+        budget = min(int(max_workspace_bytes), 3 << 30) // (len(cuts) - 1)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        rc, held = 0, []
+        for k in range(len(cuts) - 1):
+            b0, b1 = cuts[k], cuts[k + 1]
+            ptrs = (C.c_void_p * (b1 - b0))(*[p[1] for p in plans[b0:b1]])
+            ws, wp, wl = _ws(budget, dev)
+            held.append(ws)
+            st = pool[k]
+            if st is not cur:
+                st.wait_event(ready)
+            rc = L.pal_render_scenes_grouped(b1 - b0, ptrs, n_arr[b0:b1].ctypes.data, first[b0:b1 + 1].ctypes.data, tau.data_ptr(),
+                                             gain.data_ptr(), pcount.data_ptr(), k_stride, idx_dev.data_ptr(), m, float(fs), n_keep,
+                                             out.data_ptr(), wp, wl, st.cuda_stream)
+            if rc != 0:
+                break
+        for st in pool:
+            if st is not cur:
+                cur.wait_stream(st)
+        if rc == 0:
+            if normalise:
+                _lib.check(L.pal_normalise_compress(out.data_ptr(), s_n * m, n_keep, 0.8, 1e-8, 1, _stream(dev)),
+                           "pal_normalise_compress")
+            for t in [base, tau, gain, pcount, job.mics, job.src, idx_dev] + held + [p[0] for p in plans]:
+                t.record_stream(cur)
+            return out
+        if rc != -4:                      # PAL_ERR_UNSUPPORTED: fall through to the per-bucket path
+            _lib.check(rc, "pal_render_scenes_grouped")
     rows_max = int(np.max(np.diff(bounds))) * m
     need, small = C.c_size_t(0), C.c_size_t(0)
     if plan_cache is None:

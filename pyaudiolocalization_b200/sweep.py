@@ -70,7 +70,7 @@ class SceneSweep:
     GCC-PHAT / TDOA pick on the rendered channels and all-gathers the lag indices of all ranks."""
 
     def __init__(self, cfg: SweepConfig, scenes_per_rank: int, chunk: int = 16384, device=None, group=None,
-                 gather: bool = True, keep_signals: int = 0, materials=None, solve: bool = False):
+                 gather: bool = True, keep_signals: int = 0, materials=None, solve: bool = False, parts: int = 4):
         from .signal_processing import generate_signal
         self.cfg = cfg
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -90,6 +90,7 @@ class SceneSweep:
         # solve=True: the sweep ends in source positions (pal_solve_positions: the reference's residuals and box, one
         # warp per scene) instead of TDOA vectors; the lag indices are gathered either way
         self.solve = bool(solve)
+        self.parts = int(parts)        # streams the grouped renderer spreads a chunk's buckets over
         self.positions = torch.empty((self.n, 3), dtype=torch.float64, device=self.dev) if self.solve else None
         self.render_ms = self.gcc_ms = self.solve_ms = 0.0
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -122,7 +123,7 @@ class SceneSweep:
             if self.timed:
                 self._ev[0].record()
             cur.wait_event(job.done)
-            sig = _scene.execute_render(job, plan_cache=self.cache)
+            sig = _scene.execute_render(job, plan_cache=self.cache, grouped_parts=self.parts)
             for t in (job.tau, job.gain, job.pcount, job.src, job.mics, job.idx_dev):
                 t.record_stream(cur)            # allocated under the side stream, consumed on this one
             if self.timed:

@@ -302,3 +302,24 @@ def test_planes_array_form_equals_list_form(pal):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     with pytest.raises(ValueError):
         scene.image_sources_batched(srcs, (arr[:, :, :3], names), 3, 500.0, CUSTOM_MATERIALS, mics, 0.01)
+
+
+def test_grouped_render_equals_per_bucket_render(pal):
+    """pal_render_scenes_grouped (every bucket of a batch in four launches per group) must reproduce the per-bucket
+    path bit for bit: 96 random rooms (nearly as many transform lengths), with a small workspace that forces several
+    groups."""
+    from pyaudiolocalization_b200 import main as M, scene, sweep
+    cfg = sweep.SweepConfig()
+    src, mic, pl = sweep.random_shoebox_scenes(96, cfg.mics, 99)
+    from pyaudiolocalization_b200.signal_processing import generate_signal
+    base = torch.as_tensor(generate_signal(cfg.signal_type, cfg.fs, cfg.duration, cfg.freq).astype(np.float32)).cuda()
+    job = M.prepare_scenes_batched(src, mic, cfg.fs, cfg.c, cfg.duration, cfg.signal_type, cfg.freq, (pl, sweep.ROOM_MATERIALS),
+                                   sweep.SWEEP_MATERIALS, cfg.max_reflections, cfg.absorption_threshold, base_signal=base)
+    assert len(job.uniq) > 40
+    cache = scene.RenderPlanCache()
+    a = scene.execute_render(job, plan_cache=cache, grouped=False)
+    b = scene.execute_render(job, plan_cache=cache, grouped=True)
+    c = scene.execute_render(job, plan_cache=cache, grouped=True, max_workspace_bytes=96 << 20)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    assert float(a.abs().max()) == 1.0

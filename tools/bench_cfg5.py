@@ -25,7 +25,8 @@ def main():
     ap.add_argument("--scenes-per-gpu", type=int, default=32768)
     ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--parts", type=int, default=4, help="streams the grouped renderer spreads its buckets over")
+    ap.add_argument("--warmup", type=int, default=3)
     args = ap.parse_args()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -39,7 +40,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = sweep.SweepConfig()
     s_n = args.scenes_per_gpu
-    sw = sweep.SceneSweep(cfg, s_n, chunk=args.chunk, device=dev)
+    sw = sweep.SceneSweep(cfg, s_n, chunk=args.chunk, device=dev, parts=args.parts)
     sets = [sweep.random_shoebox_scenes(s_n, cfg.mics, 5000 + rank + 1000 * i) for i in range(args.warmup + args.steps)]
 
     def barrier():
