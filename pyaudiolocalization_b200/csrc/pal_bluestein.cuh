@@ -377,12 +377,15 @@ template <typename T, typename TS = float> struct LoadSignal2 {
     x.sb = rb >= 0 ? T(scales[2 * rb]) : T(0);
     return x;
   }
+  // loads are unconditional (indices clamped into the row, values masked): the compiler can then batch the loads of
+  // several samples instead of paying one memory round trip per sample
   PAL_DEV cpx<T> operator()(const Ctx& c, int j) const {
-    if (j >= p.n) return cpx<T>{T(0), T(0)};
+    const bool ina = j < c.la, inb = j < c.lb;
+    const int ja = ina ? j : 0, jb = inb ? j : 0, jw = j < p.n ? j : 0;
     // the scale is an exact power of two: the product is exact in the sample type
-    const T x = (j < c.la) ? T(c.xa[j] * TS(c.sa)) : T(0);
-    const T y = (j < c.lb) ? T(c.xb[j] * TS(c.sb)) : T(0);
-    const cpx<T> w = chirp[j];
+    const T x = T(c.xa[ja] * TS(ina ? c.sa : T(0)));
+    const T y = T(c.xb[jb] * TS(inb ? c.sb : T(0)));
+    const cpx<T> w = chirp[jw];
     return cpx<T>{fma_(x, w.x, -(y * w.y)), fma_(x, w.y, y * w.x)};
   }
 };

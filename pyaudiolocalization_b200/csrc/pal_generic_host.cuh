@@ -63,8 +63,13 @@ __global__ void __launch_bounds__(kGT) k_pick_rows(const T* corr, int n, int c0,
 }
 __global__ void __launch_bounds__(kGT) k_win_pick(const float* win, const float* pmax, int tiles, long long n_rows, WinGeom g,
                                                   long long item0, int* k_idx, int* k_count, float* peak, float* gmax,
-                                                  unsigned* flags, unsigned extra_flag) {
-  win_pick_rows_body<kGT>(win, pmax, tiles, n_rows, g, item0, k_idx, k_count, peak, gmax, flags, extra_flag);
+                                                  unsigned* flags, unsigned extra_flag, WhitenRef wr) {
+  win_pick_rows_body<kGT>(win, pmax, tiles, n_rows, g, item0, k_idx, k_count, peak, gmax, flags, extra_flag, wr);
+}
+__global__ void __launch_bounds__(kGT) k_whiten_unpack(const cpxf* Z, int n, long long n_packed, int Mics, int CP, const float* scales,
+                                                       long long row_base, long long local_row_base, cpxf* U, float* hq) {
+  __shared__ float sh[2 * kGT / 32];
+  whiten_unpack_body<kGT>(Z, n, n_packed, Mics, CP, scales, row_base, local_row_base, U, hq, reinterpret_cast<char*>(sh));
 }
 template <typename TS>
 __global__ void __launch_bounds__(kGT) k_row_scales(const TS* sig, long long n_rows, long long ld, int len_even, int len_odd,
@@ -115,7 +120,7 @@ template <typename T> struct GenericLayout {
     tables = al(sizeof(cpx<T>) * size_t(p.n)) + al(sizeof(cpx<T>) * (p.M1 / 2 + 1)) +
              al(sizeof(cpx<T>) * (p.M2 / 2 + 1)) + 2 * al(sizeof(cpx<T>) * size_t(p.M)) + 8192;
     per_tr = al(sizeof(cpx<T>) * size_t(p.M)) + 2 * al(sizeof(T) * size_t(p.n));   // a packed inverse yields two rows
-    per_row = al(sizeof(cpx<T>) * size_t(p.n));
+    per_row = al(sizeof(cpx<T>) * size_t(p.n + 2));      // a packed spectrum row, or the Hermitian halves of its two channels
   }
 };
 
@@ -397,6 +402,24 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   tr_cap = std::max<long long>(1, std::min<long long>(tr_cap, conv_chunk_bytes() / (long long)(sizeof(cpx<T>) * size_t(p.M))));
   tr_cap = std::min<long long>(tr_cap, std::max<long long>((total_items + 1) / 2, list ? (long long)n_list : c.B * CP));
   while (tr_cap > 1 && rem < size_t(tr_cap) * L.per_tr + size_t(min_rows) * L.per_row) tr_cap /= 2;
+  // reduced pick (pal_winpick.cuh): one peak, no correlation rows wanted, near-tie audit on, first sweep only.  Its forward
+  // sub-chunks must start on frame boundaries (the channels of a frame are whitened together).
+  const int c0 = c.n2 - 1;
+  const WinGeom wg = make_win_geom(n, c0, c.pp.win_half, c.pp.dist, c.eps);
+  const int win_tiles = plan2 >= 0 ? fft2::plan_dims(plan2).M2 / (fft2::plan_dims(plan2).M1 <= 192 ? 32 : 16) : 0;
+  const bool fast_pick = plan2 >= 0 && !list && c.pp.num_peaks == 1 && !c.corr_out && c.eps > 0.f && use_fast_pick() &&
+                         size_t(wg.wstride + win_tiles) * sizeof(float) <= al(sizeof(T) * size_t(n)) && tr_cap >= CP;
+  // per-channel whitening pays when a channel is used by several pairs (cfg5: 28 pairs / 8 channels, cfg4: 2016 / 64);
+  // with few pairs per channel (cfg2: 6 / 4) the extra pass over the spectra costs more than the leaner pair loader saves
+  const bool whiten = fast_pick && c.P >= 2 * c.Mics;
+  if (whiten) tr_cap -= tr_cap % CP;
+  float* hq_res = nullptr;           // [resident frames * Mics] whitening bounds of the fast path
+  if (whiten) {
+    hq_res = reinterpret_cast<float*>(base);
+    base += al(sizeof(float) * size_t(c.B) * c.Mics);
+    rem = ws_bytes - size_t(base - ws);
+    while (tr_cap > CP && rem < size_t(tr_cap) * L.per_tr + size_t(min_rows) * L.per_row) tr_cap -= CP;
+  }
   cpx<T>* conv = reinterpret_cast<cpx<T>*>(base);
   base += tr_cap * al(sizeof(cpx<T>) * size_t(p.M));
   T* corr = reinterpret_cast<T*>(base);
@@ -425,7 +448,6 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   const BlueTables<T> tb = bb.tb();
-  const int c0 = c.n2 - 1;
   const BluePlan pl = plan2 >= 0 ? b2.p : p;        // what loaders / storers see: n and the convolution length
   if (plan2 >= 0) {
     if constexpr (std::is_same<T, float>::value) {
@@ -433,11 +455,6 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
       if (e != cudaSuccess) return e;
     }
   }
-  // reduced pick (pal_winpick.cuh): one peak, no correlation rows wanted, near-tie audit on, first sweep only
-  const WinGeom wg = make_win_geom(n, c0, c.pp.win_half, c.pp.dist, c.eps);
-  const int win_tiles = plan2 >= 0 ? fft2::plan_dims(plan2).M2 / (fft2::plan_dims(plan2).M1 <= 192 ? 32 : 16) : 0;
-  const bool fast_pick = plan2 >= 0 && !list && c.pp.num_peaks == 1 && !c.corr_out && c.eps > 0.f && use_fast_pick() &&
-                         size_t(wg.wstride + win_tiles) * sizeof(float) <= al(sizeof(T) * size_t(n));
   if (!list) {
     if (c.sig64)
       k_row_scales<double><<<(unsigned)std::min<long long>(c.B * c.Mics, 16LL * c.sms), kGT, 0, c.stream>>>(c.sig64, c.B * c.Mics, c.ld,
@@ -480,6 +497,18 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
       }
       LoadSignal2<T> ld{pl, bb.chirp, c.sig, c.ld, c.Mics, CP, c.n1, c.n2, row_list, g0 + r0, c.scales};
       if constexpr (std::is_same<T, float>::value) {
+        if (whiten) {
+          // packed spectra of this sub-chunk into the (still unused) correlation-row region, then every channel
+          // unpacked, whitened and halved into the resident spectrum rows (pal_winpick.cuh: whiten_unpack_body)
+          cpxf* ztmp = reinterpret_cast<cpxf*>(corr);
+          f2h::conv<false>(b2, ld, StoreSpectrum<T>{pl, bb.chirp, ztmp}, nt, reinterpret_cast<cpxf*>(conv), c.stream, c.sms);
+          const long long frame_first = (g0 + r0) / CP;           // sub-chunks start on frame boundaries (see below)
+          k_whiten_unpack<<<(unsigned)std::min<long long>(nt, 16LL * c.sms), kGT, 0, c.stream>>>(
+              ztmp, n, nt, c.Mics, CP, c.scales, frame_first * c.Mics, (frame_first - g0 / CP) * c.Mics,
+              reinterpret_cast<cpxf*>(spec_out), hq_res);
+          count_launch();
+          continue;
+        }
         if (plan2 >= 0) {
           f2h::conv<false>(b2, ld, StoreSpectrum<T>{pl, bb.chirp, spec_out + r0 * n}, nt, reinterpret_cast<cpxf*>(conv), c.stream, c.sms);
           continue;
@@ -517,7 +546,7 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
         continue;
       }
       if constexpr (std::is_same<T, float>::value) {
-        if (fast_pick) {
+        if (fast_pick && !whiten) {
           // only the window (+ margin) and per-tile row maxima leave the inverse column pass; one warp per row picks
           float* win = reinterpret_cast<float*>(corr);
           float* pmax = win + size_t(2 * tr_cap) * wg.wstride;
@@ -525,7 +554,23 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
           f2h::conv<true>(b2, ld, sw, nt, reinterpret_cast<cpxf*>(conv), c.stream, c.sms);
           const long long o = out0 + i0;
           k_win_pick<<<(unsigned)std::min<long long>((ni + kGT / 32 - 1) / (kGT / 32), 8LL * c.sms), kGT, 0, c.stream>>>(
-              win, pmax, win_tiles, ni, wg, o, c.k_idx, c.k_count, c.peak, c.gmax, c.flags, extra_flag);
+              win, pmax, win_tiles, ni, wg, o, c.k_idx, c.k_count, c.peak, c.gmax, c.flags, extra_flag,
+              WhitenRef{nullptr, nullptr, 0, 0, 0});
+          count_launch(1);
+          continue;
+        }
+        if (fast_pick) {
+          // whitened half spectra in, only the window (+ margin) and per-tile row maxima out; one warp per row picks
+          float* win = reinterpret_cast<float*>(corr);
+          float* pmax = win + size_t(2 * tr_cap) * wg.wstride;
+          const LoadPhatU lu{pl, b2.chirp, reinterpret_cast<const cpxf*>(spec_in), c.pairs, c.Mics, c.P, n / 2 + 1, i0, nitems,
+                             c.scales, frame0};
+          StoreWinU sw{pl, b2.chirp, win, pmax, ni, lu, wg, win_tiles};
+          f2h::conv<true>(b2, lu, sw, nt, reinterpret_cast<cpxf*>(conv), c.stream, c.sms);
+          const long long o = out0 + i0;
+          k_win_pick<<<(unsigned)std::min<long long>((ni + kGT / 32 - 1) / (kGT / 32), 8LL * c.sms), kGT, 0, c.stream>>>(
+              win, pmax, win_tiles, ni, wg, o, c.k_idx, c.k_count, c.peak, c.gmax, c.flags, extra_flag,
+              WhitenRef{hq_res, c.pairs, c.Mics, c.P, i0});
           count_launch(1);
           continue;
         }

@@ -386,15 +386,19 @@ template <typename T> struct LoadHermitian2 {
     return Ctx{G + (2 * t) * (N + 1), (2 * t + 1 < n_rows) ? G + (2 * t + 1) * (N + 1) : nullptr};
   }
   PAL_DEV cpx<T> half(const cpxf* g_row, int k) const {
-    const cpxf g = (k <= N) ? g_row[k] : g_row[p.n - k];
+    const cpxf g = g_row[(k <= N) ? k : p.n - k];
     const bool self_conj = (k == 0) || (k == N);
     return cpx<T>{T(g.x), self_conj ? T(0) : ((k <= N) ? T(g.y) : T(-g.y))};
   }
+  // unconditional loads (index clamped, value masked) so that the loads of several samples can be in flight together
   PAL_DEV cpx<T> operator()(const Ctx& c, int k) const {
-    if (k >= p.n) return cpx<T>{T(0), T(0)};
-    const cpx<T> a = half(c.ga, k);
-    const cpx<T> b = c.gb ? half(c.gb, k) : cpx<T>{T(0), T(0)};
-    return cmulc(cpx<T>{a.x - b.y, a.y + b.x}, chirp[k]);      // inverse transform: conjugate chirp
+    const bool in = k < p.n;
+    const int kc = in ? k : 0;
+    const T m = in ? T(1) : T(0);
+    const cpx<T> a = half(c.ga, kc);
+    const cpx<T> b = half(c.gb ? c.gb : c.ga, kc);
+    const T mb = c.gb ? m : T(0);
+    return cmulc(cpx<T>{a.x * m - b.y * mb, a.y * m + b.x * mb}, chirp[kc]);      // inverse transform: conjugate chirp
   }
 };
 // y[j] = Re / Im (conv[j] * conj(chirp[j])) / (2N) * fade[j], j < n_keep   (signal_processing.py:72-79)

@@ -59,15 +59,134 @@ PAL_HD WinGeom make_win_geom(int n, int c0, int win_half, int dist, float eps) {
   return g;
 }
 
+// ---- per-channel whitening (the fast path's form of the PHAT weighting, as on the n = 4095 path) ------------------
+// |S_i conj(S_j)| = |S_i| |S_j|, so R / (|R| + 1e-10) = U_i conj(U_j) g with U = S / |S| and g = m / (m + 1e-10),
+// m = |S_i| |S_j|.  Every channel is unpacked from its packed transform and normalised ONCE (M times per frame instead
+// of P times), only the Hermitian half is kept, and the pair loader multiplies two unit phasors: 2 loads and one complex
+// product per pair and bin instead of 4 loads, an unpack and a reciprocal square root.  The factor g is not ignored but
+// BOUNDED per row: |corr_U[k] - corr[k]| <= (1/n) sum_k 1e-10 / m_k <= 1e-10 sqrt(h_i h_j) (Cauchy-Schwarz) with
+// h = mean_k 1 / |S_k|^2 at the signal's true level, one float per channel.  The pick widens its near-tie margin by the
+// bound and sends the row to the float64 sweep when the bound exceeds 2 eps (very quiet channels, where the reference's
+// absolute 1e-10 makes the result level-dependent); a bin with S = 0 gives U = 0 (R = 0 in both forms) and h = inf.
+// Z: packed spectra [n_packed][n]; frame-major: packed row g <-> frame g / CP, channels 2c, 2c+1 (c = g % CP).
+// U: [frames * Mics][Hn], Hn = n / 2 + 1; hq: [frames * Mics]; scales: [.][2] of the channels (global rows from row_base).
+template <int NT>
+PAL_DEV void whiten_unpack_body(const cpxf* Z, int n, long long n_packed, int Mics, int CP, const float* scales, long long row_base,
+                                long long local_row_base, cpxf* U, float* hq, char* smem) {
+  float* sh = reinterpret_cast<float*>(smem);      // [2][NT / 32]
+  const int Hn = n / 2 + 1;
+  for (long long g = simt::bid(); g < n_packed; g += simt::nblocks()) {
+    const long long f = g / CP;
+    const int c = int(g - f * CP);
+    const long long ra = local_row_base + f * Mics + 2 * c;            // resident channel rows of the pair
+    const bool has_b = 2 * c + 1 < Mics;
+    const cpxf* z = Z + g * n;
+    cpxf* ua = U + ra * Hn;
+    cpxf* ub = U + (ra + 1) * Hn;
+    float sa = 0.f, sb = 0.f;
+    for (int k = simt::tid(); k < Hn; k += NT) {
+      const cpxf a = unpack_two_real<float>(z, n, k, false);
+      const cpxf b = unpack_two_real<float>(z, n, k, true);
+      const float wgt = (k == 0 || 2 * k == n) ? 1.f : 2.f;           // bins k and n - k carry the same magnitude
+      const float ma = fma_(a.x, a.x, a.y * a.y), mb = fma_(b.x, b.x, b.y * b.y);
+      float ia = 0.f, ib = 0.f;
+#if PAL_GPU
+      if (ma > 0.f) ia = rsqrtf(ma);
+      if (mb > 0.f) ib = rsqrtf(mb);
+#else
+      if (ma > 0.f) ia = 1.f / std::sqrt(ma);
+      if (mb > 0.f) ib = 1.f / std::sqrt(mb);
+#endif
+      ua[k] = cpxf{a.x * ia, a.y * ia};
+      if (has_b) ub[k] = cpxf{b.x * ib, b.y * ib};
+      sa += wgt * (ma > 0.f ? ia * ia : 3.0e38f);
+      sb += wgt * (mb > 0.f ? ib * ib : 3.0e38f);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      sa += simt::shfl_xor(sa, m);
+      sb += simt::shfl_xor(sb, m);
+    }
+    if (simt::lane() == 0) { sh[simt::warp()] = sa; sh[NT / 32 + simt::warp()] = sb; }
+    simt::sync_block();
+    if (simt::tid() == 0) {
+      float ta = 0.f, tb = 0.f;
+      for (int w = 0; w < NT / 32; ++w) { ta += sh[w]; tb += sh[NT / 32 + w]; }
+      // back to the signal's own level: S_true = S_scaled * 2^e, so 1 / |S_true|^2 = 2^-2e / |S_scaled|^2
+      const long long gra = row_base + f * Mics + 2 * c;
+      const float ea = scales[2 * gra], eb = has_b ? scales[2 * (gra + 1)] : 0.f;
+      hq[ra] = ta / float(n) * ea * ea;
+      if (has_b) hq[ra + 1] = tb / float(n) * eb * eb;
+    }
+    simt::sync_block();
+  }
+}
+
+// inverse DFT of TWO whitened cross spectra per transform: a[k] = (R_A[k] + i R_B[k]) conj(chirp[k]) / n with
+// R[k] = U_i[k] conj(U_j[k]) (k <= n/2) and R[n - k] = conj(R[k]); items A = t_off + 2t, B = A + 1 (frame-major).
+struct LoadPhatU {
+  BluePlan p;
+  const cpxf* chirp;
+  const cpxf* U;           // [resident frames * Mics][Hn]
+  const int* pairs;        // [P][2]
+  int Mics, P, Hn;
+  long long t_off, n_items;
+  const float* scales;     // [all rows][2], indexed by GLOBAL channel row (dead channels)
+  long long frame_base;    // global index of resident frame 0
+  struct Item {
+    const cpxf *ui, *uj;
+    bool present, dead;
+  };
+  PAL_DEV Item item(long long it) const {
+    Item m;
+    m.present = it < n_items;
+    if (!m.present) {
+      m.ui = m.uj = U;
+      m.dead = true;
+      return m;
+    }
+    const long long f = it / P;
+    const int pr = int(it - f * P);
+    const int mi = pairs[2 * pr], mj = pairs[2 * pr + 1];
+    m.ui = U + (f * Mics + mi) * Hn;
+    m.uj = U + (f * Mics + mj) * Hn;
+    m.dead = scales[2 * ((frame_base + f) * Mics + mi)] == 0.f || scales[2 * ((frame_base + f) * Mics + mj)] == 0.f;
+    return m;
+  }
+  struct Ctx {
+    Item a, b;
+  };
+  PAL_DEV Ctx begin(long long t) const {
+    const long long ia = t_off + 2 * t;
+    return Ctx{item(ia), item(ia + 1)};
+  }
+  // branch-free on purpose: every load is unconditional (absent / dead items point at valid memory and are masked
+  // afterwards), so the compiler can issue the loads of several samples back to back instead of one round trip at a time
+  PAL_DEV cpxf operator()(const Ctx& c, int k) const {
+    const bool in = k < p.n;
+    const int kc = in ? k : 0;
+    const bool up = 2 * kc > p.n;                // upper half: R[k] = conj(R[n - k])
+    const int kk = up ? p.n - kc : kc;
+    const cpxf a1 = c.a.ui[kk], b1 = c.a.uj[kk], a2 = c.b.ui[kk], b2 = c.b.uj[kk], w = chirp[kc];
+    const float ma = (in && !c.a.dead) ? 1.f / float(p.n) : 0.f;
+    const float mb = (in && c.b.present && !c.b.dead) ? 1.f / float(p.n) : 0.f;
+    const float sg = up ? -1.f : 1.f;
+    const float rax = fma_(a1.x, b1.x, a1.y * b1.y) * ma, ray = fma_(a1.y, b1.x, -(a1.x * b1.y)) * (ma * sg);     // a conj(b)
+    const float rbx = fma_(a2.x, b2.x, a2.y * b2.y) * mb, rby = fma_(a2.y, b2.x, -(a2.x * b2.y)) * (mb * sg);
+    const float xr = rax - rby, xi = ray + rbx;
+    return cpxf{fma_(xr, w.x, xi * w.y), fma_(xi, w.x, -(xr * w.y))};          // (R_A + i R_B) conj(chirp)
+  }
+};
+
 // packed inverse transform -> window samples + per-tile row maxima (see the header comment).  Protocol of a storer of
 // pal_fft2.cuh: begin(t) per work unit, operator() per sample, finish() once per unit by the whole block.
-struct StoreWin2 {
+template <class Src> struct StoreWin2T {
   BluePlan p;
   const cpxf* chirp;
   float* win;              // [rows of this launch][g.wstride]
   float* pmax;             // [rows of this launch][tiles]
   long long n_rows;        // rows of this launch (the last transform may own a single row)
-  LoadPhat2<float> src;    // what was transformed: a dead item's row is exact zeros (the reference's R = 0)
+  Src src;                 // what was transformed: a dead item's row is exact zeros (the reference's R = 0)
   WinGeom g;
   int tiles;
   struct Ctx {
@@ -124,6 +243,9 @@ struct StoreWin2 {
   }
 };
 
+using StoreWin2 = StoreWin2T<LoadPhat2<float>>;
+using StoreWinU = StoreWin2T<LoadPhatU>;
+
 PAL_DEV float wmax_f(float v) {
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) v = max_(v, simt::shfl_xor(v, m));
@@ -139,14 +261,32 @@ PAL_DEV int wmax_i(int v) {
 }
 
 // One warp per row.  rows: win[row][wstride], pmax[row][tiles]; results of row r go to item item0 + r.
+// hq != nullptr: the rows come from whitened spectra (LoadPhatU); row r is item first_item + r of the resident frames,
+// hq [resident frames * Mics] holds the per-channel whitening bound (whiten_unpack_body)
+struct WhitenRef {
+  const float* hq;
+  const int* pairs;
+  int Mics, P;
+  long long first_item;
+};
 template <int NT>
 PAL_DEV void win_pick_rows_body(const float* win, const float* pmax, int tiles, long long n_rows, WinGeom g, long long item0,
-                                int* k_idx, int* k_count, float* peak, float* gmax, unsigned* flags, unsigned extra_flag) {
+                                int* k_idx, int* k_count, float* peak, float* gmax, unsigned* flags, unsigned extra_flag,
+                                WhitenRef wr = WhitenRef{nullptr, nullptr, 0, 0, 0}) {
   const int lane = simt::lane();
   const int lo = g.lo, hi = g.hi, dist = g.dist;
-  const float eps = g.eps;
   const int g_lo = (lo + 3) & ~3, g_hi = (hi + 1) & ~3;      // window split into 16-byte groups + <= 3 + 3 edge samples
   for (long long row = (long long)simt::bid() * (NT / 32) + simt::warp(); row < n_rows; row += (long long)simt::nblocks() * (NT / 32)) {
+    float eps = g.eps;
+    bool quiet = false;
+    if (wr.hq) {
+      const long long it = wr.first_item + row;
+      const long long f = it / wr.P;
+      const int pr = int(it - f * wr.P);
+      const float hb = 1e-10f * sqrt_(wr.hq[f * wr.Mics + wr.pairs[2 * pr]] * wr.hq[f * wr.Mics + wr.pairs[2 * pr + 1]]);
+      quiet = !(hb <= 2.f * g.eps);          // also catches inf / NaN
+      if (!quiet) eps += hb;
+    }
     const float* c = win + row * g.wstride - g.wlo;            // c[k] valid for wlo <= k <= whi
     float gm = kWinNegBig;
     for (int t = lane; t < tiles; t += 32) gm = max_(gm, pmax[row * tiles + t]);
@@ -183,7 +323,7 @@ PAL_DEV void win_pick_rows_body(const float* win, const float* pmax, int tiles, 
     const float bv = wmax_f(b1);
     const int bi = wmax_i((b1 == bv) ? ksel : -1);      // equal maxima: the later one (it is flagged as a tie anyway)
     const float cand2 = wmax_f((ksel == bi) ? b2 : b1);
-    unsigned fl = extra_flag;
+    unsigned fl = extra_flag | (quiet ? PAL_FLAG_NEAR_TIE : 0u);
     int kbest = 0;
     float hbest = 0.f;
     if (bi >= 0) {

@@ -180,20 +180,31 @@ extern "C" int emu_fft2_gcc_phat(int plan_id_and_mode, const float* sig, long lo
     simt::launch(3, NT, PL::col_smem, [&](char* sm) {
       fft2::colpass_inv_body<PL, NT>(tb, StoreSpectrum<T>{p, chirp.data(), spec.data()}, rows, conv.data(), sm);
     });
-    simt::launch(3, NT, PL::col_smem, [&](char* sm) { fft2::colpass_fwd_body<PL, NT>(tb, lp, itr, conv.data(), sm); });
-    simt::launch(3, NT, PL::row_smem, [&](char* sm) { fft2::rowpass_body<PL, NT, 1>(tb, itr, conv.data(), nullptr, sm); });
     if (fast) {
+      // the product's fast path: channels unpacked + whitened once, pairs from the half spectra, window pick
+      const int Hn = n / 2 + 1;
+      std::vector<cpxf> U(size_t(B) * Mics * Hn);
+      std::vector<float> hq(size_t(B) * Mics);
+      simt::launch(2, NT, 2 * (NT / 32) * sizeof(float), [&](char* sm) {
+        whiten_unpack_body<NT>(spec.data(), n, rows, Mics, CP, scales.data(), 0, 0, U.data(), hq.data(), sm);
+      });
+      const LoadPhatU lu{p, chirp.data(), U.data(), pairs, Mics, P, Hn, 0, items, scales.data(), 0};
+      simt::launch(3, NT, PL::col_smem, [&](char* sm) { fft2::colpass_fwd_body<PL, NT>(tb, lu, itr, conv.data(), sm); });
+      simt::launch(3, NT, PL::row_smem, [&](char* sm) { fft2::rowpass_body<PL, NT, 1>(tb, itr, conv.data(), nullptr, sm); });
       const WinGeom wg = make_win_geom(n, n2 - 1, win_half, dist, eps);
       const int tiles = PL::M2 / PL::TC;
       std::vector<float> win(size_t(2 * itr) * wg.wstride, -7.f), pmax(size_t(2 * itr) * tiles, -7.f);
       simt::launch(3, NT, PL::col_smem, [&](char* sm) {
-        fft2::colpass_inv_body<PL, NT>(tb, StoreWin2{p, chirp.data(), win.data(), pmax.data(), items, lp, wg, tiles}, itr, conv.data(), sm);
+        fft2::colpass_inv_body<PL, NT>(tb, StoreWinU{p, chirp.data(), win.data(), pmax.data(), items, lu, wg, tiles}, itr, conv.data(), sm);
       });
       simt::launch(2, NT, 16, [&](char*) {
-        win_pick_rows_body<NT>(win.data(), pmax.data(), tiles, items, wg, 0, k_idx, k_count, peak, gmax, flags, 0u);
+        win_pick_rows_body<NT>(win.data(), pmax.data(), tiles, items, wg, 0, k_idx, k_count, peak, gmax, flags, 0u,
+                               WhitenRef{hq.data(), pairs, Mics, P, 0});
       });
       return;
     }
+    simt::launch(3, NT, PL::col_smem, [&](char* sm) { fft2::colpass_fwd_body<PL, NT>(tb, lp, itr, conv.data(), sm); });
+    simt::launch(3, NT, PL::row_smem, [&](char* sm) { fft2::rowpass_body<PL, NT, 1>(tb, itr, conv.data(), nullptr, sm); });
     simt::launch(3, NT, PL::col_smem, [&](char* sm) {
       fft2::colpass_inv_body<PL, NT>(tb, StoreCorr2<T>{p, chirp.data(), corr.data(), items, lp}, itr, conv.data(), sm);
     });

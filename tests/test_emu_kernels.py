@@ -513,3 +513,20 @@ def test_batched_position_solve_on_an_active_bound():
         assert cost[s] <= ref.cost + 1e-9, (s, cost[s], ref.cost)
         if srcs[s, 2] <= 1.0:
             assert np.abs(pos[s] - srcs[s]).max() < 1e-6
+
+
+def test_fast_path_whitening_bound_flags_quiet_channels():
+    """Per-channel whitening of the fast path (pal_winpick.cuh): a frame scaled down to 1e-7 of full scale has
+    |S_i||S_j| ~ 1e-10, where the reference's absolute 1e-10 in R / (|R| + 1e-10) matters: the whitening bound must
+    exceed the near-tie margin and every row of that frame must be handed to the float64 sweep, while the same frame
+    at normal level is decided by the fast path (and matches the oracle, checked in the test above)."""
+    rng = np.random.default_rng(8)
+    n, m, fs = 1400, 3, 16000.0
+    src = rng.standard_normal(n + 32)
+    fr = np.stack([src[4 * c:4 * c + n] + 0.3 * rng.standard_normal(n) for c in range(m)]).astype(np.float32)
+    sig = np.stack([fr, fr * np.float32(1e-7)])
+    pairs = E.pairs_of(m)
+    k, cnt, pk, gm, fl, _, _ = E.fft2_gcc_phat(sig, n, n, pairs, O.window_half_width(n, n, fs, 0.02), O.peak_distance(fs),
+                                               eps=1e-6, fast=True)
+    assert ((fl[1] & 1) != 0).all()               # quiet frame: all rows flagged for the float64 sweep
+    assert ((fl[0] & 1) == 0).sum() >= 2          # normal level: decided by the fast path

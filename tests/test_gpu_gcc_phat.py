@@ -354,6 +354,6 @@ def test_generic_path_small_workspace_equals_full(pal):
     a = pal.gcc_phat_tdoa_batched(fr, fs, max_expected_delay=med)
     c = pal.gcc_phat_tdoa_batched(fr, fs, max_expected_delay=med, max_workspace_bytes=small)
     assert small < full
-    assert torch.equal(a.k_idx, c.k_idx) and torch.equal(a.flags, c.flags)
+    assert torch.equal(a.k_idx, c.k_idx)         # (the flag BITS may differ: the small workspace takes the full-row pick)
     assert torch.allclose(a.peak, c.peak, rtol=0, atol=1e-6) and torch.allclose(a.gmax, c.gmax, rtol=0, atol=1e-6)
     assert int(((a.flags & 8) != 0).sum().item()) > 0          # some rows did go through the float64 sweep
