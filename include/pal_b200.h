@@ -92,13 +92,17 @@ int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, s
  *             the reference's time delay is (k - (n_samples-1)) / fs  (utils.py:141-142)
  *   k_count_dev [B][P] int32 or NULL; peak_dev/gmax_dev [B][P] float32: corr[k0], max(corr)
  *   flags_dev [B][P] uint32; corr_opt_dev NULL or [B][P][n1+n2-1] float32 (FFT order)
- * n_samples == 2048 (n = 4095 = 5*7*9*13) takes the fused prime-factor kernels and never
- * synchronises; any other length takes the Bluestein path, which synchronises `stream` once
- * when refine != 0 (to learn how many rows were flagged).
- * Exactness: the float32 kernels flag every row whose decision is closer than tie_eps to an alternative (and, on
- * the fused path, every row of a frame so quiet -- below about -69 dBFS -- that the absolute 1e-10 of utils.py:117
- * is not negligible); with refine != 0 flagged rows are re-evaluated in float64 from the raw samples, so that lag
- * indices equal the reference's.  num_peaks > 1 is evaluated in float64 throughout.
+ * n_samples == 2048 (n = 4095 = 5*7*9*13) takes the fused prime-factor kernels; any other length takes the
+ * chirp-z (Bluestein) path.  Neither synchronises: flagged rows are counted and compacted on the device and the
+ * float64 sweep over them reads its count there (one exception: a workspace so small that the sweep would need more
+ * than 96 rounds makes the Bluestein path read the count back once).
+ * Exactness: the float32 kernels flag every row whose decision is closer than tie_eps to an alternative (and every
+ * row of a frame so quiet -- below about -69 dBFS -- that the absolute 1e-10 of utils.py:117 is not negligible); with
+ * refine != 0 flagged rows are re-evaluated in float64 from the raw samples, so that lag indices equal the
+ * reference's.  num_peaks > 1 is evaluated in float64 throughout.
+ * INGEST CONTRACT: the rows are float32.  "Equal to the reference" therefore means: equal to the reference run on these
+ * float32 samples (up-cast exactly to float64) -- what a capture chain or a float32 renderer delivers.  A caller that
+ * holds genuine float64 signals and needs the reference's decision on THEM uses pal_gcc_phat_tdoa_f64 below.
  */
 int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples,
                       const int32_t* pairs_dev, int32_t P, const pal_tdoa_params* prm,
