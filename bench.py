@@ -276,15 +276,22 @@ def run_scenes(args, world, rank, dev, dist, torch, peak_gbs):
 
     for i in range(warm):
         sw.step(*sets[i])
+        if i == 0:      # the renderer's per-length plans for the whole range of padded lengths this workload produces
+            lo, hi = sw.n_seen
+            planned = sw.warm_plans(lo - (hi - lo) // 8, hi + (hi - lo) // 8)
     barrier()
     l0 = pal.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     t0.record()
+    marks[0].record()
     for i in range(steps):
         sw.step(*sets[warm + i])
+        marks[i + 1].record()
     t1.record()
     barrier()
     ms = t0.elapsed_time(t1) / steps
+    step_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
     launches = (pal.launch_count() - l0) // steps
     if world > 1:
         tt = torch.tensor([ms], device=dev)
@@ -329,7 +336,7 @@ def run_scenes(args, world, rank, dev, dist, torch, peak_gbs):
     alg2 = 20 * m * n + 16 * p * n + 16 * p          # SURVEY 8d stage-2 bytes per scene (2 432 448 at cfg5)
     gcc_s = sw.gcc_ms * 1e-3
     return {"metric": "scenes_per_s (render + GCC-PHAT TDOA + gather)", "value": world * s_n / (ms * 1e-3), "unit": "scenes/s",
-            "ms_per_step": ms, "steps": steps, "warmup": warm, "scenes_per_gpu": s_n, "chunk_scenes": sw.chunk,
+            "ms_per_step": ms, "step_ms_rank0": step_ms, "steps": steps, "warmup": warm, "scenes_per_gpu": s_n, "chunk_scenes": sw.chunk,
             "pair_corr_per_s": world * s_n * p / (ms * 1e-3),
             "workload": "cfg5: random shoebox rooms, 8 mics, 0.25 s @ 16 kHz chirp 500 Hz, max_reflections=3, rendered then "
                         "GCC-PHAT TDOA (28 pairs, n = 7999), max_expected_delay=0.05 s; a different scene set per step",
@@ -343,7 +350,10 @@ def run_scenes(args, world, rank, dev, dist, torch, peak_gbs):
                          "achieved": alg2 * s_n / gcc_s / 1e9 if gcc_s > 0 else None, "peak": peak_gbs, "unit": "GB/s",
                          "frac": alg2 * s_n / gcc_s / 1e9 / peak_gbs if gcc_s > 0 else None},
             "refined_row_fraction": refined, "gpu_launches": int(launches), "parity": par,
-            "render_plan_cache": {"hits": sw.cache.hits, "misses": sw.cache.misses, "plans": len(sw.cache.plans)}}
+            "render_plan_cache": {"hits": sw.cache.hits, "misses": sw.cache.misses, "plans": len(sw.cache.plans),
+                                  "prebuilt_in_warmup": planned,
+                                  "note": "plans depend on (padded length N, base signal) only; the range of N seen in the first "
+                                          "warm-up step (+- 1/8) is planned before the timed steps"}}
 
 
 # ----------------------------------------------------------------------------- GPU arm

@@ -429,3 +429,113 @@ template <class F> inline void with_plan(int id, F&& f) {
 
 }  // namespace fft2
 }  // namespace pal
+
+namespace pal {
+// ---------------------------------------------------------------------------------------------- whole convolution in one CTA
+// For M <= 16384 the M1 x M2 matrix fits one CTA's shared memory (128 x 129 x 8 B = 129 KB with the pitch that keeps both
+// the column passes -- lanes along a row -- and the row passes -- lanes along a column -- free of bank conflicts).  The
+// three kernels of the general engine then collapse into one: loader -> column FFT -> twiddle -> row FFT -> x chirp
+// spectrum -> inverse row FFT -> conjugate twiddle -> inverse column FFT -> storer, 12 shared-memory accesses per point
+// instead of 20 plus three round trips through global memory.  Same radix steps, same digit-reversed orders, same twf
+// table; the chirp spectrum is kept in the order THIS kernel's middle step holds it (bhat_s[pos * M1 + row], built by
+// the kernel itself in MODE 2).
+namespace fft2 {
+
+template <class P> struct SmemConv {
+  static constexpr int PITCH = P::M2 + 1;
+  static constexpr size_t smem = sizeof(f2) * size_t(P::M1) * PITCH + sizeof(f2) * (P::M1 + P::M2);
+  static constexpr bool fits = P::M <= 16384;       // power-of-two plans 64 x 64, 128 x 64, 128 x 128
+};
+
+// MODE 0: x bhat_s, 1: x conj(bhat_s), 2: plan set-up (forward only, bhat_s <- spectrum / M)
+template <class P, int NT, int MODE, class Loader, class Storer>
+PAL_DEV void conv_smem_body(Tables tb, const cpxf* bhat_s, cpxf* bhat_out, Loader load, Storer store, long long n_tr, char* smem) {
+  constexpr int M1 = P::M1, M2 = P::M2, PITCH = SmemConv<P>::PITCH;
+  constexpr int NS1 = Radices<M1>::NS, NS2 = Radices<M2>::NS, RL = P::RL;
+  f2* A = reinterpret_cast<f2*>(smem);
+  f2* tw1 = A + M1 * PITCH;
+  f2* tw2 = tw1 + M1;
+  for (int i = simt::tid(); i < M1; i += NT) tw1[i] = ld_f2(tb.tw1 + i);
+  for (int i = simt::tid(); i < M2; i += NT) tw2[i] = ld_f2(tb.tw2 + i);
+  simt::sync_block();
+  // column passes: element `pos` (row index) of column `lane`;  row passes: element `pos` (column index) of row `lane`
+  auto crd = [&](int pos, int lane) { return A[pos * PITCH + lane]; };
+  auto cwr = [&](int pos, int lane, f2 v) { A[pos * PITCH + lane] = v; };
+  auto rrd = [&](int pos, int lane) { return A[lane * PITCH + pos]; };
+  auto rwr = [&](int pos, int lane, f2 v) { A[lane * PITCH + pos] = v; };
+  for (long long t = simt::bid(); t < n_tr; t += simt::nblocks()) {
+    // ---- forward columns: loader -> registers -> shared memory; last step multiplies the M-point twiddle
+    {
+      const auto ctx = unit_begin(load, t, 0);
+      radix_step<M1, 0, false, M2, NT>(tw1, [&](int pos, int lane) { return as_f2(load(ctx, pos * M2 + lane)); }, cwr);
+    }
+    simt::sync_block();
+    if (NS1 == 3) {
+      radix_step<M1, NS1 == 3 ? 1 : 0, false, M2, NT>(tw1, crd, cwr);
+      simt::sync_block();
+    }
+    radix_step<M1, NS1 - 1, false, M2, NT>(tw1, crd, [&](int pos, int lane, f2 v) {
+      A[pos * PITCH + lane] = cmul(v, ld_f2(tb.twf + pos * M2 + lane));
+    });
+    simt::sync_block();
+    // ---- forward rows
+    radix_step<M2, 0, false, M1, NT>(tw2, rrd, rwr);
+    simt::sync_block();
+    if (NS2 == 3) {
+      radix_step<M2, NS2 == 3 ? 1 : 0, false, M1, NT>(tw2, rrd, rwr);
+      simt::sync_block();
+    }
+    // ---- middle: last forward row step, x chirp spectrum, first inverse row step, all in registers
+    {
+      constexpr int NB = M2 / RL, G = NT / M1;
+      const int lane = simt::tid() % M1, grp = simt::tid() / M1;
+#pragma unroll
+      for (int it = 0; it < (NB + G - 1) / G; ++it) {
+        const int b = grp + it * G;
+        if (NB % G != 0 && b >= NB) break;
+        f2 x[RL];
+#pragma unroll
+        for (int q = 0; q < RL; ++q) x[q] = A[lane * PITCH + b * RL + q];
+        Dft<RL, false>::run(x);
+        if (MODE == 2) {
+          const f2 sc = f2_bcast(1.0f / float(P::M));
+#pragma unroll
+          for (int q = 0; q < RL; ++q) st_f2(bhat_out + (b * RL + q) * M1 + lane, f2_mul(x[q], sc));
+        } else {
+#pragma unroll
+          for (int q = 0; q < RL; ++q) x[q] = cmul_t<MODE == 1>(x[q], ld_f2(bhat_s + (b * RL + q) * M1 + lane));
+          Dft<RL, true>::run(x);
+#pragma unroll
+          for (int q = 0; q < RL; ++q) A[lane * PITCH + b * RL + q] = x[q];
+        }
+      }
+    }
+    simt::sync_block();
+    if (MODE == 2) continue;
+    // ---- inverse rows
+    if (NS2 == 3) {
+      radix_step<M2, NS2 == 3 ? 1 : 0, true, M1, NT>(tw2, rrd, rwr);
+      simt::sync_block();
+    }
+    radix_step<M2, 0, true, M1, NT>(tw2, rrd, rwr);
+    simt::sync_block();
+    // ---- inverse columns: conjugate twiddle on the way in, storer on the way out
+    radix_step<M1, NS1 - 1, true, M2, NT>(tw1, [&](int pos, int lane) {
+      return cmulc(A[pos * PITCH + lane], ld_f2(tb.twf + pos * M2 + lane));
+    }, cwr);
+    simt::sync_block();
+    if (NS1 == 3) {
+      radix_step<M1, NS1 == 3 ? 1 : 0, true, M2, NT>(tw1, crd, cwr);
+      simt::sync_block();
+    }
+    {
+      auto ctx = unit_begin(store, t, 0);
+      radix_step<M1, 0, true, M2, NT>(tw1, crd, [&](int pos, int lane, f2 v) { store(ctx, pos * M2 + lane, as_cpx(v)); });
+      simt::sync_block();
+      unit_end(store, ctx, t, 0, reinterpret_cast<float*>(A), 0);
+    }
+  }
+}
+
+}  // namespace fft2
+}  // namespace pal

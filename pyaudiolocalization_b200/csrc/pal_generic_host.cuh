@@ -266,6 +266,37 @@ __global__ void __launch_bounds__(kNT2, PAL_FFT2_MINBLOCKS) k2_colpass_inv(Table
   extern __shared__ __align__(128) char smem[];
   colpass_inv_body<P, kNT2, Storer>(tb, st, n_tr, buf, smem);
 }
+constexpr int kNTS = 512;       // threads of the single-CTA convolution kernel (one block per SM: 129 KB of shared memory)
+template <class P, int MODE, class Loader, class Storer>
+__global__ void __launch_bounds__(kNTS, 1) k2_conv_smem(Tables tb, const cpxf* bhat_s, cpxf* bhat_out, Loader ld, Storer st,
+                                                        long long n_tr) {
+  extern __shared__ __align__(128) char smem[];
+  conv_smem_body<P, kNTS, MODE, Loader, Storer>(tb, bhat_s, bhat_out, ld, st, n_tr, smem);
+}
+// PAL_SMEM_CONV=0: every convolution through the three-kernel engine (A/B measurements)
+inline bool use_smem_conv() {
+  static const bool on = [] {
+    const char* e = std::getenv("PAL_SMEM_CONV");
+    return e ? (e[0] != '0') : true;
+  }();
+  return on;
+}
+inline bool plan_fits_smem(int plan) {
+  bool fits = false;
+  with_plan(plan, [&](auto pl) { fits = SmemConv<decltype(pl)>::fits; });
+  return fits && use_smem_conv();
+}
+template <auto kern> inline void opt_in_smem_once(size_t smem) {
+  static std::atomic<unsigned> done{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned bit = 1u << (dev & 31);
+  if (!(done.load(std::memory_order_acquire) & bit)) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    done.fetch_or(bit, std::memory_order_release);
+  }
+}
+
 __global__ void __launch_bounds__(256) k2_init_tables(int n, int M1, int M2, cpxf* chirp, cpxf* tw1, cpxf* tw2, cpxf* twf) {
   init_tables_body(n, M1, M2, chirp, tw1, tw2, twf);
 }
@@ -295,12 +326,14 @@ struct Buffers {
   int plan = -1;
   BluePlan p{};          // n and the convolution length (what the loaders / storers look at)
   cpxf *chirp = nullptr, *tw1 = nullptr, *tw2 = nullptr, *twf = nullptr, *bhat = nullptr;
+
   Tables tb() const { return Tables{chirp, tw1, tw2, twf, bhat}; }
 };
 inline size_t table_bytes(int n, int plan) {
   const PlanDims d = plan_dims(plan);
   return al(sizeof(cpxf) * size_t(n)) + al(sizeof(cpxf) * d.M1) + al(sizeof(cpxf) * d.M2) + 2 * al(sizeof(cpxf) * size_t(d.M1) * d.M2);
 }
+
 inline void carve(int n, int plan, char*& base, Buffers& b) {
   const PlanDims d = plan_dims(plan);
   const size_t M = size_t(d.M1) * d.M2;
@@ -312,12 +345,23 @@ inline void carve(int n, int plan, char*& base, Buffers& b) {
   b.twf = reinterpret_cast<cpxf*>(base);   base += al(sizeof(cpxf) * M);
   b.bhat = reinterpret_cast<cpxf*>(base);  base += al(sizeof(cpxf) * M);
 }
+// the single-CTA kernel needs only ONE chirp-spectrum table: plans that fit shared memory keep it in `bhat`'s slot
+inline bool smem_plan(const Buffers& b) { return b.plan >= 0 && plan_fits_smem(b.plan); }
 // chirp, twiddles and the chirp spectrum; `scratch` holds one convolution (M complex)
 inline cudaError_t fill(const Buffers& b, cpxf* scratch, cudaStream_t s, int sms) {
   const PlanDims d = plan_dims(b.plan);
   k2_init_tables<<<std::min(4 * sms, (b.p.M + 255) / 256), 256, 0, s>>>(b.p.n, d.M1, d.M2, b.chirp, b.tw1, b.tw2, b.twf);
   with_plan(b.plan, [&](auto pl) {
     using P = decltype(pl);
+    if constexpr (SmemConv<P>::fits) {
+      if (use_smem_conv()) {       // the chirp spectrum in the single-CTA kernel's order, built by that kernel
+        using K = StoreRaw<float>;
+        opt_in_smem_once<k2_conv_smem<P, 2, LoadBhat<float>, K>>(SmemConv<P>::smem);
+        k2_conv_smem<P, 2, LoadBhat<float>, K><<<1, kNTS, SmemConv<P>::smem, s>>>(b.tb(), nullptr, b.bhat, LoadBhat<float>{b.p, b.chirp},
+                                                                                 K{scratch, (long long)P::M}, 1);
+        return;
+      }
+    }
     k2_colpass_fwd<P, LoadBhat<float>><<<grid_for<k2_colpass_fwd<P, LoadBhat<float>>>(P::col_smem, P::M2 / P::TC, sms), kNT2, P::col_smem, s>>>(
         b.tb(), LoadBhat<float>{b.p, b.chirp}, 1, scratch);
     k2_rowpass<P, 2><<<grid_for<k2_rowpass<P, 2>>(P::row_smem, P::M1 / P::TR, sms), kNT2, P::row_smem, s>>>(b.tb(), 1, scratch, b.bhat);
@@ -330,6 +374,14 @@ template <bool CONJ, class Loader, class Storer>
 inline void conv(const Buffers& b, const Loader& ld, const Storer& st, long long nt, cpxf* buf, cudaStream_t s, int sms) {
   with_plan(b.plan, [&](auto pl) {
     using P = decltype(pl);
+    if constexpr (SmemConv<P>::fits) {
+      if (use_smem_conv()) {       // whole convolution in one CTA's shared memory (b.bhat is in that kernel's order)
+        opt_in_smem_once<k2_conv_smem<P, CONJ ? 1 : 0, Loader, Storer>>(SmemConv<P>::smem);
+        k2_conv_smem<P, CONJ ? 1 : 0, Loader, Storer><<<(unsigned)std::max<long long>(1, std::min<long long>(nt, sms)), kNTS,
+                                                        SmemConv<P>::smem, s>>>(b.tb(), b.bhat, nullptr, ld, st, nt);
+        return;
+      }
+    }
     k2_colpass_fwd<P, Loader><<<grid_for<k2_colpass_fwd<P, Loader>>(P::col_smem, nt * (P::M2 / P::TC), sms), kNT2, P::col_smem, s>>>(
         b.tb(), ld, nt, buf);
     k2_rowpass<P, CONJ ? 1 : 0><<<grid_for<k2_rowpass<P, CONJ ? 1 : 0>>(P::row_smem, nt * (P::M1 / P::TR), sms), kNT2, P::row_smem, s>>>(
@@ -406,7 +458,8 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   // sub-chunks must start on frame boundaries (the channels of a frame are whitened together).
   const int c0 = c.n2 - 1;
   const WinGeom wg = make_win_geom(n, c0, c.pp.win_half, c.pp.dist, c.eps);
-  const int win_tiles = plan2 >= 0 ? fft2::plan_dims(plan2).M2 / (fft2::plan_dims(plan2).M1 <= 192 ? 32 : 16) : 0;
+  // partial row maxima per row: one per column tile, or a single one when the whole convolution runs in one CTA
+  const int win_tiles = plan2 < 0 ? 0 : (f2h::plan_fits_smem(plan2) ? 1 : fft2::plan_dims(plan2).M2 / (fft2::plan_dims(plan2).M1 <= 192 ? 32 : 16));
   const bool fast_pick = plan2 >= 0 && !list && c.pp.num_peaks == 1 && !c.corr_out && c.eps > 0.f && use_fast_pick() &&
                          size_t(wg.wstride + win_tiles) * sizeof(float) <= al(sizeof(T) * size_t(n)) && tr_cap >= CP;
   // per-channel whitening pays when a channel is used by several pairs (cfg5: 28 pairs / 8 channels, cfg4: 2016 / 64);

@@ -266,6 +266,8 @@ inline cudaError_t render_grouped(const GroupedBucketIn* in, int n_in, RenderRow
   for (int i = 0; i < n_in; ++i) {
     plan_of[i] = fft2::choose_plan(2 * in[i].N);
     if (plan_of[i] < 0) return cudaErrorNotSupported;
+    // short transforms run as one CTA per convolution (their plans keep the chirp spectrum in that kernel's order)
+    if (f2h::plan_fits_smem(plan_of[i])) return cudaErrorNotSupported;
     if (grouped_bucket_bytes(in[i].N, in[i].count * rr_all.n_mics, plan_of[i]) + (1 << 16) > ws_bytes) return cudaErrorNotSupported;
   }
   std::vector<RenderBucket> tab;

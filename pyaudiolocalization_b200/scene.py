@@ -41,7 +41,7 @@ class RenderPlanCache:
     passes one cache to every call; each N is then planned once.  Plans are evicted oldest-first beyond `max_bytes`.
     Results are bit-identical with and without a cache."""
 
-    def __init__(self, max_bytes: int = 2 << 30):
+    def __init__(self, max_bytes: int = 16 << 30):
         self.max_bytes = int(max_bytes)
         self.bytes = 0
         self.plans: Dict[int, torch.Tensor] = {}

@@ -32,10 +32,18 @@ def solve_positions_batched(mic_positions, pairs, tdoa: torch.Tensor, c: float, 
     if mics.dim() not in (2, 3) or mics.shape[-1] != 3 or (mics.dim() == 3 and mics.shape[0] != s_n):
         raise ValueError("mic_positions must have shape [M, 3] or [S, M, 3]")
     m = int(mics.shape[-2])
-    pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
-    if len(pr) != p_n or (pr.size and (pr.min() < 0 or pr.max() >= m)):
-        raise ValueError("pairs must be [P, 2] with 0 <= index < M and P == tdoa.shape[1]")
-    pairs_dev = torch.from_numpy(pr).to(dev)
+    if isinstance(pairs, torch.Tensor) and pairs.is_cuda:
+        # a device pair list (e.g. from gcc_phat.pairs_to_device, already range-checked): no host round trip per call
+        from .gcc_phat import check_pairs_dev
+        check_pairs_dev(pairs, m)
+        pairs_dev = pairs
+        if pairs_dev.shape[0] != p_n:
+            raise ValueError("pairs must be [P, 2] with P == tdoa.shape[1]")
+    else:
+        pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        if len(pr) != p_n or (pr.size and (pr.min() < 0 or pr.max() >= m)):
+            raise ValueError("pairs must be [P, 2] with 0 <= index < M and P == tdoa.shape[1]")
+        pairs_dev = torch.from_numpy(pr).to(dev)
 
     def opt(t, shape, what):
         if t is None:

@@ -96,6 +96,31 @@ class SceneSweep:
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         self.timed = False
         self.geom_stream = torch.cuda.Stream(self.dev)
+        self.n_seen = (1 << 30, 0)       # smallest / largest padded length N rendered so far
+        self.pairs_dev = _g.pairs_to_device(_g.all_pairs(cfg.mics), cfg.mics, self.dev)
+
+    def warm_plans(self, n_lo: int, n_hi: int, max_streams: int = 16) -> int:
+        """Build the renderer's per-length plans (chirp tables, chirp spectrum, spectrum of the base signal) for every
+        padded length N in [n_lo, n_hi] ahead of time.  A plan depends on (N, base signal) only, so a long sweep pays for
+        each of the few thousand possible lengths once; a short benchmark would otherwise time that one-off work.
+        Returns the number of plans built."""
+        n_base = self.base.numel()
+        todo = [n for n in range(max(int(n_lo), n_base, 100), int(n_hi) + 1) if n not in self.cache.plans]
+        if not todo:
+            return 0
+        self.cache._reset_for(self.base, n_base, self.dev)
+        todo = [n for n in todo if n not in self.cache.plans]
+        cur = torch.cuda.current_stream(self.dev)
+        pool = _scene._stream_pool(self.dev, min(max_streams, len(todo)))
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        for st in pool:
+            st.wait_event(ev)
+        for i, n in enumerate(todo):
+            self.cache.get(self.base, n_base, n, self.dev, pool[i % len(pool)])
+        for st in pool:
+            cur.wait_stream(st)
+        return len(todo)
 
     def _prepare(self, sources, mics, planes, c0, c1):
         """Geometry of one chunk on the side stream (ends with the renderer's one read-back, which then waits for the
@@ -108,6 +133,7 @@ class SceneSweep:
                                                cfg.absorption_threshold, base_signal=self.base)
             job.done = torch.cuda.Event()
             job.done.record(self.geom_stream)
+            self.n_seen = (min(self.n_seen[0], int(job.totals.min())), max(self.n_seen[1], int(job.totals.max())))
         return job
 
     def step(self, sources: np.ndarray, mics: np.ndarray, planes: np.ndarray):
@@ -124,11 +150,12 @@ class SceneSweep:
                 self._ev[0].record()
             cur.wait_event(job.done)
             sig = _scene.execute_render(job, plan_cache=self.cache, grouped_parts=self.parts)
+            job_mics = job.mics
             for t in (job.tau, job.gain, job.pcount, job.src, job.mics, job.idx_dev):
                 t.record_stream(cur)            # allocated under the side stream, consumed on this one
             if self.timed:
                 self._ev[1].record()
-            res = _g.gcc_phat_tdoa_batched(sig, float(cfg.fs), cfg.max_expected_delay)
+            res = _g.gcc_phat_tdoa_batched(sig, float(cfg.fs), cfg.max_expected_delay, pairs_dev=self.pairs_dev)
             self.k_all[c0:c1] = res.k_idx
             self.flags[c0:c1] = res.flags
             if self.timed:
@@ -136,7 +163,9 @@ class SceneSweep:
             if self.solve:
                 from . import solver
                 td = _g.tdoa_seconds_device(res.k_idx[..., 0].contiguous(), cfg.samples, float(cfg.fs))
-                pos, _, _ = solver.solve_positions_batched(mics[c0:c1], _g.all_pairs(cfg.mics), td, cfg.c, max_iter=60,
+                # microphones and pairs are already on the device (a pageable host->device copy here would wait for
+                # everything enqueued so far and stall the pipeline)
+                pos, _, _ = solver.solve_positions_batched(job_mics, self.pairs_dev, td, cfg.c, max_iter=60,
                                                            xtol=1e-8, ftol=1e-8, gtol=1e-8)
                 self.positions[c0:c1] = pos
             if self.keep and c0 < self.keep:

@@ -102,7 +102,8 @@ def generic_gcc_phat(sig, n1, n2, pairs, win_half, dist, method=0, mult=1.0, num
     return k, cnt, pk, gm, fl, corr
 
 
-def fft2_gcc_phat(sig, n1, n2, pairs, win_half, dist, plan_id=-1, method=0, mult=1.0, num_peaks=1, eps=0.0, fast=False):
+def fft2_gcc_phat(sig, n1, n2, pairs, win_half, dist, plan_id=-1, method=0, mult=1.0, num_peaks=1, eps=0.0, fast=False,
+                  smem_conv=False):
     """Same as generic_gcc_phat(use_double=False) on the second-generation convolution engine (pal_fft2.cuh);
     plan_id -1 picks the product's plan for n.  Returns the plan used as the last element."""
     b, m, ld = sig.shape
@@ -114,7 +115,7 @@ def fft2_gcc_phat(sig, n1, n2, pairs, win_half, dist, plan_id=-1, method=0, mult
     gm = np.zeros((b, p), np.float32)
     fl = np.zeros((b, p), np.uint32)
     corr = np.zeros((b, p, n), np.float32)
-    used = lib().emu_fft2_gcc_phat(int(plan_id) + (100 if fast else 0), _p(sig, C.c_float), C.c_longlong(b), m, ld, n1, n2, _p(pairs, C.c_int), p,
+    used = lib().emu_fft2_gcc_phat(int(plan_id) + (200 if smem_conv else (100 if fast else 0)), _p(sig, C.c_float), C.c_longlong(b), m, ld, n1, n2, _p(pairs, C.c_int), p,
                                    win_half, dist, method, C.c_float(mult), num_peaks, C.c_float(eps), _p(k, C.c_int),
                                    _p(cnt, C.c_int), _p(pk, C.c_float), _p(gm, C.c_float), _p(fl, C.c_uint),
                                    _p(corr, C.c_float))

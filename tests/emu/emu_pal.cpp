@@ -152,8 +152,10 @@ extern "C" int emu_fft2_gcc_phat(int plan_id_and_mode, const float* sig, long lo
   constexpr int NT = 64;
   const int n = n1 + n2 - 1;
   // plan_id_and_mode: plan index (or -1: the product's choice); + 100: reduced pick (StoreWin2 + win_pick_rows_body)
-  const bool fast = plan_id_and_mode >= 50;
-  int plan_id = fast ? plan_id_and_mode - 100 : plan_id_and_mode;
+  // + 200: the single-CTA kernel (whole convolution in shared memory; plans of at most 16384 points), full rows
+  const bool smem_conv = plan_id_and_mode >= 150;
+  const bool fast = !smem_conv && plan_id_and_mode >= 50;
+  int plan_id = smem_conv ? plan_id_and_mode - 200 : (fast ? plan_id_and_mode - 100 : plan_id_and_mode);
   if (plan_id < 0) plan_id = fft2::choose_plan(n);
   if (plan_id < 0 || plan_id >= fft2::kNumPlans) return -1;
   const fft2::PlanDims pd = fft2::plan_dims(plan_id);
@@ -171,7 +173,30 @@ extern "C" int emu_fft2_gcc_phat(int plan_id_and_mode, const float* sig, long lo
   simt::launch(2, NT, 64, [&](char* sm) { row_scale_body<NT>(sig, B * Mics, ld, n1, n2, scales.data(), sm); });
   const LoadSignal2<T> ls{p, chirp.data(), sig, ld, Mics, CP, n1, n2, nullptr, 0, scales.data()};
   const LoadPhat2<T> lp{p, chirp.data(), spec.data(), pairs, Mics, CP, P, 0, items, false, scales.data(), 0, nullptr, 0};
-  fft2::with_plan(plan_id, [&](auto pl) {
+  bool smem_done = false;
+  if (smem_conv) {
+    fft2::with_plan(plan_id, [&](auto pl) {
+      using PL = decltype(pl);
+      if constexpr (fft2::SmemConv<PL>::fits) {
+        constexpr int NS = 128;            // threads: a multiple of the lane count of both passes
+        constexpr size_t sb = fft2::SmemConv<PL>::smem;
+        std::vector<cpxf> bs(M);
+        StoreRaw<T> none{scratch.data(), M};
+        simt::launch(1, NS, sb, [&](char* sm) {
+          fft2::conv_smem_body<PL, NS, 2>(tb, nullptr, bs.data(), LoadBhat<T>{p, chirp.data()}, none, 1, sm);
+        });
+        simt::launch(3, NS, sb, [&](char* sm) {
+          fft2::conv_smem_body<PL, NS, 0>(tb, bs.data(), nullptr, ls, StoreSpectrum<T>{p, chirp.data(), spec.data()}, rows, sm);
+        });
+        simt::launch(3, NS, sb, [&](char* sm) {
+          fft2::conv_smem_body<PL, NS, 1>(tb, bs.data(), nullptr, lp, StoreCorr2<T>{p, chirp.data(), corr.data(), items, lp}, itr, sm);
+        });
+        smem_done = true;
+      }
+    });
+    if (!smem_done) return -3;
+  }
+  if (!smem_done) fft2::with_plan(plan_id, [&](auto pl) {
     using PL = decltype(pl);
     simt::launch(2, NT, PL::col_smem, [&](char* sm) { fft2::colpass_fwd_body<PL, NT>(tb, LoadBhat<T>{p, chirp.data()}, 1, scratch.data(), sm); });
     simt::launch(2, NT, PL::row_smem, [&](char* sm) { fft2::rowpass_body<PL, NT, 2>(tb, 1, scratch.data(), bhat.data(), sm); });

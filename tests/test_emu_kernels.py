@@ -530,3 +530,28 @@ def test_fast_path_whitening_bound_flags_quiet_channels():
                                                eps=1e-6, fast=True)
     assert ((fl[1] & 1) != 0).all()               # quiet frame: all rows flagged for the float64 sweep
     assert ((fl[0] & 1) == 0).sum() >= 2          # normal level: decided by the fast path
+
+
+@pytest.mark.parametrize("plan,n1,n2", [(0, 700, 650), (1, 1500, 1500), (2, 4000, 4000)])
+def test_single_cta_convolution_vs_oracle(plan, n1, n2):
+    """pal_fft2.cuh conv_smem_body: the whole convolution (column FFT, twiddle, row FFT, chirp spectrum, inverse) in one
+    CTA's shared memory, for the plans of at most 16384 points; through the whole GCC-PHAT path against the reference
+    algorithm, and equal to the three-kernel engine to float32 rounding."""
+    rng = np.random.default_rng(n1 + plan)
+    x = rng.standard_normal(max(n1, n2) + 40)
+    ld = max(n1, n2)
+    sig = np.zeros((2, 2, ld), np.float32)
+    for f in range(2):
+        sig[f, 0, :n1] = x[7 + f:7 + f + n1] + 0.1 * rng.standard_normal(n1)
+        sig[f, 1, :n2] = x[:n2] + 0.1 * rng.standard_normal(n2)
+    fs, med = 8000.0, 0.01
+    pairs = np.array([[0, 1]], np.int32)
+    wh, dist = O.window_half_width(n1, n2, fs, med), O.peak_distance(fs)
+    a = E.fft2_gcc_phat(sig, n1, n2, pairs, wh, dist, plan_id=plan, smem_conv=True)
+    b = E.fft2_gcc_phat(sig, n1, n2, pairs, wh, dist, plan_id=plan)
+    assert np.abs(a[5] - b[5]).max() <= 2e-6 and np.array_equal(a[0], b[0])
+    for f in range(2):
+        want_td, want_corr, _ = O.get_time_delays_phat(sig[f, 0, :n1].astype(np.float64), sig[f, 1, :n2].astype(np.float64), fs,
+                                                       max_expected_delay=med)
+        assert np.abs(a[5][f, 0] - want_corr).max() <= 1e-4 * np.abs(want_corr).max()
+        assert O.tdoa_from_index(int(a[0][f, 0, 0]), n2, fs) == want_td[0]

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--scenes-per-gpu", type=int, default=32768)
     ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--solve", action="store_true", help="end in source positions (pal_solve_positions)")
+    ap.add_argument("--keep", type=int, default=0)
     ap.add_argument("--parts", type=int, default=4, help="streams the grouped renderer spreads its buckets over")
     ap.add_argument("--warmup", type=int, default=3)
     args = ap.parse_args()
@@ -40,7 +42,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = sweep.SweepConfig()
     s_n = args.scenes_per_gpu
-    sw = sweep.SceneSweep(cfg, s_n, chunk=args.chunk, device=dev, parts=args.parts)
+    sw = sweep.SceneSweep(cfg, s_n, chunk=args.chunk, device=dev, parts=args.parts, solve=args.solve, keep_signals=args.keep)
     sets = [sweep.random_shoebox_scenes(s_n, cfg.mics, 5000 + rank + 1000 * i) for i in range(args.warmup + args.steps)]
 
     def barrier():
@@ -50,6 +52,9 @@ def main():
 
     for i in range(args.warmup):
         sw.step(*sets[i])
+        if i == 0:
+            lo, hi = sw.n_seen
+            sw.warm_plans(lo - (hi - lo) // 8, hi + (hi - lo) // 8)
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = pal.launch_count()
