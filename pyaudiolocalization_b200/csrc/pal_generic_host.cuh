@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <type_traits>
 
 #include "pal_bluestein.cuh"
@@ -144,6 +146,21 @@ struct GenericCall {
   const double* sig64 = nullptr;   // float64 rows (pal_gcc_phat_tdoa_f64): the float64 sweep then reads these instead of `sig`
 };
 
+// Opt a kernel into `bytes` of dynamic shared memory.  The attribute is per kernel and process-wide, and the first-generation
+// engine sizes its tiles at run time: the limit therefore only ever GROWS (a smaller plan on another host thread must not
+// shrink it between this call and the launch that relies on it).
+inline void grow_smem(const void* kern, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> cur;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  size_t& c = cur[{kern, dev}];
+  if (bytes > c) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    c = bytes;
+  }
+}
 inline void count_launch(int k = 1) {
   if (g_launch_counter) g_launch_counter->fetch_add((unsigned long long)(long long)k);
 }
@@ -196,12 +213,12 @@ inline void launch_rowpass(const BluePlan& p, const BlueTables<T>& tb, long long
   if (wide_rows<T>(p)) {
     const size_t sm = fft_tile_smem(sizeof(T), p.M2, kWideRows + 1);
     auto kern = k_rowpass<T, CONV, CONJ, kWideRows>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    grow_smem(reinterpret_cast<const void*>(kern), sm);
     kern<<<(unsigned)std::min<long long>(nt * (p.M1 / kWideRows), max_blocks), kGT, sm, s>>>(p, tb, n_arg, n_tr_dev, buf);
   } else {
     const size_t sm = row_smem<T>(p);
     auto kern = k_rowpass<T, CONV, CONJ>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    grow_smem(reinterpret_cast<const void*>(kern), sm);
     kern<<<(unsigned)std::min<long long>(nt * row_units<T>(p), max_blocks), kGT, sm, s>>>(p, tb, n_arg, n_tr_dev, buf);
   }
 }
@@ -218,7 +235,7 @@ template <typename T> void carve_plan(const BluePlan& p, char*& base, BlueBuffer
 template <typename T> cudaError_t fill_plan(const BluePlan& p, const BlueBuffers<T>& bb, cudaStream_t s, int sms) {
   k_blue_init<T><<<std::min(4 * sms, (p.M + kGT - 1) / kGT), kGT, 0, s>>>(p, bb.chirp, bb.tw1, bb.tw2, bb.twM);
   const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
-  cudaFuncSetAttribute(k_colpass_fwd<T, LoadBhat<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  grow_smem(reinterpret_cast<const void*>(k_colpass_fwd<T, LoadBhat<T>>), cs);
   const int tiles = p.M2 / std::min(p.M2, ColTile<T>::TC);
   k_colpass_fwd<T, LoadBhat<T>><<<std::min(tiles, 8 * sms), kGT, cs, s>>>(p, bb.tb(), LoadBhat<T>{p, bb.chirp}, 1, nullptr,
                                                                           bb.bhat);
@@ -229,12 +246,12 @@ template <typename T> cudaError_t fill_plan(const BluePlan& p, const BlueBuffers
 // opt every transform kernel of precision T into the shared memory this plan needs
 template <typename T> void plan_kernel_attributes(const BluePlan& p) {
   const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
-  cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignal<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignal2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  cudaFuncSetAttribute(k_colpass_fwd<T, LoadPhat2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  cudaFuncSetAttribute(k_colpass_inv<T, StoreCorr2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  cudaFuncSetAttribute(k_colpass_inv<T, StoreSpectrum<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  cudaFuncSetAttribute(k_colpass_inv<T, StoreCorr<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  grow_smem(reinterpret_cast<const void*>(k_colpass_fwd<T, LoadSignal<T>>), cs);
+  grow_smem(reinterpret_cast<const void*>(k_colpass_fwd<T, LoadSignal2<T>>), cs);
+  grow_smem(reinterpret_cast<const void*>(k_colpass_fwd<T, LoadPhat2<T>>), cs);
+  grow_smem(reinterpret_cast<const void*>(k_colpass_inv<T, StoreCorr2<T>>), cs);
+  grow_smem(reinterpret_cast<const void*>(k_colpass_inv<T, StoreSpectrum<T>>), cs);
+  grow_smem(reinterpret_cast<const void*>(k_colpass_inv<T, StoreCorr<T>>), cs);
 }
 // carve + fill (the one-shot form every non-cached caller uses)
 template <typename T> cudaError_t setup_plan(const BluePlan& p, char*& base, BlueBuffers<T>& bb, cudaStream_t s, int sms) {
@@ -266,7 +283,10 @@ __global__ void __launch_bounds__(kNT2, PAL_FFT2_MINBLOCKS) k2_colpass_inv(Table
   extern __shared__ __align__(128) char smem[];
   colpass_inv_body<P, kNT2, Storer>(tb, st, n_tr, buf, smem);
 }
-constexpr int kNTS = 512;       // threads of the single-CTA convolution kernel (one block per SM: 129 KB of shared memory)
+#ifndef PAL_SMEM_NT
+#define PAL_SMEM_NT 512
+#endif
+constexpr int kNTS = PAL_SMEM_NT;   // threads of the single-CTA convolution kernel (one block per SM: 129 KB of shared memory)
 template <class P, int MODE, class Loader, class Storer>
 __global__ void __launch_bounds__(kNTS, 1) k2_conv_smem(Tables tb, const cpxf* bhat_s, cpxf* bhat_out, Loader ld, Storer st,
                                                         long long n_tr) {
@@ -292,7 +312,7 @@ template <auto kern> inline void opt_in_smem_once(size_t smem) {
   cudaGetDevice(&dev);
   const unsigned bit = 1u << (dev & 31);
   if (!(done.load(std::memory_order_acquire) & bit)) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    grow_smem(reinterpret_cast<const void*>(kern), smem);
     done.fetch_or(bit, std::memory_order_release);
   }
 }
@@ -312,7 +332,7 @@ template <auto kern> inline int resident_blocks(size_t smem) {
   dev &= 31;
   int v = cache[dev].load(std::memory_order_acquire);
   if (v > 0) return v;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  grow_smem(reinterpret_cast<const void*>(kern), smem);
   int occ = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kNT2, smem) != cudaSuccess || occ < 1) occ = 1;
   cache[dev].store(occ, std::memory_order_release);
@@ -537,7 +557,7 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
       if constexpr (std::is_same<T, double>::value) {
         if (c.sig64) {       // float64 rows straight into the float64 transforms
           LoadSignal2<T, double> ld64{pl, bb.chirp, c.sig64, c.ld, c.Mics, CP, c.n1, c.n2, row_list, g0 + r0, c.scales};
-          cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignal2<T, double>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+          grow_smem(reinterpret_cast<const void*>(k_colpass_fwd<T, LoadSignal2<T, double>>), cs);
           k_colpass_fwd<T, LoadSignal2<T, double>><<<(unsigned)std::min<long long>(nt * tiles, 16LL * c.sms), kGT, cs, c.stream>>>(
               p, tb, ld64, nt, nullptr, conv);
           launch_rowpass<T, true, false>(p, tb, nt, conv, c.stream, 16LL * c.sms);
@@ -727,8 +747,8 @@ template <typename T> cudaError_t run_sync_align(const SyncCall& c, char* ws, si
   cudaError_t e = setup_plan<T>(p, base, bb, c.stream, c.sms);
   if (e != cudaSuccess) return e;
   const size_t cs = col_smem<T>(p), rs = row_smem<T>(p);
-  cudaFuncSetAttribute(k_colpass_fwd<T, LoadSignalF64<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-  cudaFuncSetAttribute(k_colpass_fwd<T, LoadCross<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+  grow_smem(reinterpret_cast<const void*>(k_colpass_fwd<T, LoadSignalF64<T>>), cs);
+  grow_smem(reinterpret_cast<const void*>(k_colpass_fwd<T, LoadCross<T>>), cs);
   size_t rem = ws_bytes - size_t(base - ws);
   long long tr_cap = std::max<long long>(1, std::min<long long>(2048, (long long)((rem / 4) / L.per_tr)));
   tr_cap = std::min<long long>(tr_cap, c.S * c.Mics);

@@ -156,13 +156,13 @@ inline cudaError_t render_rows_planned(const RenderPlan& rp, int N, RenderRows r
   const BlueTables<T> tb = rp.bb.tb();
   if (rp.b2.plan < 0) {
     plan_kernel_attributes<T>(p);
-    cudaFuncSetAttribute(k_colpass_fwd<T, LoadHermitian2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
-    cudaFuncSetAttribute(k_colpass_inv<T, StoreRender2<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs);
+    grow_smem(reinterpret_cast<const void*>(k_colpass_fwd<T, LoadHermitian2<T>>), cs);
+    grow_smem(reinterpret_cast<const void*>(k_colpass_inv<T, StoreRender2<T>>), cs);
   }
   const int xtiles = (N + 1 + kGT * kXferJ - 1) / (kGT * kXferJ);
   const int kcap = rr.k_stride;
   const size_t ts = 4 * size_t((kcap + 3) & ~3) + 16 * size_t(kcap) + 16;
-  if (ts > 48 * 1024) cudaFuncSetAttribute(k_transfer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts);
+  if (ts > 48 * 1024) grow_smem(reinterpret_cast<const void*>(k_transfer), ts);
   const int fade = int(0.01 * N);
   for (long long r0 = 0; r0 < n_rows; r0 += cap) {
     const long long nt = std::min<long long>(cap, n_rows - r0);
@@ -261,7 +261,7 @@ inline cudaError_t render_grouped(const GroupedBucketIn* in, int n_in, RenderRow
   if (!use_fft2()) return cudaErrorNotSupported;
   const int kcap = rr_all.k_stride;
   const size_t ts = 4 * size_t((kcap + 3) & ~3) + 16 * size_t(kcap) + 16;
-  if (ts > 48 * 1024) cudaFuncSetAttribute(k_transfer_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts);
+  if (ts > 48 * 1024) grow_smem(reinterpret_cast<const void*>(k_transfer_group), ts);
   std::vector<int> plan_of(n_in);
   for (int i = 0; i < n_in; ++i) {
     plan_of[i] = fft2::choose_plan(2 * in[i].N);

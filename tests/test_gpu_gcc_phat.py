@@ -357,3 +357,26 @@ def test_generic_path_small_workspace_equals_full(pal):
     assert torch.equal(a.k_idx, c.k_idx)         # (the flag BITS may differ: the small workspace takes the full-row pick)
     assert torch.allclose(a.peak, c.peak, rtol=0, atol=1e-6) and torch.allclose(a.gmax, c.gmax, rtol=0, atol=1e-6)
     assert int(((a.flags & 8) != 0).sum().item()) > 0          # some rows did go through the float64 sweep
+
+
+def test_fast_path_odd_microphone_count_and_short_plans(pal):
+    """Arbitrary-length fast path with an ODD number of microphones (the last packed forward transform carries a single
+    channel; per-channel whitening on: 10 pairs for 5 channels) at three lengths that take the three single-CTA plans
+    (n = 1999, 3999, 7999): TDOAs bit-exact against the oracle."""
+    rng = np.random.default_rng(123)
+    fs, med = 16000.0, 0.02
+    for n in (1000, 2000, 4000):
+        b, m = 6, 5
+        src = rng.standard_normal((b, n + 64)).astype(np.float32)
+        d = rng.integers(0, 48, size=(b, m))
+        fr = np.stack([np.stack([src[f, 48 - d[f, c]:48 - d[f, c] + n] for c in range(m)]) for f in range(b)])
+        fr = (fr + 0.4 * rng.standard_normal(fr.shape)).astype(np.float32)
+        res = pal.gcc_phat_tdoa_batched(torch.from_numpy(fr).cuda(), fs, max_expected_delay=med)
+        td = res.tdoa_seconds()[..., 0]
+        gm = res.gmax.cpu().numpy()
+        frd = fr.astype(np.float64)
+        for f in range(b):
+            for p, (i, j) in enumerate(pal.all_pairs(m)):
+                want, corr, _ = O.get_time_delays_phat(frd[f, i], frd[f, j], fs, max_expected_delay=med)
+                assert td[f, p] == want[0], (n, f, p)
+                assert abs(gm[f, p] - corr.max()) <= CORR_RTOL * corr.max()

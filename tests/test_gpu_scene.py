@@ -323,3 +323,35 @@ def test_grouped_render_equals_per_bucket_render(pal):
     torch.cuda.synchronize()
     assert torch.equal(a, b) and torch.equal(a, c)
     assert float(a.abs().max()) == 1.0
+
+
+def test_grouped_render_across_two_convolution_plans(pal):
+    """Rooms large enough that some padded lengths need the 256 x 128 convolution plan while the others take 192 x 128
+    (4N - 1 > 24576 for N > 6144): the grouped renderer must split the batch into groups per plan and still reproduce the
+    per-bucket path bit for bit, and the rendered channels must match the oracle."""
+    from pyaudiolocalization_b200 import main as M, scene, sweep
+    from pyaudiolocalization_b200.signal_processing import generate_signal
+    cfg = sweep.SweepConfig()
+    rng = np.random.default_rng(77)
+    n = 40
+    dims = rng.uniform([3, 3, 2.5], [90, 60, 8], size=(n, 3))      # direct paths beyond 46 m push N past 6144
+    mic = 0.3 + rng.uniform(size=(n, cfg.mics, 3)) * (dims[:, None, :] - 0.6)
+    src = 0.3 + rng.uniform(size=(n, 3)) * (dims - 0.6)
+    pl = np.zeros((n, 6, 4))
+    pl[:, 0, 0] = pl[:, 1, 0] = pl[:, 2, 1] = pl[:, 3, 1] = pl[:, 4, 2] = pl[:, 5, 2] = 1.0
+    pl[:, 1, 3], pl[:, 3, 3], pl[:, 5, 3] = -dims[:, 0], -dims[:, 1], -dims[:, 2]
+    base = torch.as_tensor(generate_signal(cfg.signal_type, cfg.fs, cfg.duration, cfg.freq).astype(np.float32)).cuda()
+    job = M.prepare_scenes_batched(src, mic, cfg.fs, cfg.c, cfg.duration, cfg.signal_type, cfg.freq, (pl, sweep.ROOM_MATERIALS),
+                                   sweep.SWEEP_MATERIALS, cfg.max_reflections, cfg.absorption_threshold, base_signal=base)
+    assert job.totals.min() <= 6144 < job.totals.max(), (job.totals.min(), job.totals.max())
+    cache = scene.RenderPlanCache()
+    a = scene.execute_render(job, plan_cache=cache, grouped=False)
+    b = scene.execute_render(job, plan_cache=cache, grouped=True, grouped_parts=3)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    s = int(np.argmax(job.totals))
+    want = np.array(O.simulate_signals_with_multipath(src[s], mic[s], cfg.fs, cfg.c, duration=cfg.duration, signal_type=cfg.signal_type,
+                                                      freq=cfg.freq, reflective_planes=sweep.planes_as_dicts(pl[s]),
+                                                      material_properties=sweep.SWEEP_MATERIALS, max_reflections=cfg.max_reflections,
+                                                      absorption_threshold=cfg.absorption_threshold))
+    assert np.abs(b[s].cpu().numpy() - want).max() <= RENDER_ATOL
