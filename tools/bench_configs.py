@@ -55,6 +55,38 @@ def stage2(name, B, M, N, fs, med, seed):
                       "algorithmic_GBps": alg * B / sec / 1e9, "refined_row_fraction": refined}), flush=True)
 
 
+def cfg4_full():
+    """BASELINE cfg4 at its stated size: all 1024 source positions rendered (64 mics, order 6, 1 s @ 48 kHz; chunks of 64
+    sources), then stage 2 on 8 of the rendered sources (8 x 2016 pairs, n = 95 999)."""
+    rng0, rng1 = np.random.default_rng(0), np.random.default_rng(1)
+    mics = rng0.uniform([1, 1, 0.5], [5, 4, 2.5], size=(64, 3))
+    srcs = rng1.uniform([0.5, 0.5, 0.3], [5.5, 4.5, 2.7], size=(1024, 3))
+    planes = shoebox(6, 5, 3)
+    base = torch.as_tensor(generate_signal("chirp", 48000, 1.0, 1000).astype(np.float32)).cuda()
+    cache = scene.RenderPlanCache()
+
+    def render_all(keep=0):
+        kept = None
+        for s0 in range(0, 1024, 64):
+            out = pmain.simulate_scenes_batched(srcs[s0:s0 + 64], mics, 48000, 343.62, 1.0, "chirp", 1000, planes, MATS, 6, 0.01,
+                                                base_signal=base, plan_cache=cache)
+            if s0 == 0 and keep:
+                kept = out[:keep].clone()
+        return kept
+    render_all()
+    sec = timed(render_all, reps=1, warm=0)
+    print(json.dumps({"config": "cfg4 (full size)", "stage": "render", "mics": 64, "order": 6, "fs": 48000, "sources": 1024,
+                      "seconds": sec, "sources_per_s": 1024 / sec, "rendered_samples_per_s": 1024 * 64 * 48000 / sec,
+                      "reference_estimate": "about 2000 s per source position on one core (SURVEY section 6)"}), flush=True)
+    fr = render_all(keep=8)
+    P = 64 * 63 // 2
+    sec = timed(lambda: pal.gcc_phat_tdoa_batched(fr, 48000.0, 0.05), reps=2)
+    r = pal.gcc_phat_tdoa_batched(fr, 48000.0, 0.05)
+    print(json.dumps({"config": "cfg4 (full size)", "stage": "gcc_phat_tdoa on 8 rendered sources", "units": 8, "mics": 64, "pairs": P,
+                      "samples": 48000, "n_fft": 95999, "ms": sec * 1e3, "pair_corr_per_s": 8 * P / sec,
+                      "refined_row_fraction": float(((r.flags & 8) != 0).float().mean().item())}), flush=True)
+
+
 def cfg4(small):
     rng0, rng1 = np.random.default_rng(0), np.random.default_rng(1)
     mics = rng0.uniform([1, 1, 0.5], [5, 4, 2.5], size=(64, 3))
@@ -136,9 +168,12 @@ def filt(small):
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")] or ["img", "cfg5", "cfg2", "cfg4", "filter"]
     small = "--small" in sys.argv
+    full = "--full" in sys.argv          # the sizes BASELINE.json states: cfg2 4096 scenes, cfg4 1024 sources
     for a in args:
         if a == "cfg2":
-            stage2("cfg2", 64 if small else 256, 4, 44100, 44100.0, 0.05, 2000)
+            stage2("cfg2" + (" (full size)" if full else ""), 4096 if full else (64 if small else 256), 4, 44100, 44100.0, 0.05, 2000)
+        elif a == "cfg4" and full:
+            cfg4_full()
         elif a == "cfg5":
             stage2("cfg5", 1024 if small else 8192, 8, 4000, 16000.0, 0.05, 5000)
             cfg5_render(small)
