@@ -221,7 +221,7 @@ int generic_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, 
   if (int rc = device_info(di)) return rc;
   const size_t list_bytes = align_up(size_t(B) * P * sizeof(int), 256) + kListTail;
   const size_t rows_bytes = align_up(size_t(B) * P * 2 * sizeof(int), 256);
-  const size_t scale_bytes = align_up(size_t(B) * M * 2 * sizeof(float), 256);
+  const size_t scale_bytes = 2 * align_up(size_t(B) * M * 2 * sizeof(float), 256);     // scales [B*M][2], then bounds [B*M][2]
   const int n = n1 + n2 - 1;
   if (ws_bytes < list_bytes + rows_bytes + scale_bytes + std::max(palhost::generic_min_bytes<float>(n, M, di.sms),
                                                    palhost::generic_min_bytes<double>(n, 2, di.sms)))
@@ -237,6 +237,7 @@ int generic_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samples, 
                          PickParams{prm->win_half, prm->peak_dist, prm->thr_method, prm->thr_mult, prm->num_peaks},
                          prm->refine ? prm->tie_eps : 0.f, k_idx_dev, k_count_dev, peak_dev, gmax_dev, flags_dev,
                          corr_opt_dev, stream, di.sms, scales};
+  c.hq = scales + scale_bytes / (2 * sizeof(float));
   // num_peaks > 1 is not the hot path (main.py:204 always asks for one peak): the audit only covers the first peak,
   // so every row is handed to the float64 sweep, as on the n = 4095 path
   if (sig64_dev) {
@@ -316,7 +317,7 @@ int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, s
   const size_t list = align_up(size_t(B) * P * sizeof(int), 256) + kListTail;
   if (n_samples == kFrame2048) {
     const size_t per_frame = align_up(size_t(M) * kSpecSlots * sizeof(cpxf), 256);
-    const size_t hq_frame = size_t(M) * sizeof(float);     // whitening bound, one float per channel
+    const size_t hq_frame = size_t(M) * 2 * sizeof(float);     // per channel: whitening bound h, rounding-noise term q
     *bytes = (per_frame + hq_frame) * size_t(B > 0 ? B : 1) + list + 256;
     if (min_bytes) *min_bytes = per_frame + hq_frame + list + 256;
     return PAL_OK;
@@ -326,7 +327,7 @@ int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, s
   DevInfo di;
   if (device_info(di) == PAL_OK && di.sms > 0) sms = di.sms;
   const int n = 2 * n_samples - 1;
-  const size_t rows = align_up(size_t(B) * P * 2 * sizeof(int), 256) + align_up(size_t(B > 0 ? B : 1) * M * 2 * sizeof(float), 256);
+  const size_t rows = align_up(size_t(B) * P * 2 * sizeof(int), 256) + 2 * align_up(size_t(B > 0 ? B : 1) * M * 2 * sizeof(float), 256);
   const size_t dmin = palhost::generic_min_bytes<double>(n, 2, sms);
   const size_t fmin = palhost::generic_min_bytes<float>(n, M, sms);
   const size_t ffull = palhost::generic_full_bytes<float>(n, B > 0 ? B : 1, M, P, sms);
@@ -363,14 +364,14 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
 
   const size_t per_frame = align_up(size_t(M) * kSpecSlots * sizeof(cpxf), 256);
   const size_t list_bytes = align_up(size_t(B) * P * sizeof(int), 256) + kListTail;
-  const size_t hq_frame = size_t(M) * sizeof(float);
+  const size_t hq_frame = size_t(M) * 2 * sizeof(float);
   if (ws_bytes < per_frame + hq_frame + list_bytes + 256) return fail(PAL_ERR_WORKSPACE, "pal_gcc_phat_tdoa: workspace too small");
   char* ws = static_cast<char*>(ws_dev);
   int* list = reinterpret_cast<int*>(ws);
   int* count = reinterpret_cast<int*>(ws + list_bytes - kListTail);
   cpxf* spec = reinterpret_cast<cpxf*>(ws + list_bytes);
   const int64_t chunk = std::min<int64_t>(B, int64_t((ws_bytes - list_bytes - 256) / (per_frame + hq_frame)));
-  float* hq = reinterpret_cast<float*>(ws + list_bytes + align_up(size_t(chunk) * per_frame, 256));   // [chunk][M]
+  float* hq = reinterpret_cast<float*>(ws + list_bytes + align_up(size_t(chunk) * per_frame, 256));   // [chunk][M][2]
 
   const PickParams pp{prm->win_half, prm->peak_dist, prm->thr_method, prm->thr_mult, prm->num_peaks};
   const size_t fwd_smem = sizeof(FwdSmem);

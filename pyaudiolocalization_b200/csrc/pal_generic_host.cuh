@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kGT) k_win_pick(const float* win, const float*
 }
 __global__ void __launch_bounds__(kGT) k_whiten_unpack(const cpxf* Z, int n, long long n_packed, int Mics, int CP, const float* scales,
                                                        long long row_base, long long local_row_base, cpxf* U, float* hq) {
-  __shared__ float sh[2 * kGT / 32];
+  __shared__ float sh[4 * kGT / 32];
   whiten_unpack_body<kGT>(Z, n, n_packed, Mics, CP, scales, row_base, local_row_base, U, hq, reinterpret_cast<char*>(sh));
 }
 template <typename TS>
@@ -78,6 +78,12 @@ __global__ void __launch_bounds__(kGT) k_row_scales(const TS* sig, long long n_r
                                                     float* scales) {
   __shared__ float sh[kGT / 32];
   row_scale_body<kGT, TS>(sig, n_rows, ld, len_even, len_odd, scales, reinterpret_cast<char*>(sh));
+}
+// sweeps that pick from full rows (k_pick_rows: several peaks, correlation rows wanted, short transforms) carry no
+// per-row margin: rows whose rounding-noise bound is not small against the tie margin go to the float64 sweep outright
+__global__ void k_noise_flags(WhitenRef wr, long long n_items, int n, float eps, unsigned* flags) {
+  const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it < n_items && !(pair_bound(wr, it, n) <= 0.5f * eps)) flags[it] |= PAL_FLAG_NEAR_TIE;
 }
 // device-side chunking of a list whose length only the device knows: round k of `chunk` items holds
 // items[k] = clamp(count - k * chunk, 0, chunk) items = packed[k] = ceil(items[k] / 2) packed inverse transforms
@@ -144,6 +150,7 @@ struct GenericCall {
   int sms;
   float* scales;     // [B * Mics][2] per-row power-of-two normalisation (filled by the first sweep, reused by the float64 one)
   const double* sig64 = nullptr;   // float64 rows (pal_gcc_phat_tdoa_f64): the float64 sweep then reads these instead of `sig`
+  float* hq = nullptr;             // [B * Mics][2] per-channel bounds of the float32 sweep (pal_winpick.cuh: whiten_unpack_body)
 };
 
 // Opt a kernel into `bytes` of dynamic shared memory.  The attribute is per kernel and process-wide, and the first-generation
@@ -486,13 +493,13 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
   // with few pairs per channel (cfg2: 6 / 4) the extra pass over the spectra costs more than the leaner pair loader saves
   const bool whiten = fast_pick && c.P >= 2 * c.Mics;
   if (whiten) tr_cap -= tr_cap % CP;
-  float* hq_res = nullptr;           // [resident frames * Mics] whitening bounds of the fast path
-  if (whiten) {
-    hq_res = reinterpret_cast<float*>(base);
-    base += al(sizeof(float) * size_t(c.B) * c.Mics);
-    rem = ws_bytes - size_t(base - ws);
-    while (tr_cap > CP && rem < size_t(tr_cap) * L.per_tr + size_t(min_rows) * L.per_row) tr_cap -= CP;
+  // near-tie audit on: the rounding noise of the float32 forward transforms is bounded per channel (and, on whitened
+  // spectra, the neglected factor g); [resident frames * Mics][2], see whiten_unpack_body
+  float* hq_res = nullptr;
+  if constexpr (std::is_same<T, float>::value) {
+    if (!list && c.eps > 0.f) hq_res = c.hq;
   }
+  if (whiten && !hq_res) return cudaErrorInvalidValue;
   cpx<T>* conv = reinterpret_cast<cpx<T>*>(base);
   base += tr_cap * al(sizeof(cpx<T>) * size_t(p.M));
   T* corr = reinterpret_cast<T*>(base);
@@ -628,7 +635,7 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
           const long long o = out0 + i0;
           k_win_pick<<<(unsigned)std::min<long long>((ni + kGT / 32 - 1) / (kGT / 32), 8LL * c.sms), kGT, 0, c.stream>>>(
               win, pmax, win_tiles, ni, wg, o, c.k_idx, c.k_count, c.peak, c.gmax, c.flags, extra_flag,
-              WhitenRef{nullptr, nullptr, 0, 0, 0});
+              WhitenRef{hq_res, c.pairs, c.Mics, c.P, i0, false});
           count_launch(1);
           continue;
         }
@@ -674,8 +681,22 @@ cudaError_t run_generic(const GenericCall& c, char* ws, size_t ws_bytes, const i
     for (long long f0 = 0; f0 < c.B; f0 += fchunk) {
       const long long nf = std::min(fchunk, c.B - f0);
       forward(f0 * CP, nf * CP, nullptr, spec);
+      if constexpr (std::is_same<T, float>::value) {
+        if (hq_res && !whiten) {      // statistics of the packed spectra (the whitened sweep gathers them while it unpacks)
+          k_whiten_unpack<<<(unsigned)std::min<long long>(nf * CP, 16LL * c.sms), kGT, 0, c.stream>>>(
+              reinterpret_cast<const cpxf*>(spec), n, nf * CP, c.Mics, CP, c.scales, f0 * c.Mics, 0, nullptr, hq_res);
+          count_launch();
+        }
+      }
       // the resident spectra start at frame f0: item ids handed to the loader are relative to it
       inverse(nf * c.P, spec, f0 * c.P, nullptr, f0, 0);
+      if constexpr (std::is_same<T, float>::value) {
+        if (hq_res && !fast_pick) {
+          k_noise_flags<<<(unsigned)((nf * c.P + 255) / 256), 256, 0, c.stream>>>(WhitenRef{hq_res, c.pairs, c.Mics, c.P, 0, false},
+                                                                                nf * c.P, n, c.eps, c.flags + f0 * c.P);
+          count_launch();
+        }
+      }
     }
   } else {
     const long long ichunk = std::max<long long>(1, std::min<long long>(n_list, row_cap));

@@ -110,6 +110,7 @@ struct alignas(16) FwdSmem {
   mbar_t bar;
   float red[32];                // per-warp partials of the two whitening bounds (NT <= 512)
   float lvl[32];                // per-warp partials of the two channel levels max|x|
+  float ssq[32];                // per-warp partials of the two channel energies sum x^2
 };
 
 // Exact power-of-two normalisation of a channel to unit level before two channels are packed into one complex
@@ -138,6 +139,17 @@ PAL_DEV void level_scale(float mx, float& sc, float& inv) {
 // h is accumulated here (one float per channel); the pair kernel widens its near-tie margin by the bound and sends
 // the row to the float64 kernel when the bound itself is not negligible (frames quieter than about -69 dBFS).
 // Bins with S == 0 give R == 0 in both forms and are left out of h.
+//
+// Rounding noise of the float32 transform.  A bin of the computed spectrum carries noise of about eps32 * rms|S|
+// whatever its own size, so the PHASE of a weak bin -- which PHAT then weights like any other -- is off by
+// delta_k ~ sigma / |S_k|, sigma = 2^-24 sqrt(sum x^2).  The correlation moves by (1/n) sum_k U_k (e^{i delta_k} - 1) w^{kl}:
+// independent errors, standard deviation sqrt(q_i + q_j) / sqrt(n) per sample with q = mean_k sigma^2 / |S_k|^2 = sigma^2 h
+// per channel (capped at 4: a phasor cannot move by more than 2) -- no work per bin beyond h.  The pair kernels add
+// kNoiseK standard deviations to the near-tie margin and send rows whose VALUES it threatens to the float64 kernel
+// (band-limited or tonal frames whose stop band sits below the float32 noise of the pass band).  Calibrated against the
+// oracle on the host emulation: rms error / model 0.8 .. 2.3, largest sample error of a row <= 7 model deviations.
+constexpr float kNoiseK = 20.f;
+constexpr float kEps32Sq = 3.5527137e-15f;      // (2^-24)^2
 PAL_DEV f2 whiten_bin(f2 s, float weight, float& hacc) {
   const float x = f2_lo(s), y = f2_hi(s);
   const float m2 = fmaf(x, x, y * y);
@@ -210,26 +222,35 @@ PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil
     // channel levels -> exact power-of-two scales (level_scale)
     float sc0, sc1, inv0, inv1;
     {
-      float m0 = 0.f, m1 = 0.f;
+      float m0 = 0.f, m1 = 0.f, e0 = 0.f, e1 = 0.f;
       for (int j = tid; j < kFrame2048 / 4; j += NT) {
         const float4 a = reinterpret_cast<const float4*>(sm->stage[0])[j];
         m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+        e0 += fmaf(a.x, a.x, a.y * a.y) + fmaf(a.z, a.z, a.w * a.w);
         if (two) {
           const float4 b = reinterpret_cast<const float4*>(sm->stage[1])[j];
           m1 = fmaxf(m1, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+          e1 += fmaf(b.x, b.x, b.y * b.y) + fmaf(b.z, b.z, b.w * b.w);
         }
       }
 #pragma unroll
       for (int m = 16; m >= 1; m >>= 1) {
         m0 = fmaxf(m0, simt::shfl_xor(m0, m));
         m1 = fmaxf(m1, simt::shfl_xor(m1, m));
+        e0 += simt::shfl_xor(e0, m);
+        e1 += simt::shfl_xor(e1, m);
       }
-      if (simt::lane() == 0) { sm->lvl[simt::warp()] = m0; sm->lvl[16 + simt::warp()] = m1; }
+      if (simt::lane() == 0) {
+        sm->lvl[simt::warp()] = m0; sm->lvl[16 + simt::warp()] = m1;
+        sm->ssq[simt::warp()] = e0; sm->ssq[16 + simt::warp()] = e1;
+      }
       simt::sync_block();
 #pragma unroll
       for (int w = 0; w < NT / 32; ++w) { m0 = fmaxf(m0, sm->lvl[w]); m1 = fmaxf(m1, sm->lvl[16 + w]); }
       level_scale(m0, sc0, inv0);
       level_scale(m1, sc1, inv1);
+      // (the energy partials stay in shared memory until thread 0 needs them at the end of the unit: nothing more is
+      // kept in registers across the four stages, which are tuned to 64 registers)
     }
     pfa_stage_p<13, NT, true>(sm->z, sm->stage[0], sm->stage[1], two, f2_make(sc0, sc1));
     simt::sync_block();
@@ -284,12 +305,22 @@ PAL_DEV void fwd4095_body(const float* sig, int M, long long n_units /* B * ceil
     simt::sync_block();
 #if PAL_PREWHITEN
     if (tid == 0) {
-      float a0 = 0.f, a1 = 0.f;
+      float a0 = 0.f, a1 = 0.f, e0 = 0.f, e1 = 0.f;
 #pragma unroll
-      for (int w = 0; w < NT / 32; ++w) { a0 += sm->red[w]; a1 += sm->red[16 + w]; }
-      // h is wanted at the signal's own level: |S| = |S_scaled| / sc
-      hq[frame * M + ch0] = a0 * (1.0f / float(kN4095)) * sc0 * sc0;
-      if (two) hq[frame * M + ch0 + 1] = a1 * (1.0f / float(kN4095)) * sc1 * sc1;
+      for (int w = 0; w < NT / 32; ++w) { a0 += sm->red[w]; a1 += sm->red[16 + w]; e0 += sm->ssq[w]; e1 += sm->ssq[16 + w]; }
+      a0 *= 1.0f / float(kN4095);
+      a1 *= 1.0f / float(kN4095);
+      // sigma^2 of the transform's rounding noise at the level the spectra were computed at (see whiten_bin)
+      const float sg0 = kEps32Sq * e0 * sc0 * sc0, sg1 = kEps32Sq * e1 * sc1 * sc1;
+      // hq[row] = (h, q).  h is wanted at the signal's own level: |S| = |S_scaled| / sc; q = sigma^2 mean(1 / |S_scaled|^2)
+      // is level-free (NaN from an overflowed energy ends as 4: the row goes to the float64 kernel)
+      float* o = hq + 2 * (frame * M + ch0);
+      o[0] = a0 * sc0 * sc0;
+      o[1] = (sg0 > 0.f) ? fminf(4.f, sg0 * a0) : 0.f;
+      if (two) {
+        o[2] = a1 * sc1 * sc1;
+        o[3] = (sg1 > 0.f) ? fminf(4.f, sg1 * a1) : 0.f;
+      }
     }
 #endif
   }
@@ -441,11 +472,13 @@ PAL_DEV f2 phat_bin_p(f2 a, f2 b) {
 #endif
 }
 
-// Bound (in the unscaled row, n * corr) on what the factor g neglected by the whitened spectra can move a
-// correlation sample of pair (i, j): n * 1e-10 * sqrt(h_i h_j); see whiten_bin.
+// Bound (in the unscaled row, n * corr) on what the fast path neglects for pair (i, j): the factor g of the whitened
+// spectra, n * 1e-10 * sqrt(h_i h_j), plus kNoiseK standard deviations of the transform's rounding noise,
+// n * kNoiseK * sqrt((q_i + q_j) / n); see whiten_bin.  hq: [rows][2] = (h, q).
 PAL_DEV float whiten_bound(const float* hq, long long row_i, long long row_j) {
 #if PAL_PREWHITEN
-  return (1e-10f * float(kN4095)) * sqrt_(hq[row_i] * hq[row_j]);
+  const cpxf a = *reinterpret_cast<const cpxf*>(hq + 2 * row_i), b = *reinterpret_cast<const cpxf*>(hq + 2 * row_j);
+  return (1e-10f * float(kN4095)) * sqrt_(a.x * b.x) + kNoiseK * sqrt_(float(kN4095) * (a.y + b.y));
 #else
   return 0.f;
 #endif
@@ -533,15 +566,16 @@ template <bool WRITE_CORR>
 PAL_DEV void fast_pick_row(const float* c, long long item, float gm, int lane, const FastPick& pk, float wbound,
                            int* k_idx, float* peak, float* gmax, unsigned* flags, float* corr_out) {
   const int lo = pk.lo, hi = pk.hi, g_lo = pk.g_lo, g_hi = pk.g_hi, dist = pk.dist;
-  // wbound: see whiten_bound.  Small: it widens the near-tie margin.  Not small (or NaN/inf): the row's VALUES
-  // are off by more than the float32 noise -> float64 kernel.
-  const bool quiet = !(wbound <= 2.f * pk.eps_s);
+  gm = warp_max_f32(gm);
+  // wbound: see whiten_bound.  Small: it widens the near-tie margin.  Not small against the tie margin and against
+  // the row's maximum (or NaN/inf): the row's VALUES may be off by a third of the 1e-4 tolerance (the bound is about 3 x the largest error seen) ->
+  // float64 kernel.
+  const bool quiet = !(wbound <= 2.f * pk.eps_s + 1e-4f * fmaxf(gm, 0.f));
   const float eps_s = pk.eps_s + (quiet ? 0.f : wbound), mean_bound = pk.mean_bound, inv_n = pk.inv_n;
   if (WRITE_CORR) {
     float* dst = corr_out + item * kN4095;
     for (int k = lane; k < kN4095; k += 32) dst[k] = c[k] * inv_n;
   }
-  gm = warp_max_f32(gm);
 
   // largest and second largest SAMPLE of the window (vectorised, no neighbour tests): the
   // largest one is the answer whenever it is a strict local maximum, which is then verified

@@ -68,12 +68,17 @@ PAL_HD WinGeom make_win_geom(int n, int c0, int win_half, int dist, float eps) {
 // h = mean_k 1 / |S_k|^2 at the signal's true level, one float per channel.  The pick widens its near-tie margin by the
 // bound and sends the row to the float64 sweep when the bound exceeds 2 eps (very quiet channels, where the reference's
 // absolute 1e-10 makes the result level-dependent); a bin with S = 0 gives U = 0 (R = 0 in both forms) and h = inf.
+// The rounding noise of the float32 forward transform is bounded the same way as on the n = 4095 path
+// (pal_pfa4095.cuh: whiten_bin): q = mean_k min(4, sigma^2 / |S_k|^2), sigma^2 = 2^-48 mean_k |S_k|^2 (Parseval), one
+// more float per channel; the pick adds kNoiseK sqrt((q_i + q_j) / n) to the margin.
 // Z: packed spectra [n_packed][n]; frame-major: packed row g <-> frame g / CP, channels 2c, 2c+1 (c = g % CP).
-// U: [frames * Mics][Hn], Hn = n / 2 + 1; hq: [frames * Mics]; scales: [.][2] of the channels (global rows from row_base).
+// U: [frames * Mics][Hn], Hn = n / 2 + 1 (nullptr: statistics only, for the sweeps that keep the packed spectra);
+// hq: [frames * Mics][2] = (h, q); scales: [.][2] of the channels (global rows from row_base).
 template <int NT>
 PAL_DEV void whiten_unpack_body(const cpxf* Z, int n, long long n_packed, int Mics, int CP, const float* scales, long long row_base,
                                 long long local_row_base, cpxf* U, float* hq, char* smem) {
-  float* sh = reinterpret_cast<float*>(smem);      // [2][NT / 32]
+  float* sh = reinterpret_cast<float*>(smem);      // [4][NT / 32]
+  constexpr int NW = NT / 32;
   const int Hn = n / 2 + 1;
   for (long long g = simt::bid(); g < n_packed; g += simt::nblocks()) {
     const long long f = g / CP;
@@ -81,9 +86,29 @@ PAL_DEV void whiten_unpack_body(const cpxf* Z, int n, long long n_packed, int Mi
     const long long ra = local_row_base + f * Mics + 2 * c;            // resident channel rows of the pair
     const bool has_b = 2 * c + 1 < Mics;
     const cpxf* z = Z + g * n;
-    cpxf* ua = U + ra * Hn;
-    cpxf* ub = U + (ra + 1) * Hn;
-    float sa = 0.f, sb = 0.f;
+    // pass 1: energies of the two channels (the row is read again from L1 / L2 below)
+    float ea2 = 0.f, eb2 = 0.f;
+    for (int k = simt::tid(); k < Hn; k += NT) {
+      const cpxf a = unpack_two_real<float>(z, n, k, false);
+      const cpxf b = unpack_two_real<float>(z, n, k, true);
+      const float wgt = (k == 0 || 2 * k == n) ? 1.f : 2.f;
+      ea2 = fma_(wgt, fma_(a.x, a.x, a.y * a.y), ea2);
+      eb2 = fma_(wgt, fma_(b.x, b.x, b.y * b.y), eb2);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      ea2 += simt::shfl_xor(ea2, m);
+      eb2 += simt::shfl_xor(eb2, m);
+    }
+    if (simt::lane() == 0) { sh[simt::warp()] = ea2; sh[NW + simt::warp()] = eb2; }
+    simt::sync_block();
+    ea2 = eb2 = 0.f;
+    for (int w = 0; w < NW; ++w) { ea2 += sh[w]; eb2 += sh[NW + w]; }
+    simt::sync_block();
+    const float sga = 3.5527137e-15f * ea2 / float(n), sgb = 3.5527137e-15f * eb2 / float(n);      // sigma^2
+    cpxf* ua = U ? U + ra * Hn : nullptr;
+    cpxf* ub = U ? U + (ra + 1) * Hn : nullptr;
+    float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
     for (int k = simt::tid(); k < Hn; k += NT) {
       const cpxf a = unpack_two_real<float>(z, n, k, false);
       const cpxf b = unpack_two_real<float>(z, n, k, true);
@@ -97,26 +122,39 @@ PAL_DEV void whiten_unpack_body(const cpxf* Z, int n, long long n_packed, int Mi
       if (ma > 0.f) ia = 1.f / std::sqrt(ma);
       if (mb > 0.f) ib = 1.f / std::sqrt(mb);
 #endif
-      ua[k] = cpxf{a.x * ia, a.y * ia};
-      if (has_b) ub[k] = cpxf{b.x * ib, b.y * ib};
+      if (U) {
+        ua[k] = cpxf{a.x * ia, a.y * ia};
+        if (has_b) ub[k] = cpxf{b.x * ib, b.y * ib};
+      }
       sa += wgt * (ma > 0.f ? ia * ia : 3.0e38f);
       sb += wgt * (mb > 0.f ? ib * ib : 3.0e38f);
+      qa += wgt * (ma > 0.f ? min_(4.f, sga * ia * ia) : (sga > 0.f ? 4.f : 0.f));
+      qb += wgt * (mb > 0.f ? min_(4.f, sgb * ib * ib) : (sgb > 0.f ? 4.f : 0.f));
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
       sa += simt::shfl_xor(sa, m);
       sb += simt::shfl_xor(sb, m);
+      qa += simt::shfl_xor(qa, m);
+      qb += simt::shfl_xor(qb, m);
     }
-    if (simt::lane() == 0) { sh[simt::warp()] = sa; sh[NT / 32 + simt::warp()] = sb; }
+    if (simt::lane() == 0) {
+      sh[simt::warp()] = sa; sh[NW + simt::warp()] = sb;
+      sh[2 * NW + simt::warp()] = qa; sh[3 * NW + simt::warp()] = qb;
+    }
     simt::sync_block();
     if (simt::tid() == 0) {
-      float ta = 0.f, tb = 0.f;
-      for (int w = 0; w < NT / 32; ++w) { ta += sh[w]; tb += sh[NT / 32 + w]; }
-      // back to the signal's own level: S_true = S_scaled * 2^e, so 1 / |S_true|^2 = 2^-2e / |S_scaled|^2
+      float ta = 0.f, tb = 0.f, ua_ = 0.f, ub_ = 0.f;
+      for (int w = 0; w < NW; ++w) { ta += sh[w]; tb += sh[NW + w]; ua_ += sh[2 * NW + w]; ub_ += sh[3 * NW + w]; }
+      // back to the signal's own level: S_true = S_scaled * 2^e, so 1 / |S_true|^2 = 2^-2e / |S_scaled|^2 (q is level-free)
       const long long gra = row_base + f * Mics + 2 * c;
       const float ea = scales[2 * gra], eb = has_b ? scales[2 * (gra + 1)] : 0.f;
-      hq[ra] = ta / float(n) * ea * ea;
-      if (has_b) hq[ra + 1] = tb / float(n) * eb * eb;
+      hq[2 * ra] = ta / float(n) * ea * ea;
+      hq[2 * ra + 1] = ua_ / float(n);
+      if (has_b) {
+        hq[2 * ra + 2] = tb / float(n) * eb * eb;
+        hq[2 * ra + 3] = ub_ / float(n);
+      }
     }
     simt::sync_block();
   }
@@ -268,7 +306,21 @@ struct WhitenRef {
   const int* pairs;
   int Mics, P;
   long long first_item;
+  bool whitened = true;      // false: the rows come from the raw spectra (LoadPhat2), only the rounding-noise term applies
 };
+// the chirp-z forward transforms (two FFTs of 2-4 n points and three chirp products) are about twice as noisy as the
+// prime-factor transform of the n = 4095 path: rms error / model 1.5 .. 3.5, largest sample error <= 11.3 deviations
+constexpr float kWinNoiseK = 40.f;
+// what the float32 sweep neglects for the pair of item `it` (normalised correlation units): factor g of the whitened
+// spectra + kWinNoiseK standard deviations of the forward transforms' rounding noise
+PAL_DEV float pair_bound(const WhitenRef& wr, long long it, int n) {
+  const long long f = it / wr.P;
+  const int pr = int(it - f * wr.P);
+  const float* a = wr.hq + 2 * (f * wr.Mics + wr.pairs[2 * pr]);
+  const float* b = wr.hq + 2 * (f * wr.Mics + wr.pairs[2 * pr + 1]);
+  const float hb = wr.whitened ? 1e-10f * sqrt_(a[0] * b[0]) : 0.f;
+  return hb + kWinNoiseK * sqrt_((a[1] + b[1]) / float(n));
+}
 template <int NT>
 PAL_DEV void win_pick_rows_body(const float* win, const float* pmax, int tiles, long long n_rows, WinGeom g, long long item0,
                                 int* k_idx, int* k_count, float* peak, float* gmax, unsigned* flags, unsigned extra_flag,
@@ -277,20 +329,19 @@ PAL_DEV void win_pick_rows_body(const float* win, const float* pmax, int tiles, 
   const int lo = g.lo, hi = g.hi, dist = g.dist;
   const int g_lo = (lo + 3) & ~3, g_hi = (hi + 1) & ~3;      // window split into 16-byte groups + <= 3 + 3 edge samples
   for (long long row = (long long)simt::bid() * (NT / 32) + simt::warp(); row < n_rows; row += (long long)simt::nblocks() * (NT / 32)) {
-    float eps = g.eps;
-    bool quiet = false;
-    if (wr.hq) {
-      const long long it = wr.first_item + row;
-      const long long f = it / wr.P;
-      const int pr = int(it - f * wr.P);
-      const float hb = 1e-10f * sqrt_(wr.hq[f * wr.Mics + wr.pairs[2 * pr]] * wr.hq[f * wr.Mics + wr.pairs[2 * pr + 1]]);
-      quiet = !(hb <= 2.f * g.eps);          // also catches inf / NaN
-      if (!quiet) eps += hb;
-    }
     const float* c = win + row * g.wstride - g.wlo;            // c[k] valid for wlo <= k <= whi
     float gm = kWinNegBig;
     for (int t = lane; t < tiles; t += 32) gm = max_(gm, pmax[row * tiles + t]);
     gm = wmax_f(gm);
+    float eps = g.eps;
+    bool quiet = false;
+    if (wr.hq) {
+      // small: widens the near-tie margin.  Not small against the margin and the row's maximum (or inf / NaN): the
+      // VALUES may be off by a third of the 1e-4 tolerance (the bound is >= 3.5 x the largest error seen) -> float64 sweep
+      const float hb = pair_bound(wr, wr.first_item + row, g.n);
+      quiet = !(hb <= 2.f * g.eps + 1e-4f * max_(gm, 0.f));
+      if (!quiet) eps += hb;
+    }
     float b1 = kWinNegBig, b2 = kWinNegBig;
     int ksel = -1;
     if (hi >= lo) {

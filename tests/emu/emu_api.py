@@ -24,7 +24,8 @@ def pairs_of(m):
 
 
 class Spectra(np.ndarray):
-    """[B, M, 2080, 2] whitened spectra plus .hq [B, M], the per-channel whitening bound (pal_pfa4095.cuh: whiten_bin)."""
+    """[B, M, 2080, 2] whitened spectra plus .hq [B, M, 2]: per channel the whitening bound h and the rounding-noise term q
+    (pal_pfa4095.cuh: whiten_bin)."""
     hq = None
 
 
@@ -32,7 +33,7 @@ def fwd4095(sig):
     b, m, n = sig.shape
     assert n == 2048 and sig.dtype == np.float32
     spec = np.zeros((b, m, 2080, 2), np.float32).view(Spectra)
-    spec.hq = np.zeros((b, m), np.float32)
+    spec.hq = np.zeros((b, m, 2), np.float32)
     lib().emu_fwd4095(_p(sig, C.c_float), m, C.c_longlong(b), _p(spec, C.c_float), _p(spec.hq, C.c_float), 2)
     return spec
 
@@ -46,7 +47,7 @@ def pair_fast(spec, pairs, win_half, dist, eps=2e-6, want_corr=False, phase_sync
     fl = np.zeros((b, p), np.uint32)
     corr = np.zeros((b, p, 4095), np.float32) if want_corr else None
     hq = getattr(spec, "hq", None)
-    hq = np.zeros((b, m), np.float32) if hq is None else np.ascontiguousarray(hq, np.float32)
+    hq = np.zeros((b, m, 2), np.float32) if hq is None else np.ascontiguousarray(hq, np.float32)
     lib().emu_pair4095_fast(_p(spec, C.c_float), _p(hq, C.c_float), _p(pairs, C.c_int), m, p, C.c_longlong(b), win_half, dist,
                             C.c_float(eps), _p(k, C.c_int), _p(pk, C.c_float), _p(gm, C.c_float),
                             _p(fl, C.c_uint), _p(corr, C.c_float), 3, int(phase_sync))

@@ -7,7 +7,7 @@ using namespace pal;
 
 extern "C" {
 
-void emu_fwd4095(const float* sig, int M, long long B, float* spec /* [B][M][2080][2] */, float* hq /* [B][M] */, int grid) {
+void emu_fwd4095(const float* sig, int M, long long B, float* spec /* [B][M][2080][2] */, float* hq /* [B][M][2] */, int grid) {
   const long long units = B * ((M + 1) / 2);
   simt::launch(grid, 128, sizeof(FwdSmem), [&](char* smem) {
     fwd4095_body<128>(sig, M, units, reinterpret_cast<cpxf*>(spec), hq, smem);
@@ -209,8 +209,8 @@ extern "C" int emu_fft2_gcc_phat(int plan_id_and_mode, const float* sig, long lo
       // the product's fast path: channels unpacked + whitened once, pairs from the half spectra, window pick
       const int Hn = n / 2 + 1;
       std::vector<cpxf> U(size_t(B) * Mics * Hn);
-      std::vector<float> hq(size_t(B) * Mics);
-      simt::launch(2, NT, 2 * (NT / 32) * sizeof(float), [&](char* sm) {
+      std::vector<float> hq(size_t(B) * Mics * 2);
+      simt::launch(2, NT, 4 * (NT / 32) * sizeof(float), [&](char* sm) {
         whiten_unpack_body<NT>(spec.data(), n, rows, Mics, CP, scales.data(), 0, 0, U.data(), hq.data(), sm);
       });
       const LoadPhatU lu{p, chirp.data(), U.data(), pairs, Mics, P, Hn, 0, items, scales.data(), 0};

@@ -36,7 +36,10 @@ def test_forward_spectra_layout(frames, spectra):
         assert np.abs(got * np.abs(want) - want).max() <= 2e-7 * np.abs(want).max() * 8
         assert np.abs(np.abs(got) - 1).max() < 1e-6
         h = np.mean(1.0 / np.abs(s) ** 2)
-        assert abs(spectra.hq[0, m] - h) <= 1e-3 * h
+        assert abs(spectra.hq[0, m, 0] - h) <= 1e-3 * h
+        # rounding-noise term of the channel (whiten_bin): mean_k min(4, sigma^2 / |S_k|^2), sigma^2 = 2^-48 sum x^2
+        q = np.mean(np.minimum(4.0, 2.0 ** -48 * np.sum(frames[0, m].astype(np.float64) ** 2) / np.abs(s) ** 2))
+        assert abs(spectra.hq[0, m, 1] - q) <= 2e-3 * q
 
 
 def test_whitening_bound_sends_quiet_frames_to_float64():
@@ -51,7 +54,7 @@ def test_whitening_bound_sends_quiet_frames_to_float64():
         for p, (i, j) in enumerate(E.pairs_of(3)):
             c = O.phat_correlation(fr[0, i].astype(np.float64), fr[0, j].astype(np.float64))
             dev = np.abs(corr[0, p] - c).max()
-            bound = 1e-10 * np.sqrt(float(sp.hq[0, i]) * float(sp.hq[0, j]))
+            bound = 1e-10 * np.sqrt(float(sp.hq[0, i, 0]) * float(sp.hq[0, j, 0]))
             assert dev <= bound + 5e-7
             if expect_flag:
                 assert fl[0, p] & 1
@@ -313,7 +316,7 @@ def test_dead_and_weak_channels_next_to_a_loud_one():
     fr[0, 1] = 0.0                                                         # ... and a dead partner of the loud channel 0
     fr[0, 3] = 1e-3 * src[20:2068]
     sp = E.fwd4095(fr)
-    assert not np.asarray(sp[0, 1]).any() and sp.hq[0, 1] == 0
+    assert not np.asarray(sp[0, 1]).any() and not sp.hq[0, 1].any()
     pairs = E.pairs_of(4)
     k, pk, gm, fl, corr = E.pair_fast(sp, pairs, 800, 16, want_corr=True)
     for p, (i, j) in enumerate(pairs):
@@ -555,3 +558,32 @@ def test_single_cta_convolution_vs_oracle(plan, n1, n2):
                                                        max_expected_delay=med)
         assert np.abs(a[5][f, 0] - want_corr).max() <= 1e-4 * np.abs(want_corr).max()
         assert O.tdoa_from_index(int(a[0][f, 0, 0]), n2, fs) == want_td[0]
+
+
+def test_rounding_noise_bound_covers_high_dynamic_range_frames():
+    """Windowed tones over a -80 dB floor: the float32 transform's rounding noise turns the phases of the stop-band bins
+    (which PHAT weights like any other) by ~1e-3 rad, and the correlation moves by far more than the tie margin.  The
+    per-channel term q (whiten_bin) must bound the deviation row by row, send such rows to the float64 kernel, and
+    leave ordinary frames alone."""
+    rng = np.random.default_rng(12)
+    n, fs = 2048, 16000.0
+    t = np.arange(n) / fs
+    tones = np.zeros((1, 3, n), np.float32)
+    for c in range(3):
+        d = int(rng.integers(0, 300))
+        x = sum(np.sin(2 * np.pi * f * (t - d / fs)) for f in (440.0, 1234.5, 0.21 * fs))
+        tones[0, c] = x * np.hanning(n) + 1e-4 * rng.standard_normal(n)
+    noise = rng.standard_normal((1, 3, n)).astype(np.float32)
+    pairs = E.pairs_of(3)
+    for fr, high in ((tones, True), (noise, False)):
+        sp = E.fwd4095(fr)
+        k, pk, gm, fl, corr = E.pair_fast(sp, pairs, 800, 16, eps=1e-6, want_corr=True)
+        for p, (i, j) in enumerate(pairs):
+            c = O.phat_correlation(fr[0, i].astype(np.float64), fr[0, j].astype(np.float64))
+            dev = np.abs(corr[0, p] - c).max()
+            bound = 20.0 * np.sqrt((float(sp.hq[0, i, 1]) + float(sp.hq[0, j, 1])) / N)
+            assert dev <= bound / 2.5 + 2e-7, (high, i, j, dev, bound)
+            if high:
+                assert dev > 1e-5 and bound > 1e-4 * c.max() and (fl[0, p] & 1)
+            else:
+                assert bound < 2e-7

@@ -128,7 +128,7 @@ def main():
             refined += int((fl[r] & 8) != 0)
             ok = cnt[r] == len(wtd) and np.array_equal(td[r, :cnt[r]], wtd)
             if wgm > 0:
-                e = abs(gm[r] - wgm) / wgm
+                e = float(abs(float(gm[r]) - wgm) / wgm)
                 worst_gm = max(worst_gm, e)
                 ok = ok and e <= 1e-4
             else:
@@ -140,7 +140,7 @@ def main():
                                    {"row": r, "got": td[r, :cnt[r]].tolist(), "want": wtd.tolist(), "gmax": [float(gm[r]), wgm],
                                     "flags": int(fl[r])})
     print(json.dumps({"tool": "soak_parity", "seed": a.seed, "cases": len(cases), "rows": rows, "mismatches": bad,
-                      "refined_rows": refined, "max_rel_gmax_err": worst_gm, "rows_by_family": fam_rows,
+                      "refined_rows": refined, "max_rel_gmax_err": float(worst_gm), "rows_by_family": fam_rows,
                       "gpu_seconds": round(gpu_s, 2)}))
     for item in listing:
         print("MISMATCH", json.dumps(item))
