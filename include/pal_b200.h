@@ -96,10 +96,14 @@ int pal_gcc_phat_workspace(int64_t B, int32_t M, int32_t n_samples, int32_t P, s
  * chirp-z (Bluestein) path.  Neither synchronises: flagged rows are counted and compacted on the device and the
  * float64 sweep over them reads its count there (one exception: a workspace so small that the sweep would need more
  * than 96 rounds makes the Bluestein path read the count back once).
- * Exactness: the float32 kernels flag every row whose decision is closer than tie_eps to an alternative (and every
- * row of a frame so quiet -- below about -69 dBFS -- that the absolute 1e-10 of utils.py:117 is not negligible); with
- * refine != 0 flagged rows are re-evaluated in float64 from the raw samples, so that lag indices equal the
- * reference's.  num_peaks > 1 is evaluated in float64 throughout.
+ * Exactness: the float32 kernels flag every row whose decision is closer to an alternative than the row's margin:
+ * tie_eps plus a per-row bound on what float32 costs THAT row -- the rounding noise of the forward transforms seen
+ * through PHAT's unit weights (large for tonal or band-limited frames whose stop band lies below the float32 noise of
+ * the pass band) and the absolute 1e-10 of utils.py:117 (frames below about -69 dBFS).  Rows whose bound threatens the
+ * VALUES (more than 1e-4 of max(corr)) are flagged whole.  With refine != 0 flagged rows are re-evaluated in float64
+ * from the raw samples, so that lag indices equal the reference's and peak / gmax stay within 1e-4.  num_peaks > 1 is
+ * evaluated in float64 throughout.  With refine == 0 flagged rows keep the float32 answer (the chirp-z path then skips
+ * the audit altogether and leaves the flags 0): nothing is guaranteed for rows a float64 look would decide differently.
  * INGEST CONTRACT: the rows are float32.  "Equal to the reference" therefore means: equal to the reference run on these
  * float32 samples (up-cast exactly to float64) -- what a capture chain or a float32 renderer delivers.  A caller that
  * holds genuine float64 signals and needs the reference's decision on THEM uses pal_gcc_phat_tdoa_f64 below.
