@@ -69,8 +69,8 @@ PAL_HD WinGeom make_win_geom(int n, int c0, int win_half, int dist, float eps) {
 // bound and sends the row to the float64 sweep when the bound exceeds 2 eps (very quiet channels, where the reference's
 // absolute 1e-10 makes the result level-dependent); a bin with S = 0 gives U = 0 (R = 0 in both forms) and h = inf.
 // The rounding noise of the float32 forward transform is bounded the same way as on the n = 4095 path
-// (pal_pfa4095.cuh: whiten_bin): q = mean_k min(4, sigma^2 / |S_k|^2), sigma^2 = 2^-48 mean_k |S_k|^2 (Parseval), one
-// more float per channel; the pick adds kNoiseK sqrt((q_i + q_j) / n) to the margin.
+// (pal_pfa4095.cuh: whiten_bin): q = min(4, sigma^2 mean_k 1 / |S_k|^2), sigma^2 = 2^-48 mean_k |S_k|^2 (Parseval), one
+// more float per channel, gathered in the same pass; the pick adds kNoiseK sqrt((q_i + q_j) / n) to the margin.
 // Z: packed spectra [n_packed][n]; frame-major: packed row g <-> frame g / CP, channels 2c, 2c+1 (c = g % CP).
 // U: [frames * Mics][Hn], Hn = n / 2 + 1 (nullptr: statistics only, for the sweeps that keep the packed spectra);
 // hq: [frames * Mics][2] = (h, q); scales: [.][2] of the channels (global rows from row_base).
@@ -86,29 +86,9 @@ PAL_DEV void whiten_unpack_body(const cpxf* Z, int n, long long n_packed, int Mi
     const long long ra = local_row_base + f * Mics + 2 * c;            // resident channel rows of the pair
     const bool has_b = 2 * c + 1 < Mics;
     const cpxf* z = Z + g * n;
-    // pass 1: energies of the two channels (the row is read again from L1 / L2 below)
-    float ea2 = 0.f, eb2 = 0.f;
-    for (int k = simt::tid(); k < Hn; k += NT) {
-      const cpxf a = unpack_two_real<float>(z, n, k, false);
-      const cpxf b = unpack_two_real<float>(z, n, k, true);
-      const float wgt = (k == 0 || 2 * k == n) ? 1.f : 2.f;
-      ea2 = fma_(wgt, fma_(a.x, a.x, a.y * a.y), ea2);
-      eb2 = fma_(wgt, fma_(b.x, b.x, b.y * b.y), eb2);
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      ea2 += simt::shfl_xor(ea2, m);
-      eb2 += simt::shfl_xor(eb2, m);
-    }
-    if (simt::lane() == 0) { sh[simt::warp()] = ea2; sh[NW + simt::warp()] = eb2; }
-    simt::sync_block();
-    ea2 = eb2 = 0.f;
-    for (int w = 0; w < NW; ++w) { ea2 += sh[w]; eb2 += sh[NW + w]; }
-    simt::sync_block();
-    const float sga = 3.5527137e-15f * ea2 / float(n), sgb = 3.5527137e-15f * eb2 / float(n);      // sigma^2
     cpxf* ua = U ? U + ra * Hn : nullptr;
     cpxf* ub = U ? U + (ra + 1) * Hn : nullptr;
-    float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
+    float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;        // sums of 1 / |S|^2 and of |S|^2
     for (int k = simt::tid(); k < Hn; k += NT) {
       const cpxf a = unpack_two_real<float>(z, n, k, false);
       const cpxf b = unpack_two_real<float>(z, n, k, true);
@@ -128,8 +108,8 @@ PAL_DEV void whiten_unpack_body(const cpxf* Z, int n, long long n_packed, int Mi
       }
       sa += wgt * (ma > 0.f ? ia * ia : 3.0e38f);
       sb += wgt * (mb > 0.f ? ib * ib : 3.0e38f);
-      qa += wgt * (ma > 0.f ? min_(4.f, sga * ia * ia) : (sga > 0.f ? 4.f : 0.f));
-      qb += wgt * (mb > 0.f ? min_(4.f, sgb * ib * ib) : (sgb > 0.f ? 4.f : 0.f));
+      qa = fma_(wgt, ma, qa);
+      qb = fma_(wgt, mb, qb);
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
@@ -149,11 +129,15 @@ PAL_DEV void whiten_unpack_body(const cpxf* Z, int n, long long n_packed, int Mi
       // back to the signal's own level: S_true = S_scaled * 2^e, so 1 / |S_true|^2 = 2^-2e / |S_scaled|^2 (q is level-free)
       const long long gra = row_base + f * Mics + 2 * c;
       const float ea = scales[2 * gra], eb = has_b ? scales[2 * (gra + 1)] : 0.f;
-      hq[2 * ra] = ta / float(n) * ea * ea;
-      hq[2 * ra + 1] = ua_ / float(n);
+      ta /= float(n);
+      tb /= float(n);
+      // q = sigma^2 mean(1 / |S|^2), sigma^2 = 2^-48 mean |S|^2 (Parseval), capped at 4; NaN (0 * inf) ends as 4
+      const float qa_ = 3.5527137e-15f * (ua_ / float(n)) * ta, qb_ = 3.5527137e-15f * (ub_ / float(n)) * tb;
+      hq[2 * ra] = ta * ea * ea;
+      hq[2 * ra + 1] = (ua_ > 0.f) ? min_(4.f, qa_) : 0.f;
       if (has_b) {
-        hq[2 * ra + 2] = tb / float(n) * eb * eb;
-        hq[2 * ra + 3] = ub_ / float(n);
+        hq[2 * ra + 2] = tb * eb * eb;
+        hq[2 * ra + 3] = (ub_ > 0.f) ? min_(4.f, qb_) : 0.f;
       }
     }
     simt::sync_block();
