@@ -380,3 +380,29 @@ def test_fast_path_odd_microphone_count_and_short_plans(pal):
                 want, corr, _ = O.get_time_delays_phat(frd[f, i], frd[f, j], fs, max_expected_delay=med)
                 assert td[f, p] == want[0], (n, f, p)
                 assert abs(gm[f, p] - corr.max()) <= CORR_RTOL * corr.max()
+
+
+@pytest.mark.parametrize("n,m,kw", [(2048, 4, {}), (1500, 5, {}), (4000, 3, {}), (3000, 3, dict(return_corr=True)), (700, 3, {})])
+def test_tonal_frames_over_a_deep_noise_floor(pal, n, m, kw):
+    """Windowed tones over a -80 dB floor: the stop-band bins sit below the rounding noise of a float32 transform, PHAT
+    gives them unit weight all the same, and a float32 correlation is off by 1e-3 of its maximum.  The per-channel
+    rounding-noise bound must send such rows to the float64 sweep on every code path: the fused
+    n = 4095 kernels, the whitened and the per-pair chirp-z sweeps, full-row picks and the short-transform engine."""
+    rng = np.random.default_rng(n + m)
+    fs = 16000.0
+    t = np.arange(n) / fs
+    fr = np.zeros((2, m, n), np.float32)
+    for f in range(2):
+        for c in range(m):
+            d = int(rng.integers(0, 300))
+            x = sum(np.sin(2 * np.pi * fq * (t - d / fs)) for fq in (440.0, 1234.5, 0.21 * fs))
+            fr[f, c] = x * np.hanning(n) + 1e-4 * rng.standard_normal(n)
+    res = pal.gcc_phat_tdoa_batched(torch.from_numpy(fr).cuda(), fs, max_expected_delay=0.05, **kw)
+    td = res.tdoa_seconds()[..., 0]
+    gm, fl = res.gmax.cpu().numpy(), res.flags.cpu().numpy()
+    for f in range(2):
+        for p, (i, j) in enumerate(pal.all_pairs(m)):
+            want_td, c, _ = O.get_time_delays_phat(fr[f, i].astype(np.float64), fr[f, j].astype(np.float64), fs, max_expected_delay=0.05)
+            assert td[f, p] == want_td[0], (f, i, j)
+            assert abs(gm[f, p] - c.max()) <= 1e-5 * c.max(), (f, i, j, gm[f, p], c.max())
+            assert fl[f, p] & 8          # re-evaluated in float64
