@@ -91,10 +91,10 @@ __global__ void __launch_bounds__(kTmemWarps * 32, 1)
     k_pair4095_tmem(const cpxf* __restrict__ spec, const float* __restrict__ hq, const int* __restrict__ pairs, int M, int P,
                     long long n_items,
                     int win_half, int dist, float eps, int* __restrict__ k_idx, float* __restrict__ peak,
-                    float* __restrict__ gmax, unsigned* __restrict__ flags, float* __restrict__ corr_out) {
+                    float* __restrict__ gmax, unsigned* __restrict__ flags, float* __restrict__ corr_out, int pairs_in_smem) {
   extern __shared__ __align__(128) char smem[];
   pair4095_tmem_body<kTmemWarps, WRITE_CORR>(spec, hq, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax, flags,
-                                             corr_out, smem);
+                                             corr_out, smem, pairs_in_smem);
 }
 // Which fused pair kernel runs (read once): PAL_PAIR_KERNEL=tmem (default; 12 warps per SM, register
 // tiles parked in tensor memory; measured 10 % faster on B200) or PAL_PAIR_KERNEL=regs (8 warps per SM,
@@ -190,11 +190,15 @@ inline int solve_grid(int sms) { return 8 * sms; }
 struct DevInfo {
   int sms = 0;
   int dev = -1;
+  size_t smem_optin = 0;     // largest dynamic shared-memory size a block may opt in to
 };
 std::atomic<int> g_reserved_sms{0};      // pal_reserve_sms: SMs the persistent grids leave to other work (a collective)
 int device_info(DevInfo& d) {
   PAL_CUDA(cudaGetDevice(&d.dev));
   PAL_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.dev));
+  int optin = 0;
+  PAL_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.dev));
+  d.smem_optin = size_t(optin);
   const int keep = g_reserved_sms.load(std::memory_order_relaxed);
   if (keep > 0 && d.sms > 2 * keep) d.sms -= keep;
   return PAL_OK;
@@ -382,9 +386,17 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
   const size_t exd_smem = sizeof(ExactSmem<double>);
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-  const size_t tmem_smem = kTmemWarps * sizeof(FastWarpSmem) + 16;
-  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_tmem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmem_smem));
-  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_tmem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmem_smem));
+  // warp tiles + the tensor-memory slot + (when it fits the opt-in limit) a copy of the pair table
+  size_t tmem_smem = kTmemWarps * sizeof(FastWarpSmem) + 16;
+#ifndef PAL_FIX_PAIRS
+#define PAL_FIX_PAIRS 1
+#endif
+  const int pairs_in_smem = (PAL_FIX_PAIRS && tmem_smem + sizeof(int) * 2 * size_t(P) <= di.smem_optin) ? 1 : 0;
+  if (pairs_in_smem) tmem_smem += sizeof(int) * 2 * size_t(P);
+  // (the cap is the device's opt-in limit whatever P is: callers with different pair counts never shrink it under each other)
+  const int tmem_cap = (int)std::max(tmem_smem, di.smem_optin);
+  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_tmem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tmem_cap));
+  PAL_CUDA(cudaFuncSetAttribute(k_pair4095_tmem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tmem_cap));
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_exact<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exd_smem));
   PAL_CUDA(cudaFuncSetAttribute(k_fwd4095, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
 
@@ -430,7 +442,7 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
           auto kern = corr ? k_pair4095_tmem<true> : k_pair4095_tmem<false>;
           kern<<<gt, kTmemWarps * 32, tmem_smem, stream>>>(spec, hq, pairs_dev, M, P, n_items, pp.win_half, pp.dist,
                                                            prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
-                                                           gmax_dev + item0, flags_dev + item0, corr);
+                                                           gmax_dev + item0, flags_dev + item0, corr, pairs_in_smem);
         } else {
           auto kern = corr ? k_pair4095_fast<true> : k_pair4095_fast<false>;
           kern<<<gp, kFastWarps * 32, fast_smem, stream>>>(spec, hq, pairs_dev, M, P, n_items, pp.win_half, pp.dist,

@@ -899,7 +899,7 @@ template <int WARPS> struct TmemPlan {
 template <int WARPS, bool WRITE_CORR>
 PAL_DEV void pair4095_tmem_body(const cpxf* spec, const float* hq, const int* pairs, int M, int P, long long n_items,
                                 int win_half, int dist, float eps, int* k_idx, float* peak, float* gmax,
-                                unsigned* flags, float* corr_out, char* smem_raw) {
+                                unsigned* flags, float* corr_out, char* smem_raw, int pairs_in_smem = 0) {
   using P65 = Pfa2<5, 13>;
   using P63 = Pfa2<7, 9>;
   const int lane = simt::lane();
@@ -909,6 +909,12 @@ PAL_DEV void pair4095_tmem_body(const cpxf* spec, const float* hq, const int* pa
   const int warp = simt::shfl(simt::warp(), 0);
   FastWarpSmem* sm = reinterpret_cast<FastWarpSmem*>(smem_raw) + warp;
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(reinterpret_cast<FastWarpSmem*>(smem_raw) + WARPS);
+  // The microphone indices of the NEXT pair steer thirty spectrum loads; read from global memory they cost a full
+  // L2 round trip in front of those loads (2 % of the kernel's stall samples).  When the table fits behind the warp
+  // tiles (pairs_in_smem: P <= ~2500) it is copied there once per block.
+  int* const pairs_s = reinterpret_cast<int*>(tmem_slot + 4);
+  if (pairs_in_smem)
+    for (int i = simt::tid(); i < 2 * P; i += WARPS * 32) pairs_s[i] = pairs[i];
   if (warp == 0) simt::tmem_alloc512(tmem_slot);
   simt::tmem_fence_before_sync();
   simt::sync_block();
@@ -1119,9 +1125,11 @@ PAL_DEV void pair4095_tmem_body(const cpxf* spec, const float* hq, const int* pa
         if (pair_it >= P) { pair_it -= P; ++frame_it; }
         const long long frame = frame_it;
         const int p = pair_it;
-        si = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p]) * kSpecSlots) + lane;
-        sj = reinterpret_cast<const f2*>(spec + (frame * M + pairs[2 * p + 1]) * kSpecSlots) + lane;
-        wb_next = whiten_bound(hq, frame * M + pairs[2 * p], frame * M + pairs[2 * p + 1]);
+        const int mi = pairs_in_smem ? pairs_s[2 * p] : pairs[2 * p];
+        const int mj = pairs_in_smem ? pairs_s[2 * p + 1] : pairs[2 * p + 1];
+        si = reinterpret_cast<const f2*>(spec + (frame * M + mi) * kSpecSlots) + lane;
+        sj = reinterpret_cast<const f2*>(spec + (frame * M + mj) * kSpecSlots) + lane;
+        wb_next = whiten_bound(hq, frame * M + mi, frame * M + mj);
 #pragma unroll
         for (int g = 0; g < kLA; ++g)
 #pragma unroll

@@ -19,12 +19,13 @@ void emu_pair4095_fast(const float* spec, const float* hq, const int* pairs, int
                        int grid, int phase_sync) {
   constexpr int W = 2;
   const cpxf* sp = reinterpret_cast<const cpxf*>(spec);
-  simt::launch(grid, 32 * W, W * sizeof(FastWarpSmem) + 16, [&](char* smem) {
-    if (phase_sync == 2) {     // TMEM-assisted variant
+  simt::launch(grid, 32 * W, W * sizeof(FastWarpSmem) + 16 + sizeof(int) * 2 * size_t(P), [&](char* smem) {
+    if (phase_sync >= 2) {     // TMEM-assisted variant; 2: pair table copied to shared memory, 3: read from global memory
+      const int ps = phase_sync == 2 ? 1 : 0;
       if (corr_out)
-        pair4095_tmem_body<W, true>(sp, hq, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
+        pair4095_tmem_body<W, true>(sp, hq, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem, ps);
       else
-        pair4095_tmem_body<W, false>(sp, hq, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
+        pair4095_tmem_body<W, false>(sp, hq, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem, ps);
       return;
     }
     if (corr_out)

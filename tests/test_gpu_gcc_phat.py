@@ -406,3 +406,34 @@ def test_tonal_frames_over_a_deep_noise_floor(pal, n, m, kw):
             assert td[f, p] == want_td[0], (f, i, j)
             assert abs(gm[f, p] - c.max()) <= 1e-5 * c.max(), (f, i, j, gm[f, p], c.max())
             assert fl[f, p] & 8          # re-evaluated in float64
+
+
+def test_pair_table_in_shared_and_in_global_memory(pal):
+    """The fused n = 4095 kernel keeps the pair table in shared memory when it fits behind the warp tiles (P <= ~2500)
+    and reads it from global memory otherwise.  73 microphones give 2628 pairs (global-memory table); the same rows
+    asked for in two halves (shared-memory tables) must come back bit-identical, and a spread of them must match the
+    oracle."""
+    rng = np.random.default_rng(73)
+    fs, med, m = 16000.0, 0.05, 73
+    src = rng.standard_normal((2, 2048 + 128)).astype(np.float32)
+    d = rng.integers(0, 96, size=(2, m))
+    fr = np.stack([np.stack([src[f, 96 - d[f, c]:96 - d[f, c] + 2048] for c in range(m)]) for f in range(2)])
+    fr = (fr + 0.3 * rng.standard_normal(fr.shape)).astype(np.float32)
+    frd = torch.from_numpy(fr).cuda()
+    pairs = np.asarray(pal.all_pairs(m), np.int32)
+    assert len(pairs) == 2628
+    whole = pal.gcc_phat_tdoa_batched(frd, fs, max_expected_delay=med, pairs=pairs)
+    half = len(pairs) // 2
+    parts = [pal.gcc_phat_tdoa_batched(frd, fs, max_expected_delay=med, pairs=pairs[s]) for s in (slice(0, half), slice(half, None))]
+    for name in ("k_idx", "peak", "gmax"):
+        a = getattr(whole, name).cpu().numpy()
+        b = np.concatenate([getattr(q, name).cpu().numpy() for q in parts], axis=1)
+        assert np.array_equal(a, b), name
+    td = whole.tdoa_seconds()[..., 0]
+    f64 = fr.astype(np.float64)
+    for f in range(2):
+        for p in range(0, len(pairs), 41):
+            i, j = pairs[p]
+            want, corr, _ = O.get_time_delays_phat(f64[f, i], f64[f, j], fs, max_expected_delay=med)
+            assert td[f, p] == want[0], (f, p)
+            assert abs(whole.gmax[f, p].item() - corr.max()) <= CORR_RTOL * corr.max()
