@@ -96,24 +96,6 @@ __global__ void __launch_bounds__(kTmemWarps * 32, 1)
   pair4095_tmem_body<kTmemWarps, WRITE_CORR>(spec, hq, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax, flags,
                                              corr_out, smem, pairs_in_smem);
 }
-template <bool WRITE_CORR>
-__global__ void __launch_bounds__(kTmemWarps * 32, 1)
-    k_pair4095_tile(const cpxf* __restrict__ spec, const float* __restrict__ hq, const int* __restrict__ pairs, int M, int P,
-                    long long n_items,
-                    int win_half, int dist, float eps, int* __restrict__ k_idx, float* __restrict__ peak,
-                    float* __restrict__ gmax, unsigned* __restrict__ flags, float* __restrict__ corr_out) {
-  extern __shared__ __align__(128) char smem[];
-  pair4095_tile_body<kTmemWarps, WRITE_CORR>(spec, hq, pairs, M, P, n_items, win_half, dist, eps, k_idx, peak, gmax, flags,
-                                             corr_out, smem);
-}
-// PAL_PAIR_KERNEL=tile: the experimental variant with the round's first-channel spectrum in shared memory
-bool want_tile_kernel() {
-  static const bool on = [] {
-    const char* e = std::getenv("PAL_PAIR_KERNEL");
-    return e && e[0] == 't' && e[1] == 'i';
-  }();
-  return on;
-}
 // Which fused pair kernel runs (read once): PAL_PAIR_KERNEL=tmem (default; 12 warps per SM, register
 // tiles parked in tensor memory; measured 10 % faster on B200) or PAL_PAIR_KERNEL=regs (8 warps per SM,
 // everything in registers; also used automatically when the tensor-memory kernel cannot be launched).
@@ -415,12 +397,6 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
   const int tmem_cap = (int)std::max(tmem_smem, di.smem_optin);
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_tmem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tmem_cap));
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_tmem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tmem_cap));
-  const size_t tile_smem = kTmemWarps * sizeof(TileWarpSmem) + sizeof(TileShared) + sizeof(int) * 2 * size_t(P);
-  const bool use_tile = want_tile_kernel() && tile_smem <= di.smem_optin;
-  if (use_tile) {
-    PAL_CUDA(cudaFuncSetAttribute(k_pair4095_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.smem_optin));
-    PAL_CUDA(cudaFuncSetAttribute(k_pair4095_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.smem_optin));
-  }
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_exact<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exd_smem));
   PAL_CUDA(cudaFuncSetAttribute(k_fwd4095, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
 
@@ -461,13 +437,7 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
       float* corr = corr_opt_dev ? corr_opt_dev + item0 * kN4095 : nullptr;
       {
         ProfScope ps(2, stream);
-        if (use_tile) {
-          const int gt = (int)std::min<long long>((n_items + kTmemWarps - 1) / kTmemWarps, (long long)di.sms);
-          auto kern = corr ? k_pair4095_tile<true> : k_pair4095_tile<false>;
-          kern<<<gt, kTmemWarps * 32, tile_smem, stream>>>(spec, hq, pairs_dev, M, P, n_items, pp.win_half, pp.dist,
-                                                           prm->tie_eps, k_idx_dev + item0, peak_dev + item0,
-                                                           gmax_dev + item0, flags_dev + item0, corr);
-        } else if (use_tmem_kernel()) {
+        if (use_tmem_kernel()) {
           const int gt = (int)std::min<long long>((n_items + kTmemWarps - 1) / kTmemWarps, (long long)di.sms);
           auto kern = corr ? k_pair4095_tmem<true> : k_pair4095_tmem<false>;
           kern<<<gt, kTmemWarps * 32, tmem_smem, stream>>>(spec, hq, pairs_dev, M, P, n_items, pp.win_half, pp.dist,

@@ -1148,375 +1148,4 @@ PAL_DEV void pair4095_tmem_body(const cpxf* spec, const float* hq, const int* pa
   if (warp == 0) simt::tmem_dealloc512(tbase);
 }
 
-// read-only (non-coherent) 64-bit global load: what the compiler emits by itself for the spectra in the plain kernels;
-// the tile kernel's fences and bulk copies stop it from proving that on its own
-PAL_DEV f2 ld_nc(const f2* p) {
-#if PAL_GPU
-  f2 r;
-  r.v = __ldg(reinterpret_cast<const unsigned long long*>(p));
-  return r;
-#else
-  return *p;
-#endif
-}
-// ---------------------------------------------------------------- fast pair kernel, TMEM-assisted, shared first-channel tile
-// (experimental, PAL_PAIR_KERNEL=tile)  Same arithmetic as pair4095_tmem_body.  The 12 pairs a block works on in one
-// round are consecutive items, so most of them share their FIRST microphone: its spectrum (16.6 KB, contiguous) is
-// brought into shared memory once per round by one TMA bulk copy and read from there (LDS, ~30 cycles) instead of
-// from L2 (~900 cycles under load) by every warp whose pair has that first microphone ("tile flavour": the whole
-// register ring, six DFT-5 groups deep, then serves the second channel alone).  The other warps of the round keep
-// the two three-deep rings of the plain kernel.  One tile, not two: it is only read in phase A1 (a quarter of a pair),
-// so the copy for round t+1 is issued by whichever warp finishes A1 of round t last (shared counter) and has three
-// quarters of a pair to land; warps therefore stay within one round of each other, which the mbarrier parity needs.
-// Shared memory: 12 x 17152 (the odd-column exchange moves into the tail of the union, which the correlation row
-// leaves free) + 32 + 16640 + 8 P bytes.
-struct alignas(16) TileWarpSmem {
-  union {
-    struct {
-      f2 ya[32 * 33];
-      f2 yb[32 * 33];
-      f2 y0[32];
-    } y;
-    float corr[4096 + 192];    // the row; [4096, 4288) = 768 bytes: odd-column exchange (63 complex values)
-  };
-};
-static_assert(sizeof(TileWarpSmem) == 17152, "tile-kernel warp tile");
-struct alignas(16) TileShared {
-  unsigned tmem_slot[4];
-  mbar_t full;                 // completes when the round's tile has landed
-  int count;                   // warps that are done reading the current tile
-  int pad;
-  f2 tile[kSpecSlots];
-};
-
-template <int WARPS, bool WRITE_CORR>
-PAL_DEV void pair4095_tile_body(const cpxf* spec, const float* hq, const int* pairs, int M, int P, long long n_items,
-                                int win_half, int dist, float eps, int* k_idx, float* peak, float* gmax,
-                                unsigned* flags, float* corr_out, char* smem_raw) {
-  using P65 = Pfa2<5, 13>;
-  using P63 = Pfa2<7, 9>;
-  const int lane = simt::lane();
-  // The warp index is broadcast from lane 0 so that the compiler can prove it warp-uniform: every
-  // branch on the work item is then a uniform branch, the main loop is convergent code and
-  // descriptors / tensor-memory addresses stay in uniform registers.
-  const int warp = simt::shfl(simt::warp(), 0);
-  TileWarpSmem* sm = reinterpret_cast<TileWarpSmem*>(smem_raw) + warp;
-  f2* const lx = reinterpret_cast<f2*>(sm->corr + 4096);      // odd-column exchange: the tail of the union (see TileWarpSmem)
-  TileShared* ts = reinterpret_cast<TileShared*>(reinterpret_cast<TileWarpSmem*>(smem_raw) + WARPS);
-  unsigned* tmem_slot = ts->tmem_slot;
-  int* const pairs_s = reinterpret_cast<int*>(ts + 1);         // the pair table, copied once per block
-  for (int i = simt::tid(); i < 2 * P; i += WARPS * 32) pairs_s[i] = pairs[i];
-  if (simt::tid() == 0) {
-    simt::mbar_init(&ts->full, 1);
-    ts->count = 0;
-  }
-  if (warp == 0) simt::tmem_alloc512(tmem_slot);
-  simt::tmem_fence_before_sync();
-  simt::sync_block();
-  simt::tmem_fence_after_sync();
-  const unsigned tbase = *tmem_slot;
-  const unsigned tcol = simt::tmem_addr(tbase, warp, (warp >> 2) * TmemPlan<WARPS>::kColsPerWarp);
-
-  const FastPick pk = make_fast_pick(win_half, dist, eps);
-  const int b0 = 63 * (lane + 1);
-  float* const p1 = sm->corr + b0;
-  float* const p1w = p1 - kN4095;
-  float* const p2 = p1 + 63 * 32;
-  float* const p2w = p2 - kN4095;
-
-  const long long stride = (long long)simt::nblocks() * WARPS;
-  long long item = (long long)simt::bid() * WARPS + warp;
-  // The first pair's microphone indices are fetched here, in convergent code, on purpose: it makes
-  // the compiler set up the global-memory descriptor in a uniform register once; if the first global
-  // load sits inside the (formally divergent) block below, every one of the 130 spectrum loads of a
-  // pair pays two extra R2UR instructions.
-  const long long item_c = item < n_items ? item : n_items - 1;
-  const int mi0 = pairs[2 * int(item_c % P)], mj0 = pairs[2 * int(item_c % P) + 1];
-  if (item < n_items) {
-#if PAL_GPU && PAL_STAGGER > 0
-    if (warp >= 4) {   // de-phase the warps that share a scheduler
-      const long long t0 = clock64();
-      while (clock64() - t0 < (long long)(PAL_STAGGER) * (warp >> 2)) {}
-    }
-#endif
-    // Software pipeline of the spectrum loads: the bins of DFT-5 group b + kLA are requested while
-    // group b is processed (a ring of kLA groups of 5 + 5 complex values in registers); the first
-    // kLA groups of the NEXT pair are requested before the peak pick of the current one.
-#ifndef PAL_TMEM_LOOKAHEAD
-#define PAL_TMEM_LOOKAHEAD 3
-#endif
-    constexpr int kLA = PAL_TMEM_LOOKAHEAD;
-    static_assert(kLA == 3, "the tile kernel's rings are written for a look-ahead of three groups");
-#ifndef PAL_TILE_RING
-#define PAL_TILE_RING 6
-#endif
-    constexpr int kLT = PAL_TILE_RING;       // depth of the second channel's ring in the tile flavour (<= 2 kLA)
-    static_assert(kLT >= 1 && kLT <= 2 * kLA, "tile-flavour ring depth");
-    const f2* si;
-    const f2* sj;
-    f2 rq[2 * kLA][5];           // plain flavour: [0, 3) first channel, [3, 6) second channel; tile flavour: second channel only
-    const f2* const tl = ts->tile + lane;
-    bool use_tile;               // this pair's first channel is the round's tile
-    unsigned parity = 0;
-    // first item of the block's current round, as (frame, pair); the same in every warp
-    long long first = (long long)simt::bid() * WARPS;
-    long long tframe = first / P;
-    int tpair = int(first - tframe * P);
-    if (simt::tid() == 0) {      // round 0's tile
-      simt::fence_async_smem();
-      simt::mbar_expect_tx(&ts->full, kSpecSlots * 8u);
-      simt::bulk_g2s(ts->tile, spec + (tframe * M + pairs_s[2 * tpair]) * kSpecSlots, kSpecSlots * 8u, &ts->full);
-    }
-    float wb, wb_next = 0.f;     // whiten_bound of the current / next pair
-    // (frame, pair) of the item in flight, advanced by the constant stride with an add-and-carry instead of a
-    // 64-bit division per pair
-    long long frame_it = item / P;
-    int pair_it = int(item - frame_it * P);
-    const long long stride_f = stride / P;
-    const int stride_p = int(stride - stride_f * P);
-    {
-      const long long frame = frame_it;
-      si = reinterpret_cast<const f2*>(spec + (frame * M + mi0) * kSpecSlots) + lane;
-      sj = reinterpret_cast<const f2*>(spec + (frame * M + mj0) * kSpecSlots) + lane;
-      wb = whiten_bound(hq, frame * M + mi0, frame * M + mj0);
-      use_tile = frame == tframe && mi0 == pairs_s[2 * tpair];
-      if (use_tile) {
-#pragma unroll
-        for (int g = 0; g < kLT; ++g)
-#pragma unroll
-          for (int a5 = 0; a5 < 5; ++a5) rq[g][a5] = ld_nc(sj + P65::slot(a5, g) * 32);
-      } else {
-#pragma unroll
-        for (int g = 0; g < kLA; ++g)
-#pragma unroll
-          for (int a5 = 0; a5 < 5; ++a5) { rq[g][a5] = ld_nc(si + P65::slot(a5, g) * 32); rq[kLA + g][a5] = ld_nc(sj + P65::slot(a5, g) * 32); }
-      }
-    }
-    for (;;) {
-      float gm = kNegBig;
-      // ---- phase A, pass 1: PHAT + DFT-5 over a for every b; result (a, b) parked at column 2 (13 a + b)
-      // (every warp waits for the round's tile, whatever its flavour: that keeps the arrivals of two rounds apart)
-      simt::mbar_wait(&ts->full, parity);
-      if (use_tile) {
-#pragma unroll
-        for (int b = 0; b < 13; ++b) {
-          f2 t[5];
-#pragma unroll
-          for (int a = 0; a < 5; ++a) t[a] = phat_bin_p(tl[P65::slot(a, b) * 32], rq[b % kLT][a]);
-          if (b + kLT < 13) {
-#pragma unroll
-            for (int a = 0; a < 5; ++a) rq[b % kLT][a] = ld_nc(sj + P65::slot(a, b + kLT) * 32);
-          }
-          dft_odd_p<5, +1>(t);
-#pragma unroll
-          for (int a = 0; a < 5; ++a) {
-            const f2 one[1] = {t[a]};
-            tmem_st(tcol + 2 * (13 * a + b), one);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int b = 0; b < 13; ++b) {
-          f2 t[5];
-#pragma unroll
-          for (int a = 0; a < 5; ++a) t[a] = phat_bin_p(rq[b % kLA][a], rq[kLA + b % kLA][a]);
-          if (b + kLA < 13) {
-#pragma unroll
-            for (int a = 0; a < 5; ++a) {
-              rq[b % kLA][a] = ld_nc(si + P65::slot(a, b + kLA) * 32);
-              rq[kLA + b % kLA][a] = ld_nc(sj + P65::slot(a, b + kLA) * 32);
-            }
-          }
-          dft_odd_p<5, +1>(t);
-#pragma unroll
-          for (int a = 0; a < 5; ++a) {
-            const f2 one[1] = {t[a]};
-            tmem_st(tcol + 2 * (13 * a + b), one);
-          }
-        }
-      }
-      simt::tmem_wait_st();
-      // ---- hand the tile over: the warp that finishes phase A1 of this round last requests the next round's tile
-      long long nframe = tframe + stride_f;
-      int npair = tpair + stride_p;
-      if (npair >= P) { npair -= P; ++nframe; }
-      if (first + stride < n_items) {        // a next round exists (then every warp of the block has an item in this one)
-        simt::sync_warp();
-        if (lane == 0) {
-          simt::fence_block();
-          if (simt::atom_add_shared(&ts->count, 1) == WARPS - 1) {
-            simt::store_shared_volatile(&ts->count, 0);
-            simt::fence_block();
-            simt::fence_async_smem();
-            simt::mbar_expect_tx(&ts->full, kSpecSlots * 8u);
-            simt::bulk_g2s(ts->tile, spec + (nframe * M + pairs_s[2 * npair]) * kSpecSlots, kSpecSlots * 8u, &ts->full);
-          }
-        }
-      }
-      // ---- phase A, pass 2: DFT-13 over b for every a, straight into the exchange tile
-#pragma unroll
-      for (int a = 0; a < 5; ++a) {
-        f2 t[13];
-        {
-          f2 v8[8], v4[4], v1[1];
-          tmem_ld(tcol + 26 * a, v8);
-          tmem_ld(tcol + 26 * a + 16, v4);
-          tmem_ld(tcol + 26 * a + 24, v1);
-          simt::tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = v8[i];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) t[8 + i] = v4[i];
-          t[12] = v1[0];
-        }
-        dft_odd_p<13, +1>(t);
-#pragma unroll
-        for (int b = 0; b < 13; ++b) {
-          const int kq = P65::out_index(P65::slot(a, b));
-          if (kq == 0) sm->y.y0[lane] = t[b];
-          else if (kq <= 32) sm->y.ya[lane * 33 + (kq - 1)] = t[b];
-          else sm->y.yb[lane * 33 + (kq - 33)] = t[b];
-        }
-      }
-      simt::sync_warp();
-      // ---- phase B, pass 1: the DFT-7 groups b and 9-b together (they share the rows r and 63-r of
-      // the Hermitian columns); result (a, b) parked at column 2 (9 a + b)
-#pragma unroll
-      for (int b = 0; b < 5; ++b) {
-        const int bc = (9 - b) % 9;
-        f2 t1[7], t2[7];
-#pragma unroll
-        for (int a = 0; a < 7; ++a) {
-          const int s = P63::slot(a, b);
-          const int ac = (7 - a) % 7;                       // slot(ac, bc) == (63 - s) % 63
-          if (s == 0) {
-            const f2 ya = sm->y.ya[lane], yb = sm->y.yb[lane];
-            t1[0] = f2_make(f2_lo(ya), f2_lo(yb));
-          } else if (b != 0 || s < 32) {
-            const int r = s < 32 ? s : 63 - s;
-            const f2 ya = sm->y.ya[r * 33 + lane], yb = sm->y.yb[r * 33 + lane];
-            const f2 wlo = f2_add(ya, f2_muli(yb));                 // w[r]
-            const f2 whi = f2_add(f2_conj(ya), f2_swap(yb));        // w[63 - r]
-            if (b == 0) { t1[a] = wlo; t1[ac] = whi; }              // both partners live in group 0
-            else if (s < 32) { t1[a] = wlo; t2[ac] = whi; }
-            else { t1[a] = whi; t2[ac] = wlo; }
-          }
-        }
-        dft_odd_p<7, +1>(t1);
-#pragma unroll
-        for (int a = 0; a < 7; ++a) {
-          const f2 one[1] = {t1[a]};
-          tmem_st(tcol + 2 * (9 * a + b), one);
-        }
-        if (b != 0) {
-          dft_odd_p<7, +1>(t2);
-#pragma unroll
-          for (int a = 0; a < 7; ++a) {
-            const f2 one[1] = {t2[a]};
-            tmem_st(tcol + 2 * (9 * a + bc), one);
-          }
-        }
-      }
-      // odd column kq = 0: nine DFT-7 on lanes 0..8 now, seven DFT-9 on lanes 0..6 below
-      f2 t7[7];
-      if (lane < 9) {
-#pragma unroll
-        for (int a = 0; a < 7; ++a) {
-          const int r = (a * P63::UA + lane * P63::UB) % 63;
-          const f2 v = sm->y.y0[r < 32 ? r : 63 - r];
-          t7[a] = f2_make(f2_lo(v), (r == 0) ? 0.f : (r < 32 ? f2_hi(v) : -f2_hi(v)));
-        }
-      }
-      simt::tmem_wait_st();
-      simt::sync_warp();            // every read of Y is done: the union now holds the correlation row
-      if (lane < 9) {
-        dft_odd_p<7, +1>(t7);
-#pragma unroll
-        for (int a = 0; a < 7; ++a) lx[(a * P63::UA + lane * P63::UB) % 63] = t7[a];
-      }
-      // ---- phase B, pass 2: DFT-9 over b for every a, scattered to natural order
-#pragma unroll
-      for (int a = 0; a < 7; ++a) {
-        f2 t[9];
-        {
-          f2 v8[8], v1[1];
-          tmem_ld(tcol + 18 * a, v8);
-          tmem_ld(tcol + 18 * a + 16, v1);
-          simt::tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = v8[i];
-          t[8] = v1[0];
-        }
-        dft_odd_p<9, +1>(t);
-#pragma unroll
-        for (int b = 0; b < 9; ++b) {
-          const int kr = P63::out_index(P63::slot(a, b));
-          const int c = 65 * kr;
-          const float vr = f2_lo(t[b]), vi = f2_hi(t[b]);
-          if (kr <= 31) p1[c] = vr;
-          else ((b0 + c >= kN4095) ? p1w : p1)[c] = vr;
-          if (kr == 0) p2[c] = vi;
-          else if (kr >= 32) p2w[c] = vi;
-          else ((b0 + 63 * 32 + c >= kN4095) ? p2w : p2)[c] = vi;
-          gm = fmaxf(gm, fmaxf(vr, vi));
-        }
-      }
-      simt::sync_warp();
-      if (lane < 7) {
-        f2 u[9];
-#pragma unroll
-        for (int b = 0; b < 9; ++b) u[b] = lx[(lane * P63::UA + b * P63::UB) % 63];
-        dft_odd_p<9, +1>(u);
-#pragma unroll
-        for (int b = 0; b < 9; ++b) {
-          const int kr = (9 * lane + 7 * b) % 63;
-          const float v = f2_lo(u[b]);
-          sm->corr[(65 * kr) % kN4095] = v;
-          gm = fmaxf(gm, v);
-        }
-      }
-      // ---- fetch the first bins of the NEXT pair while this one is being picked
-      const long long next = item + stride;
-      const bool has_next = next < n_items;
-      if (has_next) {
-        pair_it += stride_p;
-        frame_it += stride_f;
-        if (pair_it >= P) { pair_it -= P; ++frame_it; }
-        const long long frame = frame_it;
-        const int p = pair_it;
-        const int mi = pairs_s[2 * p];
-        const int mj = pairs_s[2 * p + 1];
-        si = reinterpret_cast<const f2*>(spec + (frame * M + mi) * kSpecSlots) + lane;
-        sj = reinterpret_cast<const f2*>(spec + (frame * M + mj) * kSpecSlots) + lane;
-        wb_next = whiten_bound(hq, frame * M + mi, frame * M + mj);
-        use_tile = frame == nframe && mi == pairs_s[2 * npair];
-        if (use_tile) {
-#pragma unroll
-          for (int g = 0; g < kLT; ++g)
-#pragma unroll
-            for (int a5 = 0; a5 < 5; ++a5) rq[g][a5] = ld_nc(sj + P65::slot(a5, g) * 32);
-        } else {
-#pragma unroll
-          for (int g = 0; g < kLA; ++g)
-#pragma unroll
-            for (int a5 = 0; a5 < 5; ++a5) { rq[g][a5] = ld_nc(si + P65::slot(a5, g) * 32); rq[kLA + g][a5] = ld_nc(sj + P65::slot(a5, g) * 32); }
-        }
-      }
-      simt::sync_warp();
-      fast_pick_row<WRITE_CORR>(sm->corr, item, gm, lane, pk, wb, k_idx, peak, gmax, flags, corr_out);
-      if (!has_next) break;
-      item = next;
-      wb = wb_next;
-      first += stride;
-      tframe = nframe;
-      tpair = npair;
-      parity ^= 1u;
-      simt::sync_warp();   // the next item overwrites the union
-    }
-  }
-  simt::tmem_fence_before_sync();
-  simt::sync_block();
-  if (warp == 0) simt::tmem_dealloc512(tbase);
-}
-
 }  // namespace pal

@@ -72,10 +72,6 @@ PAL_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, mbar
 }
 // order earlier generic-proxy accesses of shared memory before a following bulk (async-proxy) copy
 PAL_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// block-scope fence and shared-memory counter (hand-over of a shared tile between the warps of a block)
-PAL_DEV void fence_block() { __threadfence_block(); }
-PAL_DEV int atom_add_shared(int* p, int v) { return atomicAdd(p, v); }
-PAL_DEV void store_shared_volatile(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
 PAL_DEV void mbar_wait(mbar_t* b, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -228,9 +224,6 @@ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, mbar_t* b) {
   if ((before & 0xffffffffull) == bytes) mb(b)->fetch_add(1ull << 32);  // phase complete
 }
 inline void fence_async_smem() {}
-inline void fence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
-inline int atom_add_shared(int* p, int v) { return reinterpret_cast<std::atomic<int>*>(p)->fetch_add(v); }
-inline void store_shared_volatile(int* p, int v) { reinterpret_cast<std::atomic<int>*>(p)->store(v); }
 inline void mbar_wait(mbar_t* b, unsigned parity) {
   while (((mb(b)->load(std::memory_order_acquire) >> 32) & 1ull) == parity) std::this_thread::yield();
 }

@@ -19,15 +19,6 @@ void emu_pair4095_fast(const float* spec, const float* hq, const int* pairs, int
                        int grid, int phase_sync) {
   constexpr int W = 2;
   const cpxf* sp = reinterpret_cast<const cpxf*>(spec);
-  if (phase_sync == 4) {      // tile variant: the round's first-channel spectrum in shared memory
-    simt::launch(grid, 32 * W, W * sizeof(TileWarpSmem) + sizeof(TileShared) + sizeof(int) * 2 * size_t(P), [&](char* smem) {
-      if (corr_out)
-        pair4095_tile_body<W, true>(sp, hq, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
-      else
-        pair4095_tile_body<W, false>(sp, hq, pairs, M, P, B * P, win_half, dist, eps, k_idx, peak, gmax, flags, corr_out, smem);
-    });
-    return;
-  }
   simt::launch(grid, 32 * W, W * sizeof(FastWarpSmem) + 16 + sizeof(int) * 2 * size_t(P), [&](char* smem) {
     if (phase_sync >= 2) {     // TMEM-assisted variant; 2: pair table copied to shared memory, 3: read from global memory
       const int ps = phase_sync == 2 ? 1 : 0;

@@ -62,7 +62,7 @@ def test_whitening_bound_sends_quiet_frames_to_float64():
                 assert dev < 5e-7
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3, 4])   # 0: register-resident tiles; 2, 3: tiles parked in (emulated) tensor memory, pair table in shared / global memory; 4: shared first-channel tile
+@pytest.mark.parametrize("variant", [0, 2, 3])   # 0: register-resident tiles; 2, 3: tiles parked in (emulated) tensor memory, pair table in shared / global memory
 @pytest.mark.parametrize("med", [0.05, 0.01, None])
 def test_fast_pair_kernel_vs_oracle(frames, spectra, med, variant):
     pairs = E.pairs_of(frames.shape[1])
