@@ -388,10 +388,10 @@ int pal_gcc_phat_tdoa(const float* sig_dev, int64_t B, int32_t M, int32_t n_samp
   PAL_CUDA(cudaFuncSetAttribute(k_pair4095_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
   // warp tiles + the tensor-memory slot + (when it fits the opt-in limit) a copy of the pair table
   size_t tmem_smem = kTmemWarps * sizeof(FastWarpSmem) + 16;
-#ifndef PAL_FIX_PAIRS
-#define PAL_FIX_PAIRS 1
+#ifndef PAL_PAIRS_IN_SMEM   // A/B measurements: 0 = the kernel always reads the pair table from global memory
+#define PAL_PAIRS_IN_SMEM 1
 #endif
-  const int pairs_in_smem = (PAL_FIX_PAIRS && tmem_smem + sizeof(int) * 2 * size_t(P) <= di.smem_optin) ? 1 : 0;
+  const int pairs_in_smem = (PAL_PAIRS_IN_SMEM && tmem_smem + sizeof(int) * 2 * size_t(P) <= di.smem_optin) ? 1 : 0;
   if (pairs_in_smem) tmem_smem += sizeof(int) * 2 * size_t(P);
   // (the cap is the device's opt-in limit whatever P is: callers with different pair counts never shrink it under each other)
   const int tmem_cap = (int)std::max(tmem_smem, di.smem_optin);
